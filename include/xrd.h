@@ -1,0 +1,192 @@
+/*
+ * xrd.h -- C ABI of libxrd.so, the B200-native (sm_100a) implementation of the
+ * /denoise inference hot path of KushalChaudhari-16/Medical-Image-Denoising-Using-Diffusion.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; the entry
+ * points below are what a maintainer binds (via ctypes)
+ * in place of the bodies of the reference's model classes.  Each entry point
+ * cites the reference interface it replaces ("HYB" = Backend/hybrid/
+ * hybrid3diffusionspeed.py, "DDIM" = Backend/DDIM/DDIMModel.py, "NAF" =
+ * Backend/NafNet/NafnetModel.py, "RUN" = Backend/run.py).
+ *
+ * Conventions
+ *   - plain C types only: no torch, no C++ types in any signature;
+ *   - image tensors are float32, contiguous, (B,1,H,W) == (B,H,W,1), device
+ *     memory of the handle's device, owned by the caller;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     calls enqueue work and return without synchronising the host;
+ *   - every function returns 0 on success or a negative xrd_status; the message
+ *     is available from xrd_last_error() (thread local).  Nothing throws or
+ *     aborts across the ABI and there is NO CPU fallback: unsupported shapes
+ *     or a missing GPU are errors.
+ *   - a handle may be used from any one thread at a time (internal mutex);
+ *     distinct handles are independent (RUN:85-91 drives three models from
+ *     three threads).
+ */
+#ifndef XRD_H_
+#define XRD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XRD_API_VERSION 1
+#define XRD_MAX_LEVELS 8
+
+typedef struct xrd_handle xrd_handle;
+
+typedef enum xrd_status {
+  XRD_OK = 0,
+  XRD_ERR_INVALID = -1,       /* bad argument / unsupported shape or config  */
+  XRD_ERR_CUDA = -2,          /* a CUDA runtime/driver call failed           */
+  XRD_ERR_NO_DEVICE = -3,     /* no usable sm_100 GPU                        */
+  XRD_ERR_MISSING_PARAM = -4, /* a state_dict tensor the path needs is absent*/
+  XRD_ERR_STATE = -5          /* call order violated (e.g. not finalised)    */
+} xrd_status;
+
+/* Arithmetic mode (north star: bf16 tensor-core path + fp32-accumulate check mode). */
+typedef enum xrd_mode {
+  XRD_MODE_BF16 = 0,        /* NHWC bf16 activations, tcgen05 contractions, fp32 accumulate/statistics */
+  XRD_MODE_FP32_CHECK = 1,  /* NHWC fp32 activations, fp32 CUDA-core contractions (parity check mode)   */
+  XRD_MODE_FP16 = 2         /* as BF16 but IEEE half operands/storage (same kernels, 3 more mantissa bits) */
+} xrd_mode;
+
+/* Constructor arguments of the reference classes, flattened.
+ *   UNetDiffusion(in_channels, model_channels, channel_mult, num_res_blocks,
+ *                 attention_resolutions, dropout, time_emb_dim)      HYB:309-310
+ *   EnhancedNAFNet(img_channel, width, middle_blk_num, enc_blk_nums,
+ *                  dec_blk_nums)                                      HYB:173-174
+ *   NoiseAnalyzer(in_c, out_c, base_c) / FusionModule(in_c,out_c,base_c)  HYB:471,538
+ *   DiffusionDenoiser(model, noise_steps, beta_start, beta_end)       HYB:392
+ * The *_prefix strings are prepended to the reference's state_dict keys
+ * ("" for a standalone model, "diffusion_unet." etc. inside the hybrid). */
+typedef struct xrd_config {
+  int32_t unet_in_channels;
+  int32_t unet_model_channels;
+  int32_t unet_n_levels;
+  int32_t unet_channel_mult[XRD_MAX_LEVELS];
+  int32_t unet_num_res_blocks;
+  int32_t unet_n_attn;
+  int32_t unet_attention_resolutions[XRD_MAX_LEVELS];
+  int32_t unet_time_emb_dim;
+  int32_t unet_num_heads;
+
+  int32_t naf_img_channel;
+  int32_t naf_width;
+  int32_t naf_middle_blk_num;
+  int32_t naf_n_enc;
+  int32_t naf_enc_blk_nums[XRD_MAX_LEVELS];
+  int32_t naf_n_dec;
+  int32_t naf_dec_blk_nums[XRD_MAX_LEVELS];
+
+  int32_t router_base_c;
+  int32_t fusion_base_c;
+
+  int32_t noise_steps;
+  float beta_start;
+  float beta_end;
+
+  char unet_prefix[64];
+  char naf_prefix[64];
+  char router_prefix[64];
+  char fusion_prefix[64];
+} xrd_config;
+
+/* Fill *cfg with the reference's default constructor arguments. */
+void xrd_default_config(xrd_config* cfg);
+
+int xrd_api_version(void);
+const char* xrd_last_error(void);
+
+/* Number of CUDA kernels this library has launched on behalf of the calling
+ * process since load (monotonic; used by bench.py for "gpu_launches"). */
+uint64_t xrd_kernel_launch_count(void);
+
+/* Replaces: constructing the reference nn.Modules and `.to(device)` (RUN:34-36,46-47,64-68). */
+int xrd_create(int device, const xrd_config* cfg, xrd_handle** out);
+void xrd_destroy(xrd_handle* h);
+
+/* Replaces: nn.Module.load_state_dict (RUN:38,48,70).  `key` is the reference's
+ * state_dict key (with the configured prefix); `data` is float32, row-major in
+ * the reference's own tensor layout, on the host (is_device=0) or on the
+ * handle's device (is_device=1).  The data is copied; the caller keeps ownership. */
+int xrd_set_param(xrd_handle* h, const char* key, const void* data, const int64_t* shape, int ndim,
+                  int is_device);
+
+/* Repack weights for the kernels (NHWC/K-major bf16 tiles, the ConvTranspose+bilinear
+ * 3x3 pre-combination, depth-to-space orderings).  `which` is a bit mask of XRD_PART_*;
+ * parts whose parameters are absent are reported as XRD_ERR_MISSING_PARAM. */
+#define XRD_PART_UNET   1
+#define XRD_PART_NAFNET 2
+#define XRD_PART_ROUTER 4
+#define XRD_PART_FUSION 8
+#define XRD_PART_ALL    15
+int xrd_finalize_weights(xrd_handle* h, int which);
+
+int xrd_set_mode(xrd_handle* h, int mode);
+int xrd_get_mode(xrd_handle* h);
+/* 0 = plain stream launches, 1 (default) = the sampler loop is captured into one CUDA graph
+ * per (B,H,W,evals,mode) and replayed. */
+int xrd_set_use_graph(xrd_handle* h, int enable);
+
+/* Replaces: UNetDiffusion.forward(x, condition, t) (HYB:359-388, DDIM:219-248).
+ * `t` = B int64 timestep values on the device.  eps: (B,1,H,W) float32, unclamped. */
+int xrd_unet_eps(xrd_handle* h, const float* x, const float* cond, const int64_t* t, float* eps,
+                 int B, int H, int W, void* stream);
+
+/* Replaces: DiffusionDenoiser.denoise(noisy_img, inference_steps) (HYB:400-418, DDIM:268-289).
+ * Visits timesteps reversed(range(0, noise_steps, max(1, noise_steps // inference_steps))).
+ * eps_trace / xin_trace (nullable): (n_evals,B,H,W) float32 receiving every evaluation's raw
+ * eps and its input x.  teacher_x (nullable): (n_evals,B,H,W) float32; when given, the loop
+ * state is replaced by teacher_x[n] before evaluation n (teacher forcing, parity tests only). */
+int xrd_ddim_denoise(xrd_handle* h, const float* noisy, int inference_steps, float* out,
+                     float* eps_trace, float* xin_trace, const float* teacher_x,
+                     int B, int H, int W, void* stream);
+/* Number of UNet evaluations xrd_ddim_denoise performs for these arguments (host only). */
+int xrd_ddim_num_evals(int noise_steps, int inference_steps);
+
+/* Replaces: EnhancedNAFNet.forward(inp) (HYB:206-231, NAF:275-302).  Output is the raw
+ * network output (input residual added, NOT clamped), like the reference. */
+int xrd_nafnet(xrd_handle* h, const float* inp, float* out, int B, int H, int W, void* stream);
+
+/* Replaces: NoiseAnalyzer.forward(x) (HYB:511-534): soft sigmoid mask in (0,1), always
+ * evaluated in fp32 regardless of the mode. */
+int xrd_router(xrd_handle* h, const float* x, float* mask, int B, int H, int W, void* stream);
+
+/* Replaces: FusionModule.forward(nafnet_out, diffusion_out, routing_mask) (HYB:552-557). */
+int xrd_fusion(xrd_handle* h, const float* naf, const float* diff, const float* mask, float* out,
+               int B, int H, int W, void* stream);
+
+/* Replaces: HybridDenoisingRouter.forward(noisy_input) in eval mode (HYB:610-628): NAFNet ->
+ * nan_to_num+clamp; sampler -> nan_to_num+clamp; router -> nan_to_num+clamp; fusion (unclamped).
+ * naf_out / diff_out / mask_out are nullable (B,1,H,W) taps of the sanitised intermediates. */
+int xrd_hybrid(xrd_handle* h, const float* noisy, int inference_steps, float* out,
+               float* naf_out, float* diff_out, float* mask_out, int B, int H, int W, void* stream);
+
+/* ---- kernel-level hooks (tests and micro-benchmarks only; no reference counterpart) ----
+ * NCHW float32 device tensors in and out; the library converts to its internal NHWC storage
+ * of the handle's current mode, runs ONE op through the same kernel the networks use, and
+ * converts back.  They need no weights to be finalised. */
+
+/* conv2d: weight (Cout,Cin,kh,kw), bias nullable.  impl: 0 = CUDA-core kernel, 1 = tcgen05
+ * implicit-GEMM kernel (3x3/s1/p1, 3x3/s2/p1, 2x2/s2/p0 and 1x1 only). */
+int xrd_op_conv2d(xrd_handle* h, int impl, const float* x, const float* weight, const float* bias,
+                  float* y, int B, int Cin, int H, int W, int Cout, int k, int stride, int pad,
+                  void* stream);
+/* GroupNorm(groups, C, eps=1e-5) + activation (0 none, 1 SiLU, 2 erf-GELU). */
+int xrd_op_groupnorm_act(xrd_handle* h, const float* x, const float* gamma, const float* beta,
+                         float* y, int B, int C, int H, int W, int groups, int act, void* stream);
+/* softmax(q^T k / sqrt(d)) v over n = H*W tokens; qkv (B, 3*heads*d, H, W) in the reference's
+ * channel order (HYB:295-296), out (B, heads*d, H, W).  impl: 0 CUDA-core, 1 tcgen05. */
+int xrd_op_attention(xrd_handle* h, int impl, const float* qkv, float* out, int B, int heads, int d,
+                     int H, int W, void* stream);
+/* Time one op on the device: runs `iters` launches of the op configured by the preceding
+ * xrd_op_* call (cached buffers) bracketed by CUDA events on `stream`; returns ms per launch. */
+int xrd_op_time_last(xrd_handle* h, int iters, float* ms_per_launch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XRD_H_ */

@@ -1,0 +1,20 @@
+"""B200-native (sm_100a) drop-in for the /denoise inference hot path of
+KushalChaudhari-16/Medical-Image-Denoising-Using-Diffusion.
+
+The directory name contains hyphens, so import it with
+``importlib.import_module("medical-image-denoising-using-diffusion_b200")`` or
+through the alias module ``xrd_b200`` at the repository root.
+"""
+from ._lib import XrdError, LIB_PATH, load as load_library          # noqa: F401
+from .models import (                                                # noqa: F401
+    AttentionBlock, DiffusionDenoiser, EnhancedNAFNet, FusionModule, HybridDenoisingRouter,
+    LayerNorm, NAFBlock, NoiseAnalyzer, ResidualBlock, SimpleGate, SinusoidalPositionEmbeddings,
+    UNetDiffusion, ddim_timestep_indices, native_kernel_launches,
+)
+from .build import build_library                                    # noqa: F401
+
+__all__ = [
+    "XrdError", "LIB_PATH", "load_library", "build_library",
+    "UNetDiffusion", "DiffusionDenoiser", "EnhancedNAFNet", "NoiseAnalyzer", "FusionModule",
+    "HybridDenoisingRouter", "ddim_timestep_indices", "native_kernel_launches",
+]

@@ -1,0 +1,568 @@
+"""Drop-in model classes for the /denoise hot path.
+
+Same class names, constructor keyword arguments, attribute names, sub-module
+names and ``state_dict`` keys as the reference (HYB = Backend/hybrid/
+hybrid3diffusionspeed.py, DDIM = Backend/DDIM/DDIMModel.py, NAF =
+Backend/NafNet/NafnetModel.py), so ``Backend/run.py`` can import them unchanged
+(see ``compat/`` and INTEGRATION.md).  The torch ``nn`` layers created here are
+*parameter containers only*: they give the reference's key names, shapes and
+(by constructing them in the reference's order) the same random initialisation
+for a given seed.  None of their ``forward`` methods ever runs -- every
+``forward`` / ``denoise`` below hands raw device pointers to libxrd.so
+(include/xrd.h), whose kernels are hand-written CUDA for sm_100a.  There is no
+PyTorch or CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Dict, Iterable, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import XrdError
+
+_MODE_NAMES = {"bf16": _lib.MODE_BF16, "fp32": _lib.MODE_FP32_CHECK, "fp16": _lib.MODE_FP16}
+
+
+def _default_mode() -> str:
+    return os.environ.get("XRD_MODE", "bf16")
+
+
+# ---------------------------------------------------------------------------
+# parameter containers (no compute)
+# ---------------------------------------------------------------------------
+class _Container(nn.Module):
+    """A node of the module tree that only owns parameters."""
+
+    def forward(self, *a, **k):  # pragma: no cover - never a valid call
+        raise XrdError(
+            f"{type(self).__name__} is executed inside libxrd.so as part of its parent model; "
+            "call the top-level model (UNetDiffusion / EnhancedNAFNet / NoiseAnalyzer / "
+            "FusionModule / HybridDenoisingRouter) instead")
+
+
+class LayerNorm(_Container):
+    """Channel LayerNorm parameters (HYB:101-106): keys weight, bias."""
+
+    def __init__(self, normalized_shape, eps=1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(normalized_shape))
+        self.bias = nn.Parameter(torch.zeros(normalized_shape))
+        self.eps = eps
+
+
+class SimpleGate(_Container):
+    pass
+
+
+class NAFBlock(_Container):
+    """Keys conv1..conv5, sca.1, norm1, norm2, beta, gamma (HYB:124-150)."""
+
+    def __init__(self, c, DW_Expand=2, FFN_Expand=2, drop_out_rate=0.0):
+        super().__init__()
+        dw = c * DW_Expand
+        ffn = c * FFN_Expand
+        # creation order fixes the RNG stream: conv1, conv2, conv3, sca, conv4, conv5
+        self.conv1 = nn.Conv2d(c, dw, 1)
+        self.conv2 = nn.Conv2d(dw, dw, 3, padding=1, groups=dw)
+        self.conv3 = nn.Conv2d(dw // 2, c, 1)
+        self.sca = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(dw // 2, dw // 2, 1))
+        self.sg = SimpleGate()
+        self.conv4 = nn.Conv2d(c, ffn, 1)
+        self.conv5 = nn.Conv2d(ffn // 2, c, 1)
+        self.norm1 = LayerNorm(c)
+        self.norm2 = LayerNorm(c)
+        self.dropout1 = nn.Identity()
+        self.dropout2 = nn.Identity()
+        if drop_out_rate > 0.0:
+            raise XrdError("inference-only implementation: drop_out_rate must be 0")
+        self.beta = nn.Parameter(torch.zeros((1, c, 1, 1)))
+        self.gamma = nn.Parameter(torch.zeros((1, c, 1, 1)))
+
+
+class SinusoidalPositionEmbeddings(_Container):
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+
+
+class ResidualBlock(_Container):
+    """Keys time_mlp.1, block1.{0,2}, block2.{0,3}, res_conv (HYB:256-274)."""
+
+    def __init__(self, in_c, out_c, time_emb_dim, dropout=0.0):
+        super().__init__()
+        self.time_mlp = nn.Sequential(nn.SiLU(), nn.Linear(time_emb_dim, out_c))
+        self.block1 = nn.Sequential(nn.GroupNorm(8, in_c), nn.SiLU(), nn.Conv2d(in_c, out_c, 3, padding=1))
+        self.block2 = nn.Sequential(nn.GroupNorm(8, out_c), nn.SiLU(), nn.Dropout(dropout),
+                                    nn.Conv2d(out_c, out_c, 3, padding=1))
+        self.res_conv = nn.Conv2d(in_c, out_c, 1) if in_c != out_c else nn.Identity()
+
+
+class AttentionBlock(_Container):
+    """Keys norm, qkv, proj (HYB:284-290)."""
+
+    def __init__(self, channels, num_heads=2):
+        super().__init__()
+        self.num_heads = num_heads
+        self.norm = nn.GroupNorm(8, channels)
+        self.qkv = nn.Conv2d(channels, channels * 3, 1)
+        self.proj = nn.Conv2d(channels, channels, 1)
+
+
+# ---------------------------------------------------------------------------
+# native handle management
+# ---------------------------------------------------------------------------
+class _NativeModel(nn.Module):
+    """Top-level model: owns one libxrd handle per CUDA device, re-uploads the
+    weights whenever any parameter changed (load_state_dict, .to(), in-place
+    edits), and exposes the arithmetic mode.  Weights are (re)packed after
+    load_state_dict, never baked at __init__."""
+
+    _xrd_parts = 0           # XRD_PART_* mask this model needs
+    _xrd_prefix = ""
+
+    def _xrd_init(self):
+        object.__setattr__(self, "_xrd_handles", {})
+        object.__setattr__(self, "_xrd_lock", threading.Lock())
+        object.__setattr__(self, "_xrd_schedule", (50, 1e-4, 0.02))
+        self.native_mode = _default_mode()
+        self.use_cuda_graph = True
+
+    # -- configuration ------------------------------------------------------
+    def _xrd_fill_config(self, cfg: _lib.XrdConfig) -> None:
+        raise NotImplementedError
+
+    def set_native_mode(self, mode: str) -> "_NativeModel":
+        """'bf16' (default, tensor-core path), 'fp32' (check mode) or 'fp16'."""
+        if mode not in _MODE_NAMES:
+            raise XrdError(f"unknown mode {mode!r}")
+        self.native_mode = mode
+        return self
+
+    def _xrd_set_schedule(self, noise_steps: int, beta_start: float, beta_end: float) -> None:
+        sched = (int(noise_steps), float(beta_start), float(beta_end))
+        if sched != self._xrd_schedule:
+            with self._xrd_lock:
+                for ent in self._xrd_handles.values():
+                    _lib.load().xrd_destroy(ent["h"])
+                self._xrd_handles.clear()
+            object.__setattr__(self, "_xrd_schedule", sched)
+
+    # -- handle + weights ---------------------------------------------------
+    def _xrd_fingerprint(self, device) -> tuple:
+        return tuple((k, v.data_ptr(), v._version, v.device.index)
+                     for k, v in self.state_dict(keep_vars=True).items())
+
+    def _xrd_handle(self, device: torch.device):
+        lib = _lib.load()
+        if device.type != "cuda":
+            raise XrdError("this implementation runs on a CUDA sm_100 device only; there is no CPU fallback "
+                           f"(got a tensor on {device})")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        with self._xrd_lock:
+            ent = self._xrd_handles.get(idx)
+            if ent is None:
+                cfg = _lib.default_config()
+                self._xrd_fill_config(cfg)
+                cfg.noise_steps, cfg.beta_start, cfg.beta_end = self._xrd_schedule
+                h = C.c_void_p()
+                _lib.check(lib.xrd_create(idx, C.byref(cfg), C.byref(h)))
+                ent = {"h": h, "fp": None}
+                self._xrd_handles[idx] = ent
+            fp = self._xrd_fingerprint(device)
+            if fp != ent["fp"]:
+                keep = []
+                for key, v in self.state_dict(keep_vars=True).items():
+                    t = v.detach()
+                    if t.device.type != "cuda" or t.device.index != idx:
+                        raise XrdError(f"parameter {key} lives on {t.device}, the input on cuda:{idx}; "
+                                       "move the model with .to(device) first")
+                    t = t.to(torch.float32).contiguous()
+                    keep.append(t)
+                    shape = (C.c_int64 * max(1, t.dim()))(*t.shape)
+                    _lib.check(lib.xrd_set_param(ent["h"], (self._xrd_prefix + key).encode(),
+                                                 C.c_void_p(t.data_ptr()), shape, t.dim(), 1))
+                torch.cuda.current_stream(idx).synchronize()
+                _lib.check(lib.xrd_finalize_weights(ent["h"], self._xrd_parts))
+                del keep
+                ent["fp"] = fp
+            _lib.check(lib.xrd_set_mode(ent["h"], _MODE_NAMES[self.native_mode]))
+            _lib.check(lib.xrd_set_use_graph(ent["h"], 1 if self.use_cuda_graph else 0))
+            return ent["h"]
+
+    def __del__(self):
+        try:
+            lib = _lib.load()
+            for ent in self._xrd_handles.values():
+                lib.xrd_destroy(ent["h"])
+        except Exception:
+            pass
+
+    # nn.Module deep-copies/pickles __dict__; handles must not travel
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d["_xrd_handles"] = {}
+        d["_xrd_lock"] = None
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        object.__setattr__(self, "_xrd_handles", {})
+        object.__setattr__(self, "_xrd_lock", threading.Lock())
+
+
+def _image_arg(x: torch.Tensor, name: str, channels: int = 1) -> torch.Tensor:
+    if not isinstance(x, torch.Tensor) or x.dim() != 4 or x.shape[1] != channels:
+        raise XrdError(f"{name} must be a (B,{channels},H,W) tensor, got {tuple(getattr(x, 'shape', ()))}")
+    if x.device.type != "cuda":
+        raise XrdError(f"{name} is on {x.device}: this path runs on CUDA only (no CPU fallback)")
+    return x.detach().to(torch.float32).contiguous()
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+# ---------------------------------------------------------------------------
+# Enhanced NAFNet
+# ---------------------------------------------------------------------------
+class EnhancedNAFNet(_NativeModel):
+    """EnhancedNAFNet(img_channel, width, middle_blk_num, enc_blk_nums, dec_blk_nums)
+    -- constructor and key names as HYB:172-204 / NAF:232-273; forward replaced by
+    xrd_nafnet (include/xrd.h)."""
+
+    _xrd_parts = _lib.PART_NAFNET
+
+    def __init__(self, img_channel=1, width=32, middle_blk_num=8,
+                 enc_blk_nums=[2, 2, 4, 6], dec_blk_nums=[2, 2, 2, 2]):
+        super().__init__()
+        self._xrd_init()
+        self._cfg = dict(img_channel=img_channel, width=width, middle_blk_num=middle_blk_num,
+                         enc_blk_nums=list(enc_blk_nums), dec_blk_nums=list(dec_blk_nums))
+        self.intro = nn.Conv2d(img_channel, width, 3, padding=1)
+        self.ending = nn.Conv2d(width, img_channel, 3, padding=1)
+        self.encoders, self.decoders = nn.ModuleList(), nn.ModuleList()
+        self.middle_blks = nn.ModuleList()
+        self.ups, self.downs, self.skip_convs = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+        ch = width
+        for n in enc_blk_nums:
+            self.encoders.append(nn.Sequential(*(NAFBlock(ch) for _ in range(n))))
+            self.downs.append(nn.Conv2d(ch, ch * 2, 2, 2))
+            ch *= 2
+        self.middle_blks = nn.Sequential(*(NAFBlock(ch) for _ in range(middle_blk_num)))
+        for n in dec_blk_nums:
+            self.ups.append(nn.Sequential(nn.Conv2d(ch, ch * 2, 1, bias=False), nn.PixelShuffle(2)))
+            ch //= 2
+            self.decoders.append(nn.Sequential(*(NAFBlock(ch) for _ in range(n))))
+            self.skip_convs.append(nn.Conv2d(ch * 2, ch, 1))
+        self.padder_size = 2 ** len(self.encoders)
+
+    def _xrd_fill_config(self, cfg, prefix=""):
+        c = self._cfg
+        cfg.naf_img_channel, cfg.naf_width, cfg.naf_middle_blk_num = c["img_channel"], c["width"], c["middle_blk_num"]
+        cfg.naf_n_enc, cfg.naf_n_dec = len(c["enc_blk_nums"]), len(c["dec_blk_nums"])
+        for i, v in enumerate(c["enc_blk_nums"]):
+            cfg.naf_enc_blk_nums[i] = v
+        for i, v in enumerate(c["dec_blk_nums"]):
+            cfg.naf_dec_blk_nums[i] = v
+        cfg.naf_prefix = prefix.encode()
+
+    @torch.no_grad()
+    def forward(self, inp):
+        x = _image_arg(inp, "inp", self._cfg["img_channel"])
+        h = self._xrd_handle(x.device)
+        out = torch.empty_like(x)
+        B, _, H, W = x.shape
+        _lib.check(_lib.load().xrd_nafnet(h, _ptr(x), _ptr(out), B, H, W, _stream_ptr(x.device)))
+        return out.to(inp.dtype)
+
+
+# ---------------------------------------------------------------------------
+# conditional UNet + sampler
+# ---------------------------------------------------------------------------
+class UNetDiffusion(_NativeModel):
+    """UNetDiffusion(in_channels, model_channels, channel_mult, num_res_blocks,
+    attention_resolutions, dropout, time_emb_dim) -- HYB:308-357 / DDIM:166-217;
+    forward(x, condition, t) replaced by xrd_unet_eps."""
+
+    _xrd_parts = _lib.PART_UNET
+
+    def __init__(self, in_channels=1, model_channels=48, channel_mult=(1, 2, 3, 4),
+                 num_res_blocks=2, attention_resolutions=(3,), dropout=0.0, time_emb_dim=192):
+        super().__init__()
+        self._xrd_init()
+        if dropout != 0.0:
+            raise XrdError("inference-only implementation: dropout must be 0.0")
+        self._cfg = dict(in_channels=in_channels, model_channels=model_channels,
+                         channel_mult=tuple(channel_mult), num_res_blocks=num_res_blocks,
+                         attention_resolutions=tuple(attention_resolutions), time_emb_dim=time_emb_dim)
+        mc, ted = model_channels, time_emb_dim
+        self.time_mlp = nn.Sequential(SinusoidalPositionEmbeddings(mc), nn.Linear(mc, ted), nn.SiLU(),
+                                      nn.Linear(ted, ted))
+        self.in_conv = nn.Conv2d(in_channels * 2, mc, 3, padding=1)
+        levels = len(channel_mult)
+        widths = [mc * m for m in channel_mult]
+
+        self.downs = nn.ModuleList()
+        ch = mc
+        for lvl, wd in enumerate(widths):
+            for _ in range(num_res_blocks):
+                self.downs.append(ResidualBlock(ch, wd, ted, dropout))
+                ch = wd
+                if lvl in attention_resolutions:
+                    self.downs.append(AttentionBlock(ch))
+            if lvl != levels - 1:
+                self.downs.append(nn.Conv2d(ch, ch, 3, stride=2, padding=1))
+
+        self.mid_block1 = ResidualBlock(ch, ch, ted, dropout)
+        self.mid_attn = AttentionBlock(ch)
+        self.mid_block2 = ResidualBlock(ch, ch, ted, dropout)
+
+        self.ups = nn.ModuleList()
+        for lvl in range(levels - 1, -1, -1):
+            wd = widths[lvl]
+            for _ in range(num_res_blocks + 1):
+                self.ups.append(ResidualBlock(2 * ch, wd, ted, dropout))
+                ch = wd
+                if lvl in attention_resolutions:
+                    self.ups.append(AttentionBlock(ch))
+            if lvl != 0:
+                self.ups.append(nn.ConvTranspose2d(ch, ch, 4, stride=2, padding=1))
+
+        self.out_conv = nn.Sequential(nn.GroupNorm(8, ch), nn.SiLU(), nn.Conv2d(ch, in_channels, 3, padding=1))
+
+    def _xrd_fill_config(self, cfg, prefix=""):
+        c = self._cfg
+        cfg.unet_in_channels, cfg.unet_model_channels = c["in_channels"], c["model_channels"]
+        cfg.unet_n_levels = len(c["channel_mult"])
+        for i, v in enumerate(c["channel_mult"]):
+            cfg.unet_channel_mult[i] = v
+        cfg.unet_num_res_blocks = c["num_res_blocks"]
+        cfg.unet_n_attn = len(c["attention_resolutions"])
+        for i, v in enumerate(c["attention_resolutions"]):
+            cfg.unet_attention_resolutions[i] = v
+        cfg.unet_time_emb_dim = c["time_emb_dim"]
+        cfg.unet_prefix = prefix.encode()
+
+    @torch.no_grad()
+    def forward(self, x, condition, t):
+        xx = _image_arg(x, "x", self._cfg["in_channels"])
+        cc = _image_arg(condition, "condition", self._cfg["in_channels"])
+        if cc.shape != xx.shape or cc.device != xx.device:
+            raise XrdError("x and condition must have the same shape and device")
+        B, _, H, W = xx.shape
+        tt = torch.as_tensor(t, device=xx.device).to(torch.int64).reshape(-1).contiguous()
+        if tt.numel() != B:
+            raise XrdError(f"t must have {B} entries, got {tt.numel()}")
+        h = self._xrd_handle(xx.device)
+        eps = torch.empty_like(xx)
+        _lib.check(_lib.load().xrd_unet_eps(h, _ptr(xx), _ptr(cc), _ptr(tt), _ptr(eps), B, H, W,
+                                            _stream_ptr(xx.device)))
+        return eps.to(x.dtype)
+
+
+def ddim_timestep_indices(noise_steps: int, inference_steps: int):
+    """Timesteps the sampler visits (HYB:404-406) -- strided by
+    noise_steps // inference_steps, so the evaluation count can differ from
+    inference_steps (8 -> 9 evaluations at noise_steps=50)."""
+    stride = max(1, noise_steps // inference_steps)
+    return list(range(0, noise_steps, stride))[::-1]
+
+
+class DiffusionDenoiser:
+    """DiffusionDenoiser(model, noise_steps, beta_start, beta_end) -- HYB:391-418 /
+    DDIM:250-289.  ``denoise`` runs the whole reverse loop inside libxrd.so (one
+    CUDA graph): UNet, eps clamp, posterior-mean update and x clamp per step."""
+
+    def __init__(self, model, noise_steps=50, beta_start=1e-4, beta_end=0.02):
+        self.model = model
+        self.noise_steps = noise_steps
+        self._betas = (float(beta_start), float(beta_end))
+        dev = next(model.parameters()).device
+        self.beta = torch.linspace(beta_start, beta_end, noise_steps).to(dev)
+        self.alpha = 1.0 - self.beta
+        self.alpha_hat = torch.cumprod(self.alpha, dim=0)
+
+    @torch.no_grad()
+    def denoise(self, noisy_img, inference_steps=10, *, return_trace=False, teacher_x=None):
+        """``return_trace`` / ``teacher_x`` are test hooks (not in the reference):
+        per-evaluation raw eps and input x, and teacher forcing."""
+        self.model.eval()
+        x = _image_arg(noisy_img, "noisy_img")
+        B, _, H, W = x.shape
+        lib = _lib.load()
+        owner = getattr(self.model, "_xrd_owner", None) or self.model
+        owner._xrd_set_schedule(self.noise_steps, *self._betas)
+        h = owner._xrd_handle(x.device)
+        n_evals = lib.xrd_ddim_num_evals(self.noise_steps, int(inference_steps))
+        out = torch.empty_like(x)
+        eps_tr = xin_tr = None
+        if return_trace:
+            eps_tr = torch.empty((n_evals, B, H, W), dtype=torch.float32, device=x.device)
+            xin_tr = torch.empty_like(eps_tr)
+        tx = None
+        if teacher_x is not None:
+            tx = teacher_x.detach().to(device=x.device, dtype=torch.float32).reshape(n_evals, B, H, W).contiguous()
+        _lib.check(lib.xrd_ddim_denoise(h, _ptr(x), int(inference_steps), _ptr(out), _ptr(eps_tr), _ptr(xin_tr),
+                                        _ptr(tx), B, H, W, _stream_ptr(x.device)))
+        out = out.to(noisy_img.dtype)
+        if return_trace:
+            return out, eps_tr, xin_tr
+        return out
+
+
+# ---------------------------------------------------------------------------
+# router + fusion + hybrid
+# ---------------------------------------------------------------------------
+def _conv_gn(in_c, out_c, groups, stride=1):
+    return nn.Sequential(nn.Conv2d(in_c, out_c, 3, stride=stride, padding=1), nn.GroupNorm(groups, out_c), nn.GELU())
+
+
+class NoiseAnalyzer(_NativeModel):
+    """NoiseAnalyzer(in_c, out_c, base_c) -- HYB:470-509; forward replaced by xrd_router."""
+
+    _xrd_parts = _lib.PART_ROUTER
+
+    def __init__(self, in_c=1, out_c=1, base_c=32):
+        super().__init__()
+        self._xrd_init()
+        if in_c != 1 or out_c != 1:
+            raise XrdError("NoiseAnalyzer: only in_c=1, out_c=1 (grayscale) is implemented")
+        self._base_c = base_c
+        b = base_c
+        self.enc1 = _conv_gn(in_c, b, 8)
+        self.enc2 = _conv_gn(b, 2 * b, 8, stride=2)
+        self.enc3 = _conv_gn(2 * b, 4 * b, 8, stride=2)
+        self.mid = _conv_gn(4 * b, 4 * b, 8)
+        self.up3 = nn.ConvTranspose2d(4 * b, 2 * b, 2, stride=2)
+        self.dec3 = _conv_gn(4 * b, 2 * b, 8)
+        self.up2 = nn.ConvTranspose2d(2 * b, b, 2, stride=2)
+        self.dec2 = _conv_gn(2 * b, b, 8)
+        self.out_conv = nn.Conv2d(b, out_c, 1)
+
+    def _xrd_fill_config(self, cfg, prefix=""):
+        cfg.router_base_c = self._base_c
+        cfg.router_prefix = prefix.encode()
+
+    @torch.no_grad()
+    def forward(self, x):
+        xx = _image_arg(x, "x")
+        h = self._xrd_handle(xx.device)
+        out = torch.empty_like(xx)
+        B, _, H, W = xx.shape
+        _lib.check(_lib.load().xrd_router(h, _ptr(xx), _ptr(out), B, H, W, _stream_ptr(xx.device)))
+        return out.to(x.dtype)
+
+
+class FusionModule(_NativeModel):
+    """FusionModule(in_c, out_c, base_c) -- HYB:537-550; forward replaced by xrd_fusion."""
+
+    _xrd_parts = _lib.PART_FUSION
+
+    def __init__(self, in_c=3, out_c=1, base_c=48):
+        super().__init__()
+        self._xrd_init()
+        if in_c != 3 or out_c != 1:
+            raise XrdError("FusionModule: only in_c=3, out_c=1 is implemented")
+        self._base_c = base_c
+        self.conv1 = _conv_gn(in_c, base_c, 8)
+        self.conv2 = _conv_gn(base_c, base_c // 2, 4)
+        self.out_conv = nn.Conv2d(base_c // 2, out_c, 1)
+
+    def _xrd_fill_config(self, cfg, prefix=""):
+        cfg.fusion_base_c = self._base_c
+        cfg.fusion_prefix = prefix.encode()
+
+    @torch.no_grad()
+    def forward(self, nafnet_out, diffusion_out, routing_mask):
+        a = _image_arg(nafnet_out, "nafnet_out")
+        b = _image_arg(diffusion_out, "diffusion_out")
+        m = _image_arg(routing_mask, "routing_mask")
+        if not (a.shape == b.shape == m.shape):
+            raise XrdError("fusion inputs must share one shape")
+        h = self._xrd_handle(a.device)
+        out = torch.empty_like(a)
+        B, _, H, W = a.shape
+        _lib.check(_lib.load().xrd_fusion(h, _ptr(a), _ptr(b), _ptr(m), _ptr(out), B, H, W, _stream_ptr(a.device)))
+        return out.to(nafnet_out.dtype)
+
+
+class HybridDenoisingRouter(_NativeModel):
+    """HybridDenoisingRouter(nafnet_params, diffusion_params, training_diffusion_steps,
+    inference_diffusion_steps) -- HYB:560-628.  Sub-modules nafnet, diffusion_unet,
+    diffusion_wrapper, router, fusion keep their names; ``forward`` is one
+    xrd_hybrid call (NAFNet, the sampler loop, router and fusion inside the library)."""
+
+    _xrd_parts = _lib.PART_ALL
+
+    def __init__(self, nafnet_params, diffusion_params, training_diffusion_steps=10, inference_diffusion_steps=10):
+        super().__init__()
+        self._xrd_init()
+        nget, dget = nafnet_params.get, diffusion_params.get
+        self.nafnet = EnhancedNAFNet(img_channel=nget("img_channel", 1), width=nget("width", 32),
+                                     middle_blk_num=nget("middle_blk_num", 8),
+                                     enc_blk_nums=nget("enc_blk_nums", [2, 2, 4, 6]),
+                                     dec_blk_nums=nget("dec_blk_nums", [2, 2, 2, 2]))
+        self.diffusion_unet = UNetDiffusion(in_channels=dget("in_channels", 1),
+                                            model_channels=dget("model_channels", 48),
+                                            channel_mult=dget("channel_mult", (1, 2, 3, 4)),
+                                            num_res_blocks=dget("num_res_blocks", 2),
+                                            attention_resolutions=dget("attention_resolutions", (3,)),
+                                            time_emb_dim=dget("time_emb_dim", 192))
+        self.diffusion_wrapper = DiffusionDenoiser(self.diffusion_unet, noise_steps=dget("noise_steps", 50))
+        self.router = NoiseAnalyzer(in_c=1, out_c=1, base_c=32)
+        self.fusion = FusionModule(in_c=3, out_c=1, base_c=48)
+        self.training_diffusion_steps = training_diffusion_steps
+        self.inference_diffusion_steps = inference_diffusion_steps
+
+    def _xrd_fill_config(self, cfg, prefix=""):
+        self.nafnet._xrd_fill_config(cfg, "nafnet.")
+        self.diffusion_unet._xrd_fill_config(cfg, "diffusion_unet.")
+        self.router._xrd_fill_config(cfg, "router.")
+        self.fusion._xrd_fill_config(cfg, "fusion.")
+
+    def load_pretrained_models(self, nafnet_path, diffusion_path):
+        """HYB:592-599."""
+        naf = torch.load(nafnet_path, map_location="cpu", weights_only=False)
+        self.nafnet.load_state_dict(naf["model_state_dict"])
+        dif = torch.load(diffusion_path, map_location="cpu", weights_only=False)
+        self.diffusion_unet.load_state_dict(dif["model_state_dict"])
+
+    def freeze_backends(self):
+        """HYB:601-608."""
+        for p in list(self.nafnet.parameters()) + list(self.diffusion_unet.parameters()):
+            p.requires_grad = False
+        self.nafnet.eval()
+        self.diffusion_unet.eval()
+
+    @torch.no_grad()
+    def forward(self, noisy_input, *, return_parts=False):
+        """``return_parts`` is a test hook: also return the sanitised NAFNet image,
+        sampler image and routing mask that feed the fusion stack."""
+        steps = self.training_diffusion_steps if self.training else self.inference_diffusion_steps
+        x = _image_arg(noisy_input, "noisy_input")
+        w = self.diffusion_wrapper
+        self._xrd_set_schedule(w.noise_steps, *w._betas)
+        h = self._xrd_handle(x.device)
+        out = torch.empty_like(x)
+        parts = [torch.empty_like(x) for _ in range(3)] if return_parts else [None, None, None]
+        B, _, H, W = x.shape
+        _lib.check(_lib.load().xrd_hybrid(h, _ptr(x), int(steps), _ptr(out), _ptr(parts[0]), _ptr(parts[1]),
+                                          _ptr(parts[2]), B, H, W, _stream_ptr(x.device)))
+        out = out.to(noisy_input.dtype)
+        if return_parts:
+            return out, dict(naf=parts[0], diff=parts[1], mask=parts[2])
+        return out
+
+
+def native_kernel_launches() -> int:
+    """Kernels launched by libxrd in this process so far (bench.py 'gpu_launches')."""
+    return int(_lib.load().xrd_kernel_launch_count())
