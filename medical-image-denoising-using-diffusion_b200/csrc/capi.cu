@@ -1,0 +1,609 @@
+// capi.cu -- the extern "C" surface declared in include/xrd.h.  Catches every internal
+// exception at the boundary, plans/grows the arena, captures and replays the sampler graph,
+// splits large batches into micro-batches.
+#include <functional>
+#include "engine.cuh"
+
+#include <string.h>
+#include <algorithm>
+
+#define XRD_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace xrd {
+void finalize(Handle& h, int which);
+std::vector<int> ddim_timesteps(int noise_steps, int inference_steps);
+void run_unet_eps(Ctx& c, Handle& h, const float* x, const float* cond, const int64_t* t, float* eps, int B, int H, int W);
+void run_ddim_loop(Ctx& c, Handle& h, const float* noisy, float* xcur, const float* temb_table, const std::vector<int>& ts,
+                   float* eps_trace, float* xin_trace, const float* teacher_x, size_t trace_stride, int B, int H, int W);
+void run_nafnet(Ctx& c, Handle& h, const float* inp, float* out, int B, int H, int W, int sanitize);
+void run_router(Ctx& c, Handle& h, const float* x, float* mask, int B, int H, int W, int sanitize);
+void run_fusion(Ctx& c, Handle& h, const float* naf, const float* diff, const float* mask, float* out, int B, int H, int W);
+void prepack_tc(Handle& h, DType dt);
+}  // namespace xrd
+
+using namespace xrd;
+
+static thread_local std::string g_last_error;
+
+struct xrd_handle {
+  Handle h;
+  cudaStream_t cap_stream = nullptr;   // capture-only stream (the caller's stream may be the legacy default stream)
+  cudaStream_t last_stream = nullptr;
+  bool have_last_stream = false;
+  DType packed_dt = DT_F32;
+  float* scratch = nullptr;            // hybrid: sanitised NAFNet / sampler / mask planes of one micro-batch
+  size_t scratch_n = 0;
+  // op-hook state
+  ConvW op_w;
+  std::vector<void*> op_owned;
+};
+
+template <class F>
+static int guarded(F&& f) {
+  try {
+    f();
+    return XRD_OK;
+  } catch (const Error& e) {
+    g_last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return XRD_ERR_INVALID;
+  } catch (...) {
+    g_last_error = "unknown error";
+    return XRD_ERR_INVALID;
+  }
+}
+
+static DType mode_dtype(int mode) { return mode == XRD_MODE_FP32_CHECK ? DT_F32 : (mode == XRD_MODE_FP16 ? DT_F16 : DT_BF16); }
+
+static Ctx make_ctx(xrd_handle* H, cudaStream_t s, bool dry, Arena* a) {
+  Ctx c;
+  c.s = s; c.a = a; c.dry = dry;
+  c.adt = mode_dtype(H->h.mode);
+  c.tc = H->h.mode != XRD_MODE_FP32_CHECK;
+  return c;
+}
+
+static void bind_stream(xrd_handle* H, cudaStream_t s) {
+  XRD_CUDA(cudaSetDevice(H->h.device));
+  if (H->have_last_stream && H->last_stream != s) XRD_CUDA(cudaStreamSynchronize(H->last_stream));
+  H->last_stream = s; H->have_last_stream = true;
+  DType dt = mode_dtype(H->h.mode);
+  if (dt != DT_F32 && H->packed_dt != dt) {
+    prepack_tc(H->h, dt);
+    H->packed_dt = dt;
+  }
+}
+
+// Plan (dry run) + grow the arena, then run `fn` for real with the arena reset.
+static void with_arena(xrd_handle* H, cudaStream_t s, const std::string& key, const std::function<void(Ctx&)>& fn) {
+  Handle& h = H->h;
+  size_t need;
+  auto it = h.plan_cache.find(key);
+  if (it != h.plan_cache.end()) {
+    need = it->second;
+  } else {
+    Arena dry;
+    dry.dry = true;
+    Ctx c = make_ctx(H, s, true, &dry);
+    fn(c);
+    need = dry.peak + 4096;
+    h.plan_cache[key] = need;
+  }
+  if (need > h.arena.cap) {
+    XRD_CUDA(cudaDeviceSynchronize());
+    h.drop_graphs();
+    if (h.arena.base) XRD_CUDA(cudaFree(h.arena.base));
+    h.arena.base = nullptr; h.arena.cap = 0;
+    size_t cap = need + (need >> 4);
+    cudaError_t e = cudaMalloc((void**)&h.arena.base, cap);
+    if (e != cudaSuccess) fail(XRD_ERR_CUDA, "cannot allocate a %zu MiB workspace: %s", cap >> 20, cudaGetErrorString(e));
+    h.arena.cap = cap;
+  }
+  h.arena.off = 0; h.arena.peak = 0; h.arena.dry = false;
+  Ctx c = make_ctx(H, s, false, &h.arena);
+  fn(c);
+}
+
+// images per micro-batch: bounds the workspace (and keeps one graph shape for any batch size)
+static int micro_batch(int B, int H, int W) {
+  const int64_t budget = (int64_t)16 * 512 * 512;
+  int mb = (int)std::max<int64_t>(1, budget / ((int64_t)H * W));
+  return std::min(B, mb);
+}
+
+static std::string keyf(const char* tag, xrd_handle* H, int B, int Hh, int W, int e0 = 0, int e1 = 0, int e2 = 0, int e3 = 0,
+                        int e4 = 0) {
+  char buf[192];
+  snprintf(buf, sizeof(buf), "%s|%d|%d|%d|%d.%d.%d.%d.%d|m%d", tag, B, Hh, W, e0, e1, e2, e3, e4, H->h.mode);
+  return buf;
+}
+
+static void check_img(int B, int H, int W) {
+  XRD_REQUIRE(B >= 1 && H >= 1 && W >= 1, "empty batch or image (B=%d,H=%d,W=%d)", B, H, W);
+}
+static void check_unet_shape(xrd_handle* H, int Hh, int W) {
+  const int div = 1 << (H->h.cfg.unet_n_levels - 1);
+  XRD_REQUIRE(Hh % div == 0 && W % div == 0, "UNet: H and W must be multiples of %d (got %dx%d)", div, Hh, W);
+}
+
+// ------------------------------------------------------------------------------------------------
+XRD_EXPORT void xrd_default_config(xrd_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->unet_in_channels = 1; c->unet_model_channels = 48; c->unet_n_levels = 4;
+  const int cm[4] = {1, 2, 3, 4};
+  for (int i = 0; i < 4; ++i) c->unet_channel_mult[i] = cm[i];
+  c->unet_num_res_blocks = 2; c->unet_n_attn = 1; c->unet_attention_resolutions[0] = 3;
+  c->unet_time_emb_dim = 192; c->unet_num_heads = 2;
+  c->naf_img_channel = 1; c->naf_width = 32; c->naf_middle_blk_num = 8;
+  c->naf_n_enc = 4; c->naf_n_dec = 4;
+  const int eb[4] = {2, 2, 4, 6}, db[4] = {2, 2, 2, 2};
+  for (int i = 0; i < 4; ++i) { c->naf_enc_blk_nums[i] = eb[i]; c->naf_dec_blk_nums[i] = db[i]; }
+  c->router_base_c = 32; c->fusion_base_c = 48;
+  c->noise_steps = 50; c->beta_start = 1e-4f; c->beta_end = 0.02f;
+}
+
+XRD_EXPORT int xrd_api_version(void) { return XRD_API_VERSION; }
+XRD_EXPORT const char* xrd_last_error(void) { return g_last_error.c_str(); }
+XRD_EXPORT uint64_t xrd_kernel_launch_count(void) { return g_launches.load(); }
+
+XRD_EXPORT int xrd_ddim_num_evals(int noise_steps, int inference_steps) {
+  if (noise_steps < 1) return 0;
+  return (int)ddim_timesteps(noise_steps, inference_steps).size();
+}
+
+XRD_EXPORT int xrd_create(int device, const xrd_config* cfg, xrd_handle** out) {
+  return guarded([&] {
+    XRD_REQUIRE(cfg && out, "null argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      fail(XRD_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count=0");
+    XRD_REQUIRE(device >= 0 && device < ndev, "device %d out of range (have %d)", device, ndev);
+    cudaDeviceProp prop;
+    XRD_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+      fail(XRD_ERR_NO_DEVICE, "device %d is sm_%d%d; libxrd is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    XRD_REQUIRE(cfg->unet_n_levels >= 1 && cfg->unet_n_levels <= XRD_MAX_LEVELS && cfg->naf_n_enc <= XRD_MAX_LEVELS &&
+                    cfg->naf_n_dec <= XRD_MAX_LEVELS && cfg->noise_steps >= 1,
+                "invalid configuration");
+    XRD_CUDA(cudaSetDevice(device));
+    xrd_handle* H = new xrd_handle();
+    H->h.device = device;
+    H->h.cfg = *cfg;
+    H->h.cfg.unet_prefix[63] = H->h.cfg.naf_prefix[63] = H->h.cfg.router_prefix[63] = H->h.cfg.fusion_prefix[63] = 0;
+    XRD_CUDA(cudaStreamCreateWithFlags(&H->cap_stream, cudaStreamNonBlocking));
+    *out = H;
+  });
+}
+
+static void free_op_state(xrd_handle* H) {
+  for (int i = 0; i < 3; ++i)
+    if (H->op_w.wtc[i]) { cudaFree(H->op_w.wtc[i]); H->op_w.wtc[i] = nullptr; }
+  H->op_w = ConvW();
+  for (void* p : H->op_owned) cudaFree(p);
+  H->op_owned.clear();
+}
+
+XRD_EXPORT void xrd_destroy(xrd_handle* H) {
+  if (!H) return;
+  cudaSetDevice(H->h.device);
+  cudaDeviceSynchronize();
+  free_op_state(H);
+  H->h.free_owned();
+  for (auto& kv : H->h.params) cudaFree(kv.second.d);
+  if (H->h.arena.base) cudaFree(H->h.arena.base);
+  if (H->scratch) cudaFree(H->scratch);
+  if (H->cap_stream) cudaStreamDestroy(H->cap_stream);
+  delete H;
+}
+
+XRD_EXPORT int xrd_set_param(xrd_handle* H, const char* key, const void* data, const int64_t* shape, int ndim, int is_device) {
+  return guarded([&] {
+    XRD_REQUIRE(H && key && data && ndim >= 0 && ndim <= 8, "bad argument");
+    std::lock_guard<std::mutex> lk(H->h.mu);
+    XRD_CUDA(cudaSetDevice(H->h.device));
+    size_t n = 1;
+    std::vector<int64_t> shp;
+    for (int i = 0; i < ndim; ++i) { XRD_REQUIRE(shape[i] >= 0, "negative dimension"); n *= (size_t)shape[i]; shp.push_back(shape[i]); }
+    Param& p = H->h.params[key];
+    if (p.n != n || !p.d) {
+      // weights referenced by packed plans may be replaced: invalidate plans first
+      if (p.d) { XRD_CUDA(cudaDeviceSynchronize()); cudaFree(p.d); p.d = nullptr; }
+      XRD_CUDA(cudaMalloc((void**)&p.d, std::max<size_t>(n * 4, 16)));
+    }
+    p.n = n; p.shape = shp;
+    XRD_CUDA(cudaMemcpy(p.d, data, n * 4, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  });
+}
+
+XRD_EXPORT int xrd_finalize_weights(xrd_handle* H, int which) {
+  return guarded([&] {
+    XRD_REQUIRE(H, "null handle");
+    std::lock_guard<std::mutex> lk(H->h.mu);
+    finalize(H->h, which);
+    H->packed_dt = DT_F32;
+  });
+}
+
+XRD_EXPORT int xrd_set_mode(xrd_handle* H, int mode) {
+  return guarded([&] {
+    XRD_REQUIRE(H && (mode == XRD_MODE_BF16 || mode == XRD_MODE_FP32_CHECK || mode == XRD_MODE_FP16), "bad mode %d", mode);
+    std::lock_guard<std::mutex> lk(H->h.mu);
+    H->h.mode = mode;
+  });
+}
+XRD_EXPORT int xrd_get_mode(xrd_handle* H) { return H ? H->h.mode : XRD_ERR_INVALID; }
+XRD_EXPORT int xrd_set_use_graph(xrd_handle* H, int enable) {
+  if (!H) return XRD_ERR_INVALID;
+  H->h.use_graph = enable != 0;
+  return XRD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+XRD_EXPORT int xrd_unet_eps(xrd_handle* H, const float* x, const float* cond, const int64_t* t, float* eps, int B, int Hh, int W,
+                            void* stream) {
+  return guarded([&] {
+    XRD_REQUIRE(H && x && cond && t && eps, "null argument");
+    check_img(B, Hh, W);
+    std::lock_guard<std::mutex> lk(H->h.mu);
+    XRD_REQUIRE(H->h.unet.ready, "UNet weights are not finalised");
+    check_unet_shape(H, Hh, W);
+    cudaStream_t s = (cudaStream_t)stream;
+    bind_stream(H, s);
+    const int mb = micro_batch(B, Hh, W);
+    const size_t plane = (size_t)Hh * W;
+    for (int b0 = 0; b0 < B; b0 += mb) {
+      const int nb = std::min(mb, B - b0);
+      with_arena(H, s, keyf("unet", H, nb, Hh, W), [&](Ctx& c) {
+        run_unet_eps(c, H->h, x + b0 * plane, cond + b0 * plane, t + b0, eps + b0 * plane, nb, Hh, W);
+      });
+    }
+  });
+}
+
+// temb table for a list of timesteps, computed once per graph entry / eager call
+static void compute_temb_table(xrd_handle* H, cudaStream_t s, const std::vector<int>& ts, float* table_dev) {
+  int* tl = nullptr;
+  XRD_CUDA(cudaMalloc((void**)&tl, ts.size() * sizeof(int)));
+  XRD_CUDA(cudaMemcpy(tl, ts.data(), ts.size() * sizeof(int), cudaMemcpyHostToDevice));
+  Arena none;
+  Ctx c = make_ctx(H, s, false, &none);
+  time_embed(c, H->h.unet.te, nullptr, tl, (int)ts.size(), table_dev);
+  XRD_CUDA(cudaStreamSynchronize(s));
+  cudaFree(tl);
+}
+
+static uint64_t count_kernel_nodes(cudaGraph_t g) {
+  size_t n = 0;
+  if (cudaGraphGetNodes(g, nullptr, &n) != cudaSuccess || n == 0) return 0;
+  std::vector<cudaGraphNode_t> nodes(n);
+  if (cudaGraphGetNodes(g, nodes.data(), &n) != cudaSuccess) return 0;
+  uint64_t k = 0;
+  for (auto nd : nodes) {
+    cudaGraphNodeType ty;
+    if (cudaGraphNodeGetType(nd, &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel) ++k;
+  }
+  return k;
+}
+
+// one micro-batch of the sampler; noisy/out are user device pointers
+static void ddim_chunk(xrd_handle* H, cudaStream_t s, const float* noisy, int inference_steps, float* out, float* eps_trace,
+                       float* xin_trace, const float* teacher_x, size_t trace_stride, int nb, int Hh, int W) {
+  Handle& h = H->h;
+  const std::vector<int> ts = ddim_timesteps(h.cfg.noise_steps, inference_steps);
+  const size_t plane = (size_t)nb * Hh * W;
+  const bool traced = eps_trace || xin_trace || teacher_x;
+  const std::string key = keyf("ddim", H, nb, Hh, W, inference_steps);
+
+  if (!h.use_graph || traced) {
+    with_arena(H, s, key + (traced ? "|eager-trace" : "|eager"), [&](Ctx& c) {
+      float* xcur = c.allocf(plane);
+      float* temb = c.allocf(ts.size() * (size_t)h.unet.te.total);
+      int* tl = (int*)c.a->alloc(ts.size() * sizeof(int));
+      if (!c.dry) {
+        XRD_CUDA(cudaMemcpyAsync(tl, ts.data(), ts.size() * sizeof(int), cudaMemcpyHostToDevice, c.s));
+        XRD_CUDA(cudaStreamSynchronize(c.s));    // ts is a stack object
+      }
+      time_embed(c, h.unet.te, nullptr, tl, (int)ts.size(), temb);
+      copy_plane(c, noisy, xcur, plane);
+      run_ddim_loop(c, h, noisy, xcur, temb, ts, eps_trace, xin_trace, teacher_x, trace_stride, nb, Hh, W);
+      copy_plane(c, xcur, out, plane);
+    });
+    return;
+  }
+
+  // ---- graph path: plan, (re)capture if needed, replay ----
+  auto body = [&](Ctx& c, float** in_p, float** x_p, const float* temb) {
+    float* in = c.allocf(plane);
+    float* xcur = c.allocf(plane);
+    if (in_p) *in_p = in;
+    if (x_p) *x_p = xcur;
+    copy_plane(c, in, xcur, plane);
+    run_ddim_loop(c, h, in, xcur, temb, ts, nullptr, nullptr, nullptr, 0, nb, Hh, W);
+  };
+  auto git = h.graphs.find(key);
+  if (git == h.graphs.end()) {
+    // plan + make sure the arena is large enough (this may drop other graphs)
+    with_arena(H, s, key + "|plan", [&](Ctx& c) {
+      if (c.dry) body(c, nullptr, nullptr, nullptr);
+    });
+    GraphEntry ge;
+    XRD_CUDA(cudaMalloc((void**)&ge.temb, ts.size() * (size_t)h.unet.te.total * sizeof(float)));
+    compute_temb_table(H, s, ts, ge.temb);
+    // warm-up pass outside capture (sets function attributes, validates every launch configuration)
+    {
+      h.arena.off = 0;
+      Ctx c = make_ctx(H, s, false, &h.arena);
+      body(c, &ge.in, &ge.out, ge.temb);
+      XRD_CUDA(cudaStreamSynchronize(s));
+    }
+    cudaGraph_t graph = nullptr;
+    XRD_CUDA(cudaStreamBeginCapture(H->cap_stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      h.arena.off = 0;
+      Ctx c = make_ctx(H, H->cap_stream, false, &h.arena);
+      const uint64_t before = g_launches.load();
+      body(c, &ge.in, &ge.out, ge.temb);
+      g_launches.store(before);                  // capture launches nothing; replays are counted below
+    } catch (...) {
+      cudaStreamEndCapture(H->cap_stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      cudaFree(ge.temb);
+      throw;
+    }
+    XRD_CUDA(cudaStreamEndCapture(H->cap_stream, &graph));
+    ge.kernels = count_kernel_nodes(graph);
+    cudaError_t e = cudaGraphInstantiate(&ge.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { cudaFree(ge.temb); fail(XRD_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+    git = h.graphs.emplace(key, ge).first;
+  }
+  GraphEntry& ge = git->second;
+  XRD_CUDA(cudaMemcpyAsync(ge.in, noisy, plane * 4, cudaMemcpyDeviceToDevice, s));
+  XRD_CUDA(cudaGraphLaunch(ge.exec, s));
+  g_launches.fetch_add(ge.kernels);
+  XRD_CUDA(cudaMemcpyAsync(out, ge.out, plane * 4, cudaMemcpyDeviceToDevice, s));
+}
+
+XRD_EXPORT int xrd_ddim_denoise(xrd_handle* H, const float* noisy, int inference_steps, float* out, float* eps_trace, float* xin_trace,
+                                const float* teacher_x, int B, int Hh, int W, void* stream) {
+  return guarded([&] {
+    XRD_REQUIRE(H && noisy && out, "null argument");
+    XRD_REQUIRE(inference_steps >= 1, "inference_steps must be >= 1");
+    check_img(B, Hh, W);
+    std::lock_guard<std::mutex> lk(H->h.mu);
+    XRD_REQUIRE(H->h.unet.ready, "UNet weights are not finalised");
+    check_unet_shape(H, Hh, W);
+    cudaStream_t s = (cudaStream_t)stream;
+    bind_stream(H, s);
+    const int mb = micro_batch(B, Hh, W);
+    const size_t img = (size_t)Hh * W;
+    const size_t tstride = (size_t)B * img;   // traces are (n_evals, B, H, W)
+    for (int b0 = 0; b0 < B; b0 += mb) {
+      const int nb = std::min(mb, B - b0);
+      ddim_chunk(H, s, noisy + b0 * img, inference_steps, out + b0 * img, eps_trace ? eps_trace + b0 * img : nullptr,
+                 xin_trace ? xin_trace + b0 * img : nullptr, teacher_x ? teacher_x + b0 * img : nullptr, tstride, nb, Hh, W);
+    }
+  });
+}
+
+XRD_EXPORT int xrd_nafnet(xrd_handle* H, const float* inp, float* out, int B, int Hh, int W, void* stream) {
+  return guarded([&] {
+    XRD_REQUIRE(H && inp && out, "null argument");
+    check_img(B, Hh, W);
+    std::lock_guard<std::mutex> lk(H->h.mu);
+    XRD_REQUIRE(H->h.naf.ready, "NAFNet weights are not finalised");
+    cudaStream_t s = (cudaStream_t)stream;
+    bind_stream(H, s);
+    const int mb = micro_batch(B, Hh, W);
+    const size_t img = (size_t)Hh * W;
+    for (int b0 = 0; b0 < B; b0 += mb) {
+      const int nb = std::min(mb, B - b0);
+      with_arena(H, s, keyf("naf", H, nb, Hh, W), [&](Ctx& c) { run_nafnet(c, H->h, inp + b0 * img, out + b0 * img, nb, Hh, W, 0); });
+    }
+  });
+}
+
+XRD_EXPORT int xrd_router(xrd_handle* H, const float* x, float* mask, int B, int Hh, int W, void* stream) {
+  return guarded([&] {
+    XRD_REQUIRE(H && x && mask, "null argument");
+    check_img(B, Hh, W);
+    std::lock_guard<std::mutex> lk(H->h.mu);
+    XRD_REQUIRE(H->h.router.ready, "router weights are not finalised");
+    cudaStream_t s = (cudaStream_t)stream;
+    bind_stream(H, s);
+    const int mb = micro_batch(B, Hh, W);
+    const size_t img = (size_t)Hh * W;
+    for (int b0 = 0; b0 < B; b0 += mb) {
+      const int nb = std::min(mb, B - b0);
+      with_arena(H, s, keyf("router", H, nb, Hh, W), [&](Ctx& c) { run_router(c, H->h, x + b0 * img, mask + b0 * img, nb, Hh, W, 0); });
+    }
+  });
+}
+
+XRD_EXPORT int xrd_fusion(xrd_handle* H, const float* naf, const float* diff, const float* mask, float* out, int B, int Hh, int W,
+                          void* stream) {
+  return guarded([&] {
+    XRD_REQUIRE(H && naf && diff && mask && out, "null argument");
+    check_img(B, Hh, W);
+    std::lock_guard<std::mutex> lk(H->h.mu);
+    XRD_REQUIRE(H->h.fusion.ready, "fusion weights are not finalised");
+    cudaStream_t s = (cudaStream_t)stream;
+    bind_stream(H, s);
+    const int mb = micro_batch(B, Hh, W);
+    const size_t img = (size_t)Hh * W;
+    for (int b0 = 0; b0 < B; b0 += mb) {
+      const int nb = std::min(mb, B - b0);
+      with_arena(H, s, keyf("fusion", H, nb, Hh, W),
+                 [&](Ctx& c) { run_fusion(c, H->h, naf + b0 * img, diff + b0 * img, mask + b0 * img, out + b0 * img, nb, Hh, W); });
+    }
+  });
+}
+
+XRD_EXPORT int xrd_hybrid(xrd_handle* H, const float* noisy, int inference_steps, float* out, float* naf_out, float* diff_out,
+                          float* mask_out, int B, int Hh, int W, void* stream) {
+  return guarded([&] {
+    XRD_REQUIRE(H && noisy && out, "null argument");
+    XRD_REQUIRE(inference_steps >= 1, "inference_steps must be >= 1");
+    check_img(B, Hh, W);
+    std::lock_guard<std::mutex> lk(H->h.mu);
+    Handle& h = H->h;
+    XRD_REQUIRE(h.unet.ready && h.naf.ready && h.router.ready && h.fusion.ready, "hybrid weights are not finalised");
+    check_unet_shape(H, Hh, W);
+    cudaStream_t s = (cudaStream_t)stream;
+    bind_stream(H, s);
+    const int mb = micro_batch(B, Hh, W);
+    const size_t img = (size_t)Hh * W;
+    // persistent per-call planes (outside the arena, which every stage resets)
+    const size_t need = 3 * (size_t)mb * img;
+    if (H->scratch_n < need) {
+      if (H->scratch) { XRD_CUDA(cudaDeviceSynchronize()); cudaFree(H->scratch); H->scratch = nullptr; H->scratch_n = 0; }
+      XRD_CUDA(cudaMalloc((void**)&H->scratch, need * 4));
+      H->scratch_n = need;
+    }
+    float* scratch = H->scratch;
+    for (int b0 = 0; b0 < B; b0 += mb) {
+      const int nb = std::min(mb, B - b0);
+      const size_t plane = (size_t)nb * img;
+      float* nafp = naf_out ? naf_out + b0 * img : scratch;
+      float* difp = diff_out ? diff_out + b0 * img : scratch + (size_t)mb * img;
+      float* mskp = mask_out ? mask_out + b0 * img : scratch + 2 * (size_t)mb * img;
+      const float* in = noisy + b0 * img;
+      // fast path: NAFNet -> nan_to_num + clamp (HYB:614-616)
+      with_arena(H, s, keyf("naf", H, nb, Hh, W, 1), [&](Ctx& c) { run_nafnet(c, h, in, nafp, nb, Hh, W, 1); });
+      // quality path: sampler -> nan_to_num + clamp (HYB:618-620); x is already clamped to [0,1] by the last update
+      ddim_chunk(H, s, in, inference_steps, difp, nullptr, nullptr, nullptr, 0, nb, Hh, W);
+      {
+        Arena none;
+        Ctx c = make_ctx(H, s, false, &none);
+        sanitize_plane(c, difp, difp, plane);
+      }
+      // routing mask (HYB:622-624), then fusion (HYB:626)
+      with_arena(H, s, keyf("router", H, nb, Hh, W, 1), [&](Ctx& c) { run_router(c, h, in, mskp, nb, Hh, W, 1); });
+      with_arena(H, s, keyf("fusion", H, nb, Hh, W), [&](Ctx& c) { run_fusion(c, h, nafp, difp, mskp, out + b0 * img, nb, Hh, W); });
+    }
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel-level hooks
+// ------------------------------------------------------------------------------------------------
+XRD_EXPORT int xrd_op_conv2d(xrd_handle* H, int impl, const float* x, const float* weight, const float* bias, float* y, int B, int Cin,
+                             int Hh, int W, int Cout, int k, int stride, int pad, void* stream) {
+  return guarded([&] {
+    XRD_REQUIRE(H && x && weight && y, "null argument");
+    std::lock_guard<std::mutex> lk(H->h.mu);
+    cudaStream_t s = (cudaStream_t)stream;
+    bind_stream(H, s);
+    XRD_CUDA(cudaStreamSynchronize(s));
+    free_op_state(H);
+    ConvW& w = H->op_w;
+    w.kh = w.kw = k; w.stride = stride; w.pad = pad; w.cin = Cin; w.cout = Cout;
+    void* wp = nullptr;
+    XRD_CUDA(cudaMalloc(&wp, (size_t)Cout * Cin * k * k * 4));
+    H->op_owned.push_back(wp);
+    w.w = (float*)wp;
+    pack_conv_weight(s, weight, w.w, Cout, Cin, k, k);
+    w.bias = (float*)bias;
+    const DType dt = mode_dtype(H->h.mode);
+    if (impl == 1) {
+      XRD_REQUIRE(dt != DT_F32, "the tcgen05 kernel needs a 16-bit mode");
+      conv_tc_pack(s, w, dt, Cin);
+    }
+    const int Ho = (Hh + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    H->h.last_op = nullptr;
+    with_arena(H, s, keyf("opconv", H, B, Hh, W, Cin, Cout, k, stride * 8 + pad, impl), [&](Ctx& c) {
+      Tens xi = c.alloc(B, Hh, W, Cin);
+      Tens yo = c.alloc(B, Ho, Wo, Cout);
+      nchw_to_nhwc(c, x, xi);
+      auto run = [H, xi, yo, impl](Ctx& cc) mutable {
+        Tens yy = yo;
+        if (impl == 1) conv_tc(cc, xi, nullptr, H->op_w, ConvEpi(), yy);
+        else conv_simt(cc, xi, nullptr, H->op_w, ConvEpi(), yy);
+      };
+      run(c);
+      nhwc_to_nchw(c, yo, y);
+      if (!c.dry) {
+        H->h.last_op = run;
+        H->h.last_op_bytes = xi.bytes() + yo.bytes();
+      }
+    });
+  });
+}
+
+XRD_EXPORT int xrd_op_groupnorm_act(xrd_handle* H, const float* x, const float* gamma, const float* beta, float* y, int B, int C, int Hh,
+                                    int W, int groups, int act, void* stream) {
+  return guarded([&] {
+    XRD_REQUIRE(H && x && gamma && beta && y, "null argument");
+    std::lock_guard<std::mutex> lk(H->h.mu);
+    cudaStream_t s = (cudaStream_t)stream;
+    bind_stream(H, s);
+    H->h.last_op = nullptr;
+    with_arena(H, s, keyf("opgn", H, B, Hh, W, C, groups), [&](Ctx& c) {
+      Tens xi = c.alloc(B, Hh, W, C);
+      Tens yo = c.alloc(B, Hh, W, C);
+      double* sums = c.allocd((size_t)B * groups * 2);
+      nchw_to_nhwc(c, x, xi);
+      auto run = [xi, yo, sums, gamma, beta, groups, act, B](Ctx& cc) mutable {
+        Tens yy = yo;
+        zero_async(cc, sums, (size_t)B * groups * 2 * sizeof(double));
+        gn_stats(cc, xi, nullptr, groups, sums);
+        gn_act(cc, xi, nullptr, groups, sums, gamma, beta, 1e-5f, act, yy);
+      };
+      run(c);
+      nhwc_to_nchw(c, yo, y);
+      if (!c.dry) { H->h.last_op = run; H->h.last_op_bytes = 2 * xi.bytes() + yo.bytes(); }
+    });
+  });
+}
+
+XRD_EXPORT int xrd_op_attention(xrd_handle* H, int impl, const float* qkv, float* out, int B, int heads, int d, int Hh, int W,
+                                void* stream) {
+  return guarded([&] {
+    XRD_REQUIRE(H && qkv && out, "null argument");
+    std::lock_guard<std::mutex> lk(H->h.mu);
+    cudaStream_t s = (cudaStream_t)stream;
+    bind_stream(H, s);
+    H->h.last_op = nullptr;
+    with_arena(H, s, keyf("opattn", H, B, Hh, W, heads, d, impl), [&](Ctx& c) {
+      Tens q = c.alloc(B, Hh, W, 3 * heads * d);
+      Tens o = c.alloc(B, Hh, W, heads * d);
+      nchw_to_nhwc(c, qkv, q);
+      auto run = [q, o, heads, impl](Ctx& cc) mutable {
+        Tens oo = o;
+        if (impl == 1) attention_tc(cc, q, heads, oo);
+        else attention_simt(cc, q, heads, oo);
+      };
+      run(c);
+      nhwc_to_nchw(c, o, out);
+      if (!c.dry) { H->h.last_op = run; H->h.last_op_bytes = q.bytes() + o.bytes(); }
+    });
+  });
+}
+
+XRD_EXPORT int xrd_op_time_last(xrd_handle* H, int iters, float* ms_per_launch, void* stream) {
+  return guarded([&] {
+    XRD_REQUIRE(H && ms_per_launch && iters >= 1, "bad argument");
+    std::lock_guard<std::mutex> lk(H->h.mu);
+    XRD_REQUIRE((bool)H->h.last_op, "no op to time: call an xrd_op_* function first");
+    cudaStream_t s = (cudaStream_t)stream;
+    bind_stream(H, s);
+    Arena none;
+    Ctx c = make_ctx(H, s, false, &none);
+    cudaEvent_t e0, e1;
+    XRD_CUDA(cudaEventCreate(&e0));
+    XRD_CUDA(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) H->h.last_op(c);
+    XRD_CUDA(cudaEventRecord(e0, s));
+    for (int i = 0; i < iters; ++i) H->h.last_op(c);
+    XRD_CUDA(cudaEventRecord(e1, s));
+    XRD_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    XRD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_per_launch = ms / (float)iters;
+  });
+}

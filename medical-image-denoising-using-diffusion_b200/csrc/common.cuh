@@ -1,0 +1,188 @@
+// common.cuh -- shared types for libxrd (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <atomic>
+#include <stdexcept>
+#include <string>
+
+#include "xrd.h"
+
+namespace xrd {
+
+// ---------------------------------------------------------------- errors
+struct Error : public std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+[[noreturn]] inline void fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  throw Error(code, buf);
+}
+
+#define XRD_CUDA(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      ::xrd::fail(XRD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                  __LINE__);                                                                   \
+  } while (0)
+
+#define XRD_REQUIRE(cond, ...)                                  \
+  do {                                                          \
+    if (!(cond)) ::xrd::fail(XRD_ERR_INVALID, __VA_ARGS__);     \
+  } while (0)
+
+extern std::atomic<uint64_t> g_launches;
+
+// ---------------------------------------------------------------- dtypes / tensors
+enum DType : int { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
+inline size_t dsize(DType d) { return d == DT_F32 ? 4 : 2; }
+
+// NHWC activation tensor
+struct Tens {
+  void* p = nullptr;
+  int n = 0, h = 0, w = 0, c = 0;
+  DType dt = DT_F32;
+  size_t numel() const { return (size_t)n * h * w * c; }
+  size_t bytes() const { return numel() * dsize(dt); }
+  bool valid() const { return p != nullptr; }
+};
+
+// Bump allocator over one device block.  In `dry` mode only the peak is tracked
+// (planning pass); kernels are not launched.
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0, peak = 0;
+  bool dry = false;
+  void* alloc(size_t bytes) {
+    off = (off + 255) & ~(size_t)255;
+    size_t o = off;
+    off += bytes;
+    if (off > peak) peak = off;
+    if (dry) return (void*)(uintptr_t)(0x10000 + o);
+    if (off > cap) fail(XRD_ERR_STATE, "arena overflow: need %zu, have %zu", off, cap);
+    return base + o;
+  }
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }
+};
+
+struct Ctx {
+  cudaStream_t s = nullptr;
+  Arena* a = nullptr;
+  bool dry = false;     // planning pass: no launches
+  DType adt = DT_BF16;  // activation storage dtype of the current mode
+  bool tc = true;       // tcgen05 contractions (false in the fp32 check mode)
+  Tens alloc(int n, int h, int w, int c, DType dt) {
+    Tens t;
+    t.n = n; t.h = h; t.w = w; t.c = c; t.dt = dt;
+    t.p = a->alloc(t.bytes());
+    return t;
+  }
+  Tens alloc(int n, int h, int w, int c) { return alloc(n, h, w, c, adt); }
+  float* allocf(size_t n) { return (float*)a->alloc(n * 4); }
+  double* allocd(size_t n) { return (double*)a->alloc(n * 8); }
+};
+
+// launch helper: counts launches, surfaces configuration errors immediately
+#define XRD_LAUNCH(ctx, kernel, grid, block, smem, ...)                                   \
+  do {                                                                                    \
+    if (!(ctx).dry) {                                                                     \
+      kernel<<<(grid), (block), (smem), (ctx).s>>>(__VA_ARGS__);                          \
+      ::xrd::g_launches.fetch_add(1, std::memory_order_relaxed);                          \
+      cudaError_t e__ = cudaPeekAtLastError();                                            \
+      if (e__ != cudaSuccess)                                                             \
+        ::xrd::fail(XRD_ERR_CUDA, "launch of %s failed: %s (%s:%d)", #kernel,             \
+                    cudaGetErrorString(e__), __FILE__, __LINE__);                         \
+    }                                                                                     \
+  } while (0)
+
+// ---------------------------------------------------------------- device load/store helpers
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <> __device__ __forceinline__ float ldf<__half>(const __half* p) { return __half2float(*p); }
+
+template <typename T> __device__ __forceinline__ void stf(T* p, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ void stf<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+
+// 4 consecutive elements (pointer must be aligned to 4 elements)
+template <typename T> __device__ __forceinline__ void ld4(const T* p, float (&v)[4]);
+template <> __device__ __forceinline__ void ld4<float>(const float* p, float (&v)[4]) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void ld4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x), b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  v[0] = fa.x; v[1] = fa.y; v[2] = fb.x; v[3] = fb.y;
+}
+template <> __device__ __forceinline__ void ld4<__half>(const __half* p, float (&v)[4]) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  __half2 a = *reinterpret_cast<__half2*>(&t.x), b = *reinterpret_cast<__half2*>(&t.y);
+  float2 fa = __half22float2(a), fb = __half22float2(b);
+  v[0] = fa.x; v[1] = fa.y; v[2] = fb.x; v[3] = fb.y;
+}
+template <typename T> __device__ __forceinline__ void st4(T* p, const float (&v)[4]);
+template <> __device__ __forceinline__ void st4<float>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 t;
+  t.x = *reinterpret_cast<uint32_t*>(&a);
+  t.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+template <> __device__ __forceinline__ void st4<__half>(__half* p, const float (&v)[4]) {
+  __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  uint2 t;
+  t.x = *reinterpret_cast<uint32_t*>(&a);
+  t.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+
+// dispatch a lambda on a runtime dtype:  XRD_DISPATCH(dt, T, { kernel<T>... })
+#define XRD_DISPATCH(dt, T, ...)                                   \
+  do {                                                             \
+    switch (dt) {                                                  \
+      case ::xrd::DT_F32: { using T = float; __VA_ARGS__; } break; \
+      case ::xrd::DT_BF16: { using T = __nv_bfloat16; __VA_ARGS__; } break; \
+      case ::xrd::DT_F16: { using T = __half; __VA_ARGS__; } break;  \
+    }                                                              \
+  } while (0)
+
+enum Act : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_SIGMOID = 3 };
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+    case ACT_SILU: return v / (1.0f + expf(-v));
+    case ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+    case ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+    default: return v;
+  }
+}
+
+// nan_to_num(nan=0, posinf=1, neginf=0) followed by clamp(0,1)   (HYB:615-616)
+__device__ __forceinline__ float sanitize01(float v) {
+  if (v != v) return 0.0f;
+  return fminf(fmaxf(v, 0.0f), 1.0f);
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace xrd

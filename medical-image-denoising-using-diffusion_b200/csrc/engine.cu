@@ -1,0 +1,706 @@
+// engine.cu -- weight ingestion/packing and the four networks of the /denoise hot path,
+// expressed as launch sequences over the kernels in kernels_simt.cu / conv_tc.cu / attn_tc.cu.
+#include <functional>
+#include "engine.cuh"
+
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+
+namespace xrd {
+
+// ------------------------------------------------------------------------------------------------
+// handle utilities
+// ------------------------------------------------------------------------------------------------
+void* Handle::dalloc(size_t bytes) {
+  void* p = nullptr;
+  XRD_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+  owned.push_back(p);
+  return p;
+}
+float* Handle::dalloc_f(size_t n) { return (float*)dalloc(n * sizeof(float)); }
+
+void Handle::drop_graphs() {
+  for (auto& kv : graphs) {
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (kv.second.temb) cudaFree(kv.second.temb);
+  }
+  graphs.clear();
+}
+
+static void free_convw_tc(ConvW& w) {
+  for (int i = 0; i < 3; ++i)
+    if (w.wtc[i]) { cudaFree(w.wtc[i]); w.wtc[i] = nullptr; }
+  w.tc_c1 = -1;
+}
+
+void Handle::free_owned() {
+  drop_graphs();
+  auto fr = [](ResW& r) { free_convw_tc(r.c1); free_convw_tc(r.c2); free_convw_tc(r.rc); };
+  for (auto& r : unet.res) fr(r);
+  for (auto& a : unet.attn) { free_convw_tc(a.qkv); free_convw_tc(a.proj); }
+  for (auto& d : unet.down) free_convw_tc(d);
+  for (auto& u : unet.up) free_convw_tc(u);
+  auto fb = [](NafBlockW& b) { free_convw_tc(b.c1); free_convw_tc(b.c3); free_convw_tc(b.c4); free_convw_tc(b.c5); };
+  for (auto& s : naf.enc) for (auto& b : s) fb(b);
+  for (auto& s : naf.dec) for (auto& b : s) fb(b);
+  for (auto& b : naf.mid) fb(b);
+  for (auto& w : naf.downs) free_convw_tc(w);
+  for (auto& w : naf.ups) free_convw_tc(w);
+  for (auto& w : naf.skips) free_convw_tc(w);
+  for (void* p : owned) cudaFree(p);
+  owned.clear();
+  unet = UNetW(); naf = NafW(); router = RouterW(); fusion = FusionW();
+}
+
+const Param& Handle::P(const std::string& key) const {
+  auto it = params.find(key);
+  if (it == params.end()) fail(XRD_ERR_MISSING_PARAM, "missing state_dict tensor '%s'", key.c_str());
+  return it->second;
+}
+
+static void expect_shape(const Param& p, const std::string& key, std::initializer_list<int64_t> shape) {
+  std::vector<int64_t> s(shape);
+  if (p.shape != s) {
+    std::string got, want;
+    for (auto v : p.shape) got += std::to_string(v) + ",";
+    for (auto v : s) want += std::to_string(v) + ",";
+    fail(XRD_ERR_INVALID, "tensor '%s' has shape (%s) but the configuration needs (%s)", key.c_str(), got.c_str(), want.c_str());
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing
+// ------------------------------------------------------------------------------------------------
+static ConvW make_conv(Handle& h, const std::string& key, int cout, int cin, int k, int stride, int pad, bool bias = true) {
+  const Param& w = h.P(key + ".weight");
+  expect_shape(w, key + ".weight", {cout, cin, k, k});
+  ConvW c;
+  c.kh = c.kw = k; c.stride = stride; c.pad = pad; c.cin = cin; c.cout = cout;
+  c.w = h.dalloc_f((size_t)cout * cin * k * k);
+  pack_conv_weight(nullptr, w.d, c.w, cout, cin, k, k);
+  if (bias) {
+    const Param& b = h.P(key + ".bias");
+    expect_shape(b, key + ".bias", {cout});
+    c.bias = b.d;
+  }
+  return c;
+}
+
+static void finalize_unet(Handle& h) {
+  const xrd_config& cf = h.cfg;
+  const std::string p = cf.unet_prefix;
+  UNetW& u = h.unet;
+  u = UNetW();
+  XRD_REQUIRE(cf.unet_in_channels == 1, "UNet: only in_channels=1 (grayscale) is implemented, got %d", cf.unet_in_channels);
+  const int mc = cf.unet_model_channels, ted = cf.unet_time_emb_dim, levels = cf.unet_n_levels;
+  XRD_REQUIRE(mc % 16 == 0 && mc >= 16, "UNet: model_channels must be a multiple of 16");
+  u.mc = mc; u.heads = cf.unet_num_heads;
+  auto in_attn = [&](int lvl) {
+    for (int i = 0; i < cf.unet_n_attn; ++i) if (cf.unet_attention_resolutions[i] == lvl) return true;
+    return false;
+  };
+  std::vector<std::pair<std::string, int>> temb_blocks;  // (prefix, out_c) in creation order
+  int temb_total = 0;
+  auto add_res = [&](const std::string& q, int cin, int cout) {
+    ResW r;
+    r.cin = cin; r.cout = cout; r.temb_off = temb_total; temb_total += cout;
+    temb_blocks.push_back({q, cout});
+    r.g1 = h.PD(q + "block1.0.weight"); r.b1 = h.PD(q + "block1.0.bias");
+    expect_shape(h.P(q + "block1.0.weight"), q + "block1.0.weight", {cin});
+    r.c1 = make_conv(h, q + "block1.2", cout, cin, 3, 1, 1);
+    r.g2 = h.PD(q + "block2.0.weight"); r.b2 = h.PD(q + "block2.0.bias");
+    r.c2 = make_conv(h, q + "block2.3", cout, cout, 3, 1, 1);
+    r.has_rc = cin != cout;
+    if (r.has_rc) r.rc = make_conv(h, q + "res_conv", cout, cin, 1, 1, 0);
+    expect_shape(h.P(q + "time_mlp.1.weight"), q + "time_mlp.1.weight", {cout, ted});
+    u.res.push_back(r);
+    return (int)u.res.size() - 1;
+  };
+  auto add_attn = [&](const std::string& q, int c) {
+    AttnW a;
+    a.c = c;
+    a.g = h.PD(q + "norm.weight"); a.b = h.PD(q + "norm.bias");
+    a.qkv = make_conv(h, q + "qkv", 3 * c, c, 1, 1, 0);
+    a.proj = make_conv(h, q + "proj", c, c, 1, 1, 0);
+    u.attn.push_back(a);
+    return (int)u.attn.size() - 1;
+  };
+
+  {  // in_conv: (mc, 2, 3, 3)
+    u.in_conv = make_conv(h, p + "in_conv", mc, 2, 3, 1, 1);
+  }
+  int ch = mc, li = 0;
+  for (int lvl = 0; lvl < levels; ++lvl) {
+    const int oc = mc * cf.unet_channel_mult[lvl];
+    for (int r = 0; r < cf.unet_num_res_blocks; ++r) {
+      u.downs.push_back({U_RES, add_res(p + "downs." + std::to_string(li++) + ".", ch, oc)});
+      ch = oc;
+      if (in_attn(lvl)) u.downs.push_back({U_ATTN, add_attn(p + "downs." + std::to_string(li++) + ".", ch)});
+    }
+    if (lvl != levels - 1) {
+      u.down.push_back(make_conv(h, p + "downs." + std::to_string(li++), ch, ch, 3, 2, 1));
+      u.downs.push_back({U_DOWN, (int)u.down.size() - 1});
+    }
+  }
+  u.mid1 = add_res(p + "mid_block1.", ch, ch);
+  u.mid_attn = add_attn(p + "mid_attn.", ch);
+  u.mid2 = add_res(p + "mid_block2.", ch, ch);
+  li = 0;
+  for (int lvl = levels - 1; lvl >= 0; --lvl) {
+    const int oc = mc * cf.unet_channel_mult[lvl];
+    for (int r = 0; r < cf.unet_num_res_blocks + 1; ++r) {
+      u.ups.push_back({U_RES, add_res(p + "ups." + std::to_string(li++) + ".", 2 * ch, oc)});
+      ch = oc;
+      if (in_attn(lvl)) u.ups.push_back({U_ATTN, add_attn(p + "ups." + std::to_string(li++) + ".", ch)});
+    }
+    if (lvl != 0) {
+      // ConvTranspose2d(ch,ch,4,2,1): always consumed through an exact 0.5x bilinear resize (HYB:381-382), which
+      // equals a 2x2 mean; the pair is pre-combined into one 3x3 convolution on the input grid (fp32, before any
+      // 16-bit rounding).
+      const std::string q = p + "ups." + std::to_string(li++);
+      const Param& w = h.P(q + ".weight");
+      expect_shape(w, q + ".weight", {ch, ch, 4, 4});
+      ConvW c;
+      c.kh = c.kw = 3; c.stride = 1; c.pad = 1; c.cin = ch; c.cout = ch;
+      c.w = h.dalloc_f((size_t)9 * ch * ch);
+      pack_convT4_avg_weight(nullptr, w.d, c.w, ch, ch);
+      c.bias = h.P(q + ".bias").d;
+      u.up.push_back(c);
+      u.ups.push_back({U_UP, (int)u.up.size() - 1});
+    }
+  }
+  // out_conv: GN(8,ch) + SiLU + conv3x3 ch->1
+  u.out_c = ch;
+  u.og = h.PD(p + "out_conv.0.weight"); u.ob = h.PD(p + "out_conv.0.bias");
+  {
+    const Param& w = h.P(p + "out_conv.2.weight");
+    expect_shape(w, p + "out_conv.2.weight", {1, ch, 3, 3});
+    u.ow = h.dalloc_f((size_t)9 * ch);
+    pack_conv_weight(nullptr, w.d, u.ow, 1, ch, 3, 3);   // -> [9][ch][1]
+    u.obias = h.PD(p + "out_conv.2.bias");
+  }
+  // time embedding
+  expect_shape(h.P(p + "time_mlp.1.weight"), p + "time_mlp.1.weight", {ted, mc});
+  expect_shape(h.P(p + "time_mlp.3.weight"), p + "time_mlp.3.weight", {ted, ted});
+  float* wall = h.dalloc_f((size_t)temb_total * ted);
+  float* ball = h.dalloc_f(temb_total);
+  int off = 0;
+  for (auto& tb : temb_blocks) {
+    XRD_CUDA(cudaMemcpy(wall + (size_t)off * ted, h.PD(tb.first + "time_mlp.1.weight"), (size_t)tb.second * ted * 4, cudaMemcpyDeviceToDevice));
+    XRD_CUDA(cudaMemcpy(ball + off, h.PD(tb.first + "time_mlp.1.bias"), (size_t)tb.second * 4, cudaMemcpyDeviceToDevice));
+    off += tb.second;
+  }
+  u.te.mc = mc; u.te.ted = ted; u.te.total = temb_total;
+  u.te.w1 = h.PD(p + "time_mlp.1.weight"); u.te.b1 = h.PD(p + "time_mlp.1.bias");
+  u.te.w2 = h.PD(p + "time_mlp.3.weight"); u.te.b2 = h.PD(p + "time_mlp.3.bias");
+  u.te.wall = wall; u.te.ball = ball;
+  u.ready = true;
+}
+
+static NafBlockW make_nafblock(Handle& h, const std::string& q, int c) {
+  NafBlockW b;
+  b.c = c;
+  b.n1w = h.PD(q + "norm1.weight"); b.n1b = h.PD(q + "norm1.bias");
+  b.n2w = h.PD(q + "norm2.weight"); b.n2b = h.PD(q + "norm2.bias");
+  expect_shape(h.P(q + "beta"), q + "beta", {1, c, 1, 1});
+  b.beta = h.PD(q + "beta"); b.gamma = h.PD(q + "gamma");
+  b.c1 = make_conv(h, q + "conv1", 2 * c, c, 1, 1, 0);
+  b.c3 = make_conv(h, q + "conv3", c, c, 1, 1, 0);
+  b.c4 = make_conv(h, q + "conv4", 2 * c, c, 1, 1, 0);
+  b.c5 = make_conv(h, q + "conv5", c, c, 1, 1, 0);
+  expect_shape(h.P(q + "conv2.weight"), q + "conv2.weight", {2 * c, 1, 3, 3});
+  b.dw = h.dalloc_f((size_t)9 * 2 * c);
+  pack_dw_weight(nullptr, h.PD(q + "conv2.weight"), b.dw, 2 * c);
+  b.dwb = h.PD(q + "conv2.bias");
+  expect_shape(h.P(q + "sca.1.weight"), q + "sca.1.weight", {c, c, 1, 1});
+  b.scaw = h.PD(q + "sca.1.weight"); b.scab = h.PD(q + "sca.1.bias");
+  return b;
+}
+
+static void finalize_nafnet(Handle& h) {
+  const xrd_config& cf = h.cfg;
+  const std::string p = cf.naf_prefix;
+  NafW& n = h.naf;
+  n = NafW();
+  XRD_REQUIRE(cf.naf_img_channel == 1, "NAFNet: only img_channel=1 is implemented");
+  XRD_REQUIRE(cf.naf_n_enc == cf.naf_n_dec, "NAFNet: enc_blk_nums and dec_blk_nums must have equal length");
+  const int width = cf.naf_width;
+  XRD_REQUIRE(width >= 16 && (width & (width - 1)) == 0, "NAFNet: width must be a power of two >= 16 (got %d)", width);
+  n.width = width;
+  n.intro = make_conv(h, p + "intro", width, 1, 3, 1, 1);
+  int ch = width;
+  for (int s = 0; s < cf.naf_n_enc; ++s) {
+    std::vector<NafBlockW> st;
+    for (int b = 0; b < cf.naf_enc_blk_nums[s]; ++b) st.push_back(make_nafblock(h, p + "encoders." + std::to_string(s) + "." + std::to_string(b) + ".", ch));
+    n.enc.push_back(st);
+    n.downs.push_back(make_conv(h, p + "downs." + std::to_string(s), 2 * ch, ch, 2, 2, 0));
+    ch *= 2;
+  }
+  for (int b = 0; b < cf.naf_middle_blk_num; ++b) n.mid.push_back(make_nafblock(h, p + "middle_blks." + std::to_string(b) + ".", ch));
+  for (int s = 0; s < cf.naf_n_dec; ++s) {
+    // ups: 1x1 ch -> 2ch (no bias) + PixelShuffle(2) -> ch/2 channels at 2x resolution
+    const std::string q = p + "ups." + std::to_string(s) + ".0.weight";
+    expect_shape(h.P(q), q, {2 * ch, ch, 1, 1});
+    ConvW up;
+    up.kh = up.kw = 1; up.stride = 1; up.pad = 0; up.cin = ch; up.cout = 2 * ch; up.d2s = 1;
+    up.w = h.dalloc_f((size_t)ch * 2 * ch);
+    pack_pixelshuffle_weight(nullptr, h.PD(q), up.w, ch, ch / 2);
+    n.ups.push_back(up);
+    ch /= 2;
+    n.skips.push_back(make_conv(h, p + "skip_convs." + std::to_string(s), ch, 2 * ch, 1, 1, 0));
+    std::vector<NafBlockW> st;
+    for (int b = 0; b < cf.naf_dec_blk_nums[s]; ++b) st.push_back(make_nafblock(h, p + "decoders." + std::to_string(s) + "." + std::to_string(b) + ".", ch));
+    n.dec.push_back(st);
+  }
+  XRD_REQUIRE(ch == width, "NAFNet: decoder does not return to width");
+  expect_shape(h.P(p + "ending.weight"), p + "ending.weight", {1, width, 3, 3});
+  n.ending_w = h.dalloc_f((size_t)9 * width);
+  pack_conv_weight(nullptr, h.PD(p + "ending.weight"), n.ending_w, 1, width, 3, 3);
+  n.ending_b = h.PD(p + "ending.bias");
+  n.ready = true;
+}
+
+static CGG make_cgg(Handle& h, const std::string& q, int cout, int cin, int stride, int groups) {
+  CGG c;
+  c.conv = make_conv(h, q + "0", cout, cin, 3, stride, 1);
+  c.g = h.PD(q + "1.weight"); c.b = h.PD(q + "1.bias");
+  c.groups = groups;
+  return c;
+}
+static ConvW make_convT2(Handle& h, const std::string& key, int cin, int cout) {
+  expect_shape(h.P(key + ".weight"), key + ".weight", {cin, cout, 2, 2});
+  ConvW c;
+  c.kh = c.kw = 1; c.stride = 1; c.pad = 0; c.cin = cin; c.cout = 4 * cout; c.d2s = 1;
+  c.w = h.dalloc_f((size_t)cin * 4 * cout);
+  c.bias = h.dalloc_f((size_t)4 * cout);
+  pack_convT2_weight(nullptr, h.PD(key + ".weight"), h.PD(key + ".bias"), c.w, c.bias, cin, cout);
+  return c;
+}
+
+static void finalize_router(Handle& h) {
+  const std::string p = h.cfg.router_prefix;
+  const int b = h.cfg.router_base_c;
+  XRD_REQUIRE(b % 8 == 0, "router: base_c must be a multiple of 8");
+  RouterW& r = h.router;
+  r = RouterW();
+  r.enc1 = make_cgg(h, p + "enc1.", b, 1, 1, 8);
+  r.enc2 = make_cgg(h, p + "enc2.", 2 * b, b, 2, 8);
+  r.enc3 = make_cgg(h, p + "enc3.", 4 * b, 2 * b, 2, 8);
+  r.mid = make_cgg(h, p + "mid.", 4 * b, 4 * b, 1, 8);
+  r.up3 = make_convT2(h, p + "up3", 4 * b, 2 * b);
+  r.dec3 = make_cgg(h, p + "dec3.", 2 * b, 4 * b, 1, 8);
+  r.up2 = make_convT2(h, p + "up2", 2 * b, b);
+  r.dec2 = make_cgg(h, p + "dec2.", b, 2 * b, 1, 8);
+  expect_shape(h.P(p + "out_conv.weight"), p + "out_conv.weight", {1, b, 1, 1});
+  r.out_w = h.PD(p + "out_conv.weight");
+  r.out_b = h.PD(p + "out_conv.bias");
+  r.ready = true;
+}
+
+static void finalize_fusion(Handle& h) {
+  const std::string p = h.cfg.fusion_prefix;
+  const int b = h.cfg.fusion_base_c;
+  XRD_REQUIRE(b % 8 == 0, "fusion: base_c must be a multiple of 8");
+  FusionW& f = h.fusion;
+  f = FusionW();
+  f.conv1 = make_cgg(h, p + "conv1.", b, 3, 1, 8);
+  f.conv2 = make_cgg(h, p + "conv2.", b / 2, b, 1, 4);
+  expect_shape(h.P(p + "out_conv.weight"), p + "out_conv.weight", {1, b / 2, 1, 1});
+  f.out_w = h.PD(p + "out_conv.weight");
+  f.out_b = h.PD(p + "out_conv.bias");
+  f.ready = true;
+}
+
+void finalize(Handle& h, int which) {
+  XRD_CUDA(cudaSetDevice(h.device));
+  XRD_CUDA(cudaDeviceSynchronize());
+  h.free_owned();
+  if (which & XRD_PART_UNET) finalize_unet(h);
+  if (which & XRD_PART_NAFNET) finalize_nafnet(h);
+  if (which & XRD_PART_ROUTER) finalize_router(h);
+  if (which & XRD_PART_FUSION) finalize_fusion(h);
+  // sampler coefficient tables (float32 like HYB:396-398)
+  const int T = h.cfg.noise_steps;
+  h.coef1.assign(T, 0.f); h.coef2.assign(T, 0.f);
+  float ah = 1.0f;
+  for (int t = 0; t < T; ++t) {
+    double bt = T > 1 ? (double)h.cfg.beta_start + ((double)h.cfg.beta_end - (double)h.cfg.beta_start) * t / (double)(T - 1)
+                      : (double)h.cfg.beta_start;
+    float beta = (float)bt;
+    float alpha = 1.0f - beta;
+    ah = ah * alpha;
+    h.coef1[t] = 1.0f / sqrtf(alpha);
+    h.coef2[t] = (1.0f - alpha) / sqrtf(1.0f - ah);
+  }
+  XRD_CUDA(cudaDeviceSynchronize());
+}
+
+// ------------------------------------------------------------------------------------------------
+// network building blocks
+// ------------------------------------------------------------------------------------------------
+static void conv(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y) {
+  if (c.tc && conv_tc_supported(x1, x2, w, e)) conv_tc(c, x1, x2, w, e, y);
+  else conv_simt(c, x1, x2, w, e, y);
+}
+
+static double* new_sums(Ctx& c, int n, int groups) {
+  double* s = c.allocd((size_t)n * groups * 2);
+  zero_async(c, s, (size_t)n * groups * 2 * sizeof(double));
+  return s;
+}
+
+static void resblock(Ctx& c, UNetW& u, ResW& r, const Tens& x1, const Tens* x2, const float* temb, int temb_bstride, Tens& out) {
+  const size_t mk = c.a->mark();
+  const int B = x1.n, H = x1.h, W = x1.w;
+  double* s1 = new_sums(c, B, u.groups);
+  gn_stats(c, x1, x2, u.groups, s1);
+  Tens a1 = c.alloc(B, H, W, r.cin);
+  gn_act(c, x1, x2, u.groups, s1, r.g1, r.b1, 1e-5f, ACT_SILU, a1);
+  Tens hm = c.alloc(B, H, W, r.cout);
+  ConvEpi e1;
+  e1.chan_add = temb + r.temb_off; e1.chan_add_bstride = temb_bstride;
+  conv(c, a1, nullptr, r.c1, e1, hm);
+  double* s2 = new_sums(c, B, u.groups);
+  gn_stats(c, hm, nullptr, u.groups, s2);
+  Tens a2 = c.alloc(B, H, W, r.cout);
+  gn_act(c, hm, nullptr, u.groups, s2, r.g2, r.b2, 1e-5f, ACT_SILU, a2);
+  ConvEpi e2;
+  if (r.has_rc) {
+    Tens rr = c.alloc(B, H, W, r.cout);
+    conv(c, x1, x2, r.rc, ConvEpi(), rr);
+    e2.resid = rr;
+  } else {
+    XRD_REQUIRE(!x2, "resblock: identity skip with a concatenated input");
+    e2.resid = x1;
+  }
+  conv(c, a2, nullptr, r.c2, e2, out);
+  c.a->release(mk);
+}
+
+static void attention(Ctx& c, const Tens& qkv, int heads, Tens& o) {
+  if (c.tc && attention_tc_supported(qkv, heads)) attention_tc(c, qkv, heads, o);
+  else attention_simt(c, qkv, heads, o);
+}
+
+static void attnblock(Ctx& c, UNetW& u, AttnW& a, const Tens& x, Tens& out) {
+  const size_t mk = c.a->mark();
+  const int B = x.n, H = x.h, W = x.w;
+  double* s = new_sums(c, B, u.groups);
+  gn_stats(c, x, nullptr, u.groups, s);
+  Tens xn = c.alloc(B, H, W, a.c);
+  gn_act(c, x, nullptr, u.groups, s, a.g, a.b, 1e-5f, ACT_NONE, xn);
+  Tens qkv = c.alloc(B, H, W, 3 * a.c);
+  conv(c, xn, nullptr, a.qkv, ConvEpi(), qkv);
+  Tens o = c.alloc(B, H, W, a.c);
+  attention(c, qkv, u.heads, o);
+  ConvEpi e;
+  e.resid = x;
+  conv(c, o, nullptr, a.proj, e, out);
+  c.a->release(mk);
+}
+
+struct UNetOut {           // what the fused out_conv kernel does with eps
+  int mode = 0;            // 0: write eps to y; 3: sampler update
+  float* y = nullptr;      // mode 0: eps; mode 3: optional raw-eps tap
+  const float* x_cur = nullptr;
+  float* x_next = nullptr;
+  float c1 = 0, c2 = 0;
+};
+
+// One UNet evaluation (HYB:359-388).  x, cond: (B,H,W) fp32 planes.  temb: [B or 1][total] table row(s).
+static void unet_eval(Ctx& c, UNetW& u, const float* x, const float* cond, const float* temb, int temb_bstride, int B, int H, int W,
+                      const UNetOut& o) {
+  const size_t mk0 = c.a->mark();
+  Tens xin; xin.p = (void*)x; xin.n = B; xin.h = H; xin.w = W; xin.c = 1; xin.dt = DT_F32;
+  Tens cin = xin; cin.p = (void*)cond;
+  Tens h = c.alloc(B, H, W, u.mc);
+  conv_simt(c, xin, &cin, u.in_conv, ConvEpi(), h);     // cat([x, condition]) never materialised
+  std::vector<Tens> skips;
+  for (const ULayer& L : u.downs) {
+    if (L.kind == U_RES) {
+      ResW& r = u.res[L.idx];
+      Tens out = c.alloc(B, h.h, h.w, r.cout);
+      resblock(c, u, r, h, nullptr, temb, temb_bstride, out);
+      h = out;
+    } else if (L.kind == U_ATTN) {
+      Tens out = c.alloc(B, h.h, h.w, h.c);
+      attnblock(c, u, u.attn[L.idx], h, out);
+      h = out;
+    } else {
+      ConvW& d = u.down[L.idx];
+      Tens out = c.alloc(B, (h.h + 2 - 3) / 2 + 1, (h.w + 2 - 3) / 2 + 1, d.cout);
+      conv(c, h, nullptr, d, ConvEpi(), out);
+      h = out;
+    }
+    skips.push_back(h);
+  }
+  {
+    Tens o1 = c.alloc(B, h.h, h.w, h.c);
+    resblock(c, u, u.res[u.mid1], h, nullptr, temb, temb_bstride, o1);
+    Tens o2 = c.alloc(B, h.h, h.w, h.c);
+    attnblock(c, u, u.attn[u.mid_attn], o1, o2);
+    Tens o3 = c.alloc(B, h.h, h.w, h.c);
+    resblock(c, u, u.res[u.mid2], o2, nullptr, temb, temb_bstride, o3);
+    h = o3;
+  }
+  for (const ULayer& L : u.ups) {
+    if (L.kind == U_RES) {
+      XRD_REQUIRE(!skips.empty(), "UNet: skip stack underflow");
+      Tens skip = skips.back(); skips.pop_back();
+      ResW& r = u.res[L.idx];
+      Tens xs = h;
+      if (h.h != skip.h || h.w != skip.w) {
+        XRD_REQUIRE(skip.h == 2 * h.h && skip.w == 2 * h.w, "UNet: unsupported skip resize %dx%d -> %dx%d", h.h, h.w, skip.h, skip.w);
+        xs = c.alloc(B, skip.h, skip.w, h.c);
+        upsample2x(c, h, xs);                             // F.interpolate(bilinear) 2x (HYB:381-382)
+      }
+      Tens out = c.alloc(B, skip.h, skip.w, r.cout);
+      resblock(c, u, r, xs, &skip, temb, temb_bstride, out);
+      h = out;
+    } else if (L.kind == U_ATTN) {
+      Tens out = c.alloc(B, h.h, h.w, h.c);
+      attnblock(c, u, u.attn[L.idx], h, out);
+      h = out;
+    } else {
+      // ConvTranspose2d + the 0.5x bilinear that always follows it == one pre-combined 3x3 conv at this resolution
+      XRD_REQUIRE(!skips.empty() && skips.back().h == h.h && skips.back().w == h.w,
+                  "UNet: this configuration consumes a ConvTranspose2d output at full size; only the reference topology is implemented");
+      ConvW& up = u.up[L.idx];
+      Tens out = c.alloc(B, h.h, h.w, up.cout);
+      conv(c, h, nullptr, up, ConvEpi(), out);
+      h = out;
+    }
+  }
+  XRD_REQUIRE(h.h == H && h.w == W && h.c == u.out_c, "UNet: output resolution mismatch");
+  double* s = new_sums(c, B, u.groups);
+  gn_stats(c, h, nullptr, u.groups, s);
+  Cout1Args a;
+  a.x = h; a.k = 3; a.w = u.ow; a.bias = u.obias;
+  a.gn_sums = s; a.groups = u.groups; a.gamma = u.og; a.beta = u.ob; a.eps = 1e-5f; a.act_in = ACT_SILU;
+  a.mode = o.mode; a.y = o.y; a.x_cur = o.x_cur; a.x_next = o.x_next; a.c1 = o.c1; a.c2 = o.c2;
+  conv_cout1(c, a);
+  c.a->release(mk0);
+}
+
+// ---------------------------------------------------------------- NAFNet
+static void nafblock(Ctx& c, NafBlockW& b, const Tens& x, Tens& out) {
+  const size_t mk = c.a->mark();
+  const int B = x.n, H = x.h, W = x.w, C = b.c;
+  Tens t = c.alloc(B, H, W, C);
+  layernorm(c, x, b.n1w, b.n1b, 1e-6f, t);
+  Tens u = c.alloc(B, H, W, 2 * C);
+  conv(c, t, nullptr, b.c1, ConvEpi(), u);
+  Tens g = c.alloc(B, H, W, C);
+  float* pool = c.allocf((size_t)B * C);
+  zero_async(c, pool, (size_t)B * C * 4);
+  dwconv_gate_pool(c, u, b.dw, b.dwb, g, pool);
+  float* scale = c.allocf((size_t)B * C);
+  sca_scale(c, pool, B, C, H * W, b.scaw, b.scab, scale);
+  Tens y = c.alloc(B, H, W, C);
+  ConvEpi e3;
+  e3.out_scale = b.beta; e3.resid = x;
+  if (c.tc && x.dt != DT_F32) {
+    scale_nc(c, g, scale);                      // x * sca(x) (HYB:157) ahead of the tensor-core GEMM
+  } else {
+    e3.in_scale = scale;                        // folded into the A-operand load of the CUDA-core GEMM
+  }
+  conv(c, g, nullptr, b.c3, e3, y);
+  layernorm(c, y, b.n2w, b.n2b, 1e-6f, t);
+  conv(c, t, nullptr, b.c4, ConvEpi(), u);
+  simple_gate(c, u, g);
+  ConvEpi e5;
+  e5.out_scale = b.gamma; e5.resid = y;
+  conv(c, g, nullptr, b.c5, e5, out);
+  c.a->release(mk);
+}
+
+// EnhancedNAFNet.forward (HYB:206-238).  inp/out: (B,H,W) fp32 planes; `sanitize`: nan_to_num+clamp on the result.
+static void nafnet_forward(Ctx& c, NafW& n, const float* inp, float* out, int B, int H, int W, int sanitize) {
+  const size_t mk0 = c.a->mark();
+  const int mult = 1 << (int)n.enc.size();
+  const int Hp = cdiv(H, mult) * mult, Wp = cdiv(W, mult) * mult;
+  const float* ip = inp;
+  if (Hp != H || Wp != W) {
+    float* padded = c.allocf((size_t)B * Hp * Wp);
+    pad_crop_plane(c, inp, padded, B, H, W, Hp, Wp);
+    ip = padded;
+  }
+  Tens xin; xin.p = (void*)ip; xin.n = B; xin.h = Hp; xin.w = Wp; xin.c = 1; xin.dt = DT_F32;
+  Tens x = c.alloc(B, Hp, Wp, n.width);
+  conv_simt(c, xin, nullptr, n.intro, ConvEpi(), x);
+  std::vector<Tens> encs;
+  for (size_t s = 0; s < n.enc.size(); ++s) {
+    for (auto& b : n.enc[s]) {
+      Tens o = c.alloc(B, x.h, x.w, x.c);
+      nafblock(c, b, x, o);
+      x = o;
+    }
+    encs.push_back(x);
+    Tens d = c.alloc(B, x.h / 2, x.w / 2, 2 * x.c);
+    conv(c, x, nullptr, n.downs[s], ConvEpi(), d);
+    x = d;
+  }
+  for (auto& b : n.mid) {
+    Tens o = c.alloc(B, x.h, x.w, x.c);
+    nafblock(c, b, x, o);
+    x = o;
+  }
+  for (size_t s = 0; s < n.dec.size(); ++s) {
+    Tens upx = c.alloc(B, 2 * x.h, 2 * x.w, x.c / 2);
+    conv(c, x, nullptr, n.ups[s], ConvEpi(), upx);          // 1x1 + PixelShuffle(2) store
+    Tens& skip = encs[encs.size() - 1 - s];
+    XRD_REQUIRE(skip.h == upx.h && skip.w == upx.w, "NAFNet: skip size mismatch");
+    Tens m = c.alloc(B, upx.h, upx.w, upx.c);
+    conv(c, upx, &skip, n.skips[s], ConvEpi(), m);          // cat + skip_conv as a two-source GEMM
+    x = m;
+    for (auto& b : n.dec[s]) {
+      Tens o = c.alloc(B, x.h, x.w, x.c);
+      nafblock(c, b, x, o);
+      x = o;
+    }
+  }
+  Cout1Args a;
+  a.x = x; a.k = 3; a.w = n.ending_w; a.bias = n.ending_b; a.mode = 1; a.inp = ip; a.sanitize = sanitize;
+  if (Hp != H || Wp != W) {
+    float* full = c.allocf((size_t)B * Hp * Wp);
+    a.y = full;
+    conv_cout1(c, a);
+    pad_crop_plane(c, full, out, B, Hp, Wp, H, W);          // x[:, :, :H, :W]
+  } else {
+    a.y = out;
+    conv_cout1(c, a);
+  }
+  c.a->release(mk0);
+}
+
+// ---------------------------------------------------------------- router / fusion (always fp32)
+static Tens cgg(Ctx& c, CGG& L, const Tens& x1, const Tens* x2) {
+  const int Ho = (x1.h + 2 - 3) / L.conv.stride + 1, Wo = (x1.w + 2 - 3) / L.conv.stride + 1;
+  Tens y = c.alloc(x1.n, Ho, Wo, L.conv.cout, DT_F32);
+  conv_simt(c, x1, x2, L.conv, ConvEpi(), y);
+  double* s = new_sums(c, x1.n, L.groups);
+  gn_stats(c, y, nullptr, L.groups, s);
+  Tens a = c.alloc(x1.n, Ho, Wo, L.conv.cout, DT_F32);
+  gn_act(c, y, nullptr, L.groups, s, L.g, L.b, 1e-5f, ACT_GELU, a);
+  return a;
+}
+
+static void router_forward(Ctx& c, RouterW& r, const float* x, float* mask, int B, int H, int W, int sanitize) {
+  XRD_REQUIRE(H % 4 == 0 && W % 4 == 0, "router: H and W must be multiples of 4 (got %dx%d)", H, W);
+  const size_t mk0 = c.a->mark();
+  Tens xin; xin.p = (void*)x; xin.n = B; xin.h = H; xin.w = W; xin.c = 1; xin.dt = DT_F32;
+  Tens e1 = cgg(c, r.enc1, xin, nullptr);
+  Tens e2 = cgg(c, r.enc2, e1, nullptr);
+  Tens e3 = cgg(c, r.enc3, e2, nullptr);
+  Tens m = cgg(c, r.mid, e3, nullptr);
+  Tens d3u = c.alloc(B, e2.h, e2.w, r.up3.cout / 4, DT_F32);
+  conv_simt(c, m, nullptr, r.up3, ConvEpi(), d3u);
+  Tens d3 = cgg(c, r.dec3, d3u, &e2);
+  Tens d2u = c.alloc(B, e1.h, e1.w, r.up2.cout / 4, DT_F32);
+  conv_simt(c, d3, nullptr, r.up2, ConvEpi(), d2u);
+  Tens d2 = cgg(c, r.dec2, d2u, &e1);
+  Cout1Args a;
+  a.x = d2; a.k = 1; a.w = r.out_w; a.bias = r.out_b; a.mode = 2; a.sanitize = sanitize; a.y = mask;
+  conv_cout1(c, a);
+  c.a->release(mk0);
+}
+
+static void fusion_forward(Ctx& c, FusionW& f, const float* naf, const float* diff, const float* mask, float* out, int B, int H, int W) {
+  const size_t mk0 = c.a->mark();
+  Tens x3 = c.alloc(B, H, W, 3, DT_F32);
+  interleave3(c, naf, diff, mask, (float*)x3.p, (int64_t)B * H * W);
+  Tens a1 = cgg(c, f.conv1, x3, nullptr);
+  Tens a2 = cgg(c, f.conv2, a1, nullptr);
+  Cout1Args a;
+  a.x = a2; a.k = 1; a.w = f.out_w; a.bias = f.out_b; a.mode = 0; a.y = out;
+  conv_cout1(c, a);
+  c.a->release(mk0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// exported to capi.cu
+// ------------------------------------------------------------------------------------------------
+std::vector<int> ddim_timesteps(int noise_steps, int inference_steps) {
+  std::vector<int> t;
+  if (inference_steps < 1) inference_steps = 1;
+  const int step = std::max(1, noise_steps / inference_steps);
+  for (int i = 0; i < noise_steps; i += step) t.push_back(i);
+  std::reverse(t.begin(), t.end());
+  return t;
+}
+
+void run_unet_eps(Ctx& c, Handle& h, const float* x, const float* cond, const int64_t* t, float* eps, int B, int H, int W) {
+  const size_t mk = c.a->mark();
+  float* temb = c.allocf((size_t)B * h.unet.te.total);
+  time_embed(c, h.unet.te, t, nullptr, B, temb);
+  UNetOut o;
+  o.mode = 0; o.y = eps;
+  unet_eval(c, h.unet, x, cond, temb, h.unet.te.total, B, H, W, o);
+  c.a->release(mk);
+}
+
+// the reverse loop (HYB:403-418) for one micro-batch; xcur is updated in place
+void run_ddim_loop(Ctx& c, Handle& h, const float* noisy, float* xcur, const float* temb_table, const std::vector<int>& ts,
+                   float* eps_trace, float* xin_trace, const float* teacher_x, size_t trace_stride, int B, int H, int W) {
+  const size_t plane = (size_t)B * H * W;
+  for (size_t e = 0; e < ts.size(); ++e) {
+    if (teacher_x) copy_plane(c, teacher_x + e * trace_stride, xcur, plane);
+    if (xin_trace) copy_plane(c, xcur, xin_trace + e * trace_stride, plane);
+    UNetOut o;
+    o.mode = 3;
+    o.y = eps_trace ? eps_trace + e * trace_stride : nullptr;
+    o.x_cur = xcur; o.x_next = xcur;
+    o.c1 = h.coef1[ts[e]]; o.c2 = h.coef2[ts[e]];
+    unet_eval(c, h.unet, xcur, noisy, temb_table + e * h.unet.te.total, 0, B, H, W, o);
+  }
+}
+
+void run_nafnet(Ctx& c, Handle& h, const float* inp, float* out, int B, int H, int W, int sanitize) {
+  nafnet_forward(c, h.naf, inp, out, B, H, W, sanitize);
+}
+void run_router(Ctx& c, Handle& h, const float* x, float* mask, int B, int H, int W, int sanitize) {
+  router_forward(c, h.router, x, mask, B, H, W, sanitize);
+}
+void run_fusion(Ctx& c, Handle& h, const float* naf, const float* diff, const float* mask, float* out, int B, int H, int W) {
+  fusion_forward(c, h.fusion, naf, diff, mask, out, B, H, W);
+}
+
+// pre-pack tensor-core weights for every conv the current mode will route to conv_tc (cudaMalloc is illegal
+// during stream capture, so this runs before any graph is recorded)
+void prepack_tc(Handle& h, DType dt) {
+  if (dt == DT_F32) return;
+  auto pk = [&](ConvW& w, int c1) {
+    if (!w.w) return;
+    if (w.cin % 16 != 0 || c1 % 16 != 0 || (w.cin - c1) % 16 != 0 || w.cout % 8 != 0) return;
+    conv_tc_pack(nullptr, w, dt, c1);
+  };
+  UNetW& u = h.unet;
+  if (u.ready) {
+    // which ResidualBlocks see a concatenated input: exactly the ones in `ups`
+    std::vector<char> cat(u.res.size(), 0);
+    for (auto& L : u.ups) if (L.kind == U_RES) cat[L.idx] = 1;
+    for (size_t i = 0; i < u.res.size(); ++i) {
+      ResW& r = u.res[i];
+      pk(r.c1, r.cin);                                   // conv1 reads the materialised GN output (one source)
+      pk(r.c2, r.cout);
+      if (r.has_rc) pk(r.rc, cat[i] ? r.cin / 2 : r.cin);
+    }
+    for (auto& a : u.attn) { pk(a.qkv, a.c); pk(a.proj, a.c); }
+    for (auto& d : u.down) pk(d, d.cin);
+    for (auto& w : u.up) pk(w, w.cin);
+  }
+  NafW& n = h.naf;
+  if (n.ready) {
+    auto pb = [&](NafBlockW& b) { pk(b.c1, b.c); pk(b.c3, b.c); pk(b.c4, b.c); pk(b.c5, b.c); };
+    for (auto& s : n.enc) for (auto& b : s) pb(b);
+    for (auto& s : n.dec) for (auto& b : s) pb(b);
+    for (auto& b : n.mid) pb(b);
+    for (auto& w : n.downs) pk(w, w.cin);
+    for (auto& w : n.ups) pk(w, w.cin);
+    for (auto& w : n.skips) pk(w, w.cin / 2);
+  }
+  XRD_CUDA(cudaDeviceSynchronize());
+}
+
+}  // namespace xrd

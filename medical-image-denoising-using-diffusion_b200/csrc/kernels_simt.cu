@@ -1,0 +1,1007 @@
+// kernels_simt.cu -- CUDA-core kernels: the fp32 check-mode contractions, every
+// memory-bound fused kernel (GroupNorm/LayerNorm/SimpleGate/pool/sampler update),
+// layout helpers and weight packing.  NHWC everywhere; fp32 arithmetic.
+#include "kernels.cuh"
+
+namespace xrd {
+
+std::atomic<uint64_t> g_launches{0};
+
+// =====================================================================================
+// generic implicit-GEMM convolution on CUDA cores (fp32 accumulate)
+//   tile: 64 output pixels x 64 output channels, K chunks of 16 input channels per tap
+// =====================================================================================
+struct ConvP {
+  const void* x1; const void* x2; int c1, c2;
+  int N, H, W, Ho, Wo, Cout;
+  int kh, kw, stride, pad;
+  const float* w; const float* bias;
+  const float* chan_add; int chan_add_bstride;
+  const float* in_scale; const float* out_scale;
+  const void* resid; void* y;
+  int act, d2s;
+};
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) k_conv_simt(ConvP p) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int ctot = p.c1 + p.c2;
+  const int64_t npix = (int64_t)p.N * p.Ho * p.Wo;
+  const int64_t pix0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const bool vecA = ((p.c1 & 3) == 0) && ((p.c2 & 3) == 0);
+  const bool vecB = (p.Cout & 3) == 0;
+
+  // A-load assignment: one pixel, 4 consecutive channels per thread
+  const int a_pix = tid >> 2, a_k = (tid & 3) * 4;
+  int64_t gp = pix0 + a_pix;
+  const bool a_ok = gp < npix;
+  int an = 0, aoh = 0, aow = 0;
+  if (a_ok) {
+    an = (int)(gp / ((int64_t)p.Ho * p.Wo));
+    int r = (int)(gp - (int64_t)an * p.Ho * p.Wo);
+    aoh = r / p.Wo; aow = r - aoh * p.Wo;
+  }
+  // B-load assignment
+  const int b_k = tid >> 4, b_n = (tid & 15) * 4;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int ntap = p.kh * p.kw;
+  for (int tap = 0; tap < ntap; ++tap) {
+    const int ky = tap / p.kw, kx = tap - ky * p.kw;
+    const int ih = aoh * p.stride - p.pad + ky, iw = aow * p.stride - p.pad + kx;
+    const bool in_ok = a_ok && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+    const int64_t ipix = ((int64_t)an * p.H + ih) * p.W + iw;
+    for (int c0 = 0; c0 < ctot; c0 += BK) {
+      // ---- load A (activations) ----
+      float av[4] = {0.f, 0.f, 0.f, 0.f};
+      const int c = c0 + a_k;
+      if (in_ok && c < ctot) {
+        if (vecA) {
+          if (c < p.c1) {
+            ld4<TI>((const TI*)p.x1 + ipix * p.c1 + c, av);
+            if (p.in_scale) {
+              const float* sc = p.in_scale + (int64_t)an * p.c1 + c;
+              av[0] *= sc[0]; av[1] *= sc[1]; av[2] *= sc[2]; av[3] *= sc[3];
+            }
+          } else {
+            ld4<TI>((const TI*)p.x2 + ipix * p.c2 + (c - p.c1), av);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int ci = c + i;
+            if (ci < ctot) {
+              if (ci < p.c1) {
+                float v = ldf<TI>((const TI*)p.x1 + ipix * p.c1 + ci);
+                if (p.in_scale) v *= p.in_scale[(int64_t)an * p.c1 + ci];
+                av[i] = v;
+              } else {
+                av[i] = ldf<TI>((const TI*)p.x2 + ipix * p.c2 + (ci - p.c1));
+              }
+            }
+          }
+        }
+      }
+      // ---- load B (weights) ----
+      float bv[4] = {0.f, 0.f, 0.f, 0.f};
+      {
+        const int ck = c0 + b_k;
+        const int nn = n0 + b_n;
+        if (ck < ctot) {
+          const float* wp = p.w + ((int64_t)tap * ctot + ck) * p.Cout + nn;
+          if (vecB && nn + 3 < p.Cout) {
+            float4 t = *reinterpret_cast<const float4*>(wp);
+            bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (nn + i < p.Cout) bv[i] = wp[i];
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) As[a_k + i][a_pix] = av[i];
+      *reinterpret_cast<float4*>(&Bs[b_k][b_n]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        float aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+      }
+    }
+  }
+
+  // ---- epilogue ----
+  const int nn = n0 + tx * 4;
+  if (nn >= p.Cout) return;
+  const int cf = p.d2s ? (p.Cout >> 2) : p.Cout;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t op = pix0 + ty * 4 + i;
+    if (op >= npix) continue;
+    int n = (int)(op / ((int64_t)p.Ho * p.Wo));
+    int r = (int)(op - (int64_t)n * p.Ho * p.Wo);
+    int oh = r / p.Wo, ow = r - oh * p.Wo;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int co = nn + j;
+      float t = acc[i][j];
+      if (co < p.Cout) {
+        if (p.bias) t += p.bias[co];
+        if (p.chan_add) t += p.chan_add[(int64_t)n * p.chan_add_bstride + co];
+        if (p.out_scale) t *= p.out_scale[co];
+      }
+      v[j] = t;
+    }
+    int64_t obase;
+    int cbase;
+    if (p.d2s) {
+      int q = nn / cf;  // 4 consecutive columns stay inside one (i,j) block when cf % 4 == 0
+      cbase = nn - q * cf;
+      int di = q >> 1, dj = q & 1;
+      obase = (((int64_t)n * (2 * p.Ho) + (2 * oh + di)) * (2 * p.Wo) + (2 * ow + dj)) * cf;
+    } else {
+      cbase = nn;
+      obase = op * p.Cout;
+    }
+    const bool vec_out = ((cf & 3) == 0) && (nn + 3 < p.Cout);
+    if (vec_out) {
+      if (p.resid) {
+        float rv[4];
+        ld4<TO>((const TO*)p.resid + obase + cbase, rv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] += rv[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = act_apply(v[j], p.act);
+      st4<TO>((TO*)p.y + obase + cbase, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int co = nn + j;
+        if (co >= p.Cout) break;
+        int64_t o;
+        if (p.d2s) {
+          int q = co / cf, cc = co - q * cf;
+          o = (((int64_t)n * (2 * p.Ho) + (2 * oh + (q >> 1))) * (2 * p.Wo) + (2 * ow + (q & 1))) * cf + cc;
+        } else {
+          o = op * p.Cout + co;
+        }
+        float t = v[j];
+        if (p.resid) t += ldf<TO>((const TO*)p.resid + o);
+        stf<TO>((TO*)p.y + o, act_apply(t, p.act));
+      }
+    }
+  }
+}
+
+void conv_simt(Ctx& c, const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e, Tens& y) {
+  ConvP p;
+  p.x1 = x1.p; p.c1 = x1.c;
+  p.x2 = x2 ? x2->p : nullptr; p.c2 = x2 ? x2->c : 0;
+  XRD_REQUIRE(p.c1 + p.c2 == w.cin, "conv_simt: input channels %d+%d != weight cin %d", p.c1, p.c2, w.cin);
+  if (x2) XRD_REQUIRE(x2->n == x1.n && x2->h == x1.h && x2->w == x1.w && x2->dt == x1.dt, "conv_simt: source mismatch");
+  XRD_REQUIRE(!(e.in_scale && x2), "conv_simt: in_scale with two sources");
+  p.N = x1.n; p.H = x1.h; p.W = x1.w;
+  p.Ho = (x1.h + 2 * w.pad - w.kh) / w.stride + 1;
+  p.Wo = (x1.w + 2 * w.pad - w.kw) / w.stride + 1;
+  p.Cout = w.cout;
+  const int cf = w.d2s ? w.cout / 4 : w.cout;
+  const int eh = w.d2s ? 2 * p.Ho : p.Ho, ew = w.d2s ? 2 * p.Wo : p.Wo;
+  XRD_REQUIRE(y.n == x1.n && y.h == eh && y.w == ew && y.c == cf, "conv_simt: output shape (%d,%d,%d,%d) expected (%d,%d,%d,%d)",
+              y.n, y.h, y.w, y.c, x1.n, eh, ew, cf);
+  p.kh = w.kh; p.kw = w.kw; p.stride = w.stride; p.pad = w.pad;
+  p.w = w.w; p.bias = w.bias;
+  p.chan_add = e.chan_add; p.chan_add_bstride = e.chan_add_bstride;
+  p.in_scale = e.in_scale; p.out_scale = e.out_scale;
+  p.resid = e.resid.p; p.y = y.p;
+  if (e.resid.p) XRD_REQUIRE(e.resid.dt == y.dt && e.resid.numel() == y.numel(), "conv_simt: residual mismatch");
+  p.act = e.act; p.d2s = w.d2s;
+  int64_t npix = (int64_t)p.N * p.Ho * p.Wo;
+  dim3 grid((unsigned)cdiv64(npix, 64), (unsigned)cdiv(p.Cout, 64));
+  XRD_DISPATCH(x1.dt, TI, XRD_DISPATCH(y.dt, TO, XRD_LAUNCH(c, (k_conv_simt<TI, TO>), grid, 256, 0, p)));
+}
+
+// =====================================================================================
+// GroupNorm statistics and apply(+activation) over a virtual concat of two sources
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) k_gn_stats(const T* __restrict__ x1, const T* __restrict__ x2, int c1, int c2,
+                                                  int HW, int groups, int pix_per_block, double* __restrict__ sums) {
+  extern __shared__ float sm[];  // [2][ctot]
+  const int ctot = c1 + c2;
+  const int Q = ctot >> 2;
+  const int n = blockIdx.y;
+  float* s_sum = sm;
+  float* s_sq = sm + ctot;
+  for (int i = threadIdx.x; i < 2 * ctot; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int ppi = blockDim.x / Q;  // pixels per iteration
+  const int q = threadIdx.x % Q, py = threadIdx.x / Q;
+  if (py < ppi) {
+    const int c = q * 4;
+    const T* src; int cs, cc;
+    if (c < c1) { src = x1; cs = c1; cc = c; } else { src = x2; cs = c2; cc = c - c1; }
+    float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+    const int p0 = blockIdx.x * pix_per_block;
+    const int p1 = min(p0 + pix_per_block, HW);
+    for (int pp = p0 + py; pp < p1; pp += ppi) {
+      float v[4];
+      ld4<T>(src + ((int64_t)n * HW + pp) * cs + cc, v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { s[i] += v[i]; ss[i] = fmaf(v[i], v[i], ss[i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { atomicAdd(&s_sum[c + i], s[i]); atomicAdd(&s_sq[c + i], ss[i]); }
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    const int cpg = ctot / groups;
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < cpg; ++i) { a += (double)s_sum[threadIdx.x * cpg + i]; b += (double)s_sq[threadIdx.x * cpg + i]; }
+    atomicAdd(&sums[((int64_t)n * groups + threadIdx.x) * 2 + 0], a);
+    atomicAdd(&sums[((int64_t)n * groups + threadIdx.x) * 2 + 1], b);
+  }
+}
+
+void gn_stats(Ctx& c, const Tens& x1, const Tens* x2, int groups, double* sums) {
+  const int c1 = x1.c, c2 = x2 ? x2->c : 0, ctot = c1 + c2;
+  XRD_REQUIRE((c1 % 4) == 0 && (c2 % 4) == 0 && ctot % groups == 0 && ctot / 4 <= 256 && groups <= 32,
+              "gn_stats: unsupported channels %d+%d groups %d", c1, c2, groups);
+  if (x2) XRD_REQUIRE(x2->n == x1.n && x2->h == x1.h && x2->w == x1.w && x2->dt == x1.dt, "gn_stats: source mismatch");
+  const int HW = x1.h * x1.w;
+  const int ppb = 1024;
+  dim3 grid(cdiv(HW, ppb), x1.n);
+  size_t smem = 2 * ctot * sizeof(float);
+  XRD_DISPATCH(x1.dt, T, XRD_LAUNCH(c, (k_gn_stats<T>), grid, 256, smem, (const T*)x1.p, (const T*)(x2 ? x2->p : nullptr),
+                                    c1, c2, HW, groups, ppb, sums));
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) k_gn_act(const TI* __restrict__ x1, const TI* __restrict__ x2, int c1, int c2, int HW,
+                                                int groups, const double* __restrict__ sums, const float* __restrict__ gamma,
+                                                const float* __restrict__ beta, float eps, int act, TO* __restrict__ y) {
+  __shared__ float s_mean[32], s_rstd[32];
+  const int ctot = c1 + c2, cpg = ctot / groups, n = blockIdx.y;
+  if (threadIdx.x < groups) {
+    double cnt = (double)cpg * HW;
+    double m = sums[((int64_t)n * groups + threadIdx.x) * 2] / cnt;
+    double var = sums[((int64_t)n * groups + threadIdx.x) * 2 + 1] / cnt - m * m;
+    if (var < 0) var = 0;
+    s_mean[threadIdx.x] = (float)m;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int Q = ctot >> 2;
+  const int64_t total = (int64_t)HW * Q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int pp = (int)(i / Q), q = (int)(i - (int64_t)pp * Q);
+    const int c = q * 4;
+    float v[4];
+    if (c < c1) ld4<TI>(x1 + ((int64_t)n * HW + pp) * c1 + c, v);
+    else ld4<TI>(x2 + ((int64_t)n * HW + pp) * c2 + (c - c1), v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = (c + j) / cpg;
+      float t = (v[j] - s_mean[g]) * s_rstd[g] * gamma[c + j] + beta[c + j];
+      v[j] = act_apply(t, act);
+    }
+    st4<TO>(y + ((int64_t)n * HW + pp) * ctot + c, v);
+  }
+}
+
+void gn_act(Ctx& c, const Tens& x1, const Tens* x2, int groups, const double* sums, const float* gamma, const float* beta,
+            float eps, int act, Tens& y) {
+  const int c1 = x1.c, c2 = x2 ? x2->c : 0, ctot = c1 + c2;
+  XRD_REQUIRE(y.c == ctot && y.n == x1.n && y.h == x1.h && y.w == x1.w, "gn_act: output shape mismatch");
+  XRD_REQUIRE((c1 % 4) == 0 && (c2 % 4) == 0 && ctot % groups == 0 && groups <= 32, "gn_act: unsupported channels");
+  const int HW = x1.h * x1.w;
+  int64_t total = (int64_t)HW * (ctot / 4);
+  int bx = (int)std::min<int64_t>(cdiv64(total, 256 * 4), 148 * 8);
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, x1.n);
+  XRD_DISPATCH(x1.dt, TI, XRD_DISPATCH(y.dt, TO, XRD_LAUNCH(c, (k_gn_act<TI, TO>), grid, 256, 0, (const TI*)x1.p,
+                                                            (const TI*)(x2 ? x2->p : nullptr), c1, c2, HW, groups, sums, gamma,
+                                                            beta, eps, act, (TO*)y.p)));
+}
+
+void zero_async(Ctx& c, void* p, size_t bytes) {
+  if (c.dry) return;
+  XRD_CUDA(cudaMemsetAsync(p, 0, bytes, c.s));
+}
+
+// =====================================================================================
+// bilinear 2x upsample (align_corners=False): out[2k] = .25 x[k-1] + .75 x[k], out[2k+1] = .75 x[k] + .25 x[k+1], edges clamped
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) k_upsample2x(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C) {
+  const int Q = C >> 2;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const int64_t total = (int64_t)N * Ho * Wo * Q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int q = (int)(i % Q);
+    int64_t r = i / Q;
+    int ow = (int)(r % Wo); r /= Wo;
+    int oh = (int)(r % Ho);
+    int n = (int)(r / Ho);
+    int h0, h1, w0, w1; float fh, fw;  // weight of the *second* sample
+    if (oh & 1) { h0 = oh >> 1; h1 = min(h0 + 1, H - 1); fh = 0.25f; } else { h1 = oh >> 1; h0 = max(h1 - 1, 0); fh = 0.75f; }
+    if (ow & 1) { w0 = ow >> 1; w1 = min(w0 + 1, W - 1); fw = 0.25f; } else { w1 = ow >> 1; w0 = max(w1 - 1, 0); fw = 0.75f; }
+    float a[4], b[4], cc[4], d[4], o[4];
+    const T* base = x + (int64_t)n * H * W * C + q * 4;
+    ld4<T>(base + ((int64_t)h0 * W + w0) * C, a);
+    ld4<T>(base + ((int64_t)h0 * W + w1) * C, b);
+    ld4<T>(base + ((int64_t)h1 * W + w0) * C, cc);
+    ld4<T>(base + ((int64_t)h1 * W + w1) * C, d);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float top = a[j] + fw * (b[j] - a[j]);
+      float bot = cc[j] + fw * (d[j] - cc[j]);
+      o[j] = top + fh * (bot - top);
+    }
+    st4<T>(y + (((int64_t)n * Ho + oh) * Wo + ow) * C + q * 4, o);
+  }
+}
+
+void upsample2x(Ctx& c, const Tens& x, Tens& y) {
+  XRD_REQUIRE(y.n == x.n && y.h == 2 * x.h && y.w == 2 * x.w && y.c == x.c && y.dt == x.dt && (x.c % 4) == 0, "upsample2x: shape");
+  int64_t total = (int64_t)y.n * y.h * y.w * (y.c / 4);
+  int bx = (int)std::min<int64_t>(cdiv64(total, 256), 148 * 16);
+  XRD_DISPATCH(x.dt, T, XRD_LAUNCH(c, (k_upsample2x<T>), bx, 256, 0, (const T*)x.p, (T*)y.p, x.n, x.h, x.w, x.c));
+}
+
+// =====================================================================================
+// LayerNorm over channels per pixel (eps inside the sqrt, biased variance)      HYB:108-115
+// =====================================================================================
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) k_layernorm(const TI* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+                                                   float eps, TO* __restrict__ y, int64_t npix, int C, int lpp) {
+  // lpp lanes cooperate on one pixel (power of two <= 32); each lane owns quads lane, lane+lpp, ...
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % lpp;
+  const int ppw = 32 / lpp;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int Q = C >> 2;
+  const int nq = Q / lpp;  // quads per lane (<= 8)
+  for (int64_t p0 = warp * ppw; p0 < npix; p0 += nwarps * ppw) {
+    const int64_t pix = p0 + lane / lpp;
+    const bool ok = pix < npix;
+    float v[8][4];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < nq) {
+        if (ok) ld4<TI>(x + pix * C + (sub + j * lpp) * 4, v[j]);
+        else { v[j][0] = v[j][1] = v[j][2] = v[j][3] = 0.f; }
+        s += v[j][0] + v[j][1] + v[j][2] + v[j][3];
+      }
+    }
+    for (int o = lpp >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nq) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float d = v[j][i] - mean; ss = fmaf(d, d, ss); }
+      }
+    for (int o = lpp >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = 1.0f / sqrtf(ss / (float)C + eps);
+    if (ok) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nq) {
+          const int c0 = (sub + j * lpp) * 4;
+          float o4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o4[i] = (v[j][i] - mean) * rstd * g[c0 + i] + b[c0 + i];
+          st4<TO>(y + pix * C + c0, o4);
+        }
+    }
+  }
+}
+
+void layernorm(Ctx& c, const Tens& x, const float* g, const float* b, float eps, Tens& y) {
+  const int C = x.c, Q = C / 4;
+  XRD_REQUIRE(C % 4 == 0 && y.numel() == x.numel() && y.c == C, "layernorm: shape");
+  int lpp = 1;
+  while (lpp < 32 && lpp * 2 <= Q) lpp *= 2;
+  XRD_REQUIRE(Q % lpp == 0 && Q / lpp <= 8, "layernorm: unsupported channel count %d", C);
+  int64_t npix = (int64_t)x.n * x.h * x.w;
+  int ppw = 32 / lpp;
+  int bx = (int)std::min<int64_t>(cdiv64(npix, (int64_t)ppw * 8), 148 * 16);
+  if (bx < 1) bx = 1;
+  XRD_DISPATCH(x.dt, TI, XRD_DISPATCH(y.dt, TO, XRD_LAUNCH(c, (k_layernorm<TI, TO>), bx, 256, 0, (const TI*)x.p, g, b, eps,
+                                                           (TO*)y.p, npix, C, lpp)));
+}
+
+// =====================================================================================
+// depthwise 3x3 + SimpleGate + global-average-pool partial sums                 HYB:155-157
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) k_dwconv_gate_pool(const T* __restrict__ u, const float* __restrict__ w9, const float* __restrict__ bias,
+                                                          T* __restrict__ g, float* __restrict__ pool, int H, int W, int C,
+                                                          int pix_per_block) {
+  extern __shared__ float s_pool[];  // [C]
+  const int C2 = 2 * C, Q = C >> 2;
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_pool[i] = 0.f;
+  __syncthreads();
+  const int ppi = blockDim.x / Q;
+  const int q = threadIdx.x % Q, py = threadIdx.x / Q;
+  if (py < ppi) {
+    const int c = q * 4;
+    float wa[9][4], wb[9][4], ba[4], bb[4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float4 x0 = *reinterpret_cast<const float4*>(w9 + t * C2 + c);
+      float4 x1 = *reinterpret_cast<const float4*>(w9 + t * C2 + C + c);
+      wa[t][0] = x0.x; wa[t][1] = x0.y; wa[t][2] = x0.z; wa[t][3] = x0.w;
+      wb[t][0] = x1.x; wb[t][1] = x1.y; wb[t][2] = x1.z; wb[t][3] = x1.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ba[i] = bias[c + i]; bb[i] = bias[C + c + i]; }
+    float ps[4] = {0, 0, 0, 0};
+    const int HW = H * W;
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(p0 + pix_per_block, HW);
+    for (int pp = p0 + py; pp < p1; pp += ppi) {
+      const int oh = pp / W, ow = pp - oh * W;
+      float a[4] = {ba[0], ba[1], ba[2], ba[3]}, b[4] = {bb[0], bb[1], bb[2], bb[3]};
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int ih = oh + ky - 1;
+        if (ih < 0 || ih >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int iw = ow + kx - 1;
+          if (iw < 0 || iw >= W) continue;
+          const T* src = u + (((int64_t)n * H + ih) * W + iw) * C2;
+          float va[4], vb[4];
+          ld4<T>(src + c, va);
+          ld4<T>(src + C + c, vb);
+          const int t = ky * 3 + kx;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { a[i] = fmaf(va[i], wa[t][i], a[i]); b[i] = fmaf(vb[i], wb[t][i], b[i]); }
+        }
+      }
+      float o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { o[i] = a[i] * b[i]; }
+      st4<T>(g + ((int64_t)n * HW + pp) * C + c, o);
+      // the pool must see what the next layer sees: the value as stored
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ps[i] += o[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) atomicAdd(&s_pool[c + i], ps[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&pool[(int64_t)n * C + i], s_pool[i]);
+}
+
+void dwconv_gate_pool(Ctx& c, const Tens& u, const float* w9, const float* bias, Tens& g, float* pool) {
+  const int C = g.c;
+  XRD_REQUIRE(u.c == 2 * C && C % 4 == 0 && C / 4 <= 256 && g.n == u.n && g.h == u.h && g.w == u.w && g.dt == u.dt,
+              "dwconv_gate_pool: shape");
+  const int HW = u.h * u.w;
+  const int ppi = 256 / (C / 4);
+  int ppb = std::max(ppi * 8, 64);
+  dim3 grid(cdiv(HW, ppb), u.n);
+  XRD_DISPATCH(u.dt, T, XRD_LAUNCH(c, (k_dwconv_gate_pool<T>), grid, 256, C * sizeof(float), (const T*)u.p, w9, bias, (T*)g.p, pool,
+                                   u.h, u.w, C, ppb));
+}
+
+__global__ void __launch_bounds__(256) k_sca(const float* __restrict__ pool, int C, float inv_hw, const float* __restrict__ W,
+                                             const float* __restrict__ b, float* __restrict__ scale) {
+  extern __shared__ float s_mean[];
+  const int n = blockIdx.x;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_mean[i] = pool[(int64_t)n * C + i] * inv_hw;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int co = warp; co < C; co += nw) {
+    float s = 0.f;
+    for (int j = lane; j < C; j += 32) s = fmaf(W[(int64_t)co * C + j], s_mean[j], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) scale[(int64_t)n * C + co] = s + b[co];
+  }
+}
+
+void sca_scale(Ctx& c, const float* pool, int N, int C, int HW, const float* W, const float* b, float* scale) {
+  XRD_LAUNCH(c, k_sca, N, 256, C * sizeof(float), pool, C, 1.0f / (float)HW, W, b, scale);
+}
+
+// =====================================================================================
+// single-output-channel convolution with fused GroupNorm+act prologue and
+// sampler-update / residual / sigmoid epilogues                              HYB:353-357,410-416,228-229,533
+// =====================================================================================
+struct Cout1P {
+  const void* x; int N, H, W, C, k;
+  const float* w; const float* bias;
+  const double* gn_sums; int groups; const float* gamma; const float* beta; float eps; int act_in;
+  int mode, sanitize;
+  const float* inp; float* y; const float* x_cur; float* x_next; float c1, c2;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_conv_cout1(Cout1P p) {
+  extern __shared__ float sm[];  // w[k*k*C], scale[C], shift[C]
+  const int C = p.C, kk = p.k * p.k;
+  float* s_w = sm;
+  float* s_scale = sm + kk * C;
+  float* s_shift = s_scale + C;
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < kk * C; i += blockDim.x) s_w[i] = p.w[i];
+  if (p.gn_sums) {
+    const int cpg = C / p.groups;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int g = c / cpg;
+      double cnt = (double)cpg * p.H * p.W;
+      double m = p.gn_sums[((int64_t)n * p.groups + g) * 2] / cnt;
+      double var = p.gn_sums[((int64_t)n * p.groups + g) * 2 + 1] / cnt - m * m;
+      if (var < 0) var = 0;
+      float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+      float sc = rstd * p.gamma[c];
+      s_scale[c] = sc;
+      s_shift[c] = p.beta[c] - (float)m * sc;
+    }
+  }
+  __syncthreads();
+  const int HW = p.H * p.W;
+  const int pp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pp >= HW) return;
+  const int oh = pp / p.W, ow = pp - oh * p.W;
+  const int r = p.k >> 1;
+  float acc = 0.f;
+  const T* xb = (const T*)p.x + (int64_t)n * HW * C;
+  for (int ky = 0; ky < p.k; ++ky) {
+    const int ih = oh + ky - r;
+    if (ih < 0 || ih >= p.H) continue;
+    for (int kx = 0; kx < p.k; ++kx) {
+      const int iw = ow + kx - r;
+      if (iw < 0 || iw >= p.W) continue;
+      const T* src = xb + ((int64_t)ih * p.W + iw) * C;
+      const float* wt = s_w + (ky * p.k + kx) * C;
+      for (int c = 0; c < C; c += 4) {
+        float v[4];
+        ld4<T>(src + c, v);
+        if (p.gn_sums) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = act_apply(fmaf(v[i], s_scale[c + i], s_shift[c + i]), p.act_in);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc = fmaf(v[i], wt[c + i], acc);
+      }
+    }
+  }
+  float v = acc + (p.bias ? p.bias[0] : 0.f);
+  const int64_t o = (int64_t)n * HW + pp;
+  if (p.mode == 3) {
+    if (p.y) p.y[o] = v;                       // raw eps tap (parity trace)
+    float e = fminf(fmaxf(v, -5.f), 5.f);      // clamp(eps,-5,5)
+    float xn = p.c1 * (p.x_cur[o] - p.c2 * e);
+    p.x_next[o] = fminf(fmaxf(xn, 0.f), 1.f);
+    return;
+  }
+  if (p.mode == 1) v += p.inp[o];
+  if (p.mode == 2) v = 1.0f / (1.0f + expf(-v));
+  if (p.sanitize) v = sanitize01(v);
+  p.y[o] = v;
+}
+
+void conv_cout1(Ctx& c, const Cout1Args& a) {
+  XRD_REQUIRE(a.x.c % 4 == 0 && (a.k == 1 || a.k == 3), "conv_cout1: unsupported C=%d k=%d", a.x.c, a.k);
+  Cout1P p;
+  p.x = a.x.p; p.N = a.x.n; p.H = a.x.h; p.W = a.x.w; p.C = a.x.c; p.k = a.k;
+  p.w = a.w; p.bias = a.bias;
+  p.gn_sums = a.gn_sums; p.groups = a.groups; p.gamma = a.gamma; p.beta = a.beta; p.eps = a.eps; p.act_in = a.act_in;
+  p.mode = a.mode; p.sanitize = a.sanitize; p.inp = a.inp; p.y = a.y; p.x_cur = a.x_cur; p.x_next = a.x_next;
+  p.c1 = a.c1; p.c2 = a.c2;
+  size_t smem = ((size_t)a.k * a.k * a.x.c + 2 * a.x.c) * sizeof(float);
+  dim3 grid(cdiv(a.x.h * a.x.w, 128), a.x.n);
+  XRD_DISPATCH(a.x.dt, T, XRD_LAUNCH(c, (k_conv_cout1<T>), grid, 128, smem, p));
+}
+
+// =====================================================================================
+// self-attention on CUDA cores (flash style, fp32) -- check mode and reference for the tcgen05 kernel
+// =====================================================================================
+template <typename T, int D>
+__global__ void __launch_bounds__(256) k_attn_simt(const T* __restrict__ qkv, T* __restrict__ out, int HW, int heads, float scale) {
+  constexpr int BQ = 64, BK = 64, DP = D + 4, DPT = D / 16;
+  extern __shared__ __align__(16) float smf[];
+  float* Qs = smf;                 // [BQ][DP]
+  float* Ks = Qs + BQ * DP;        // [BK][DP]
+  float* Vs = Ks + BK * DP;        // [BK][DP]
+  float* Ps = Vs + BK * DP;        // [BQ][BK+4]
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int n = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * BQ;
+  const int CT = 3 * heads * D;
+  const T* base = qkv + (int64_t)n * HW * CT;
+  const int qoff = head * D, koff = heads * D + head * D, voff = 2 * heads * D + head * D;
+
+  for (int i = tid; i < BQ * (D / 4); i += 256) {
+    int r = i / (D / 4), c4 = (i - r * (D / 4)) * 4;
+    float v[4] = {0, 0, 0, 0};
+    if (q0 + r < HW) ld4<T>(base + (int64_t)(q0 + r) * CT + qoff + c4, v);
+    *reinterpret_cast<float4*>(&Qs[r * DP + c4]) = make_float4(v[0] * scale, v[1] * scale, v[2] * scale, v[3] * scale);
+  }
+  float m[4], l[4], o[4][DPT];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m[i] = -INFINITY; l[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) o[i][j] = 0.f;
+  }
+  for (int k0 = 0; k0 < HW; k0 += BK) {
+    __syncthreads();
+    for (int i = tid; i < BK * (D / 4); i += 256) {
+      int r = i / (D / 4), c4 = (i - r * (D / 4)) * 4;
+      float kv[4] = {0, 0, 0, 0}, vv[4] = {0, 0, 0, 0};
+      if (k0 + r < HW) {
+        ld4<T>(base + (int64_t)(k0 + r) * CT + koff + c4, kv);
+        ld4<T>(base + (int64_t)(k0 + r) * CT + voff + c4, vv);
+      }
+      *reinterpret_cast<float4*>(&Ks[r * DP + c4]) = make_float4(kv[0], kv[1], kv[2], kv[3]);
+      *reinterpret_cast<float4*>(&Vs[r * DP + c4]) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    }
+    __syncthreads();
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+    for (int d = 0; d < D; d += 4) {
+      float4 qa[4], kb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qa[i] = *reinterpret_cast<const float4*>(&Qs[(ty * 4 + i) * DP + d]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) kb[j] = *reinterpret_cast<const float4*>(&Ks[(tx + 16 * j) * DP + d]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          s[i][j] += qa[i].x * kb[j].x + qa[i].y * kb[j].y + qa[i].z * kb[j].z + qa[i].w * kb[j].w;
+    }
+    // keys handled by this thread: tx + 16*j
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (k0 + tx + 16 * j >= HW) s[i][j] = -INFINITY;
+        mx = fmaxf(mx, s[i][j]);
+      }
+      for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      const float mnew = fmaxf(m[i], mx);
+      const float corr = (m[i] == -INFINITY) ? 0.f : expf(m[i] - mnew);
+      float rs = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float pv = (s[i][j] == -INFINITY) ? 0.f : expf(s[i][j] - mnew);
+        rs += pv;
+        Ps[(ty * 4 + i) * (BK + 4) + tx + 16 * j] = pv;
+      }
+      for (int off = 8; off > 0; off >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
+      l[i] = l[i] * corr + rs;
+      m[i] = mnew;
+#pragma unroll
+      for (int j = 0; j < DPT; ++j) o[i][j] *= corr;
+    }
+    __syncthreads();
+    for (int k = 0; k < BK; ++k) {
+      float pv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pv[i] = Ps[(ty * 4 + i) * (BK + 4) + k];
+#pragma unroll
+      for (int j = 0; j < DPT; ++j) {
+        const float vv = Vs[k * DP + tx + 16 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i][j] = fmaf(pv[i], vv, o[i][j]);
+      }
+    }
+  }
+  const int CO = heads * D;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = q0 + ty * 4 + i;
+    if (q >= HW) continue;
+    const float inv = 1.0f / l[i];
+#pragma unroll
+    for (int j = 0; j < DPT; ++j)
+      stf<T>(out + ((int64_t)n * HW + q) * CO + head * D + tx + 16 * j, o[i][j] * inv);
+  }
+}
+
+template <typename T, int D>
+static void launch_attn_simt(Ctx& c, const Tens& qkv, int heads, Tens& out) {
+  const int HW = qkv.h * qkv.w;
+  size_t smem = (size_t)(3 * 64 * (D + 4) + 64 * 68) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    XRD_CUDA(cudaFuncSetAttribute(k_attn_simt<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  dim3 grid(cdiv(HW, 64), heads, qkv.n);
+  float scale = 1.0f / sqrtf((float)D);
+  XRD_LAUNCH(c, (k_attn_simt<T, D>), grid, 256, smem, (const T*)qkv.p, (T*)out.p, HW, heads, scale);
+}
+
+void attention_simt(Ctx& c, const Tens& qkv, int heads, Tens& out) {
+  XRD_REQUIRE(qkv.c % (3 * heads) == 0, "attention: channels %d not divisible by 3*heads", qkv.c);
+  const int d = qkv.c / (3 * heads);
+  XRD_REQUIRE(out.c == heads * d && out.n == qkv.n && out.h == qkv.h && out.w == qkv.w && out.dt == qkv.dt, "attention: output shape");
+  XRD_DISPATCH(qkv.dt, T, {
+    switch (d) {
+      case 16: launch_attn_simt<T, 16>(c, qkv, heads, out); break;
+      case 32: launch_attn_simt<T, 32>(c, qkv, heads, out); break;
+      case 48: launch_attn_simt<T, 48>(c, qkv, heads, out); break;
+      case 64: launch_attn_simt<T, 64>(c, qkv, heads, out); break;
+      case 96: launch_attn_simt<T, 96>(c, qkv, heads, out); break;
+      case 128: launch_attn_simt<T, 128>(c, qkv, heads, out); break;
+      default: fail(XRD_ERR_INVALID, "attention: unsupported head dim %d", d);
+    }
+  });
+}
+
+// =====================================================================================
+// time embedding: sinusoidal -> Linear -> SiLU -> Linear, then SiLU -> Linear(ted,out_c) of every ResidualBlock
+//                                                                       HYB:246-253,313-318,259-262
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_time_embed(TimeEmbW w, const int64_t* __restrict__ t_i64, const int* __restrict__ t_list,
+                                                    float neg_k, float* __restrict__ out) {
+  extern __shared__ float sm[];  // e[mc], h1[ted], te[ted]
+  float* e = sm;
+  float* h1 = e + w.mc;
+  float* te = h1 + w.ted;
+  const int r = blockIdx.x;
+  const float t = t_i64 ? (float)t_i64[r] : (float)t_list[r];
+  const int half = w.mc / 2;
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    float f = expf((float)i * neg_k);
+    float a = t * f;
+    e[i] = sinf(a);
+    e[half + i] = cosf(a);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int o = warp; o < w.ted; o += nw) {
+    float s = 0.f;
+    for (int j = lane; j < w.mc; j += 32) s = fmaf(w.w1[(int64_t)o * w.mc + j], e[j], s);
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) { s += w.b1[o]; h1[o] = s / (1.0f + expf(-s)); }
+  }
+  __syncthreads();
+  for (int o = warp; o < w.ted; o += nw) {
+    float s = 0.f;
+    for (int j = lane; j < w.ted; j += 32) s = fmaf(w.w2[(int64_t)o * w.ted + j], h1[j], s);
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) { s += w.b2[o]; te[o] = s / (1.0f + expf(-s)); }   // SiLU that opens every block's time_mlp
+  }
+  __syncthreads();
+  for (int o = warp; o < w.total; o += nw) {
+    float s = 0.f;
+    for (int j = lane; j < w.ted; j += 32) s = fmaf(w.wall[(int64_t)o * w.ted + j], te[j], s);
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) out[(int64_t)r * w.total + o] = s + w.ball[o];
+  }
+}
+
+void time_embed(Ctx& c, const TimeEmbW& w, const int64_t* t_i64, const int* t_list, int rows, float* out) {
+  const int half = w.mc / 2;
+  XRD_REQUIRE(half > 1, "time_embed: model_channels too small");
+  const float neg_k = -(float)(log(10000.0) / (double)(half - 1));
+  size_t smem = (size_t)(w.mc + 2 * w.ted) * sizeof(float);
+  XRD_LAUNCH(c, k_time_embed, rows, 256, smem, w, t_i64, t_list, neg_k, out);
+}
+
+// =====================================================================================
+// layout helpers
+// =====================================================================================
+template <typename T>
+__global__ void k_nchw_to_nhwc(const float* __restrict__ x, T* __restrict__ y, int N, int C, int HW) {
+  const int64_t total = (int64_t)N * C * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t r = i / C;
+    int p = (int)(r % HW);
+    int n = (int)(r / HW);
+    stf<T>(y + i, x[((int64_t)n * C + c) * HW + p]);
+  }
+}
+template <typename T>
+__global__ void k_nhwc_to_nchw(const T* __restrict__ x, float* __restrict__ y, int N, int C, int HW) {
+  const int64_t total = (int64_t)N * C * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int p = (int)(i % HW);
+    int64_t r = i / HW;
+    int c = (int)(r % C);
+    int n = (int)(r / C);
+    y[i] = ldf<T>(x + ((int64_t)n * HW + p) * C + c);
+  }
+}
+static int ew_blocks(int64_t total) { return (int)std::max<int64_t>(1, std::min<int64_t>(cdiv64(total, 256), 148 * 16)); }
+
+void nchw_to_nhwc(Ctx& c, const float* x, Tens& y) {
+  XRD_DISPATCH(y.dt, T, XRD_LAUNCH(c, (k_nchw_to_nhwc<T>), ew_blocks(y.numel()), 256, 0, x, (T*)y.p, y.n, y.c, y.h * y.w));
+}
+void nhwc_to_nchw(Ctx& c, const Tens& x, float* y) {
+  XRD_DISPATCH(x.dt, T, XRD_LAUNCH(c, (k_nhwc_to_nchw<T>), ew_blocks(x.numel()), 256, 0, (const T*)x.p, y, x.n, x.c, x.h * x.w));
+}
+
+__global__ void k_sanitize(const float* __restrict__ x, float* __restrict__ y, size_t n, int san) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = san ? sanitize01(x[i]) : x[i];
+}
+void sanitize_plane(Ctx& c, const float* x, float* y, size_t n) { XRD_LAUNCH(c, k_sanitize, ew_blocks((int64_t)n), 256, 0, x, y, n, 1); }
+void copy_plane(Ctx& c, const float* x, float* y, size_t n) { XRD_LAUNCH(c, k_sanitize, ew_blocks((int64_t)n), 256, 0, x, y, n, 0); }
+
+// =====================================================================================
+// small elementwise helpers: SimpleGate, per-(n,c) scaling, plane interleave, pad / crop
+// =====================================================================================
+template <typename T>
+__global__ void k_simple_gate(const T* __restrict__ u, T* __restrict__ g, int64_t npix, int C) {
+  const int Q = C >> 2;
+  const int64_t total = npix * Q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / Q;
+    const int c = (int)(i - pix * Q) * 4;
+    float a[4], b[4], o[4];
+    ld4<T>(u + pix * 2 * C + c, a);
+    ld4<T>(u + pix * 2 * C + C + c, b);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = a[j] * b[j];
+    st4<T>(g + pix * C + c, o);
+  }
+}
+void simple_gate(Ctx& c, const Tens& u, Tens& g) {
+  XRD_REQUIRE(u.c == 2 * g.c && g.c % 4 == 0 && u.dt == g.dt && u.n == g.n && u.h == g.h && u.w == g.w, "simple_gate: shape");
+  int64_t npix = (int64_t)g.n * g.h * g.w;
+  XRD_DISPATCH(u.dt, T, XRD_LAUNCH(c, (k_simple_gate<T>), ew_blocks(npix * (g.c / 4)), 256, 0, (const T*)u.p, (T*)g.p, npix, g.c));
+}
+
+template <typename T>
+__global__ void k_scale_nc(T* __restrict__ x, const float* __restrict__ scale, int64_t hw, int C, int64_t total_q) {
+  const int Q = C >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_q; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / Q;
+    const int c = (int)(i - pix * Q) * 4;
+    const int n = (int)(pix / hw);
+    float v[4];
+    ld4<T>(x + pix * C + c, v);
+    const float* sc = scale + (int64_t)n * C + c;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] *= sc[j];
+    st4<T>(x + pix * C + c, v);
+  }
+}
+void scale_nc(Ctx& c, Tens& x, const float* scale) {
+  XRD_REQUIRE(x.c % 4 == 0, "scale_nc: channels");
+  int64_t tq = (int64_t)x.n * x.h * x.w * (x.c / 4);
+  XRD_DISPATCH(x.dt, T, XRD_LAUNCH(c, (k_scale_nc<T>), ew_blocks(tq), 256, 0, (T*)x.p, scale, (int64_t)x.h * x.w, x.c, tq));
+}
+
+__global__ void k_interleave3(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ m, float* __restrict__ y,
+                              int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    y[3 * i + 0] = a[i]; y[3 * i + 1] = b[i]; y[3 * i + 2] = m[i];
+  }
+}
+void interleave3(Ctx& c, const float* a, const float* b, const float* m, float* y, int64_t n) {
+  XRD_LAUNCH(c, k_interleave3, ew_blocks(n), 256, 0, a, b, m, y, n);
+}
+
+// copy (N,H,W) planes between different row/plane pitches: dst is (N,Hd,Wd), src is (N,Hs,Ws); the
+// common top-left (min) region is copied and the rest of dst is zero (F.pad / crop, NAF:304-309)
+__global__ void k_pad_crop(const float* __restrict__ src, float* __restrict__ dst, int N, int Hs, int Ws, int Hd, int Wd) {
+  const int64_t total = (int64_t)N * Hd * Wd;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int w = (int)(i % Wd);
+    int64_t r = i / Wd;
+    int h = (int)(r % Hd);
+    int n = (int)(r / Hd);
+    dst[i] = (h < Hs && w < Ws) ? src[((int64_t)n * Hs + h) * Ws + w] : 0.f;
+  }
+}
+void pad_crop_plane(Ctx& c, const float* src, float* dst, int N, int Hs, int Ws, int Hd, int Wd) {
+  XRD_LAUNCH(c, k_pad_crop, ew_blocks((int64_t)N * Hd * Wd), 256, 0, src, dst, N, Hs, Ws, Hd, Wd);
+}
+
+// =====================================================================================
+// weight packing (runs once per load_state_dict)
+// =====================================================================================
+__global__ void k_pack_conv_w(const float* __restrict__ w, float* __restrict__ out, int cout, int cin, int kk) {
+  const int64_t total = (int64_t)cout * cin * kk;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int co = (int)(i % cout);
+    int64_t r = i / cout;
+    int ci = (int)(r % cin);
+    int t = (int)(r / cin);
+    out[i] = w[((int64_t)co * cin + ci) * kk + t];
+  }
+}
+void pack_conv_weight(cudaStream_t s, const float* w, float* out, int cout, int cin, int kh, int kw) {
+  int64_t total = (int64_t)cout * cin * kh * kw;
+  k_pack_conv_w<<<ew_blocks(total), 256, 0, s>>>(w, out, cout, cin, kh * kw);
+  XRD_CUDA(cudaPeekAtLastError());
+}
+
+// ConvTranspose2d(4,2,1) then 2x2 mean == 3x3 conv with taps (per axis) d=-1:{k=3}, d=0:{k=1,2}, d=+1:{k=0}, scaled by 1/4
+__global__ void k_pack_convT4_avg(const float* __restrict__ w, float* __restrict__ out, int cin, int cout) {
+  const int64_t total = (int64_t)9 * cin * cout;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int co = (int)(i % cout);
+    int64_t r = i / cout;
+    int ci = (int)(r % cin);
+    int t = (int)(r / cin);
+    int dy = t / 3, dx = t % 3;  // tap index 0..2 <-> offset -1..+1
+    const float* src = w + ((int64_t)ci * cout + co) * 16;
+    const int lo[3] = {3, 1, 0}, hi[3] = {3, 2, 0};
+    float s = 0.f;
+    for (int ky = lo[dy]; ky <= hi[dy]; ++ky)
+      for (int kx = lo[dx]; kx <= hi[dx]; ++kx) s += src[ky * 4 + kx];
+    out[i] = 0.25f * s;
+  }
+}
+void pack_convT4_avg_weight(cudaStream_t s, const float* w, float* out, int cin, int cout) {
+  k_pack_convT4_avg<<<ew_blocks((int64_t)9 * cin * cout), 256, 0, s>>>(w, out, cin, cout);
+  XRD_CUDA(cudaPeekAtLastError());
+}
+
+__global__ void k_pack_convT2(const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ out, float* __restrict__ bout,
+                              int cin, int cout) {
+  const int64_t total = (int64_t)cin * 4 * cout;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int q = (int)(i % (4 * cout));
+    int ci = (int)(i / (4 * cout));
+    int ij = q / cout, co = q - ij * cout;
+    out[i] = w[((int64_t)ci * cout + co) * 4 + ij];
+    if (ci == 0) bout[q] = b ? b[co] : 0.f;
+  }
+}
+void pack_convT2_weight(cudaStream_t s, const float* w, const float* b, float* out, float* bout, int cin, int cout) {
+  k_pack_convT2<<<ew_blocks((int64_t)cin * 4 * cout), 256, 0, s>>>(w, b, out, bout, cin, cout);
+  XRD_CUDA(cudaPeekAtLastError());
+}
+
+__global__ void k_pack_ps(const float* __restrict__ w, float* __restrict__ out, int cin, int cf) {
+  const int64_t total = (int64_t)cin * 4 * cf;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int q = (int)(i % (4 * cf));
+    int ci = (int)(i / (4 * cf));
+    int ij = q / cf, c = q - ij * cf;
+    int qref = c * 4 + ij;  // PixelShuffle(2): input channel c*4 + i*2 + j
+    out[i] = w[(int64_t)qref * cin + ci];
+  }
+}
+void pack_pixelshuffle_weight(cudaStream_t s, const float* w, float* out, int cin, int cf) {
+  k_pack_ps<<<ew_blocks((int64_t)cin * 4 * cf), 256, 0, s>>>(w, out, cin, cf);
+  XRD_CUDA(cudaPeekAtLastError());
+}
+
+__global__ void k_pack_dw(const float* __restrict__ w, float* __restrict__ out, int c2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 9 * c2) { int c = i % c2, t = i / c2; out[i] = w[c * 9 + t]; }
+}
+void pack_dw_weight(cudaStream_t s, const float* w, float* out, int c2) {
+  k_pack_dw<<<cdiv(9 * c2, 256), 256, 0, s>>>(w, out, c2);
+  XRD_CUDA(cudaPeekAtLastError());
+}
+
+}  // namespace xrd

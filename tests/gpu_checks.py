@@ -1,0 +1,287 @@
+"""GPU parity checks shared by the pytest suite (tests/test_gpu_*.py) and the diagnostic runner
+(tools/gpu_diag.py).  Every function returns a dict of measured errors; the callers apply tolerances.
+All calls go through the C ABI (ctypes -> libxrd.so); the oracle is only the checker."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import xrd_b200  # noqa: E402
+from xrd_b200 import _lib  # noqa: E402
+from oracle import xrd_oracle as O  # noqa: E402
+from conftest import load_golden, seeded_state_dict  # noqa: E402
+
+DEV = "cuda:0"
+MODES = {"bf16": _lib.MODE_BF16, "fp32": _lib.MODE_FP32_CHECK, "fp16": _lib.MODE_FP16}
+
+
+def _p(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+class OpHandle:
+    """A bare libxrd handle for the kernel-level hooks (no weights needed)."""
+
+    def __init__(self, mode="bf16"):
+        self.lib = _lib.load()
+        cfg = _lib.default_config()
+        self.h = C.c_void_p()
+        _lib.check(self.lib.xrd_create(0, C.byref(cfg), C.byref(self.h)))
+        _lib.check(self.lib.xrd_set_mode(self.h, MODES[mode]))
+
+    def close(self):
+        if self.h:
+            self.lib.xrd_destroy(self.h)
+            self.h = None
+
+    def conv2d(self, x, w, b, k, stride, pad, impl):
+        B, Cin, H, W = x.shape
+        Cout = w.shape[0]
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        y = torch.empty(B, Cout, Ho, Wo, device=x.device, dtype=torch.float32)
+        _lib.check(self.lib.xrd_op_conv2d(self.h, impl, _p(x), _p(w), _p(b), _p(y), B, Cin, H, W, Cout, k, stride, pad, None))
+        torch.cuda.synchronize()
+        return y
+
+    def time_last(self, iters=20):
+        ms = C.c_float()
+        _lib.check(self.lib.xrd_op_time_last(self.h, iters, C.byref(ms), None))
+        return ms.value
+
+    def groupnorm_act(self, x, g, b, groups, act):
+        B, Cc, H, W = x.shape
+        y = torch.empty_like(x)
+        _lib.check(self.lib.xrd_op_groupnorm_act(self.h, _p(x), _p(g), _p(b), _p(y), B, Cc, H, W, groups, act, None))
+        torch.cuda.synchronize()
+        return y
+
+    def attention(self, qkv, heads, d, impl):
+        B, _, H, W = qkv.shape
+        y = torch.empty(B, heads * d, H, W, device=qkv.device, dtype=torch.float32)
+        _lib.check(self.lib.xrd_op_attention(self.h, impl, _p(qkv), _p(y), B, heads, d, H, W, None))
+        torch.cuda.synchronize()
+        return y
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+# ------------------------------------------------------------------ kernel-level
+CONV_CASES_SIMT = [
+    # (B, Cin, H, W, Cout, k, stride, pad)
+    (2, 48, 24, 40, 48, 3, 1, 1), (1, 2, 33, 17, 48, 3, 1, 1), (2, 3, 16, 16, 48, 3, 1, 1), (1, 1, 20, 20, 32, 3, 1, 1),
+    (2, 96, 16, 16, 96, 3, 2, 1), (1, 32, 16, 24, 64, 2, 2, 0), (2, 192, 8, 8, 576, 1, 1, 0), (1, 100, 9, 11, 36, 1, 1, 0),
+    (1, 48, 12, 12, 1, 3, 1, 1),
+]
+CONV_CASES_TC = [
+    (2, 48, 32, 32, 48, 3, 1, 1), (1, 96, 16, 48, 96, 3, 1, 1), (2, 144, 16, 16, 144, 3, 1, 1), (1, 192, 8, 8, 192, 3, 1, 1),
+    (1, 384, 16, 16, 192, 3, 1, 1), (1, 288, 24, 24, 96, 3, 1, 1), (2, 64, 20, 28, 64, 3, 1, 1), (1, 192, 16, 16, 576, 1, 1, 0),
+    (1, 512, 8, 8, 1024, 1, 1, 0), (2, 32, 16, 16, 64, 1, 1, 0), (1, 96, 32, 32, 96, 3, 2, 1), (1, 48, 64, 64, 48, 3, 2, 1),
+    (1, 64, 16, 16, 128, 2, 2, 0), (1, 16, 8, 8, 32, 1, 1, 0),
+]
+
+
+def check_conv(mode, impl, cases, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    oh = OpHandle(mode)
+    out = {}
+    try:
+        for (B, Cin, H, W, Cout, k, s, p) in cases:
+            x = torch.randn(B, Cin, H, W, generator=g).to(DEV)
+            w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(DEV)
+            b = torch.randn(Cout, generator=g).to(DEV)
+            if mode != "fp32":   # operands rounded the way the kernel stores them: isolates kernel bugs from rounding
+                dt = torch.bfloat16 if mode == "bf16" else torch.float16
+                xr, wr = x.to(dt).float(), w.to(dt).float()
+            else:
+                xr, wr = x, w
+            ref = F.conv2d(xr.double(), wr.double(), b.double(), stride=s, padding=p).float()
+            y = oh.conv2d(x, w, b, k, s, p, impl)
+            out[f"{B}x{Cin}x{H}x{W}->{Cout} k{k}s{s}p{p}"] = _rel(y, ref)
+    finally:
+        oh.close()
+    return out
+
+
+def check_groupnorm(mode):
+    g = torch.Generator().manual_seed(1)
+    oh = OpHandle(mode)
+    out = {}
+    try:
+        for (B, Cc, H, W, G, act) in [(2, 48, 32, 32, 8, 1), (1, 384, 8, 8, 8, 1), (2, 288, 16, 16, 8, 0), (1, 24, 20, 12, 4, 2),
+                                      (1, 32, 16, 16, 8, 2)]:
+            x = (torch.randn(B, Cc, H, W, generator=g) * 2 + 0.5).to(DEV)
+            ga, be = torch.randn(Cc, generator=g).to(DEV), torch.randn(Cc, generator=g).to(DEV)
+            xr = x if mode == "fp32" else x.to(torch.bfloat16 if mode == "bf16" else torch.float16).float()
+            ref = F.group_norm(xr.double(), G, ga.double(), be.double(), 1e-5)
+            ref = {0: ref, 1: F.silu(ref), 2: F.gelu(ref)}[act].float()
+            y = oh.groupnorm_act(x, ga, be, G, act)
+            out[f"{B}x{Cc}x{H}x{W} g{G} act{act}"] = float((y - ref).abs().max())
+    finally:
+        oh.close()
+    return out
+
+
+def check_attention(mode, impl):
+    g = torch.Generator().manual_seed(2)
+    oh = OpHandle(mode)
+    out = {}
+    try:
+        for (B, heads, d, H, W) in [(2, 2, 96, 8, 8), (1, 2, 96, 16, 16), (1, 2, 96, 4, 4), (1, 2, 96, 32, 32), (1, 1, 64, 12, 10)]:
+            qkv = torch.randn(B, 3 * heads * d, H, W, generator=g).to(DEV)
+            qr = qkv if mode == "fp32" else qkv.to(torch.bfloat16 if mode == "bf16" else torch.float16).float()
+            t = qr.double().reshape(B, 3, heads, d, H * W)
+            q, k, v = t[:, 0], t[:, 1], t[:, 2]
+            att = torch.softmax(torch.matmul(q.transpose(-2, -1), k) * d ** -0.5, dim=-1)
+            ref = torch.matmul(att, v.transpose(-2, -1)).transpose(-2, -1).reshape(B, heads * d, H, W).float()
+            y = oh.attention(qkv, heads, d, impl)
+            out[f"{B}x{heads}x{d}x{H}x{W}"] = float((y - ref).abs().max())
+    finally:
+        oh.close()
+    return out
+
+
+# ------------------------------------------------------------------ network-level
+def _hybrid(mode):
+    m, sd = seeded_state_dict("hybrid")
+    m = m.to(DEV).eval()
+    m.set_native_mode(mode)
+    for sub in (m.nafnet, m.diffusion_unet, m.router, m.fusion):
+        sub.set_native_mode(mode)
+    return m, {k: v.detach().cpu() for k, v in m.state_dict().items()}
+
+
+def check_nafnet(mode):
+    m, sd = seeded_state_dict("nafnet")
+    m = m.to(DEV).set_native_mode(mode)
+    out = {}
+    g = load_golden("nafnet_256_b1.npz")
+    y = m(g["noisy"].to(DEV)).cpu()
+    out["golden256"] = float((y - g["out"]).abs().max())
+    g = load_golden("nafnet_40x56_b2.npz")
+    y = m(g["noisy"].to(DEV)).cpu()
+    out["golden40x56"] = float((y - g["out"]).abs().max())
+    _, noisy = O.synthetic_xray(3, 64, 96, seed=11)
+    ref = O.nafnet_forward({k: v.cpu() for k, v in m.state_dict().items()}, noisy)
+    out["oracle64x96_b3"] = float((m(noisy.to(DEV)).cpu() - ref).abs().max())
+    return out
+
+
+def check_unet_teacher(mode):
+    """Per-step eps with the reference's own x fed in (teacher forcing) + the fused sampler update."""
+    m, sd = _hybrid(mode)
+    g = load_golden("hybrid_64_b2_s50.npz")
+    out = {}
+    ts = O.ddim_timesteps(50, 50)
+    worst = 0.0
+    for j, n in enumerate(g["keep"].tolist()):
+        t = torch.full((2,), ts[n], dtype=torch.long, device=DEV)
+        eps = m.diffusion_unet(g["x_in"][j].to(DEV), g["noisy"].to(DEV), t).cpu()
+        e = float((eps - g["eps"][j]).abs().max())
+        out[f"eps@eval{n}"] = e
+        worst = max(worst, e)
+    out["eps_worst"] = worst
+    out["eps_ref_absmax"] = float(g["eps"].abs().max())
+    return out
+
+
+def check_ddim_standalone(mode):
+    m, sd = seeded_state_dict("unet")
+    m = m.to(DEV).set_native_mode(mode)
+    g = load_golden("ddim_32_b1_s8.npz")
+    w = xrd_b200.DiffusionDenoiser(m, noise_steps=50)
+    out = {}
+    # teacher forced trace through the sampler entry point
+    y, eps_tr, xin_tr = w.denoise(g["noisy"].to(DEV), inference_steps=8, return_trace=True, teacher_x=g["x_in"])
+    out["n_evals"] = int(eps_tr.shape[0])
+    out["teacher_eps_worst"] = float((eps_tr.cpu()[:, :, None] - g["eps"]).abs().max())
+    # free running, eager with trace
+    y, eps_tr, xin_tr = w.denoise(g["noisy"].to(DEV), inference_steps=8, return_trace=True)
+    out["free_eps_worst"] = float((eps_tr.cpu()[:, :, None] - g["eps"]).abs().max())
+    out["free_final"] = float((y.cpu() - g["out"]).abs().max())
+    # graph path (default) must equal the eager path bit for bit
+    y2 = w.denoise(g["noisy"].to(DEV), inference_steps=8)
+    y3 = w.denoise(g["noisy"].to(DEV), inference_steps=8)
+    out["graph_vs_eager"] = float((y2 - y).abs().max())
+    out["graph_replay_stable"] = float((y3 - y2).abs().max())
+    return out
+
+
+def check_router_fusion(mode):
+    m, sd = _hybrid(mode)
+    g = load_golden("hybrid_64_b2_s50.npz")
+    out = {}
+    mask = torch.clamp(m.router(g["noisy"].to(DEV)), 0, 1).cpu()
+    out["mask_maxabs"] = float((mask - g["mask"]).abs().max())
+    q, qr = (mask * 255).to(torch.uint8), (g["mask"] * 255).to(torch.uint8)       # RUN:145 quantisation
+    out["mask_u8_mismatch"] = int((q != qr).sum())
+    out["mask_gt05_mismatch"] = int(((mask > 0.5) != (g["mask"] > 0.5)).sum())
+    out["mask_pixels"] = int(mask.numel())
+    fused = m.fusion(g["naf"].to(DEV), g["diff"].to(DEV), g["mask"].to(DEV)).cpu()
+    out["fusion_maxabs"] = float((fused - g["fused"]).abs().max())
+    return out
+
+
+def check_hybrid(mode):
+    m, sd = _hybrid(mode)
+    m.inference_diffusion_steps = 50
+    g = load_golden("hybrid_64_b2_s50.npz")
+    fused, parts = m(g["noisy"].to(DEV), return_parts=True)
+    out = {k + "_maxabs": float((parts[k].cpu() - g[k]).abs().max()) for k in ("naf", "diff", "mask")}
+    out["fused_maxabs"] = float((fused.cpu() - g["fused"]).abs().max())
+    out["diff_at_clamp0_frac"] = float((g["diff"] == 0).float().mean())
+    return out
+
+
+def check_hybrid_oracle_128(mode):
+    """A size the golden files do not cover: CUDA vs the oracle run on this box's CPU."""
+    m, sd = _hybrid(mode)
+    m.inference_diffusion_steps = 10
+    _, noisy = O.synthetic_xray(2, 128, 128, seed=5)
+    parts = {}
+    ref = O.hybrid_forward(sd, noisy, 10, 50, parts=parts)
+    fused, got = m(noisy.to(DEV), return_parts=True)
+    out = {k + "_maxabs": float((got[k].cpu() - parts[k]).abs().max()) for k in ("naf", "diff", "mask")}
+    out["fused_maxabs"] = float((fused.cpu() - ref).abs().max())
+    return out
+
+
+CHECKS = {
+    "conv_simt_fp32": lambda: check_conv("fp32", 0, CONV_CASES_SIMT),
+    "conv_simt_bf16": lambda: check_conv("bf16", 0, CONV_CASES_SIMT),
+    "groupnorm_fp32": lambda: check_groupnorm("fp32"),
+    "groupnorm_bf16": lambda: check_groupnorm("bf16"),
+    "attention_simt_fp32": lambda: check_attention("fp32", 0),
+    "conv_tc_bf16": lambda: check_conv("bf16", 1, CONV_CASES_TC),
+    "conv_tc_fp16": lambda: check_conv("fp16", 1, CONV_CASES_TC),
+    "attention_tc_bf16": lambda: check_attention("bf16", 1),
+    "nafnet_fp32": lambda: check_nafnet("fp32"),
+    "unet_teacher_fp32": lambda: check_unet_teacher("fp32"),
+    "ddim_fp32": lambda: check_ddim_standalone("fp32"),
+    "router_fusion_fp32": lambda: check_router_fusion("fp32"),
+    "hybrid_fp32": lambda: check_hybrid("fp32"),
+    "nafnet_bf16": lambda: check_nafnet("bf16"),
+    "unet_teacher_bf16": lambda: check_unet_teacher("bf16"),
+    "ddim_bf16": lambda: check_ddim_standalone("bf16"),
+    "hybrid_bf16": lambda: check_hybrid("bf16"),
+    "unet_teacher_fp16": lambda: check_unet_teacher("fp16"),
+    "hybrid_fp16": lambda: check_hybrid("fp16"),
+    "hybrid128_fp32": lambda: check_hybrid_oracle_128("fp32"),
+    "hybrid128_bf16": lambda: check_hybrid_oracle_128("bf16"),
+}
+
+if __name__ == "__main__":
+    import json
+    name = sys.argv[1]
+    res = CHECKS[name]()
+    print("RESULT " + json.dumps({name: res}))
