@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- denoised images/sec of the full hybrid (DDIM-50 + NAFNet + router + fusion) at 512x512.
+
+    python bench.py --gpus N --steps K --warmup W              (this repo's libxrd.so path)
+    python bench.py --impl reference --gpus N --steps K ...    (the reference algorithm on host CPU cores)
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): HybridDenoisingRouter
+with inference_diffusion_steps=50, noise_steps=50, batch 16 per GPU of synthetic 512x512 grayscale
+X-ray fields, random-init weights (seed 1234, NAFBlock beta/gamma + norm affine override seed 99).
+A "step" is one forward of that batch.  N>1: one process per GPU (torchrun), images sharded by rank,
+no collective inside the sampler loop, one NCCL all_gather of the finished (B,1,H,W) outputs per step
+(weak scaling: 16 images per GPU).
+
+Prints ONE JSON line (rank 0).  `value` = whole-job images/s with inputs resident in HBM; `e2e` = the
+same through the public class API with pinned-host inputs and a host read-back inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GF_PER_IMAGE_512 = 21383.0      # algorithmic 2*MAC of the reference op list, hybrid DDIM-50 @512^2
+UNET_CONV_GF_512 = 347.34       # conv FLOPs of one UNet evaluation @512^2 per image
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], burst=d["bf16_tflops"], sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, burst=1590.0, sustained=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+
+
+def build_model(dev, mode):
+    import xrd_b200
+    from oracle import xrd_oracle as O          # only for the shared seeding helper + synthetic inputs
+    torch.manual_seed(1234)
+    m = xrd_b200.HybridDenoisingRouter({}, {}, inference_diffusion_steps=50).eval()
+    O.randomize_identity_params(m.state_dict(), 99)
+    m = m.to(dev)
+    m.set_native_mode(mode)
+    return m
+
+
+def cpu_reference_sample(size, unet_evals, threads=None):
+    """The reference algorithm (oracle port) on host cores, batch 1: `unet_evals` UNet evaluations + NAFNet +
+    router + fusion, extrapolated to the 50 evaluations of DDIM-50.  Returns (images/s, seconds of CPU work)."""
+    from oracle import xrd_oracle as O
+    import xrd_b200
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(1234)
+    sd = xrd_b200.HybridDenoisingRouter({}, {}, inference_diffusion_steps=50).state_dict()
+    O.randomize_identity_params(sd, 99)
+    _, noisy = O.synthetic_xray(1, size, size, seed=7)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        t_un = []
+        x = noisy.clone()
+        for i in range(unet_evals):
+            t1 = time.perf_counter()
+            O.unet_forward(sd, x, noisy, torch.full((1,), 49 - i, dtype=torch.long), prefix="diffusion_unet.")
+            t_un.append(time.perf_counter() - t1)
+        t1 = time.perf_counter(); naf = O._sanitize(O.nafnet_forward(sd, noisy, prefix="nafnet.")); t_naf = time.perf_counter() - t1
+        t1 = time.perf_counter(); mask = O._sanitize(O.router_forward(sd, noisy, "router.")); t_r = time.perf_counter() - t1
+        t1 = time.perf_counter(); O.fusion_forward(sd, naf, noisy, mask, "fusion."); t_f = time.perf_counter() - t1
+    spent = time.perf_counter() - t0
+    per_img = 50 * sorted(t_un)[len(t_un) // 2] + t_naf + t_r + t_f
+    return 1.0 / per_img, spent
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = torch.get_num_threads()
+    vals = []
+    for i in range(args.warmup + args.steps):
+        ips, _ = cpu_reference_sample(512, 2)
+        if i >= args.warmup:
+            vals.append(ips)
+    v = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": "denoised images/sec at 512x512 (hybrid, DDIM-50)", "value": v, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "hybrid DDIM-50 + NAFNet + router + fusion, 512x512 grayscale, batch 16 per GPU (BASELINE configs[2])",
+                   "note": "CPU port of the reference algorithm (oracle/xrd_oracle.py: same ATen ops as the reference classes); "
+                           "each step = batch 1: 2 UNet evaluations + NAFNet + router + fusion, extrapolated to 50 evaluations"},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": "batch 1 @512x512: 2 UNet evals + 1 NAFNet + 1 router + 1 fusion per step, 50*median(t_unet)+rest"},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def conv_roofline(model, dev, batch, size):
+    """Dominant kernel = k_conv_tc (tcgen05 implicit GEMM).  Time every distinct conv layer shape of one UNet
+    evaluation live (CUDA events on the launching stream, via the C ABI op hook that launches the very same
+    kernel) and return launch-weighted achieved TFLOP/s = sum(algorithmic FLOPs) / sum(kernel time)."""
+    import ctypes as C
+    from xrd_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.default_config()
+    h = C.c_void_p()
+    _lib.check(lib.xrd_create(dev.index or 0, C.byref(cfg), C.byref(h)))
+    _lib.check(lib.xrd_set_mode(h, {"bf16": 0, "fp32": 1, "fp16": 2}[model.native_mode]))
+    s = size
+    # (count per eval, Cin, Cout, H, k, stride): the 3x3/1x1 convs of UNetDiffusion.forward at the reference topology
+    layers = [(5, 48, 48, s, 3, 1), (1, 96, 48, s, 3, 1), (2, 48, 48, s // 2, 3, 1), (1, 48, 96, s // 2, 3, 1), (4, 96, 96, s // 2, 3, 1),
+              (1, 192, 96, s // 2, 3, 1), (1, 96, 96, s // 2, 3, 1), (1, 96, 48, s // 2, 3, 1), (1, 192, 48, s // 2, 3, 1),
+              (2, 96, 96, s // 4, 3, 1), (1, 96, 144, s // 4, 3, 1), (4, 144, 144, s // 4, 3, 1), (1, 288, 144, s // 4, 3, 1),
+              (1, 144, 144, s // 4, 3, 1), (1, 192, 96, s // 4, 3, 1), (1, 288, 96, s // 4, 3, 1), (2, 144, 144, s // 8, 3, 1),
+              (1, 144, 192, s // 8, 3, 1), (10, 192, 192, s // 8, 3, 1), (3, 384, 192, s // 8, 3, 1), (1, 192, 192, s // 8, 3, 1),
+              (1, 384, 144, s // 8, 3, 1), (1, 288, 144, s // 8, 3, 1), (6, 192, 576, s // 8, 1, 1), (6, 192, 192, s // 8, 1, 1),
+              (1, 48, 48, s, 3, 2), (1, 96, 96, s // 2, 3, 2), (1, 144, 144, s // 4, 3, 2)]
+    tot_ms, tot_fl, launches = 0.0, 0.0, 0
+    ms = C.c_float()
+    for cnt, ci, co, hh, k, st in layers:
+        x = torch.randn(batch, ci, hh, hh, device=dev)
+        w = torch.randn(co, ci, k, k, device=dev) * 0.05
+        b = torch.zeros(co, device=dev)
+        ho = (hh + 2 * (k // 2) - k) // st + 1
+        y = torch.empty(batch, co, ho, ho, device=dev)
+        _lib.check(lib.xrd_op_conv2d(h, 1, C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()),
+                                     C.c_void_p(y.data_ptr()), batch, ci, hh, hh, co, k, st, k // 2, None))
+        _lib.check(lib.xrd_op_time_last(h, 5, C.byref(ms), None))
+        tot_ms += cnt * ms.value
+        tot_fl += cnt * 2.0 * batch * ho * ho * co * ci * k * k
+        launches += cnt
+        del x, w, y
+    lib.xrd_destroy(h)
+    torch.cuda.empty_cache()
+    return tot_fl / tot_ms / 1e9, tot_ms, launches, tot_fl
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU")
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--mode", default=os.environ.get("XRD_MODE", "fp16"), choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    import xrd_b200
+    from oracle import xrd_oracle as O
+    model = build_model(dev, args.mode)
+    B, S = args.batch, args.size
+    _, noisy = O.synthetic_xray(B, S, S, seed=7 + rank)
+    x_dev = noisy.to(dev)
+    x_pin = noisy.pin_memory()
+    out_pin = torch.empty_like(noisy).pin_memory()
+    gathered = [torch.empty_like(x_dev) for _ in range(world)] if world > 1 else None
+
+    def step_resident():
+        y = model(x_dev)
+        if world > 1:
+            dist.all_gather(gathered, y)          # output gather only; nothing inside the sampler communicates
+        return y
+
+    def step_e2e():
+        xd = x_pin.to(dev, non_blocking=True)
+        y = model(xd)
+        if world > 1:
+            dist.all_gather(gathered, y)
+        out_pin.copy_(y, non_blocking=True)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM ----
+    for _ in range(args.warmup):
+        step_resident()
+    sync_all()
+    launches0 = xrd_b200.native_kernel_launches()
+    sampler = ClockSampler(local); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = xrd_b200.native_kernel_launches() - launches0
+    # ---- e2e: pinned host -> device -> model -> host, every step ----
+    for _ in range(2):
+        step_e2e()
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    sync_all()
+    ms_e2e = e0.elapsed_time(e1)
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    ips = world * B * args.steps / (ms / 1000.0)
+    ips_e2e = world * B * args.steps / (ms_e2e / 1000.0)
+    scale = (S / 512.0) ** 2
+    conv_tf, conv_ms, conv_launches, conv_fl = conv_roofline(model, dev, B, S) if args.mode != "fp32" else (0.0, 0.0, 0, 0.0)
+    step_tf = ips / world * GF_PER_IMAGE_512 * scale / 1000.0
+    line = {
+        "metric": "denoised images/sec at 512x512 (hybrid, DDIM-50)", "value": ips, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.mode], "data": "synthetic",
+        "config": {"workload": f"hybrid DDIM-50 + NAFNet + router + fusion, {S}x{S} grayscale, batch {B} per GPU (BASELINE configs[2])",
+                   "global_batch": B * world, "unet_evals_per_image": 50, "accumulate": "fp32",
+                   "l2": "working set per step is several GB (>> 126 MB L2): inputs larger than L2, no explicit flush",
+                   "parallelism": f"image-sharded x{world}, output all_gather only"},
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": B * S * S * 4, "d2h_bytes_per_step": B * S * S * 4},
+        "roofline": {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 implicit-GEMM conv), all UNet conv shapes of one evaluation, launch weighted",
+                     "achieved": conv_tf, "peak": pk["burst"], "unit": "TFLOP/s", "frac": conv_tf / pk["burst"] if pk["burst"] else None,
+                     "peak_kind": f"bf16 dense burst, {pk['src']}", "traffic": None,
+                     "flops_per_eval": conv_fl, "ms_per_eval_isolated": conv_ms, "launches_per_eval": conv_launches},
+        "roofline_step": {"bound": "tensor", "achieved": step_tf, "peak": pk["sustained"], "unit": "TFLOP/s",
+                          "frac": step_tf / pk["sustained"], "note": "images/s x 21383 GF algorithmic per image, of sustained measured peak"},
+    }
+    if not args.no_cpu_baseline:
+        v, spent = cpu_reference_sample(S, 2)
+        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"batch 1 @{S}x{S}: 2 UNet evals + NAFNet + router + fusion ({spent:.1f} s of CPU work), "
+                                          "50*median(t_unet)+rest"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

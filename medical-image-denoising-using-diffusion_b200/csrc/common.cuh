@@ -116,7 +116,9 @@ template <> __device__ __forceinline__ float ldf<__half>(const __half* p) { retu
 template <typename T> __device__ __forceinline__ void stf(T* p, float v);
 template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
-template <> __device__ __forceinline__ void stf<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+// f16 stores saturate (finite overflow -> +-65504) so that one large activation cannot turn into inf/NaN downstream
+__device__ __forceinline__ float sat_h(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+template <> __device__ __forceinline__ void stf<__half>(__half* p, float v) { *p = __float2half_rn(sat_h(v)); }
 
 // 4 consecutive elements (pointer must be aligned to 4 elements)
 template <typename T> __device__ __forceinline__ void ld4(const T* p, float (&v)[4]);
@@ -148,7 +150,7 @@ template <> __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p,
   *reinterpret_cast<uint2*>(p) = t;
 }
 template <> __device__ __forceinline__ void st4<__half>(__half* p, const float (&v)[4]) {
-  __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  __half2 a = __floats2half2_rn(sat_h(v[0]), sat_h(v[1])), b = __floats2half2_rn(sat_h(v[2]), sat_h(v[3]));
   uint2 t;
   t.x = *reinterpret_cast<uint32_t*>(&a);
   t.y = *reinterpret_cast<uint32_t*>(&b);

@@ -95,7 +95,7 @@ struct GraphEntry {
 struct Handle {
   int device = 0;
   xrd_config cfg;
-  int mode = XRD_MODE_BF16;
+  int mode = XRD_MODE_FP16;
   bool use_graph = true;
   std::mutex mu;
 

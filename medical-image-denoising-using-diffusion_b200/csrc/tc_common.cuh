@@ -31,8 +31,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("libxrd: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, parity);
+      __trap();
+    }
   }
 }
 

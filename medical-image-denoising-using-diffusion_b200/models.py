@@ -29,7 +29,7 @@ _MODE_NAMES = {"bf16": _lib.MODE_BF16, "fp32": _lib.MODE_FP32_CHECK, "fp16": _li
 
 
 def _default_mode() -> str:
-    return os.environ.get("XRD_MODE", "bf16")
+    return os.environ.get("XRD_MODE", "fp16")
 
 
 # ---------------------------------------------------------------------------
@@ -137,7 +137,7 @@ class _NativeModel(nn.Module):
         raise NotImplementedError
 
     def set_native_mode(self, mode: str) -> "_NativeModel":
-        """'bf16' (default, tensor-core path), 'fp32' (check mode) or 'fp16'."""
+        """'fp16' (default tensor-core path), 'bf16' (same kernels, bf16 operands) or 'fp32' (check mode)."""
         if mode not in _MODE_NAMES:
             raise XrdError(f"unknown mode {mode!r}")
         self.native_mode = mode

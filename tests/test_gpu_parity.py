@@ -1,0 +1,163 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every comparison goes CUDA (through the C ABI)
+versus the reference-pinned oracle / golden vectors.  Tolerances, as BASELINE.json's north star states them:
+   fp32 check mode   : 1e-4 max-abs on per-step eps, final image, NAFNet, fused output; mask quantised bit-exact
+   16-bit tensor mode: 1e-2 max-abs on per-step eps and final image (default mode = f16 operands)
+   bf16 operands     : reported and bounded at 6e-2 -- single-pass bf16 operands cannot reach 1e-2 on this
+                       network (PyTorch's own bf16 autocast sits at 3-4.6e-2); see DESIGN.md.
+"""
+import pytest
+import torch
+
+import gpu_checks as G
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 1e-4
+TOL_16 = 1e-2
+TOL_BF16 = 6e-2
+
+
+# ------------------------------------------------------------------ kernels
+def test_conv_cuda_core_fp32():
+    for k, e in G.check_conv("fp32", 0, G.CONV_CASES_SIMT).items():
+        assert e < 1e-5, (k, e)
+
+
+def test_conv_tcgen05_f16_and_bf16():
+    # operands are pre-rounded to the storage format, so what remains is fp32 accumulation order plus ONE
+    # rounding of the output to the 16-bit storage format: 2^-12 (f16) / 2^-9 (bf16) relative
+    for k, e in G.check_conv("fp16", 1, G.CONV_CASES_TC).items():
+        assert e < 6e-4, (k, e)
+    for k, e in G.check_conv("bf16", 1, G.CONV_CASES_TC).items():
+        assert e < 5e-3, (k, e)
+
+
+def test_groupnorm_act():
+    for k, e in G.check_groupnorm("fp32").items():
+        assert e < 5e-6, (k, e)
+    for k, e in G.check_groupnorm("fp16").items():
+        assert e < 8e-3, (k, e)       # output magnitudes up to ~8 stored in f16 (ulp 2^-8 at 4..8)
+
+
+def test_attention_cuda_core():
+    for k, e in G.check_attention("fp32", 0).items():
+        assert e < 5e-6, (k, e)
+
+
+# ------------------------------------------------------------------ fp32 check mode (1e-4)
+def test_fp32_nafnet_config1_and_ragged():
+    r = G.check_nafnet("fp32")
+    assert max(r.values()) < TOL_FP32, r
+
+
+def test_fp32_unet_per_step_eps_teacher_forced():
+    r = G.check_unet_teacher("fp32")
+    assert r["eps_worst"] < TOL_FP32, r
+
+
+def test_fp32_sampler_trace_graph_and_final():
+    r = G.check_ddim_standalone("fp32")
+    assert r["n_evals"] == 9                       # inference_steps=8 -> 9 evaluations
+    assert r["teacher_eps_worst"] < TOL_FP32 and r["free_eps_worst"] < TOL_FP32 and r["free_final"] < TOL_FP32, r
+    assert r["graph_vs_eager"] < 1e-5 and r["graph_replay_stable"] < 1e-5, r
+
+
+def test_fp32_routing_mask_bit_exact_and_fusion():
+    r = G.check_router_fusion("fp32")
+    assert r["mask_u8_mismatch"] == 0 and r["mask_gt05_mismatch"] == 0, r   # quantised as RUN:145 does
+    assert r["mask_maxabs"] < 2e-6 and r["fusion_maxabs"] < TOL_FP32, r
+
+
+def test_fp32_hybrid_free_running_50_steps():
+    r = G.check_hybrid("fp32")
+    assert max(r["naf_maxabs"], r["diff_maxabs"], r["fused_maxabs"]) < TOL_FP32, r
+
+
+def test_fp32_hybrid_vs_oracle_128():
+    r = G.check_hybrid_oracle_128("fp32")
+    assert max(r.values()) < TOL_FP32, r
+
+
+# ------------------------------------------------------------------ 16-bit tensor-core mode (1e-2)
+def test_f16_unet_per_step_eps_teacher_forced():
+    r = G.check_unet_teacher("fp16")
+    assert r["eps_worst"] < TOL_16, r
+
+
+def test_f16_nafnet():
+    r = G.check_nafnet("fp16")
+    assert max(r.values()) < TOL_16, r
+
+
+def test_f16_sampler_and_graph():
+    r = G.check_ddim_standalone("fp16")
+    assert r["teacher_eps_worst"] < TOL_16 and r["free_final"] < TOL_16, r
+    assert r["graph_vs_eager"] < 5e-3 and r["graph_replay_stable"] < 5e-3, r   # atomics order in GroupNorm sums
+
+
+def test_f16_hybrid_final_image_and_mask():
+    r = G.check_hybrid("fp16")
+    assert max(r["naf_maxabs"], r["diff_maxabs"], r["fused_maxabs"]) < TOL_16, r
+    assert r["mask_maxabs"] < 2e-6, r               # the router always runs in fp32
+
+
+def test_f16_hybrid_vs_oracle_128():
+    r = G.check_hybrid_oracle_128("fp16")
+    assert max(r.values()) < TOL_16, r
+
+
+def test_bf16_operands_bounded():
+    r = G.check_unet_teacher("bf16")
+    assert r["eps_worst"] < TOL_BF16, r
+    r = G.check_hybrid("bf16")
+    assert max(r["naf_maxabs"], r["diff_maxabs"], r["fused_maxabs"]) < TOL_BF16, r
+
+
+# ------------------------------------------------------------------ edge cases / boundary behaviour
+def test_errors_are_loud():
+    import xrd_b200
+    m, _ = G.seeded_state_dict("unet")
+    m = m.to(G.DEV)
+    w = xrd_b200.DiffusionDenoiser(m)
+    with pytest.raises(xrd_b200.XrdError):
+        w.denoise(torch.zeros(1, 1, 36, 36, device=G.DEV), 5)       # not a multiple of 8
+    with pytest.raises(xrd_b200.XrdError):
+        w.denoise(torch.zeros(1, 1, 32, 32), 5)                     # CPU tensor: no fallback
+    with pytest.raises(xrd_b200.XrdError):
+        m(torch.zeros(2, 1, 32, 32, device=G.DEV), torch.zeros(2, 1, 32, 32, device=G.DEV), torch.zeros(3, device=G.DEV))
+
+
+def test_state_dict_reload_repacks_weights():
+    import xrd_b200
+    from oracle import xrd_oracle as O
+    m, sd = G.seeded_state_dict("nafnet")
+    m = m.to(G.DEV).set_native_mode("fp32")
+    _, noisy = O.synthetic_xray(1, 32, 32, seed=3)
+    y0 = m(noisy.to(G.DEV)).cpu()
+    sd2 = {k: v.clone() for k, v in m.state_dict().items()}
+    for k in sd2:
+        if k.endswith("intro.weight"):
+            sd2[k] = sd2[k] * 0.5
+    m.load_state_dict(sd2)
+    y1 = m(noisy.to(G.DEV)).cpu()
+    ref = O.nafnet_forward({k: v.cpu() for k, v in sd2.items()}, noisy)
+    assert (y1 - ref).abs().max() < TOL_FP32 and (y1 - y0).abs().max() > 1e-3
+
+
+def test_full_size_properties_config3():
+    """BASELINE configs[2] size (512x512, batch 16, DDIM-50): too large for the CPU oracle in test time, so
+    check size-independent properties: per-image independence of the batch, determinism of the graph replay,
+    ranges of the clamped intermediates."""
+    m, sd = G._hybrid("fp16")
+    m.inference_diffusion_steps = 50
+    from oracle import xrd_oracle as O
+    _, noisy = O.synthetic_xray(16, 512, 512, seed=21)
+    x = noisy.to(G.DEV)
+    y, parts = m(x, return_parts=True)
+    y2 = m(x)
+    assert torch.isfinite(y).all()
+    assert (y - y2).abs().max() < 5e-3                       # replay-stable up to atomic summation order
+    assert parts["diff"].min() >= 0 and parts["diff"].max() <= 1 and parts["mask"].min() > 0 and parts["mask"].max() < 1
+    for i in (0, 7, 15):                                     # image i alone == image i inside the batch
+        yi = m(x[i:i + 1])
+        assert (yi - y[i:i + 1]).abs().max() < 5e-3, i
