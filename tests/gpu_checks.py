@@ -265,6 +265,7 @@ CHECKS = {
     "conv_tc_bf16": lambda: check_conv("bf16", 1, CONV_CASES_TC),
     "conv_tc_fp16": lambda: check_conv("fp16", 1, CONV_CASES_TC),
     "attention_tc_bf16": lambda: check_attention("bf16", 1),
+    "attention_tc_fp16": lambda: check_attention("fp16", 1),
     "nafnet_fp32": lambda: check_nafnet("fp32"),
     "unet_teacher_fp32": lambda: check_unet_teacher("fp32"),
     "ddim_fp32": lambda: check_ddim_standalone("fp32"),

@@ -44,6 +44,14 @@ def test_attention_cuda_core():
         assert e < 5e-6, (k, e)
 
 
+def test_attention_tcgen05():
+    # inputs pre-rounded; remaining error = P rounded to 16 bit before P.V plus the 16-bit output store
+    for k, e in G.check_attention("fp16", 1).items():
+        assert e < 2e-3, (k, e)
+    for k, e in G.check_attention("bf16", 1).items():
+        assert e < 1.5e-2, (k, e)
+
+
 # ------------------------------------------------------------------ fp32 check mode (1e-4)
 def test_fp32_nafnet_config1_and_ragged():
     r = G.check_nafnet("fp32")
