@@ -14,6 +14,7 @@
 #include "tc_common.cuh"
 
 #include <mutex>
+#include <stdlib.h>
 
 namespace xrd {
 
@@ -57,7 +58,7 @@ constexpr int kTcThreads = 192;
 constexpr int kABytes = 128 * 128;  // 128 pixels x 64 ch x 2 B
 
 template <typename T>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
           const __grid_constant__ CUtensorMap tmB, const ConvTcP p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -328,8 +329,15 @@ void conv_tc(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e,
   p.tmem_cols = cols;
   const uint32_t b_bytes = (uint32_t)bn * 128u;
   const uint32_t stage_bytes = kABytes + ((b_bytes + 1023u) & ~1023u);
-  int stages = (int)((200 * 1024) / stage_bytes);
+  // Several CTAs per SM overlap one tile's epilogue/prologue with another's main loop (TMEM: ctas * cols <= 512).
+  static const int env_ctas = getenv("XRD_TC_CTAS") ? atoi(getenv("XRD_TC_CTAS")) : 0;
+  static const int env_stages = getenv("XRD_TC_STAGES") ? atoi(getenv("XRD_TC_STAGES")) : 0;
+  int ctas = env_ctas > 0 ? env_ctas : (bn <= 64 ? 3 : 2);
+  while (ctas > 1 && (int)cols * ctas > 512) --ctas;
+  int stages = (int)((220 * 1024 / ctas - 2048) / stage_bytes);
+  if (env_stages > 0) stages = env_stages;
   if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
   if (stages > p.nkb) stages = std::max(1, p.nkb);
   p.stages = stages;
   p.bias = w.bias;

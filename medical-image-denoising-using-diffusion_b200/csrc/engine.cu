@@ -344,6 +344,11 @@ static void conv(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi
   else conv_simt(c, x1, x2, w, e, y);
 }
 
+static void conv_first(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, Tens& y) {
+  if (conv_smallcin_supported(x1, x2, w)) conv_smallcin(c, x1, x2, w, y);
+  else conv_simt(c, x1, x2, w, ConvEpi(), y);
+}
+
 static double* new_sums(Ctx& c, int n, int groups) {
   double* s = c.allocd((size_t)n * groups * 2);
   zero_async(c, s, (size_t)n * groups * 2 * sizeof(double));
@@ -415,7 +420,7 @@ static void unet_eval(Ctx& c, UNetW& u, const float* x, const float* cond, const
   Tens xin; xin.p = (void*)x; xin.n = B; xin.h = H; xin.w = W; xin.c = 1; xin.dt = DT_F32;
   Tens cin = xin; cin.p = (void*)cond;
   Tens h = c.alloc(B, H, W, u.mc);
-  conv_simt(c, xin, &cin, u.in_conv, ConvEpi(), h);     // cat([x, condition]) never materialised
+  conv_first(c, xin, &cin, u.in_conv, h);                // cat([x, condition]) never materialised
   std::vector<Tens> skips;
   for (const ULayer& L : u.downs) {
     if (L.kind == U_RES) {
@@ -528,7 +533,7 @@ static void nafnet_forward(Ctx& c, NafW& n, const float* inp, float* out, int B,
   }
   Tens xin; xin.p = (void*)ip; xin.n = B; xin.h = Hp; xin.w = Wp; xin.c = 1; xin.dt = DT_F32;
   Tens x = c.alloc(B, Hp, Wp, n.width);
-  conv_simt(c, xin, nullptr, n.intro, ConvEpi(), x);
+  conv_first(c, xin, nullptr, n.intro, x);
   std::vector<Tens> encs;
   for (size_t s = 0; s < n.enc.size(); ++s) {
     for (auto& b : n.enc[s]) {
@@ -578,7 +583,7 @@ static void nafnet_forward(Ctx& c, NafW& n, const float* inp, float* out, int B,
 static Tens cgg(Ctx& c, CGG& L, const Tens& x1, const Tens* x2) {
   const int Ho = (x1.h + 2 - 3) / L.conv.stride + 1, Wo = (x1.w + 2 - 3) / L.conv.stride + 1;
   Tens y = c.alloc(x1.n, Ho, Wo, L.conv.cout, DT_F32);
-  conv_simt(c, x1, x2, L.conv, ConvEpi(), y);
+  conv_first(c, x1, x2, L.conv, y);
   double* s = new_sums(c, x1.n, L.groups);
   gn_stats(c, y, nullptr, L.groups, s);
   Tens a = c.alloc(x1.n, Ho, Wo, L.conv.cout, DT_F32);

@@ -37,6 +37,10 @@ bool conv_tc_supported(const Tens& x1, const Tens* x2, const ConvW& w, const Con
 // build w.wtc[dt] from w.w (device side); c1 = channels of source 1
 void conv_tc_pack(cudaStream_t s, ConvW& w, DType dt, int c1);
 
+// direct 3x3/s1/p1 conv for Cin <= 4 read from fp32 planes (first conv of every network)
+bool conv_smallcin_supported(const Tens& x1, const Tens* x2, const ConvW& w);
+void conv_smallcin(Ctx& c, const Tens& x1, const Tens* x2, const ConvW& w, Tens& y);
+
 // softmax(q^T k / sqrt(d)) v; qkv [N,HW,3*heads*d] (channel = s*heads*d + head*d + j), out [N,HW,heads*d]
 void attention_simt(Ctx& c, const Tens& qkv, int heads, Tens& out);
 void attention_tc(Ctx& c, const Tens& qkv, int heads, Tens& out);

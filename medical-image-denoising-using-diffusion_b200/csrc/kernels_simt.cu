@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256) k_gn_stats(const T* __restrict__ x1, cons
   }
 }
 
-void gn_stats(Ctx& c, const Tens& x1, const Tens* x2, int groups, double* sums) {
+void gn_stats_v1(Ctx& c, const Tens& x1, const Tens* x2, int groups, double* sums) {
   const int c1 = x1.c, c2 = x2 ? x2->c : 0, ctot = c1 + c2;
   XRD_REQUIRE((c1 % 4) == 0 && (c2 % 4) == 0 && ctot % groups == 0 && ctot / 4 <= 256 && groups <= 32,
               "gn_stats: unsupported channels %d+%d groups %d", c1, c2, groups);
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256) k_gn_act(const TI* __restrict__ x1, const
   }
 }
 
-void gn_act(Ctx& c, const Tens& x1, const Tens* x2, int groups, const double* sums, const float* gamma, const float* beta,
+void gn_act_v1(Ctx& c, const Tens& x1, const Tens* x2, int groups, const double* sums, const float* gamma, const float* beta,
             float eps, int act, Tens& y) {
   const int c1 = x1.c, c2 = x2 ? x2->c : 0, ctot = c1 + c2;
   XRD_REQUIRE(y.c == ctot && y.n == x1.n && y.h == x1.h && y.w == x1.w, "gn_act: output shape mismatch");
@@ -606,7 +606,7 @@ __global__ void __launch_bounds__(128) k_conv_cout1(Cout1P p) {
   p.y[o] = v;
 }
 
-void conv_cout1(Ctx& c, const Cout1Args& a) {
+void conv_cout1_v1(Ctx& c, const Cout1Args& a) {
   XRD_REQUIRE(a.x.c % 4 == 0 && (a.k == 1 || a.k == 3), "conv_cout1: unsupported C=%d k=%d", a.x.c, a.k);
   Cout1P p;
   p.x = a.x.p; p.N = a.x.n; p.H = a.x.h; p.W = a.x.w; p.C = a.x.c; p.k = a.k;
