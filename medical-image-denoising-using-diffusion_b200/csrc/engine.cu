@@ -340,7 +340,8 @@ void finalize(Handle& h, int which) {
 // network building blocks
 // ------------------------------------------------------------------------------------------------
 static void conv(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y) {
-  if (c.tc && conv_tc_supported(x1, x2, w, e)) conv_tc(c, x1, x2, w, e, y);
+  if (c.tc && conv_halo_supported(x1, x2, w, e)) conv_halo(c, x1, w, e, y);
+  else if (c.tc && conv_tc_supported(x1, x2, w, e)) conv_tc(c, x1, x2, w, e, y);
   else conv_simt(c, x1, x2, w, e, y);
 }
 

@@ -34,6 +34,9 @@ void conv_simt(Ctx& c, const Tens& x1, const Tens* x2, const ConvW& w, const Con
 // tcgen05 implicit GEMM (conv_tc.cu); same contract, bf16/f16 operands.
 void conv_tc(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y);
 bool conv_tc_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e);
+// persistent halo-reusing variant for 3x3/s1/p1 on maps whose width is a multiple of 128 (conv_halo.cu)
+bool conv_halo_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e);
+void conv_halo(Ctx& c, const Tens& x, ConvW& w, const ConvEpi& e, Tens& y);
 // build w.wtc[dt] from w.w (device side); c1 = channels of source 1
 void conv_tc_pack(cudaStream_t s, ConvW& w, DType dt, int c1);
 

@@ -91,6 +91,12 @@ CONV_CASES_TC = [
 ]
 
 
+CONV_CASES_HALO = [   # 3x3/s1/p1, W % 128 == 0 (persistent halo kernel)
+    (1, 48, 8, 128, 48, 3, 1, 1), (2, 96, 6, 256, 96, 3, 1, 1), (1, 144, 5, 128, 144, 3, 1, 1), (1, 192, 4, 128, 96, 3, 1, 1),
+    (1, 96, 7, 128, 48, 3, 1, 1), (3, 48, 16, 256, 96, 3, 1, 1), (1, 288, 4, 128, 144, 3, 1, 1), (1, 48, 40, 512, 48, 3, 1, 1),
+]
+
+
 def check_conv(mode, impl, cases, seed=0):
     g = torch.Generator(device="cpu").manual_seed(seed)
     oh = OpHandle(mode)
@@ -264,6 +270,8 @@ CHECKS = {
     "attention_simt_fp32": lambda: check_attention("fp32", 0),
     "conv_tc_bf16": lambda: check_conv("bf16", 1, CONV_CASES_TC),
     "conv_tc_fp16": lambda: check_conv("fp16", 1, CONV_CASES_TC),
+    "conv_halo_fp16": lambda: check_conv("fp16", 2, CONV_CASES_HALO),
+    "conv_halo_bf16": lambda: check_conv("bf16", 2, CONV_CASES_HALO),
     "attention_tc_bf16": lambda: check_attention("bf16", 1),
     "attention_tc_fp16": lambda: check_attention("fp16", 1),
     "nafnet_fp32": lambda: check_nafnet("fp32"),

@@ -20,7 +20,7 @@ SHAPES = [  # (B, Cin, H, W, Cout, k, stride, pad) -- BASELINE config 3 layer sh
 
 def main():
     mode = sys.argv[1] if len(sys.argv) > 1 else "bf16"
-    impls = [1, 0] if "--simt" in sys.argv else [1]
+    impls = [1, 0] if "--simt" in sys.argv else ([2] if "--halo" in sys.argv else [1])
     res = []
     for (B, Cin, H, W, Cout, k, s, p) in SHAPES:
         x = torch.randn(B, Cin, H, W, device=DEV)
@@ -29,6 +29,8 @@ def main():
         Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
         flops = 2.0 * B * Ho * Wo * Cout * Cin * k * k
         for impl in impls:
+            if impl == 2 and (k != 3 or s != 1 or W % 128 != 0):
+                continue
             oh = OpHandle(mode)
             try:
                 oh.conv2d(x, w, b, k, s, p, impl)
