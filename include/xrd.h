@@ -173,11 +173,19 @@ int xrd_hybrid(xrd_handle* h, const float* noisy, int inference_steps, float* ou
  * of the handle's current mode, runs ONE op through the same kernel the networks use, and
  * converts back.  They need no weights to be finalised. */
 
-/* conv2d: weight (Cout,Cin,kh,kw), bias nullable.  impl: 0 = CUDA-core kernel, 1 = tcgen05
- * implicit-GEMM kernel (3x3/s1/p1, 3x3/s2/p1, 2x2/s2/p0 and 1x1 only). */
+/* conv2d: weight (Cout,Cin,kh,kw), bias nullable.  impl: 0 = CUDA-core kernel, 1 = tcgen05 per-tap
+ * implicit-GEMM kernel (3x3/s1/p1, 3x3/s2/p1, 2x2/s2/p0 and 1x1 only), 2 = persistent halo-reusing
+ * tcgen05 kernel (3x3/s1/p1, W % 128 == 0, Cout in {48,96,144}), 3 / 4 = kernels 2 / 1 reading x as a
+ * virtual concat of its two channel halves (B must be 1). */
 int xrd_op_conv2d(xrd_handle* h, int impl, const float* x, const float* weight, const float* bias,
                   float* y, int B, int Cin, int H, int W, int Cout, int k, int stride, int pad,
                   void* stream);
+/* Same; `stats` (nullable, device, [B][8][2] float64) additionally receives the per-(image, channel
+ * group of Cout/8) sum and sum of squares of the output that kernel 2/3 accumulates in its epilogue for
+ * the GroupNorm that follows (HYB:264,269). */
+int xrd_op_conv2d_stats(xrd_handle* h, int impl, const float* x, const float* weight, const float* bias,
+                        float* y, double* stats, int B, int Cin, int H, int W, int Cout, int k,
+                        int stride, int pad, void* stream);
 /* GroupNorm(groups, C, eps=1e-5) + activation (0 none, 1 SiLU, 2 erf-GELU). */
 int xrd_op_groupnorm_act(xrd_handle* h, const float* x, const float* gamma, const float* beta,
                          float* y, int B, int C, int H, int W, int groups, int act, void* stream);

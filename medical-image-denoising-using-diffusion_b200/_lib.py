@@ -74,6 +74,7 @@ SYMBOLS = {
     "xrd_fusion": (C.c_int, [_P, _F, _F, _F, _F, C.c_int, C.c_int, C.c_int, _P]),
     "xrd_hybrid": (C.c_int, [_P, _F, C.c_int, _F, _F, _F, _F, C.c_int, C.c_int, C.c_int, _P]),
     "xrd_op_conv2d": (C.c_int, [_P, C.c_int, _F, _F, _F, _F] + [C.c_int] * 8 + [_P]),
+    "xrd_op_conv2d_stats": (C.c_int, [_P, C.c_int, _F, _F, _F, _F, _P] + [C.c_int] * 8 + [_P]),
     "xrd_op_groupnorm_act": (C.c_int, [_P, _F, _F, _F, _F] + [C.c_int] * 6 + [_P]),
     "xrd_op_attention": (C.c_int, [_P, C.c_int, _F, _F] + [C.c_int] * 5 + [_P]),
     "xrd_op_time_last": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), _P]),

@@ -492,6 +492,11 @@ XRD_EXPORT int xrd_hybrid(xrd_handle* H, const float* noisy, int inference_steps
 // ------------------------------------------------------------------------------------------------
 XRD_EXPORT int xrd_op_conv2d(xrd_handle* H, int impl, const float* x, const float* weight, const float* bias, float* y, int B, int Cin,
                              int Hh, int W, int Cout, int k, int stride, int pad, void* stream) {
+  return xrd_op_conv2d_stats(H, impl, x, weight, bias, y, nullptr, B, Cin, Hh, W, Cout, k, stride, pad, stream);
+}
+
+XRD_EXPORT int xrd_op_conv2d_stats(xrd_handle* H, int impl, const float* x, const float* weight, const float* bias, float* y, double* stats,
+                                   int B, int Cin, int Hh, int W, int Cout, int k, int stride, int pad, void* stream) {
   return guarded([&] {
     XRD_REQUIRE(H && x && weight && y, "null argument");
     std::lock_guard<std::mutex> lk(H->h.mu);
@@ -508,23 +513,36 @@ XRD_EXPORT int xrd_op_conv2d(xrd_handle* H, int impl, const float* x, const floa
     pack_conv_weight(s, weight, w.w, Cout, Cin, k, k);
     w.bias = (float*)bias;
     const DType dt = mode_dtype(H->h.mode);
+    // impl: 0 CUDA cores, 1 tcgen05 per-tap, 2 tcgen05 persistent halo (conv3), 3 = conv3 over a virtual concat of the two
+    // channel halves of x (B must be 1 so that each half is a contiguous NCHW block), 4 = per-tap kernel over the same concat
+    const bool split = impl == 3 || impl == 4;
+    if (split) XRD_REQUIRE(B == 1 && Cin % 32 == 0, "split-input conv hook needs B == 1 and Cin %% 32 == 0");
     if (impl >= 1) {
       XRD_REQUIRE(dt != DT_F32, "the tcgen05 kernels need a 16-bit mode");
-      conv_tc_pack(s, w, dt, Cin);
+      conv_tc_pack(s, w, dt, split ? Cin / 2 : Cin);
     }
     const int Ho = (Hh + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
     H->h.last_op = nullptr;
     with_arena(H, s, keyf("opconv", H, B, Hh, W, Cin, Cout, k, stride * 8 + pad, impl), [&](Ctx& c) {
-      Tens xi = c.alloc(B, Hh, W, Cin);
+      Tens xi = c.alloc(B, Hh, W, split ? Cin / 2 : Cin);
+      Tens xj = split ? c.alloc(B, Hh, W, Cin / 2) : Tens();
       Tens yo = c.alloc(B, Ho, Wo, Cout);
+      double* st = c.allocd((size_t)B * 16);
       nchw_to_nhwc(c, x, xi);
-      auto run = [H, xi, yo, impl](Ctx& cc) mutable {
+      if (split) nchw_to_nhwc(c, x + (size_t)(Cin / 2) * Hh * W, xj);
+      auto run = [H, xi, xj, yo, st, impl, split](Ctx& cc) mutable {
         Tens yy = yo;
-        if (impl == 2) conv_halo(cc, xi, H->op_w, ConvEpi(), yy);
-        else if (impl == 1) conv_tc(cc, xi, nullptr, H->op_w, ConvEpi(), yy);
-        else conv_simt(cc, xi, nullptr, H->op_w, ConvEpi(), yy);
+        ConvEpi e;
+        if (impl == 2 || impl == 3) {
+          e.stats_out = st;
+          zero_async(cc, st, (size_t)yo.n * 16 * sizeof(double));
+          conv3(cc, xi, split ? &xj : nullptr, H->op_w, e, yy);
+        }
+        else if (impl == 1 || impl == 4) conv_tc(cc, xi, split ? &xj : nullptr, H->op_w, e, yy);
+        else conv_simt(cc, xi, nullptr, H->op_w, e, yy);
       };
       run(c);
+      if (!c.dry && stats && (impl == 2 || impl == 3)) XRD_CUDA(cudaMemcpyAsync(stats, st, (size_t)B * 16 * sizeof(double), cudaMemcpyDeviceToDevice, s));
       nhwc_to_nchw(c, yo, y);
       if (!c.dry) {
         H->h.last_op = run;

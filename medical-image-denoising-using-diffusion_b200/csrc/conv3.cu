@@ -1,0 +1,545 @@
+// conv3.cu -- persistent, halo-reusing tcgen05 implicit-GEMM 3x3 convolution (stride 1, pad 1) for feature maps
+// whose width is a multiple of 128.  This is the dominant kernel of the UNet's three high-resolution levels.
+//
+// What bounds a 3x3 conv with few output channels on B200 (measured, tools/probes/mma_probe.cu + profiles/):
+//   * tcgen05.mma M=128, K=16 with both operands in shared memory costs max(N/2, 32 + N/4) cycles: below N=128 the
+//     instruction is limited by the 128 B/clk shared-memory read of A (4 KB) + B (32*N B), not by the tensor pipe;
+//   * one issuing thread retires ~1 dependent integer instruction per 4 cycles, so every descriptor must be a
+//     compile-time offset from a per-stage base (a runtime-indexed issue loop costs >100 cycles per MMA);
+//   * L2 -> SM delivers ~6.4 TB/s chip-wide, i.e. no more than HBM: operand re-fetches are as expensive as DRAM.
+// Hence:
+//   * one CTA per SM walks tiles of TH image rows x 128 columns (persistent, static round robin);
+//   * per 64-channel chunk ONE TMA box {64 ch, 130, TH+2} brings the tile plus its halo into shared memory (zero
+//     padding, image borders and channel tails by TMA out-of-bounds fill); the nine taps are nine descriptor
+//     offsets into that buffer: tap (dy,dx) of tile row s starts at buffer pixel (s+dy)*130 + dx.  The start
+//     address is then not 1024-byte aligned; the 128B swizzle is a function of the absolute shared-memory address
+//     (as TMA wrote it), so the descriptor base-offset field stays 0 (verified bit-exact on B200);
+//   * a virtual channel concat (x1 | x2) is walked as the chunks of x1 followed by the chunks of x2;
+//   * weights stay resident in shared memory when all (chunk, tap) blocks fit, else they stream through a ring
+//     once per tile (not once per 128 pixels);
+//   * TH accumulators (one per image row) live in TMEM, double buffered when they fit, so the epilogue of tile i
+//     overlaps the MMAs of tile i+1;
+//   * the MMA issue loop is fully unrolled over (tap, row, k-step);
+//   * epilogue: TMEM -> registers, + bias + time-embedding row + residual (prefetched), GroupNorm partial sums
+//     of the OUTPUT (so the next GroupNorm needs no statistics pass), 16-bit pack, 16-byte stores of whole
+//     sectors straight from registers; eight epilogue warps (a single warp retires ~1 instruction per 3-4
+//     cycles, four warps cannot drain 128x48 accumulators as fast as the tensor core refills them).
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+#include <stdlib.h>
+
+namespace xrd {
+
+struct Conv3P {
+  int H, W, nimg;
+  int tiles_w, tiles_h, ntiles;
+  int c0, c1;               // channels of the two sources (c1 = 0: single source)
+  int nchunk0, nchunk;      // 64-channel chunks of source 0 / of both
+  int nb;                   // weight ring slots when streaming
+  int dbg;
+  int rowload;              // 1: one TMA instruction per halo row instead of one per (TH+2)-row box
+  const float* bias;
+  const float* chan_add; int chan_add_bstride;
+  const void* resid;
+  void* y;
+  double* stats;            // optional [nimg][8][2] (sum, sum of squares) of the stored output, 8 channel groups
+  long long* prof;          // optional clock64 trace of block 0
+};
+
+constexpr int kC3Threads = 320;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kC3Pitch = 136;   // smem pixels per halo row: 130 used (128 + one halo column each side); 136*128 B keeps rows 1024-aligned
+constexpr int kC3Box = 130;
+
+#define C3PROF(tile, slot) do { if (p.prof && blockIdx.x == 0 && (tile) < 64) p.prof[(tile) * 8 + (slot)] = clock64(); } while (0)
+
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <typename T> __device__ __forceinline__ void unpack8(const uint4& t, float (&v)[8]);
+template <> __device__ __forceinline__ void unpack8<__half>(const uint4& t, float (&v)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& t, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+
+// All MMAs of one 64-channel chunk: 9 taps x TH rows x KS k-steps, every descriptor a compile-time offset.
+template <int COUT, int TH, int KS, bool WRES>
+__device__ __forceinline__ void c3_issue_chunk(uint64_t adesc0, uint64_t bdesc0, uint32_t sB_addr, uint64_t* b_full, uint64_t* b_empty,
+                                               uint32_t& wslot, uint32_t& wphase, int nb, uint32_t acc0, uint32_t idesc, uint32_t not_first) {
+  constexpr uint32_t B_BYTES = COUT * 128;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    uint64_t bdesc;
+    if (WRES) {
+      bdesc = bdesc0 + (uint64_t)(tap * (B_BYTES >> 4));
+    } else {
+      tc::mbar_wait(&b_full[wslot], wphase);
+      tc::tc_fence_after();
+      bdesc = tc::umma_desc_sw128(sB_addr + wslot * B_BYTES);
+    }
+    const int dy = tap / 3, dx = tap % 3;
+#pragma unroll
+    for (int s = 0; s < TH; ++s) {
+#pragma unroll
+      for (int k = 0; k < KS; ++k)
+        tc::umma_f16(acc0 + (uint32_t)(s * COUT), adesc0 + (uint64_t)(((s + dy) * kC3Pitch + dx) * 8 + k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                     (tap == 0 && k == 0) ? not_first : 1u);
+    }
+    if (!WRES) {
+      tc::umma_commit(&b_empty[wslot]);
+      if (++wslot == (uint32_t)nb) { wslot = 0; wphase ^= 1; }
+    }
+  }
+}
+
+template <typename T, int COUT, int TH, int NACC, bool WRES>
+__global__ void __launch_bounds__(kC3Threads, 1)
+k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB,
+        const Conv3P p) {
+  constexpr uint32_t A_BYTES = (uint32_t)(((TH + 2) * kC3Pitch * 128 + 1023) & ~1023);
+  constexpr uint32_t B_BYTES = COUT * 128;
+  constexpr int CPG = COUT / 8;                            // channels per GroupNorm group (8 groups)
+  constexpr int NBLK = COUT / 48;                          // 48-column epilogue blocks
+  constexpr uint32_t TMEM_COLS = (NACC * TH * COUT <= 32) ? 32 : (NACC * TH * COUT <= 64) ? 64 : (NACC * TH * COUT <= 128) ? 128
+                                 : (NACC * TH * COUT <= 256) ? 256 : 512;
+  static_assert(COUT % 48 == 0 && NACC * TH * COUT <= 512, "accumulators must fit TMEM");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int nkb = p.nchunk * 9;
+  const int nbslots = WRES ? nkb : p.nb;
+  uint8_t* sA = smem;                                       // [2][A_BYTES]
+  uint8_t* sB = sA + 2 * (size_t)A_BYTES;                   // [nbslots][B_BYTES]
+  float* s_badd = (float*)(sB + (size_t)nbslots * B_BYTES);   // [8 warps][COUT] bias + time-embedding row of the current image
+  uint64_t* bars = (uint64_t*)(s_badd + 8 * COUT);
+  uint64_t* a_full = bars;            // [2]
+  uint64_t* a_empty = bars + 2;       // [2]
+  uint64_t* acc_full = bars + 4;      // [2]
+  uint64_t* acc_empty = bars + 6;     // [2]
+  uint64_t* w_full = bars + 8;        // [1] resident weights
+  uint64_t* b_full = bars + 9;        // [16]
+  uint64_t* b_empty = b_full + 16;    // [16]
+  uint32_t* tmem_slot = (uint32_t*)(b_empty + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmA0);
+    tc::tma_prefetch_desc(&tmA1);
+    tc::tma_prefetch_desc(&tmB);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1);
+      tc::mbar_init(&acc_full[s], 1); tc::mbar_init(&acc_empty[s], 256);
+    }
+    tc::mbar_init(w_full, 1);
+    for (int s = 0; s < 16; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  // One CTA per SM (shared-memory limited) and this is its only allocation: the allocator returns column 0 / lane 0.
+  // Treating it as the constant 0 keeps every tcgen05.mma operand in uniform registers.
+  if (*tmem_slot != 0u) {
+    if (threadIdx.x == 0) printf("libxrd: conv3 expects TMEM base 0, got %u\n", *tmem_slot);
+    __trap();
+  }
+  constexpr uint32_t tmem_base = 0u;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one elected lane issues; the warp stays converged) =====================
+    if (WRES && tc::elect_one()) {
+      tc::mbar_expect_tx(w_full, (uint32_t)nkb * B_BYTES);
+      for (int kb = 0; kb < nkb; ++kb) tc::tma_load_3d(sB + (size_t)kb * B_BYTES, &tmB, w_full, 0, 0, kb);
+    }
+    __syncwarp();
+    uint32_t ai = 0, wslot = 0, wphase = 0;
+    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+      int r = t;
+      const int txi = r % p.tiles_w; r /= p.tiles_w;
+      const int tyi = r % p.tiles_h;
+      const int img = r / p.tiles_h;
+      const int w0 = txi * 128 - 1, h0 = tyi * TH - 1;
+      for (int c = 0; c < p.nchunk; ++c, ++ai) {
+        const int st = ai & 1;
+        tc::mbar_wait(&a_empty[st], ((ai >> 1) & 1) ^ 1);
+        if (lane == 0) C3PROF(ai, 0);
+        uint32_t leader;
+        if (tc::elect_one(leader)) {
+          if ((p.dbg & 4) && ai >= 2) {
+            tc::mbar_arrive(&a_full[st]);
+          } else {
+            tc::mbar_expect_tx(&a_full[st], (uint32_t)(TH + 2) * kC3Box * 128u);
+            const bool second = c >= p.nchunk0;
+            const CUtensorMap* tm = second ? &tmA1 : &tmA0;
+            const int cc0 = (second ? c - p.nchunk0 : c) * 64;
+#pragma unroll
+            for (int rr = 0; rr < TH + 2; ++rr)
+              tc::tma_load_4d(sA + (size_t)st * A_BYTES + (size_t)rr * kC3Pitch * 128, tm, &a_full[st], cc0, w0, h0 + rr, img);
+          }
+          if (!WRES) {
+            for (int tap = 0; tap < 9; ++tap) {
+              tc::mbar_wait(&b_empty[wslot], wphase ^ 1);
+              tc::mbar_expect_tx(&b_full[wslot], B_BYTES);
+              tc::tma_load_3d(sB + (size_t)wslot * B_BYTES, &tmB, &b_full[wslot], 0, 0, c * 9 + tap);
+              if (++wslot == (uint32_t)p.nb) { wslot = 0; wphase ^= 1; }
+            }
+          }
+        }
+        __syncwarp();
+        if (!WRES) {   // every lane tracks the ring position the leader advanced
+          wslot = __shfl_sync(0xffffffffu, wslot, leader);
+          wphase = __shfl_sync(0xffffffffu, wphase, leader);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (WRES) tc::mbar_wait(w_full, 0);
+    const uint32_t idesc = tc::umma_idesc(128, COUT, tc::umma_fmt<T>());
+    const uint32_t sB_addr = tc::smem_u32(sB);
+    uint32_t ai = 0, ti = 0, wslot = 0, wphase = 0;
+    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
+      const int ab = NACC == 2 ? (int)(ti & 1) : 0;
+      const uint32_t use = NACC == 2 ? (ti >> 1) : ti;       // how many times this accumulator buffer was used before
+      if (lane == 0) C3PROF(ti, 1);
+      tc::mbar_wait(&acc_empty[ab], (use & 1) ^ 1);
+      tc::tc_fence_after();
+      if (lane == 0) C3PROF(ti, 2);
+      const uint32_t acc0 = tmem_base + (uint32_t)(ab * TH * COUT);
+      for (int c = 0; c < p.nchunk; ++c, ++ai) {
+        const int st = ai & 1;
+        tc::mbar_wait(&a_full[st], (ai >> 1) & 1);
+        tc::tc_fence_after();
+        if (c == 0 && lane == 0) C3PROF(ti, 3);
+        const bool second = c >= p.nchunk0;
+        const int cl = second ? c - p.nchunk0 : c;
+        const int ks = min(64, (second ? p.c1 : p.c0) - cl * 64) >> 4;
+        uint32_t leader;
+        if (tc::elect_one(leader)) {
+          const uint64_t adesc0 = tc::umma_desc_sw128(tc::smem_u32(sA + (size_t)st * A_BYTES));
+          const uint64_t bdesc0 = tc::umma_desc_sw128(sB_addr + (uint32_t)(c * 9) * B_BYTES);
+          const uint32_t nf = c ? 1u : 0u;
+          if (!(p.dbg & 2)) {
+            switch (ks) {
+              case 4: c3_issue_chunk<COUT, TH, 4, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, p.nb, acc0, idesc, nf); break;
+              case 3: c3_issue_chunk<COUT, TH, 3, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, p.nb, acc0, idesc, nf); break;
+              case 2: c3_issue_chunk<COUT, TH, 2, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, p.nb, acc0, idesc, nf); break;
+              default: c3_issue_chunk<COUT, TH, 1, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, p.nb, acc0, idesc, nf); break;
+            }
+          } else if (!WRES) {   // experiment: consume the weight ring without issuing MMAs
+            for (int tap = 0; tap < 9; ++tap) {
+              tc::mbar_wait(&b_full[wslot], wphase);
+              tc::mbar_arrive(&b_empty[wslot]);
+              if (++wslot == (uint32_t)p.nb) { wslot = 0; wphase ^= 1; }
+            }
+          }
+          tc::umma_commit(&a_empty[st]);
+          if (c == p.nchunk - 1) tc::umma_commit(&acc_full[ab]);
+        }
+        __syncwarp();
+        if (!WRES) {
+          wslot = __shfl_sync(0xffffffffu, wslot, leader);
+          wphase = __shfl_sync(0xffffffffu, wphase, leader);
+        }
+      }
+      if (lane == 0) C3PROF(ti, 4);
+    }
+  } else {
+    // ===================== epilogue (warps 2..9, two groups of four) =====================
+    // Group g = (warp-2)/4 drains the tile rows s with s % 2 == g; inside a group warp w owns TMEM lanes
+    // 32*(w%4).., i.e. 32 consecutive output pixels of that image row.  Every thread holds ONE pixel: its COUT
+    // channels are COUT*2 contiguous bytes of the NHWC output (whole 32-byte sectors), stored straight from
+    // registers with 16-byte stores -- no staging buffer, no CTA-wide barrier.
+    const int quad = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    T* yp = (T*)p.y;
+    const T* rp = (const T*)p.resid;
+    float* badd = s_badd + (warp - 2) * COUT;                         // per-warp copy of bias + time-embedding row
+    float gs[8], gq[8];                                               // GroupNorm partial sums of this thread's pixels
+#pragma unroll
+    for (int g = 0; g < 8; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
+    auto flush_stats = [&](int img) {
+      if (!p.stats || img < 0) return;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          gs[g] += __shfl_xor_sync(0xffffffffu, gs[g], o);
+          gq[g] += __shfl_xor_sync(0xffffffffu, gq[g], o);
+        }
+      }
+      if (lane < 16) {
+        float v = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) { if (lane == 2 * g) v = gs[g]; if (lane == 2 * g + 1) v = gq[g]; }
+        atomicAdd(p.stats + (size_t)img * 16 + lane, (double)v);
+      }
+#pragma unroll
+      for (int g = 0; g < 8; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
+    };
+    uint32_t ti = 0;
+    int cur_img = -1;
+    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
+      int r = t;
+      const int txi = r % p.tiles_w; r /= p.tiles_w;
+      const int tyi = r % p.tiles_h;
+      const int img = r / p.tiles_h;
+      const int ab = NACC == 2 ? (int)(ti & 1) : 0;
+      const uint32_t use = NACC == 2 ? (ti >> 1) : ti;
+      if (img != cur_img) {
+        flush_stats(cur_img);
+        __syncwarp();
+        for (int cc = lane; cc < COUT; cc += 32)
+          badd[cc] = (p.bias ? __ldg(p.bias + cc) : 0.f) + (p.chan_add ? __ldg(p.chan_add + (int64_t)img * p.chan_add_bstride + cc) : 0.f);
+        cur_img = img;
+        __syncwarp();
+      }
+      const int ow = txi * 128 + quad * 32 + lane;
+      // residual of this group's first (row, block): issued before the accumulator wait so its latency hides behind the MMAs
+      uint4 rcur[6], rnext[6];
+      const int64_t pix0 = ((int64_t)img * p.H + (int64_t)tyi * TH + grp) * p.W + ow;
+      if (rp && tyi * TH + grp < p.H) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) rcur[j] = __ldg(reinterpret_cast<const uint4*>(rp + pix0 * COUT) + j);
+      }
+      if (warp == 2 && lane == 0) C3PROF(ti, 5);
+      tc::mbar_wait(&acc_full[ab], use & 1);
+      tc::tc_fence_after();
+      if (warp == 2 && lane == 0) C3PROF(ti, 6);
+#pragma unroll
+      for (int s0 = 0; s0 < TH; s0 += 2) {
+        const int s = s0 + grp;
+        if (s < TH) {
+          const int oh = tyi * TH + s;
+          const bool row_ok = oh < p.H;
+          const int64_t opix = pix0 + (int64_t)s0 * p.W;
+          const uint32_t tacc = tmem_base + (uint32_t)((ab * TH + s) * COUT) + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+          for (int cb = 0; cb < NBLK; ++cb) {
+            uint32_t v[48];
+            if (!(p.dbg & 8)) {
+              tmem_ld16_nowait(tacc + (uint32_t)(cb * 48), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+              tmem_ld16_nowait(tacc + (uint32_t)(cb * 48 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+              tmem_ld16_nowait(tacc + (uint32_t)(cb * 48 + 32), *reinterpret_cast<uint32_t(*)[16]>(&v[32]));
+            }
+            // prefetch the residual of the next (row, block) this thread will process in this tile
+            const bool has_next = rp && (cb + 1 < NBLK || (s + 2 < TH && oh + 2 < p.H));
+            if (has_next) {
+              const T* nsrc = (cb + 1 < NBLK) ? rp + opix * COUT + (cb + 1) * 48 : rp + (opix + 2 * (int64_t)p.W) * COUT;
+#pragma unroll
+              for (int j = 0; j < 6; ++j) rnext[j] = __ldg(reinterpret_cast<const uint4*>(nsrc) + j);
+            }
+            if (!(p.dbg & 8)) tmem_wait_ld();
+#pragma unroll
+            for (int h8 = 0; h8 < 6; ++h8) {
+              const int co = cb * 48 + h8 * 8;
+              const float4 b0 = *reinterpret_cast<const float4*>(badd + co), b1 = *reinterpret_cast<const float4*>(badd + co + 4);
+              float r8[8];
+              r8[0] = __uint_as_float(v[h8 * 8 + 0]) + b0.x; r8[1] = __uint_as_float(v[h8 * 8 + 1]) + b0.y;
+              r8[2] = __uint_as_float(v[h8 * 8 + 2]) + b0.z; r8[3] = __uint_as_float(v[h8 * 8 + 3]) + b0.w;
+              r8[4] = __uint_as_float(v[h8 * 8 + 4]) + b1.x; r8[5] = __uint_as_float(v[h8 * 8 + 5]) + b1.y;
+              r8[6] = __uint_as_float(v[h8 * 8 + 6]) + b1.z; r8[7] = __uint_as_float(v[h8 * 8 + 7]) + b1.w;
+              if (rp && row_ok) {
+                float q8[8];
+                unpack8<T>(rcur[h8], q8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r8[j] += q8[j];
+              }
+              if (p.stats && row_ok) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const int g = (co + j) / CPG;
+                  gs[g] += r8[j];
+                  gq[g] = fmaf(r8[j], r8[j], gq[g]);
+                }
+              }
+              uint4 pk;
+              pk.x = tc::pack2<T>(r8[0], r8[1]); pk.y = tc::pack2<T>(r8[2], r8[3]);
+              pk.z = tc::pack2<T>(r8[4], r8[5]); pk.w = tc::pack2<T>(r8[6], r8[7]);
+              if (row_ok && !(p.dbg & 1)) *reinterpret_cast<uint4*>(yp + opix * COUT + co) = pk;
+            }
+            if (has_next) {
+#pragma unroll
+              for (int j = 0; j < 6; ++j) rcur[j] = rnext[j];
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(&acc_empty[ab]);
+      if (warp == 2 && lane == 0) C3PROF(ti, 7);
+    }
+    flush_stats(cur_img);
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+static int c3_env(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+bool conv3_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e) {
+  static const int enabled = c3_env("XRD_CONV3", 1);
+  if (!enabled) return false;
+  if (x1.dt == DT_F32) return false;
+  if (!(w.kh == 3 && w.kw == 3 && w.stride == 1 && w.pad == 1) || w.d2s) return false;
+  if (x1.c % 16 != 0 || (x2 && x2->c % 16 != 0)) return false;
+  if (!(w.cout == 48 || w.cout == 96 || w.cout == 144)) return false;
+  if (x1.w % 128 != 0) return false;
+  if (e.in_scale || e.out_scale || e.act != ACT_NONE) return false;
+  return true;
+}
+
+namespace {
+struct C3Cfg { int th, nacc; bool wres; int nb; size_t smem; };
+
+// shared-memory plan: two A stages + weights (resident or ring) + per-warp bias rows + barriers
+C3Cfg c3_plan(int cout, int nkb) {
+  const size_t budget = 227 * 1024 - 1024 /*alignment slack*/;
+  C3Cfg c{};
+  c.th = 2;
+  c.nacc = cout <= 96 ? 2 : 1;
+  const size_t a = (((size_t)(c.th + 2) * kC3Pitch * 128 + 1023) & ~(size_t)1023);
+  const size_t f = 2 * a + 8 * cout * 4 + (9 + 32) * 8 + 64;
+  const size_t bb = (size_t)cout * 128;
+  c.wres = f + (size_t)nkb * bb <= budget;
+  if (c3_env("XRD_C3_WRES", 1) == 0) c.wres = false;
+  c.nb = 0;
+  if (!c.wres) {
+    c.nb = (int)std::min<size_t>(12, (budget - f) / bb);
+    XRD_REQUIRE(c.nb >= 2, "conv3: shared memory budget exceeded (cout=%d)", cout);
+  }
+  c.smem = 1024 + f + (size_t)(c.wres ? nkb : c.nb) * bb;
+  return c;
+}
+
+template <typename T, int COUT, int TH, int NACC, bool WRES>
+void c3_launch(Ctx& c, int grid, size_t smem, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const Conv3P& p) {
+  static bool attr = false;
+  if (!attr) {
+    XRD_CUDA(cudaFuncSetAttribute(k_conv3<T, COUT, TH, NACC, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  XRD_LAUNCH(c, (k_conv3<T, COUT, TH, NACC, WRES>), grid, kC3Threads, smem, a0, a1, b, p);
+}
+
+template <typename T>
+void c3_dispatch(Ctx& c, int cout, const C3Cfg& g, int grid, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                 const Conv3P& p) {
+  if (cout == 48) {
+    if (g.wres) c3_launch<T, 48, 2, 2, true>(c, grid, g.smem, a0, a1, b, p);
+    else c3_launch<T, 48, 2, 2, false>(c, grid, g.smem, a0, a1, b, p);
+  } else if (cout == 96) {
+    if (g.wres) c3_launch<T, 96, 2, 2, true>(c, grid, g.smem, a0, a1, b, p);
+    else c3_launch<T, 96, 2, 2, false>(c, grid, g.smem, a0, a1, b, p);
+  } else {
+    if (g.wres) c3_launch<T, 144, 2, 1, true>(c, grid, g.smem, a0, a1, b, p);
+    else c3_launch<T, 144, 2, 1, false>(c, grid, g.smem, a0, a1, b, p);
+  }
+}
+
+void c3_encode_act(CUtensorMap* m, const Tens& x, int th) {
+  const cuuint64_t dims[4] = {(cuuint64_t)x.c, (cuuint64_t)x.w, (cuuint64_t)x.h, (cuuint64_t)x.n};
+  const cuuint64_t strides[3] = {(cuuint64_t)x.c * 2, (cuuint64_t)x.w * x.c * 2, (cuuint64_t)x.h * x.w * x.c * 2};
+  const cuuint32_t box[4] = {64, (cuuint32_t)kC3Box, 1, 1};   // one halo row per TMA instruction
+  (void)th;
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = get_encode_tiled()(m, tmap_dtype(x.dt), 4, x.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(XRD_ERR_CUDA, "cuTensorMapEncodeTiled(conv3 activations) failed: %d", (int)r);
+}
+}  // namespace
+
+void conv3(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y) {
+  XRD_REQUIRE(conv3_supported(x1, x2, w, e), "conv3: unsupported configuration");
+  const int c0 = x1.c, c1 = x2 ? x2->c : 0;
+  XRD_REQUIRE(c0 + c1 == w.cin && y.n == x1.n && y.h == x1.h && y.w == x1.w && y.c == w.cout && y.dt == x1.dt, "conv3: shape mismatch");
+  if (x2) XRD_REQUIRE(x2->n == x1.n && x2->h == x1.h && x2->w == x1.w && x2->dt == x1.dt, "conv3: source mismatch");
+  if (e.resid.p) XRD_REQUIRE(e.resid.dt == y.dt && e.resid.numel() == y.numel(), "conv3: residual mismatch");
+  if (c.dry) return;
+  if (!w.wtc[x1.dt] || w.tc_c1 != c0) conv_tc_pack(c.s, w, x1.dt, c0);
+  Conv3P p;
+  p.H = x1.h; p.W = x1.w; p.nimg = x1.n;
+  p.c0 = c0; p.c1 = c1;
+  p.nchunk0 = (c0 + 63) / 64;
+  p.nchunk = p.nchunk0 + (c1 + 63) / 64;
+  const int nkb = p.nchunk * 9;
+  XRD_REQUIRE(nkb == w.tc_nkb && w.tc_npad == w.cout, "conv3: packed weights out of date");
+  const C3Cfg g = c3_plan(w.cout, nkb);
+  p.nb = g.nb;
+  p.tiles_w = x1.w / 128;
+  p.tiles_h = cdiv(x1.h, g.th);
+  p.ntiles = p.tiles_w * p.tiles_h * x1.n;
+  p.dbg = c3_env("XRD_C3_DBG", 0);
+  p.rowload = 1;
+  p.bias = w.bias;
+  p.chan_add = e.chan_add; p.chan_add_bstride = e.chan_add_bstride;
+  p.resid = e.resid.p; p.y = y.p;
+  p.stats = e.stats_out;
+  p.prof = nullptr;
+  static long long* prof_buf = nullptr;
+  const int want_prof = c3_env("XRD_C3_PROF", 0);
+  if (want_prof) {
+    if (!prof_buf) { XRD_CUDA(cudaMalloc(&prof_buf, 64 * 8 * sizeof(long long))); }
+    XRD_CUDA(cudaMemsetAsync(prof_buf, 0, 64 * 8 * sizeof(long long), c.s));
+    p.prof = prof_buf;
+  }
+
+  alignas(64) CUtensorMap tmA0, tmA1, tmB;
+  c3_encode_act(&tmA0, x1, g.th);
+  if (x2) c3_encode_act(&tmA1, *x2, g.th); else tmA1 = tmA0;
+  {
+    const cuuint64_t dims[3] = {64, (cuuint64_t)w.cout, (cuuint64_t)nkb};
+    const cuuint64_t strides[2] = {128, (cuuint64_t)w.cout * 128};
+    const cuuint32_t box[3] = {64, (cuuint32_t)w.cout, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = get_encode_tiled()(&tmB, tmap_dtype(x1.dt), 3, w.wtc[x1.dt], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) fail(XRD_ERR_CUDA, "cuTensorMapEncodeTiled(conv3 weights) failed: %d", (int)r);
+  }
+  static int nsm = 0;
+  if (!nsm) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+  const int grid = std::min(p.ntiles, nsm);
+  if (x1.dt == DT_BF16) c3_dispatch<__nv_bfloat16>(c, w.cout, g, grid, tmA0, tmA1, tmB, p);
+  else c3_dispatch<__half>(c, w.cout, g, grid, tmA0, tmA1, tmB, p);
+
+  if (want_prof == 2) {   // dump: per tile, cycles relative to the first sample
+    XRD_CUDA(cudaStreamSynchronize(c.s));
+    long long h[64 * 8];
+    XRD_CUDA(cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost));
+    long long t0 = h[0];
+    for (int i = 0; i < 64 * 8; ++i) if (h[i] && h[i] < t0) t0 = h[i];
+    fprintf(stderr, "CONV3 PROF cin=%d+%d cout=%d W=%d th=%d wres=%d nb=%d nacc=%d dbg=%d: tile prodAempty mmaTop mmaAccFree mmaAfull mmaDone epiTop epiAccFull epiDone\n",
+            c0, c1, w.cout, x1.w, g.th, (int)g.wres, g.nb, g.nacc, p.dbg);
+    for (int t = 0; t < 24; ++t) {
+      fprintf(stderr, "  %2d:", t);
+      for (int j = 0; j < 8; ++j) fprintf(stderr, " %8lld", h[t * 8 + j] ? h[t * 8 + j] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+  }
+}
+
+}  // namespace xrd

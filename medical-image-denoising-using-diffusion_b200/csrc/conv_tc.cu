@@ -13,7 +13,9 @@
 #include "kernels.cuh"
 #include "tc_common.cuh"
 
+#include <algorithm>
 #include <mutex>
+#include <vector>
 #include <stdlib.h>
 
 namespace xrd {
@@ -52,12 +54,15 @@ struct ConvTcP {
   const void* resid;
   void* y;
   int act, d2s;
+  double* stats;            // optional [nimg][8][2] sums of the stored output (stats kernel variant only)
 };
 
 constexpr int kTcThreads = 192;
 constexpr int kABytes = 128 * 128;  // 128 pixels x 64 ch x 2 B
 
-template <typename T>
+// BNS == 0: generic epilogue (runtime bn).  BNS in {48,96,144,192}: bn == cout == BNS, no depth-to-space; the
+// epilogue additionally accumulates the GroupNorm partial sums (8 groups of BNS/8 channels) of what it stores.
+template <typename T, int BNS>
 __global__ void __launch_bounds__(kTcThreads)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
           const __grid_constant__ CUtensorMap tmB, const ConvTcP p) {
@@ -156,6 +161,69 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     const int64_t opix = ((int64_t)img * p.Ho + oh) * p.Wo + ow;
     T* yp = (T*)p.y;
     const T* rp = (const T*)p.resid;
+    if (BNS > 0) {
+      constexpr int CPG = BNS > 0 ? BNS / 8 : 1;
+      float gs[8], gq[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
+#pragma unroll
+      for (int c0 = 0; c0 < BNS; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          const int co = c0 + h8 * 8;
+          float r8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float tv = v[h8 * 8 + j];
+            if (p.bias) tv += __ldg(p.bias + co + j);
+            if (p.chan_add) tv += __ldg(p.chan_add + (int64_t)img * p.chan_add_bstride + co + j);
+            if (p.out_scale) tv *= __ldg(p.out_scale + co + j);
+            r8[j] = tv;
+          }
+          if (pix_ok) {
+            const int64_t o = opix * BNS + co;
+            if (rp) {
+              float q8[8];
+              tc::ld8<T>(rp + o, q8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) r8[j] += q8[j];
+            }
+            if (p.act != ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) r8[j] = act_apply(r8[j], p.act);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int g = (co + j) / CPG;
+              gs[g] += r8[j];
+              gq[g] = fmaf(r8[j], r8[j], gq[g]);
+            }
+            uint4 pk;
+            pk.x = tc::pack2<T>(r8[0], r8[1]); pk.y = tc::pack2<T>(r8[2], r8[3]);
+            pk.z = tc::pack2<T>(r8[4], r8[5]); pk.w = tc::pack2<T>(r8[6], r8[7]);
+            *reinterpret_cast<uint4*>(yp + o) = pk;
+          }
+        }
+      }
+      if (p.stats) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            gs[g] += __shfl_xor_sync(0xffffffffu, gs[g], o);
+            gq[g] += __shfl_xor_sync(0xffffffffu, gq[g], o);
+          }
+        }
+        if (lane < 16) {
+          float sv = 0.f;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) { if (lane == 2 * g) sv = gs[g]; if (lane == 2 * g + 1) sv = gq[g]; }
+          atomicAdd(p.stats + (size_t)img * 16 + lane, (double)sv);
+        }
+      }
+    } else
     for (int c0 = 0; c0 < p.bn; c0 += 16) {
       float v[16];
       __syncwarp();
@@ -266,8 +334,13 @@ void conv_tc_pack(cudaStream_t s, ConvW& w, DType dt, int c1) {
   XRD_CUDA(cudaPeekAtLastError());
 }
 
+bool conv_tc_stats_supported(const ConvW& w) {
+  return !w.d2s && (w.cout == 48 || w.cout == 96 || w.cout == 144 || w.cout == 192);
+}
+
 bool conv_tc_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e) {
   if (x1.dt == DT_F32) return false;
+  if (e.stats_out && !conv_tc_stats_supported(w)) return false;
   if (x1.c % 16 != 0 || (x2 && x2->c % 16 != 0)) return false;
   if (w.cout % 8 != 0) return false;
   if (e.in_scale) return false;
@@ -360,14 +433,36 @@ void conv_tc(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e,
   }
   size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16;
   dim3 grid(p.tiles_w * p.tiles_h * x1.n, npad / bn);
+  // statistics variant: whole cout in one N tile, plain NHWC store
+  const bool want_stats = e.stats_out != nullptr;
+  if (want_stats) XRD_REQUIRE(!w.d2s && bn == w.cout && (bn == 48 || bn == 96 || bn == 144 || bn == 192), "conv_tc: no statistics epilogue for cout=%d", w.cout);
+  p.stats = e.stats_out;
+  auto launch = [&](auto kern) {
+    static std::mutex mu;
+    static std::vector<const void*> done;          // kernels whose dynamic shared-memory limit was already raised
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (std::find(done.begin(), done.end(), (const void*)kern) == done.end()) {
+        XRD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        done.push_back((const void*)kern);
+      }
+    }
+    XRD_LAUNCH(c, kern, grid, kTcThreads, smem, tmA0, tmA1, tmB, p);
+  };
   if (x1.dt == DT_BF16) {
-    static bool attr = false;
-    if (!attr) { XRD_CUDA(cudaFuncSetAttribute(k_conv_tc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
-    XRD_LAUNCH(c, k_conv_tc<__nv_bfloat16>, grid, kTcThreads, smem, tmA0, tmA1, tmB, p);
+    using T = __nv_bfloat16;
+    if (!want_stats) launch(k_conv_tc<T, 0>);
+    else if (bn == 48) launch(k_conv_tc<T, 48>);
+    else if (bn == 96) launch(k_conv_tc<T, 96>);
+    else if (bn == 144) launch(k_conv_tc<T, 144>);
+    else launch(k_conv_tc<T, 192>);
   } else {
-    static bool attr = false;
-    if (!attr) { XRD_CUDA(cudaFuncSetAttribute(k_conv_tc<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
-    XRD_LAUNCH(c, k_conv_tc<__half>, grid, kTcThreads, smem, tmA0, tmA1, tmB, p);
+    using T = __half;
+    if (!want_stats) launch(k_conv_tc<T, 0>);
+    else if (bn == 48) launch(k_conv_tc<T, 48>);
+    else if (bn == 96) launch(k_conv_tc<T, 96>);
+    else if (bn == 144) launch(k_conv_tc<T, 144>);
+    else launch(k_conv_tc<T, 192>);
   }
 }
 

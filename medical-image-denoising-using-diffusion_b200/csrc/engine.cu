@@ -339,10 +339,17 @@ void finalize(Handle& h, int which) {
 // ------------------------------------------------------------------------------------------------
 // network building blocks
 // ------------------------------------------------------------------------------------------------
+// A contraction.  e.stats_out (optional, [N][8][2], zeroed here) receives the GroupNorm sums of the output: from the
+// kernel's own epilogue where it has one, else from a statistics pass over the stored tensor.
 static void conv(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y) {
-  if (c.tc && conv_halo_supported(x1, x2, w, e)) conv_halo(c, x1, w, e, y);
-  else if (c.tc && conv_tc_supported(x1, x2, w, e)) conv_tc(c, x1, x2, w, e, y);
-  else conv_simt(c, x1, x2, w, e, y);
+  if (e.stats_out) zero_async(c, e.stats_out, (size_t)y.n * 16 * sizeof(double));
+  if (c.tc && conv3_supported(x1, x2, w, e)) { conv3(c, x1, x2, w, e, y); return; }
+  if (c.tc && conv_tc_supported(x1, x2, w, e)) { conv_tc(c, x1, x2, w, e, y); return; }
+  ConvEpi e2 = e;
+  e2.stats_out = nullptr;
+  if (c.tc && conv_tc_supported(x1, x2, w, e2)) conv_tc(c, x1, x2, w, e2, y);
+  else conv_simt(c, x1, x2, w, e2, y);
+  if (e.stats_out) gn_stats(c, y, nullptr, 8, e.stats_out);
 }
 
 static void conv_first(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, Tens& y) {
@@ -356,31 +363,60 @@ static double* new_sums(Ctx& c, int n, int groups) {
   return s;
 }
 
-static void resblock(Ctx& c, UNetW& u, ResW& r, const Tens& x1, const Tens* x2, const float* temb, int temb_bstride, Tens& out) {
+// An activation tensor together with the GroupNorm sums of its 8 channel groups ([N][8][2] doubles; null = unknown).
+// Producers fill them in their epilogues so that the consuming GroupNorm (HYB:264,269,288,354) needs no pass of its own.
+struct TS {
+  Tens t;
+  double* st = nullptr;
+};
+
+// sums over the 8 groups of GroupNorm(8, C1 + C2) applied to the virtual concat [x1 | x2]
+static double* concat_stats(Ctx& c, const TS& x1, const TS* x2, int groups) {
+  const int B = x1.t.n;
+  if (!x2) {
+    if (x1.st && groups == 8) return x1.st;
+    double* s = new_sums(c, B, groups);
+    gn_stats(c, x1.t, nullptr, groups, s);
+    return s;
+  }
+  if (x1.st && x2->st && groups == 8 && x1.t.c == x2->t.c) {
+    double* s = c.allocd((size_t)B * 16);
+    gn_merge_stats(c, x1.st, x2->st, s, B);      // groups 0..3 = pairs of x1's groups, 4..7 = pairs of x2's
+    return s;
+  }
+  double* s = new_sums(c, B, groups);
+  gn_stats(c, x1.t, &x2->t, groups, s);
+  return s;
+}
+
+static void resblock(Ctx& c, UNetW& u, ResW& r, const TS& x1, const TS* x2, const float* temb, int temb_bstride, TS& out) {
+  // `out.t` is allocated by the caller; out.st is allocated here (it must outlive this block's scratch)
+  const int B = x1.t.n, H = x1.t.h, W = x1.t.w;
+  out.st = c.allocd((size_t)B * 16);
   const size_t mk = c.a->mark();
-  const int B = x1.n, H = x1.h, W = x1.w;
-  double* s1 = new_sums(c, B, u.groups);
-  gn_stats(c, x1, x2, u.groups, s1);
+  const Tens* x2t = x2 ? &x2->t : nullptr;
+  double* s1 = concat_stats(c, x1, x2, u.groups);
   Tens a1 = c.alloc(B, H, W, r.cin);
-  gn_act(c, x1, x2, u.groups, s1, r.g1, r.b1, 1e-5f, ACT_SILU, a1);
+  gn_act(c, x1.t, x2t, u.groups, s1, r.g1, r.b1, 1e-5f, ACT_SILU, a1);
   Tens hm = c.alloc(B, H, W, r.cout);
+  double* s2 = c.allocd((size_t)B * 16);
   ConvEpi e1;
   e1.chan_add = temb + r.temb_off; e1.chan_add_bstride = temb_bstride;
+  e1.stats_out = s2;
   conv(c, a1, nullptr, r.c1, e1, hm);
-  double* s2 = new_sums(c, B, u.groups);
-  gn_stats(c, hm, nullptr, u.groups, s2);
   Tens a2 = c.alloc(B, H, W, r.cout);
   gn_act(c, hm, nullptr, u.groups, s2, r.g2, r.b2, 1e-5f, ACT_SILU, a2);
   ConvEpi e2;
   if (r.has_rc) {
     Tens rr = c.alloc(B, H, W, r.cout);
-    conv(c, x1, x2, r.rc, ConvEpi(), rr);
+    conv(c, x1.t, x2t, r.rc, ConvEpi(), rr);
     e2.resid = rr;
   } else {
     XRD_REQUIRE(!x2, "resblock: identity skip with a concatenated input");
-    e2.resid = x1;
+    e2.resid = x1.t;
   }
-  conv(c, a2, nullptr, r.c2, e2, out);
+  e2.stats_out = out.st;
+  conv(c, a2, nullptr, r.c2, e2, out.t);
   c.a->release(mk);
 }
 
@@ -389,20 +425,21 @@ static void attention(Ctx& c, const Tens& qkv, int heads, Tens& o) {
   else attention_simt(c, qkv, heads, o);
 }
 
-static void attnblock(Ctx& c, UNetW& u, AttnW& a, const Tens& x, Tens& out) {
+static void attnblock(Ctx& c, UNetW& u, AttnW& a, const TS& x, TS& out) {
+  const int B = x.t.n, H = x.t.h, W = x.t.w;
+  out.st = c.allocd((size_t)B * 16);
   const size_t mk = c.a->mark();
-  const int B = x.n, H = x.h, W = x.w;
-  double* s = new_sums(c, B, u.groups);
-  gn_stats(c, x, nullptr, u.groups, s);
+  double* s = concat_stats(c, x, nullptr, u.groups);
   Tens xn = c.alloc(B, H, W, a.c);
-  gn_act(c, x, nullptr, u.groups, s, a.g, a.b, 1e-5f, ACT_NONE, xn);
+  gn_act(c, x.t, nullptr, u.groups, s, a.g, a.b, 1e-5f, ACT_NONE, xn);
   Tens qkv = c.alloc(B, H, W, 3 * a.c);
   conv(c, xn, nullptr, a.qkv, ConvEpi(), qkv);
   Tens o = c.alloc(B, H, W, a.c);
   attention(c, qkv, u.heads, o);
   ConvEpi e;
-  e.resid = x;
-  conv(c, o, nullptr, a.proj, e, out);
+  e.resid = x.t;
+  e.stats_out = out.st;
+  conv(c, o, nullptr, a.proj, e, out.t);
   c.a->release(mk);
 }
 
@@ -420,69 +457,86 @@ static void unet_eval(Ctx& c, UNetW& u, const float* x, const float* cond, const
   const size_t mk0 = c.a->mark();
   Tens xin; xin.p = (void*)x; xin.n = B; xin.h = H; xin.w = W; xin.c = 1; xin.dt = DT_F32;
   Tens cin = xin; cin.p = (void*)cond;
-  Tens h = c.alloc(B, H, W, u.mc);
-  conv_first(c, xin, &cin, u.in_conv, h);                // cat([x, condition]) never materialised
-  std::vector<Tens> skips;
+  TS h;
+  h.t = c.alloc(B, H, W, u.mc);
+  conv_first(c, xin, &cin, u.in_conv, h.t);              // cat([x, condition]) never materialised
+  std::vector<TS> skips;
   for (const ULayer& L : u.downs) {
     if (L.kind == U_RES) {
       ResW& r = u.res[L.idx];
-      Tens out = c.alloc(B, h.h, h.w, r.cout);
+      TS out;
+      out.t = c.alloc(B, h.t.h, h.t.w, r.cout);
       resblock(c, u, r, h, nullptr, temb, temb_bstride, out);
       h = out;
     } else if (L.kind == U_ATTN) {
-      Tens out = c.alloc(B, h.h, h.w, h.c);
+      TS out;
+      out.t = c.alloc(B, h.t.h, h.t.w, h.t.c);
       attnblock(c, u, u.attn[L.idx], h, out);
       h = out;
     } else {
       ConvW& d = u.down[L.idx];
-      Tens out = c.alloc(B, (h.h + 2 - 3) / 2 + 1, (h.w + 2 - 3) / 2 + 1, d.cout);
-      conv(c, h, nullptr, d, ConvEpi(), out);
+      TS out;
+      out.t = c.alloc(B, (h.t.h + 2 - 3) / 2 + 1, (h.t.w + 2 - 3) / 2 + 1, d.cout);
+      out.st = c.allocd((size_t)B * 16);
+      ConvEpi e;
+      e.stats_out = out.st;
+      conv(c, h.t, nullptr, d, e, out.t);
       h = out;
     }
     skips.push_back(h);
   }
   {
-    Tens o1 = c.alloc(B, h.h, h.w, h.c);
+    TS o1, o2, o3;
+    o1.t = c.alloc(B, h.t.h, h.t.w, h.t.c);
     resblock(c, u, u.res[u.mid1], h, nullptr, temb, temb_bstride, o1);
-    Tens o2 = c.alloc(B, h.h, h.w, h.c);
+    o2.t = c.alloc(B, h.t.h, h.t.w, h.t.c);
     attnblock(c, u, u.attn[u.mid_attn], o1, o2);
-    Tens o3 = c.alloc(B, h.h, h.w, h.c);
+    o3.t = c.alloc(B, h.t.h, h.t.w, h.t.c);
     resblock(c, u, u.res[u.mid2], o2, nullptr, temb, temb_bstride, o3);
     h = o3;
   }
   for (const ULayer& L : u.ups) {
     if (L.kind == U_RES) {
       XRD_REQUIRE(!skips.empty(), "UNet: skip stack underflow");
-      Tens skip = skips.back(); skips.pop_back();
+      TS skip = skips.back(); skips.pop_back();
       ResW& r = u.res[L.idx];
-      Tens xs = h;
-      if (h.h != skip.h || h.w != skip.w) {
-        XRD_REQUIRE(skip.h == 2 * h.h && skip.w == 2 * h.w, "UNet: unsupported skip resize %dx%d -> %dx%d", h.h, h.w, skip.h, skip.w);
-        xs = c.alloc(B, skip.h, skip.w, h.c);
-        upsample2x(c, h, xs);                             // F.interpolate(bilinear) 2x (HYB:381-382)
+      TS xs = h;
+      if (h.t.h != skip.t.h || h.t.w != skip.t.w) {
+        XRD_REQUIRE(skip.t.h == 2 * h.t.h && skip.t.w == 2 * h.t.w, "UNet: unsupported skip resize %dx%d -> %dx%d", h.t.h, h.t.w, skip.t.h,
+                    skip.t.w);
+        xs.t = c.alloc(B, skip.t.h, skip.t.w, h.t.c);
+        xs.st = nullptr;                                  // sums of the resized tensor are not those of its source
+        upsample2x(c, h.t, xs.t);                         // F.interpolate(bilinear) 2x (HYB:381-382)
+        xs.st = new_sums(c, B, 8);
+        gn_stats(c, xs.t, nullptr, 8, xs.st);
       }
-      Tens out = c.alloc(B, skip.h, skip.w, r.cout);
+      TS out;
+      out.t = c.alloc(B, skip.t.h, skip.t.w, r.cout);
       resblock(c, u, r, xs, &skip, temb, temb_bstride, out);
       h = out;
     } else if (L.kind == U_ATTN) {
-      Tens out = c.alloc(B, h.h, h.w, h.c);
+      TS out;
+      out.t = c.alloc(B, h.t.h, h.t.w, h.t.c);
       attnblock(c, u, u.attn[L.idx], h, out);
       h = out;
     } else {
       // ConvTranspose2d + the 0.5x bilinear that always follows it == one pre-combined 3x3 conv at this resolution
-      XRD_REQUIRE(!skips.empty() && skips.back().h == h.h && skips.back().w == h.w,
+      XRD_REQUIRE(!skips.empty() && skips.back().t.h == h.t.h && skips.back().t.w == h.t.w,
                   "UNet: this configuration consumes a ConvTranspose2d output at full size; only the reference topology is implemented");
       ConvW& up = u.up[L.idx];
-      Tens out = c.alloc(B, h.h, h.w, up.cout);
-      conv(c, h, nullptr, up, ConvEpi(), out);
+      TS out;
+      out.t = c.alloc(B, h.t.h, h.t.w, up.cout);
+      out.st = c.allocd((size_t)B * 16);
+      ConvEpi e;
+      e.stats_out = out.st;
+      conv(c, h.t, nullptr, up, e, out.t);
       h = out;
     }
   }
-  XRD_REQUIRE(h.h == H && h.w == W && h.c == u.out_c, "UNet: output resolution mismatch");
-  double* s = new_sums(c, B, u.groups);
-  gn_stats(c, h, nullptr, u.groups, s);
+  XRD_REQUIRE(h.t.h == H && h.t.w == W && h.t.c == u.out_c, "UNet: output resolution mismatch");
+  double* s = concat_stats(c, h, nullptr, u.groups);
   Cout1Args a;
-  a.x = h; a.k = 3; a.w = u.ow; a.bias = u.obias;
+  a.x = h.t; a.k = 3; a.w = u.ow; a.bias = u.obias;
   a.gn_sums = s; a.groups = u.groups; a.gamma = u.og; a.beta = u.ob; a.eps = 1e-5f; a.act_in = ACT_SILU;
   a.mode = o.mode; a.y = o.y; a.x_cur = o.x_cur; a.x_next = o.x_next; a.c1 = o.c1; a.c2 = o.c2;
   conv_cout1(c, a);

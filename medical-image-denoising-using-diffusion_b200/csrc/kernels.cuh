@@ -26,6 +26,7 @@ struct ConvEpi {
   const float* out_scale = nullptr; // per-cout scale applied to (acc+bias) (NAFNet beta/gamma)
   Tens resid;                       // optional residual with the output's layout
   int act = ACT_NONE;
+  double* stats_out = nullptr;      // optional [N][8][2] += (sum, sum of squares) of the stored output over 8 channel groups
 };
 
 // --- contractions ---------------------------------------------------------
@@ -34,9 +35,10 @@ void conv_simt(Ctx& c, const Tens& x1, const Tens* x2, const ConvW& w, const Con
 // tcgen05 implicit GEMM (conv_tc.cu); same contract, bf16/f16 operands.
 void conv_tc(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y);
 bool conv_tc_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e);
-// persistent halo-reusing variant for 3x3/s1/p1 on maps whose width is a multiple of 128 (conv_halo.cu)
-bool conv_halo_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e);
-void conv_halo(Ctx& c, const Tens& x, ConvW& w, const ConvEpi& e, Tens& y);
+bool conv_tc_stats_supported(const ConvW& w);   // can the epilogue emit GroupNorm sums (ConvEpi::stats_out) for this layer
+// persistent halo-reusing variant for 3x3/s1/p1 on maps whose width is a multiple of 128 (conv3.cu)
+bool conv3_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e);
+void conv3(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y);
 // build w.wtc[dt] from w.w (device side); c1 = channels of source 1
 void conv_tc_pack(cudaStream_t s, ConvW& w, DType dt, int c1);
 
@@ -55,6 +57,8 @@ void gn_stats(Ctx& c, const Tens& x1, const Tens* x2, int groups, double* sums);
 void gn_act(Ctx& c, const Tens& x1, const Tens* x2, int groups, const double* sums, const float* gamma,
             const float* beta, float eps, int act, Tens& y);
 void zero_async(Ctx& c, void* p, size_t bytes);
+// out[n][g] = a[n][2g] + a[n][2g+1] (g < 4), b[n][2(g-4)] + b[n][2(g-4)+1] (g >= 4): sums of GroupNorm(8, 2C) over [a | b]
+void gn_merge_stats(Ctx& c, const double* a, const double* b, double* out, int N);
 void upsample2x(Ctx& c, const Tens& x, Tens& y);       // bilinear, align_corners=False, exact 2x
 void layernorm(Ctx& c, const Tens& x, const float* g, const float* b, float eps, Tens& y);
 // depthwise 3x3 (pad 1) on u[...,2C] -> SimpleGate -> g[...,C]; pool[N][C] += spatial sums (caller zeroes)

@@ -104,6 +104,18 @@ static int pick_ppb(int HW, int N, int ppi) {
   return (int)std::min<int64_t>(ppb, std::max(HW, 1));
 }
 
+__global__ void k_gn_merge_stats(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;     // (n, g, which)
+  if (i >= N * 16) return;
+  const int n = i >> 4, g = (i >> 1) & 7, k = i & 1;
+  const double* src = (g < 4 ? a : b) + (size_t)n * 16 + (size_t)(g & 3) * 4 + k;
+  out[i] = src[0] + src[2];
+}
+
+void gn_merge_stats(Ctx& c, const double* a, const double* b, double* out, int N) {
+  XRD_LAUNCH(c, k_gn_merge_stats, cdiv(N * 16, 128), 128, 0, a, b, out, N);
+}
+
 void gn_stats(Ctx& c, const Tens& x1, const Tens* x2, int groups, double* sums) {
   const int c1 = x1.c, c2 = x2 ? x2->c : 0, ctot = c1 + c2;
   const int VN = (int)(16 / dsize(x1.dt));

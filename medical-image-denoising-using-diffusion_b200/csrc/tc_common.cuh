@@ -9,6 +9,23 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// exactly one lane of a converged warp (full mask); lets ptxas issue tcgen05/TMA from the uniform datapath
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// same, also returning the elected lane (to broadcast state the leader updated)
+__device__ __forceinline__ bool elect_one(uint32_t& leader) {
+  uint32_t pred, l;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync %1|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred), "=r"(l));
+  leader = l;
+  return pred != 0;
+}
+template <typename T> __device__ __forceinline__ constexpr int umma_fmt();      // kind::f16 operand format field
+template <> __device__ __forceinline__ constexpr int umma_fmt<__half>() { return 0; }
+template <> __device__ __forceinline__ constexpr int umma_fmt<__nv_bfloat16>() { return 1; }
+
 // ---- mbarrier -------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

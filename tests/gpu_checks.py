@@ -52,6 +52,17 @@ class OpHandle:
         torch.cuda.synchronize()
         return y
 
+    def conv2d_stats(self, x, w, b, k, stride, pad, impl):
+        """conv + the per-(image, 8 channel groups) sum / sum of squares its epilogue accumulates"""
+        B, Cin, H, W = x.shape
+        Cout = w.shape[0]
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        y = torch.empty(B, Cout, Ho, Wo, device=x.device, dtype=torch.float32)
+        st = torch.zeros(B, 8, 2, device=x.device, dtype=torch.float64)
+        _lib.check(self.lib.xrd_op_conv2d_stats(self.h, impl, _p(x), _p(w), _p(b), _p(y), _p(st), B, Cin, H, W, Cout, k, stride, pad, None))
+        torch.cuda.synchronize()
+        return y, st
+
     def time_last(self, iters=20):
         ms = C.c_float()
         _lib.check(self.lib.xrd_op_time_last(self.h, iters, C.byref(ms), None))
@@ -95,6 +106,34 @@ CONV_CASES_HALO = [   # 3x3/s1/p1, W % 128 == 0 (persistent halo kernel)
     (1, 48, 8, 128, 48, 3, 1, 1), (2, 96, 6, 256, 96, 3, 1, 1), (1, 144, 5, 128, 144, 3, 1, 1), (1, 192, 4, 128, 96, 3, 1, 1),
     (1, 96, 7, 128, 48, 3, 1, 1), (3, 48, 16, 256, 96, 3, 1, 1), (1, 288, 4, 128, 144, 3, 1, 1), (1, 48, 40, 512, 48, 3, 1, 1),
 ]
+
+
+CONV_CASES_HALO_CAT = [   # same kernel over a virtual concat of the two channel halves (B = 1)
+    (1, 96, 7, 128, 48, 3, 1, 1), (1, 192, 6, 256, 96, 3, 1, 1), (1, 288, 5, 128, 144, 3, 1, 1), (1, 192, 9, 128, 48, 3, 1, 1),
+    (1, 96, 4, 128, 96, 3, 1, 1), (1, 288, 3, 128, 96, 3, 1, 1),
+]
+
+
+def check_conv_stats(mode, impl, cases, seed=5):
+    """GroupNorm partial sums from the conv epilogue vs the sums of the (fp64) reference output."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    oh = OpHandle(mode)
+    out = {}
+    try:
+        for (B, Cin, H, W, Cout, k, s, p) in cases:
+            x = torch.randn(B, Cin, H, W, generator=g).to(DEV)
+            w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(DEV)
+            b = torch.randn(Cout, generator=g).to(DEV)
+            dt = torch.bfloat16 if mode == "bf16" else torch.float16
+            ref = F.conv2d(x.to(dt).double(), w.to(dt).double(), b.double(), stride=s, padding=p)
+            y, st = oh.conv2d_stats(x, w, b, k, s, p, impl)
+            r = ref.reshape(B, 8, -1)
+            rs = torch.stack([r.sum(-1), (r * r).sum(-1)], dim=-1)
+            n = r.shape[-1]
+            out[f"{B}x{Cin}x{H}x{W}->{Cout}"] = float(((st - rs).abs() / n).max())    # error of the mean / mean square
+    finally:
+        oh.close()
+    return out
 
 
 def check_conv(mode, impl, cases, seed=0):
@@ -272,6 +311,9 @@ CHECKS = {
     "conv_tc_fp16": lambda: check_conv("fp16", 1, CONV_CASES_TC),
     "conv_halo_fp16": lambda: check_conv("fp16", 2, CONV_CASES_HALO),
     "conv_halo_bf16": lambda: check_conv("bf16", 2, CONV_CASES_HALO),
+    "conv_halo_cat_fp16": lambda: check_conv("fp16", 3, CONV_CASES_HALO_CAT),
+    "conv_tc_cat_fp16": lambda: check_conv("fp16", 4, CONV_CASES_HALO_CAT),
+    "conv_halo_stats_fp16": lambda: check_conv_stats("fp16", 2, CONV_CASES_HALO),
     "attention_tc_bf16": lambda: check_attention("bf16", 1),
     "attention_tc_fp16": lambda: check_attention("fp16", 1),
     "nafnet_fp32": lambda: check_nafnet("fp32"),

@@ -38,6 +38,13 @@ def test_conv_tcgen05_halo_persistent():
         assert e < 6e-4, (k, e)
     for k, e in G.check_conv("bf16", 2, G.CONV_CASES_HALO).items():
         assert e < 5e-3, (k, e)
+    # virtual channel concat (torch.cat([x, skip]) in the up path, HYB:383) through both tcgen05 kernels
+    for impl in (3, 4):
+        for k, e in G.check_conv("fp16", impl, G.CONV_CASES_HALO_CAT).items():
+            assert e < 6e-4, (impl, k, e)
+    # GroupNorm statistics accumulated by the epilogue (replace the separate statistics pass of HYB:264,269)
+    for k, e in G.check_conv_stats("fp16", 2, G.CONV_CASES_HALO).items():
+        assert e < 2e-3, (k, e)
 
 
 def test_groupnorm_act():
