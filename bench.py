@@ -134,7 +134,7 @@ def run_reference(args, rank, world):
 
 
 def conv_roofline(model, dev, batch, size):
-    """Dominant kernel = k_conv_tc (tcgen05 implicit GEMM).  Time every distinct conv layer shape of one UNet
+    """Dominant kernels = k_conv3 / k_conv_tc (tcgen05 implicit GEMM).  Time every distinct conv layer shape of one UNet
     evaluation live (CUDA events on the launching stream, via the C ABI op hook that launches the very same
     kernel) and return launch-weighted achieved TFLOP/s = sum(algorithmic FLOPs) / sum(kernel time)."""
     import ctypes as C
@@ -161,7 +161,9 @@ def conv_roofline(model, dev, batch, size):
         b = torch.zeros(co, device=dev)
         ho = (hh + 2 * (k // 2) - k) // st + 1
         y = torch.empty(batch, co, ho, ho, device=dev)
-        _lib.check(lib.xrd_op_conv2d(h, 1, C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()),
+        # same dispatch as the engine: the persistent halo kernel (conv3.cu) where it applies, else the per-tap kernel
+        impl = 2 if (k == 3 and st == 1 and hh % 128 == 0 and co in (48, 96, 144)) else 1
+        _lib.check(lib.xrd_op_conv2d(h, impl, C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()),
                                      C.c_void_p(y.data_ptr()), batch, ci, hh, hh, co, k, st, k // 2, None))
         _lib.check(lib.xrd_op_time_last(h, 5, C.byref(ms), None))
         tot_ms += cnt * ms.value
@@ -284,7 +286,7 @@ def main():
                    "parallelism": f"image-sharded x{world}, output all_gather only"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": B * S * S * 4, "d2h_bytes_per_step": B * S * S * 4},
-        "roofline": {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 implicit-GEMM conv), all UNet conv shapes of one evaluation, launch weighted",
+        "roofline": {"bound": "tensor", "kernel": "k_conv3 + k_conv_tc (tcgen05 implicit-GEMM convolutions), all UNet conv shapes of one evaluation, launch weighted",
                      "achieved": conv_tf, "peak": pk["burst"], "unit": "TFLOP/s", "frac": conv_tf / pk["burst"] if pk["burst"] else None,
                      "peak_kind": f"bf16 dense burst, {pk['src']}", "traffic": None,
                      "flops_per_eval": conv_fl, "ms_per_eval_isolated": conv_ms, "launches_per_eval": conv_launches},

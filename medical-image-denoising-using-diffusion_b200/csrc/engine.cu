@@ -352,9 +352,18 @@ static void conv(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi
   if (e.stats_out) gn_stats(c, y, nullptr, 8, e.stats_out);
 }
 
-static void conv_first(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, Tens& y) {
+// first conv of a network (1..3 fp32 input planes).  stats (nullable, [N][8][2]): GroupNorm sums of y, zeroed here.
+// Returns false when the statistics were not produced (the caller then runs a statistics pass).
+static bool conv_first(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, Tens& y, double* stats = nullptr) {
+  if (conv_smallcin2_supported(x1, x2, w)) {
+    const bool st = stats && conv_smallcin2_stats_supported(x1);
+    if (st) zero_async(c, stats, (size_t)y.n * 16 * sizeof(double));
+    conv_smallcin2(c, x1, x2, w, y, st ? stats : nullptr);
+    return st;
+  }
   if (conv_smallcin_supported(x1, x2, w)) conv_smallcin(c, x1, x2, w, y);
   else conv_simt(c, x1, x2, w, ConvEpi(), y);
+  return false;
 }
 
 static double* new_sums(Ctx& c, int n, int groups) {
@@ -459,7 +468,10 @@ static void unet_eval(Ctx& c, UNetW& u, const float* x, const float* cond, const
   Tens cin = xin; cin.p = (void*)cond;
   TS h;
   h.t = c.alloc(B, H, W, u.mc);
-  conv_first(c, xin, &cin, u.in_conv, h.t);              // cat([x, condition]) never materialised
+  {
+    double* st = c.allocd((size_t)B * 16);
+    if (conv_first(c, xin, &cin, u.in_conv, h.t, st)) h.st = st;   // cat([x, condition]) never materialised
+  }
   std::vector<TS> skips;
   for (const ULayer& L : u.downs) {
     if (L.kind == U_RES) {
@@ -505,10 +517,8 @@ static void unet_eval(Ctx& c, UNetW& u, const float* x, const float* cond, const
         XRD_REQUIRE(skip.t.h == 2 * h.t.h && skip.t.w == 2 * h.t.w, "UNet: unsupported skip resize %dx%d -> %dx%d", h.t.h, h.t.w, skip.t.h,
                     skip.t.w);
         xs.t = c.alloc(B, skip.t.h, skip.t.w, h.t.c);
-        xs.st = nullptr;                                  // sums of the resized tensor are not those of its source
-        upsample2x(c, h.t, xs.t);                         // F.interpolate(bilinear) 2x (HYB:381-382)
-        xs.st = new_sums(c, B, 8);
-        gn_stats(c, xs.t, nullptr, 8, xs.st);
+        xs.st = new_sums(c, B, 8);                        // sums of the resized tensor are not those of its source
+        upsample2x_stats(c, h.t, xs.t, xs.st);            // F.interpolate(bilinear) 2x (HYB:381-382)
       }
       TS out;
       out.t = c.alloc(B, skip.t.h, skip.t.w, r.cout);

@@ -45,6 +45,10 @@ void conv_tc_pack(cudaStream_t s, ConvW& w, DType dt, int c1);
 // direct 3x3/s1/p1 conv for Cin <= 4 read from fp32 planes (first conv of every network)
 bool conv_smallcin_supported(const Tens& x1, const Tens* x2, const ConvW& w);
 void conv_smallcin(Ctx& c, const Tens& x1, const Tens* x2, const ConvW& w, Tens& y);
+// one pixel per thread, all output channels (Cin <= 3, Cout in {32,48}); stats: optional GroupNorm sums [N][8][2] of y
+bool conv_smallcin2_supported(const Tens& x1, const Tens* x2, const ConvW& w);
+bool conv_smallcin2_stats_supported(const Tens& x1);
+void conv_smallcin2(Ctx& c, const Tens& x1, const Tens* x2, const ConvW& w, Tens& y, double* stats);
 
 // softmax(q^T k / sqrt(d)) v; qkv [N,HW,3*heads*d] (channel = s*heads*d + head*d + j), out [N,HW,heads*d]
 void attention_simt(Ctx& c, const Tens& qkv, int heads, Tens& out);
@@ -60,6 +64,8 @@ void zero_async(Ctx& c, void* p, size_t bytes);
 // out[n][g] = a[n][2g] + a[n][2g+1] (g < 4), b[n][2(g-4)] + b[n][2(g-4)+1] (g >= 4): sums of GroupNorm(8, 2C) over [a | b]
 void gn_merge_stats(Ctx& c, const double* a, const double* b, double* out, int N);
 void upsample2x(Ctx& c, const Tens& x, Tens& y);       // bilinear, align_corners=False, exact 2x
+// same, 16 bytes per access, fused with the GroupNorm sums of y (stats nullable, [N][8][2], zeroed by the caller)
+void upsample2x_stats(Ctx& c, const Tens& x, Tens& y, double* stats);
 void layernorm(Ctx& c, const Tens& x, const float* g, const float* b, float eps, Tens& y);
 // depthwise 3x3 (pad 1) on u[...,2C] -> SimpleGate -> g[...,C]; pool[N][C] += spatial sums (caller zeroes)
 void dwconv_gate_pool(Ctx& c, const Tens& u, const float* w9, const float* bias, Tens& g, float* pool);
@@ -92,6 +98,8 @@ struct Cout1Args {
   float c1 = 0.f, c2 = 0.f;        // mode 3: 1/sqrt(alpha_t), (1-alpha_t)/sqrt(1-alpha_hat_t)
 };
 void conv_cout1(Ctx& c, const Cout1Args& a);
+bool conv_cout1_v2_supported(const Cout1Args& a);     // C in {32,48}, 3x3: per-pixel tap dot products + smem gather (kernels_edge.cu)
+void conv_cout1_v2(Ctx& c, const Cout1Args& a);
 
 // --- time embedding -----------------------------------------------------------
 struct TimeEmbW {

@@ -388,6 +388,7 @@ __global__ void __launch_bounds__(256) k_conv_cout1_tiled(Cout1T p) {
 }
 
 void conv_cout1(Ctx& c, const Cout1Args& a) {
+  if (conv_cout1_v2_supported(a)) { conv_cout1_v2(c, a); return; }
   const int VN = (int)(16 / dsize(a.x.dt));
   const size_t smem = ((size_t)a.x.c * 324 + 11 * (size_t)a.x.c) * sizeof(float);
   if (a.k != 3 || a.x.c % VN != 0 || smem > 200 * 1024) { conv_cout1_v1(c, a); return; }
