@@ -125,28 +125,32 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      const int nkb0 = p.nchunk0 * p.ntaps;
-      for (int kb = 0; kb < p.nkb; ++kb) {
-        tc::mbar_wait(&full_bar[stage], phase);
-        tc::tc_fence_after();
-        const bool second = kb >= nkb0;
-        const int k2 = second ? kb - nkb0 : kb;
-        const int chunk = k2 / p.ntaps;
-        const int cs = second ? p.c_src1 : p.c_src0;
-        const int ksteps = min(64, cs - chunk * 64) >> 4;
+    // The warp stays converged; one elected lane issues with compile-time k offsets (issuing from an `if (lane == 0)`
+    // branch makes ptxas wrap every tcgen05.mma in an ELECT/BRA loop).
+    int stage = 0; uint32_t phase = 0;
+    const int nkb0 = p.nchunk0 * p.ntaps;
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      tc::mbar_wait(&full_bar[stage], phase);
+      tc::tc_fence_after();
+      const bool second = kb >= nkb0;
+      const int k2 = second ? kb - nkb0 : kb;
+      const int chunk = k2 / p.ntaps;
+      const int cs = second ? p.c_src1 : p.c_src0;
+      const int ksteps = min(64, cs - chunk * 64) >> 4;
+      if (tc::elect_one()) {
         const uint32_t sa = tc::smem_u32(smem + (size_t)stage * stage_bytes);
         const uint64_t adesc = tc::umma_desc_sw128(sa);
         const uint64_t bdesc = tc::umma_desc_sw128(sa + kABytes);
-        for (int k = 0; k < ksteps; ++k) {
-          // +32 B per 16-element K step inside the 128 B swizzle row (start-address field is in 16 B units)
-          tc::umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kb | k) ? 1u : 0u);
-        }
+        // +32 B per 16-element K step inside the 128 B swizzle row (start-address field is in 16 B units)
+        tc::umma_f16(tmem_base, adesc, bdesc, p.idesc, kb ? 1u : 0u);
+        if (ksteps > 1) tc::umma_f16(tmem_base, adesc + 2, bdesc + 2, p.idesc, 1u);
+        if (ksteps > 2) tc::umma_f16(tmem_base, adesc + 4, bdesc + 4, p.idesc, 1u);
+        if (ksteps > 3) tc::umma_f16(tmem_base, adesc + 6, bdesc + 6, p.idesc, 1u);
         tc::umma_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs retire
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        if (kb == p.nkb - 1) tc::umma_commit(tmem_full);   // accumulator complete
       }
-      tc::umma_commit(tmem_full);             // accumulator complete
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
