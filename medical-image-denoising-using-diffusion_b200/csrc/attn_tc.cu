@@ -1,31 +1,37 @@
 // attn_tc.cu -- flash-style self-attention on tcgen05 (AttentionBlock, HYB:292-305).
 //
-//   per CTA: 128 queries of one (image, head); loop over 128-key tiles j:
-//     S_j = Q K_j^T        tcgen05.mma, A = Q smem (K-major), B = K smem (K-major), D = TMEM S[j&1] (double buffered)
-//     P_j = exp2((S_j - m) * scale * log2e)   softmax warps: ONE tcgen05.ld pass -> registers -> f16/bf16 -> smem P[j&1]
-//     O  += P_j V_j        tcgen05.mma, A = P smem, B = V smem (MN-major: keys are the K dimension), D = TMEM O, accumulating
-//   The running output never leaves TMEM: the reference maximum m is only raised when a row's new maximum exceeds
-//   it by more than 2^8 (P stays below 256, exact after the final division by the row sum accumulated with the same
-//   m); only then is O rescaled in place (tcgen05.ld / tcgen05.st), which after the first tiles almost never happens.
-//   So the per-tile critical path is the softmax warpgroup alone; Q K^T of tile j+1 and P V of tile j-1 run under it.
-//   warp 0 = TMA producer (Q once, K/V double buffered), warp 1 = MMA issuer + TMEM owner,
-//   warps 2..5 = softmax / correction / epilogue.  The (n, N, N) score matrix never exists in HBM.
+//   per CTA: 256 queries (two 128-row Q tiles) of one (image, head); loop over 64-key tiles j; for each Q tile t:
+//     S_t,j = Q_t K_j^T     tcgen05.mma, A = Q smem (K-major), B = K smem (K-major), D = TMEM S[t][j&1]
+//     P_t,j = exp2((S - m) * scale * log2e)   softmax warps: one tcgen05.ld pass -> registers -> f16/bf16 -> smem P[t][j&1]
+//     O_t  += P_t,j V_j     tcgen05.mma, A = P smem, B = V smem (MN-major: keys are the K dimension), D = TMEM O[t]
+//   * K/V tiles are what every CTA re-streams from L2 (measured: that traffic, not the tensor pipe, bounded the
+//     one-Q-tile version); two Q tiles per CTA halve it, and two softmax warpgroups keep the MUFU pipe busy.
+//   * The running output never leaves TMEM: the reference maximum m is only raised when a row's new maximum exceeds
+//     it by more than 2^8 (P stays below 256, exact after the final division by the row sum accumulated with the
+//     same m); only then is O rescaled in place (tcgen05.ld / tcgen05.st) -- after the first tiles almost never.
+//   * 64-key tiles keep S in 64 registers per thread and leave room for a 6-deep K/V ring in shared memory.
+//   warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 / 6..9 = softmax of Q tile 0 / 1.
+//   The (n, N, N) score matrix never exists in HBM.
 #include "kernels.cuh"
 #include "tc_common.cuh"
+
+#include <stdlib.h>
 
 namespace xrd {
 
 struct AttnTcP {
   int HW, heads, d;
-  int nkv;                 // number of 128-key tiles
+  int nkv;                 // number of 64-key tiles
   int nchunk;              // 64-channel chunks of the head dim (1 or 2)
   float scale_log2e;       // d^-0.5 * log2(e)
   uint32_t idesc_qk, idesc_pv;
   void* out;
 };
 
-constexpr int kAttThreads = 192;
-constexpr int kTile = 128 * 128;       // one [128 rows x 64 x 16-bit] swizzled tile = 16 KB
+constexpr int kAttThreads = 320;       // warp 0 TMA, warp 1 MMA issuer, warps 2..9 softmax
+constexpr int kTile = 128 * 128;       // Q / P tile: [128 rows x 64 x 16-bit], 128B-swizzled = 16 KB
+constexpr int kKvTile = 64 * 128;      // K / V chunk tile: [64 keys x 64 ch] = 8 KB
+constexpr int kRing = 3;               // K ring slots and V ring slots (2 chunk tiles each)
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -84,38 +90,51 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 constexpr float kRescaleLog2 = 8.0f;   // raise the reference maximum only when P would exceed 2^8
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 template <typename T, int DC>   // DC = ceil(d / 32): 32-column chunks of the output row
-__global__ void __launch_bounds__(kAttThreads, 1) k_attn_tc(const __grid_constant__ CUtensorMap tmQKV, const AttnTcP p) {
+__global__ void __launch_bounds__(kAttThreads, 1)
+k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnTcP p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  // layout: Q [2 tiles] | KV stage 0: K [2 tiles] V [2 tiles] | KV stage 1 | P buffer 0 [2 tiles] | P buffer 1 | barriers
+  // layout: Q [2 q-tiles][2 chunks] | P [2 q-tiles][2 buffers] | K ring [kRing][2 chunks] | V ring [kRing][2 chunks] | barriers
   uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + 2 * kTile;
-  uint8_t* sP = sKV + 2 * 4 * kTile;
-  uint64_t* bars = (uint64_t*)(sP + 4 * kTile);
+  uint8_t* sP = sQ + 4 * kTile;
+  uint8_t* sK = sP + 4 * kTile;
+  uint8_t* sV = sK + kRing * 2 * kKvTile;
+  uint64_t* bars = (uint64_t*)(sV + kRing * 2 * kKvTile);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;    // [2]
-  uint64_t* kv_empty = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;     // [2]
-  uint64_t* s_free = bars + 7;     // [2]
-  uint64_t* p_full = bars + 9;     // [2]
-  uint64_t* p_free = bars + 11;    // [2]
-  uint64_t* o_done = bars + 13;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 14);
+  uint64_t* k_full = bars + 1;              // [kRing]
+  uint64_t* k_empty = k_full + kRing;       // [kRing]
+  uint64_t* v_full = k_empty + kRing;       // [kRing]
+  uint64_t* v_empty = v_full + kRing;       // [kRing]
+  uint64_t* s_full = v_empty + kRing;       // [2 q-tiles][2]
+  uint64_t* s_free = s_full + 4;
+  uint64_t* p_full = s_free + 4;
+  uint64_t* p_free = p_full + 4;
+  uint64_t* o_done = p_free + 4;            // [2] one phase per P V (parity waits are only valid one phase back)
+  uint64_t* o_final = o_done + 2;           // [2] completes once, after the last P V
+  uint32_t* tmem_slot = (uint32_t*)(o_final + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, head = blockIdx.y, img = blockIdx.z;
+  const int q0 = blockIdx.x * 256, head = blockIdx.y, img = blockIdx.z;
   const int qoff = head * p.d, koff = p.heads * p.d + head * p.d, voff = 2 * p.heads * p.d + head * p.d;
 
   if (warp == 0 && lane == 0) {
-    tc::tma_prefetch_desc(&tmQKV);
+    tc::tma_prefetch_desc(&tmQ);
+    tc::tma_prefetch_desc(&tmKV);
     tc::mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 1);
+    for (int s = 0; s < kRing; ++s) {
+      tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1); tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], 1);
+    }
+    for (int s = 0; s < 4; ++s) {
       tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_free[s], 128);
       tc::mbar_init(&p_full[s], 128); tc::mbar_init(&p_free[s], 1);
     }
-    tc::mbar_init(o_done, 1);
+    tc::mbar_init(&o_done[0], 1); tc::mbar_init(&o_done[1], 1);
+    tc::mbar_init(&o_final[0], 1); tc::mbar_init(&o_final[1], 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) {
@@ -126,119 +145,136 @@ __global__ void __launch_bounds__(kAttThreads, 1) k_attn_tc(const __grid_constan
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_O = tmem_base + 256;      // S buffers at +0 and +128
+  // TMEM columns: S[t][b] at t*128 + b*64 (64 wide), O[t] at 256 + t*128 (d <= 128 wide)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (tc::elect_one()) {
-      tc::mbar_expect_tx(q_full, (uint32_t)p.nchunk * kTile);
-      for (int c = 0; c < p.nchunk; ++c) tc::tma_load_3d(sQ + c * kTile, &tmQKV, q_full, qoff + 64 * c, q0, img);
+      tc::mbar_expect_tx(q_full, (uint32_t)(2 * p.nchunk) * kTile);
+      for (int t = 0; t < 2; ++t)
+        for (int c = 0; c < p.nchunk; ++c) tc::tma_load_3d(sQ + (t * 2 + c) * kTile, &tmQ, q_full, qoff + 64 * c, q0 + t * 128, img);
+      uint32_t slot = 0, phase = 0;
       for (int j = 0; j < p.nkv; ++j) {
-        const int st = j & 1;
-        tc::mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-        uint8_t* sK = sKV + st * 4 * kTile;
-        uint8_t* sV = sK + 2 * kTile;
-        tc::mbar_expect_tx(&kv_full[st], (uint32_t)(2 * p.nchunk) * kTile);
-        for (int c = 0; c < p.nchunk; ++c) {
-          tc::tma_load_3d(sK + c * kTile, &tmQKV, &kv_full[st], koff + 64 * c, j * 128, img);
-          tc::tma_load_3d(sV + c * kTile, &tmQKV, &kv_full[st], voff + 64 * c, j * 128, img);
-        }
+        tc::mbar_wait(&k_empty[slot], phase ^ 1);
+        tc::mbar_expect_tx(&k_full[slot], (uint32_t)p.nchunk * kKvTile);
+        for (int c = 0; c < p.nchunk; ++c) tc::tma_load_3d(sK + (slot * 2 + c) * kKvTile, &tmKV, &k_full[slot], koff + 64 * c, j * 64, img);
+        tc::mbar_wait(&v_empty[slot], phase ^ 1);
+        tc::mbar_expect_tx(&v_full[slot], (uint32_t)p.nchunk * kKvTile);
+        for (int c = 0; c < p.nchunk; ++c) tc::tma_load_3d(sV + (slot * 2 + c) * kKvTile, &tmKV, &v_full[slot], voff + 64 * c, j * 64, img);
+        if (++slot == kRing) { slot = 0; phase ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer (one elected lane; the warp stays converged) =====================
-    const uint32_t aQ = tc::smem_u32(sQ);
+    // order per step j: Q K^T of tile j for both Q tiles (S is double buffered, so this runs under the softmax of
+    // tile j-1), then P V of tile j-1 as soon as its P tiles are published.
+    const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK), aPb = tc::smem_u32(sP), aV = tc::smem_u32(sV);
     const int ks0 = min(64, p.d) >> 4, ks1 = p.nchunk > 1 ? (min(64, p.d - 64) >> 4) : 0;
-    auto issue_pv = [&](int j) {      // O (+)= P_j V_j
-      const int st = j & 1, pb = j & 1;
-      tc::mbar_wait(&p_full[pb], (j >> 1) & 1);
-      tc::tc_fence_after();
-      if (tc::elect_one()) {
-        const uint32_t aP = tc::smem_u32(sP + pb * 2 * kTile);
-        const uint32_t bV = tc::smem_u32(sKV + st * 4 * kTile + 2 * kTile);
+    uint32_t kslot = 0, kphase = 0, vslot = 0, vphase = 0;
+    auto issue_pv = [&](int j) {      // O_t (+)= P_t,j V_j for both Q tiles
+      const int b = j & 1, u = j >> 1;
+      tc::mbar_wait(&v_full[vslot], vphase);
+      for (int t = 0; t < 2; ++t) {
+        tc::mbar_wait(&p_full[t * 2 + b], u & 1);
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
+          // one base descriptor per operand tile, compile-time offsets per k-step (a descriptor rebuilt per MMA costs the
+          // issuing thread ~100 cycles of dependent integer work + R2UR moves, more than the MMA itself)
+          const uint64_t aD = tc::umma_desc_sw128(aPb + (uint32_t)(t * 2 + b) * kTile);
+          const uint64_t bD = umma_desc_mn_sw128(aV + vslot * 2 * kKvTile, kKvTile);
+          const uint32_t tO = tmem_base + 256u + (uint32_t)t * 128u;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {   // 8 x 16 keys
-          const uint64_t ad = tc::umma_desc_sw128(aP + (k >> 2) * kTile + (k & 3) * 32);
-          const uint64_t bd = umma_desc_mn_sw128(bV + k * 2048, kTile);
-          tc::umma_f16(tmem_O, ad, bd, p.idesc_pv, (j | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)     // 4 x 16 keys: +32 B in the K-major P tile, +2048 B (16 key rows) in the MN-major V tile
+            tc::umma_f16(tO, aD + (uint64_t)(k * 2), bD + (uint64_t)(k * (2048 >> 4)), p.idesc_pv, (j | k) ? 1u : 0u);
+          tc::umma_commit(&p_free[t * 2 + b]);
+          tc::umma_commit(&o_done[t]);
+          if (j == p.nkv - 1) tc::umma_commit(&o_final[t]);
+          if (t == 1) tc::umma_commit(&v_empty[vslot]);
         }
-        tc::umma_commit(&p_free[pb]);
-        tc::umma_commit(&kv_empty[st]);
-        tc::umma_commit(o_done);
+        __syncwarp();
       }
-      __syncwarp();
+      if (++vslot == kRing) { vslot = 0; vphase ^= 1; }
     };
     tc::mbar_wait(q_full, 0);
     for (int j = 0; j < p.nkv; ++j) {
-      const int st = j & 1, sb = j & 1;
-      tc::mbar_wait(&kv_full[st], (j >> 1) & 1);
-      tc::mbar_wait(&s_free[sb], ((j >> 1) & 1) ^ 1);       // softmax has drained S_{j-2} from this TMEM buffer
-      tc::tc_fence_after();
-      if (tc::elect_one()) {
-        const uint32_t bK = tc::smem_u32(sKV + st * 4 * kTile);
-        const uint32_t tS = tmem_base + (uint32_t)sb * 128u;
+      const int b = j & 1, u = j >> 1;
+      tc::mbar_wait(&k_full[kslot], kphase);          // K_j
+      for (int t = 0; t < 2; ++t) {
+        tc::mbar_wait(&s_free[t * 2 + b], (u & 1) ^ 1);         // softmax has drained S_t,j-2 from this TMEM buffer
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
+          const uint64_t aD = tc::umma_desc_sw128(aQ + (uint32_t)t * 2 * kTile);
+          const uint64_t bD = tc::umma_desc_sw128(aK + kslot * 2 * kKvTile);
+          const uint32_t tS = tmem_base + (uint32_t)t * 128u + (uint32_t)b * 64u;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < ks0) tc::umma_f16(tS, tc::umma_desc_sw128(aQ + k * 32), tc::umma_desc_sw128(bK + k * 32), p.idesc_qk, k ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            if (k < ks0) tc::umma_f16(tS, aD + (uint64_t)(k * 2), bD + (uint64_t)(k * 2), p.idesc_qk, k ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < ks1) tc::umma_f16(tS, tc::umma_desc_sw128(aQ + kTile + k * 32), tc::umma_desc_sw128(bK + kTile + k * 32), p.idesc_qk, 1u);
-        tc::umma_commit(&s_full[sb]);
+          for (int k = 0; k < 4; ++k)
+            if (k < ks1) tc::umma_f16(tS, aD + (uint64_t)((kTile >> 4) + k * 2), bD + (uint64_t)((kKvTile >> 4) + k * 2), p.idesc_qk, 1u);
+          tc::umma_commit(&s_full[t * 2 + b]);
+          if (t == 1) tc::umma_commit(&k_empty[kslot]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
+      if (++kslot == kRing) { kslot = 0; kphase ^= 1; }
       if (j > 0) issue_pv(j - 1);
     }
     issue_pv(p.nkv - 1);
   } else {
-    // ===================== softmax / correction / epilogue (warps 2..5, one query row per thread) =====================
-    const int quad = warp & 3;
+    // ===================== softmax / correction / epilogue (warps 2..9, one query row per thread) =====================
+    const int t = (warp - 2) >> 2;                 // Q tile
+    const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const int q = q0 + row;
+    const int q = q0 + t * 128 + row;
+    const uint32_t tO = tmem_base + 256u + (uint32_t)t * 128u + lane_addr;
     float m_run = -INFINITY, l_run = 0.f;
     const int sw = row & 7;
+    const uint32_t prow0 = tc::smem_u32(sP) + (uint32_t)(t * 2) * kTile + (uint32_t)row * 128u;
     for (int j = 0; j < p.nkv; ++j) {
-      const int sb = j & 1;
-      tc::mbar_wait(&s_full[sb], (j >> 1) & 1);
+      const int b = j & 1, u = j >> 1;
+      tc::mbar_wait(&s_full[t * 2 + b], u & 1);
       tc::tc_fence_after();
-      float v[128];
-      const uint32_t tS = tmem_base + (uint32_t)sb * 128u + lane_addr;
+      float v[64];
+      const uint32_t tS = tmem_base + (uint32_t)t * 128u + (uint32_t)b * 64u + lane_addr;
       tmem_ld32_nowait(tS, v);
       tmem_ld32_nowait(tS + 32, v + 32);
-      tmem_ld32_nowait(tS + 64, v + 64);
-      tmem_ld32_nowait(tS + 96, v + 96);
       tmem_ld_wait();
       tc::tc_fence_before();
-      tc::mbar_arrive(&s_free[sb]);                  // S_j is in registers: Q K^T of tile j+2 may overwrite this buffer
-      const int kvalid = min(128, p.HW - j * 128);
-      if (kvalid < 128) {
+      tc::mbar_arrive(&s_free[t * 2 + b]);           // S is in registers: Q K^T of tile j+2 may overwrite this buffer
+      const int kvalid = min(64, p.HW - j * 64);
+      if (kvalid < 64) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
+        for (int i = 0; i < 64; ++i)
           if (i >= kvalid) v[i] = -INFINITY;
       }
       float mx0 = v[0], mx1 = v[1], mx2 = v[2], mx3 = v[3];
 #pragma unroll
-      for (int i = 4; i < 128; i += 4) {
+      for (int i = 4; i < 64; i += 4) {
         mx0 = fmaxf(mx0, v[i]); mx1 = fmaxf(mx1, v[i + 1]); mx2 = fmaxf(mx2, v[i + 2]); mx3 = fmaxf(mx3, v[i + 3]);
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // P V of tile j-2 has consumed P[t][b].  It also means o_done has completed at least j-1 phases, which makes the
+      // parity wait for phase j-1 below (and the one of the epilogue) unambiguous.
+      tc::mbar_wait(&p_free[t * 2 + b], (u & 1) ^ 1);
       // lazy reference maximum: keep m_run unless this tile would push P above 2^kRescaleLog2
       const bool need = (mx - m_run) * p.scale_log2e > kRescaleLog2;      // true on the first tile (m_run = -inf)
       if (__any_sync(0xffffffffu, need)) {
         const float m_new = need ? mx : m_run;
         if (j > 0) {
           const float alpha = need ? ex2((m_run - m_new) * p.scale_log2e) : 1.0f;
-          tc::mbar_wait(o_done, (j - 1) & 1);          // P V of tile j-1 has landed in O
+          tc::mbar_wait(&o_done[t], (j - 1) & 1);      // P V of tile j-1 has landed in O
           tc::tc_fence_after();
 #pragma unroll
           for (int c = 0; c < DC; ++c) {
             float o[32];
-            tmem_ld32_nowait(tmem_O + lane_addr + c * 32, o);
+            tmem_ld32_nowait(tO + c * 32, o);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] *= alpha;
-            tmem_st32(tmem_O + lane_addr + c * 32, o);
+            tmem_st32(tO + c * 32, o);
           }
           tmem_st_wait();
           tc::tc_fence_before();
@@ -246,42 +282,33 @@ __global__ void __launch_bounds__(kAttThreads, 1) k_attn_tc(const __grid_constan
         }
         m_run = m_new;
       }
-      const float mb = m_run * p.scale_log2e;
-      // P = exp2(S*c - m*c), rounded to the MMA operand format, written K-major / 128B-swizzled into P[j&1]
-      tc::mbar_wait(&p_free[sb], ((j >> 1) & 1) ^ 1);   // P V of tile j-2 has consumed this buffer
-      uint8_t* prow = sP + sb * 2 * kTile + row * 128;
-      float rs0 = 0.f, rs1 = 0.f;
+      const float sc = p.scale_log2e;
+      const float mb = m_run * sc;
+      // P = exp2(S*c - m*c), rounded to the MMA operand format, written K-major / 128B-swizzled into P[t][b]
+      const uint32_t prow = prow0 + (uint32_t)b * kTile;
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float a = ex2(fmaf(v[c * 32 + i], p.scale_log2e, -mb));
-          const float b = ex2(fmaf(v[c * 32 + i + 1], p.scale_log2e, -mb));
-          rs0 += a; rs1 += b;
-          pk[i >> 1] = pack2<T>(a, b);
-        }
-        // 32 keys = 64 B = 4 x 16 B chunks of this row; keys [64*t, 64*t+64) live in tile t
-        uint8_t* trow = prow + (c >> 1) * kTile;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int chunk = (c & 1) * 4 + u;
-          *reinterpret_cast<uint4*>(trow + ((chunk ^ sw) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-        }
+      for (int c = 0; c < 8; ++c) {                 // 8 keys = one 16-byte chunk of this row
+        const float e0 = ex2(fmaf(v[c * 8 + 0], sc, -mb)), e1 = ex2(fmaf(v[c * 8 + 1], sc, -mb));
+        const float e2 = ex2(fmaf(v[c * 8 + 2], sc, -mb)), e3 = ex2(fmaf(v[c * 8 + 3], sc, -mb));
+        const float e4 = ex2(fmaf(v[c * 8 + 4], sc, -mb)), e5 = ex2(fmaf(v[c * 8 + 5], sc, -mb));
+        const float e6 = ex2(fmaf(v[c * 8 + 6], sc, -mb)), e7 = ex2(fmaf(v[c * 8 + 7], sc, -mb));
+        rs0 += e0; rs1 += e1; rs2 += e2; rs3 += e3; rs0 += e4; rs1 += e5; rs2 += e6; rs3 += e7;
+        st_shared_v4(prow + (uint32_t)((c ^ sw) << 4), pack2<T>(e0, e1), pack2<T>(e2, e3), pack2<T>(e4, e5), pack2<T>(e6, e7));
       }
       tc::fence_async_smem();                       // generic-proxy stores -> visible to the tensor core (async proxy)
-      tc::mbar_arrive(&p_full[sb]);
-      l_run += rs0 + rs1;
+      tc::mbar_arrive(&p_full[t * 2 + b]);
+      l_run += (rs0 + rs1) + (rs2 + rs3);
     }
     // epilogue: O / l -> 16-bit -> out[img, q, head*d + :]
-    tc::mbar_wait(o_done, (p.nkv - 1) & 1);
+    tc::mbar_wait(&o_final[t], 0);
     tc::tc_fence_after();
     const float inv = 1.0f / l_run;
     T* dst = (T*)p.out + ((int64_t)img * p.HW + q) * (p.heads * p.d) + head * p.d;
 #pragma unroll
     for (int c = 0; c < DC; ++c) {
       float o[32];
-      tmem_ld32_nowait(tmem_O + lane_addr + c * 32, o);
+      tmem_ld32_nowait(tO + c * 32, o);
       tmem_ld_wait();
       if (q < p.HW) {
 #pragma unroll
@@ -321,31 +348,32 @@ void attention_tc(Ctx& c, const Tens& qkv, int heads, Tens& out) {
   const int HW = qkv.h * qkv.w;
   AttnTcP p;
   p.HW = HW; p.heads = heads; p.d = d;
-  p.nkv = cdiv(HW, 128);
+  p.nkv = cdiv(HW, 64);
   p.nchunk = cdiv(d, 64);
   p.scale_log2e = (float)((1.0 / sqrt((double)d)) * 1.4426950408889634);
   const int fmt = qkv.dt == DT_BF16 ? 1 : 0;
-  p.idesc_qk = tc::umma_idesc(128, 128, fmt);
+  p.idesc_qk = tc::umma_idesc(128, 64, fmt);
   p.idesc_pv = tc::umma_idesc(128, d, fmt) | (1u << 16);   // B (V) is MN-major
   p.out = out.p;
-  alignas(64) CUtensorMap tm;
-  {
+  alignas(64) CUtensorMap tmQ, tmKV;
+  for (int which = 0; which < 2; ++which) {
     const cuuint64_t dims[3] = {(cuuint64_t)qkv.c, (cuuint64_t)HW, (cuuint64_t)qkv.n};
     const cuuint64_t strides[2] = {(cuuint64_t)qkv.c * 2, (cuuint64_t)HW * qkv.c * 2};
-    const cuuint32_t box[3] = {64, 128, 1};
+    const cuuint32_t box[3] = {64, which == 0 ? 128u : 64u, 1};     // Q tiles: 128 queries; K/V tiles: 64 keys
     const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = get_encode_tiled()(&tm, tmap_dtype(qkv.dt), 3, qkv.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = get_encode_tiled()(which == 0 ? &tmQ : &tmKV, tmap_dtype(qkv.dt), 3, qkv.p, dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) fail(XRD_ERR_CUDA, "cuTensorMapEncodeTiled(qkv) failed: %d", (int)r);
   }
-  const size_t smem = 1024 + (size_t)(2 + 8 + 4) * kTile + 16 * 8;
-  dim3 grid(cdiv(HW, 128), heads, qkv.n);
+  const size_t smem = 1024 + (size_t)8 * kTile + (size_t)2 * kRing * 2 * kKvTile + 64 * 8;
+  dim3 grid(cdiv(HW, 256), heads, qkv.n);
   const int dc = cdiv(d, 32);
 #define XRD_ATT_CASE(TT, DCV)                                                                                             \
   case DCV: {                                                                                                             \
     static bool attr = false;                                                                                             \
     if (!attr) { XRD_CUDA(cudaFuncSetAttribute(k_attn_tc<TT, DCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; } \
-    XRD_LAUNCH(c, (k_attn_tc<TT, DCV>), grid, kAttThreads, smem, tm, p);                                                  \
+    XRD_LAUNCH(c, (k_attn_tc<TT, DCV>), grid, kAttThreads, smem, tmQ, tmKV, p);                                                  \
   } break;
   if (qkv.dt == DT_BF16) {
     switch (dc) { XRD_ATT_CASE(__nv_bfloat16, 1) XRD_ATT_CASE(__nv_bfloat16, 2) XRD_ATT_CASE(__nv_bfloat16, 3) XRD_ATT_CASE(__nv_bfloat16, 4) }

@@ -182,15 +182,26 @@ def check_attention(mode, impl):
     oh = OpHandle(mode)
     out = {}
     try:
-        for (B, heads, d, H, W) in [(2, 2, 96, 8, 8), (1, 2, 96, 16, 16), (1, 2, 96, 4, 4), (1, 2, 96, 32, 32), (1, 1, 64, 12, 10)]:
-            qkv = torch.randn(B, 3 * heads * d, H, W, generator=g).to(DEV)
+        # last two cases: peaked softmax whose row maximum keeps growing along the key axis -- exercises the in-TMEM
+        # rescale of the running output (the reference maximum is only raised when a tile exceeds it by 2^8)
+        for (B, heads, d, H, W, peaked) in [(2, 2, 96, 8, 8, 0), (1, 2, 96, 16, 16, 0), (1, 2, 96, 4, 4, 0), (1, 2, 96, 32, 32, 0),
+                                            (1, 1, 64, 12, 10, 0), (1, 2, 96, 32, 32, 1), (2, 2, 96, 24, 24, 1)]:
+            qkv = torch.randn(B, 3 * heads * d, H, W, generator=g)
+            if peaked:
+                ramp = torch.linspace(0.2, 4.0, H * W).reshape(1, 1, H, W)
+                qkv[:, :heads * d] *= 2.0                      # q
+                qkv[:, heads * d:2 * heads * d] *= ramp        # k: later keys score (much) higher or lower
+            qkv = qkv.to(DEV)
             qr = qkv if mode == "fp32" else qkv.to(torch.bfloat16 if mode == "bf16" else torch.float16).float()
             t = qr.double().reshape(B, 3, heads, d, H * W)
             q, k, v = t[:, 0], t[:, 1], t[:, 2]
             att = torch.softmax(torch.matmul(q.transpose(-2, -1), k) * d ** -0.5, dim=-1)
             ref = torch.matmul(att, v.transpose(-2, -1)).transpose(-2, -1).reshape(B, heads * d, H, W).float()
             y = oh.attention(qkv, heads, d, impl)
-            out[f"{B}x{heads}x{d}x{H}x{W}"] = float((y - ref).abs().max())
+            err = float((y - ref).abs().max())
+            if peaked:      # near one-hot attention: outputs are single V rows (|v| up to ~4), so compare relative to max|ref|
+                err /= float(ref.abs().max())
+            out[f"{B}x{heads}x{d}x{H}x{W}" + ("p" if peaked else "")] = err
     finally:
         oh.close()
     return out
