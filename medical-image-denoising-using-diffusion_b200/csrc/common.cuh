@@ -92,6 +92,15 @@ struct Ctx {
   Tens alloc(int n, int h, int w, int c) { return alloc(n, h, w, c, adt); }
   float* allocf(size_t n) { return (float*)a->alloc(n * 4); }
   double* allocd(size_t n) { return (double*)a->alloc(n * 8); }
+  // pre-zeroed pool for GroupNorm sums: one memset per network evaluation instead of one per tensor
+  double* zpool = nullptr;
+  size_t zpool_off = 0, zpool_cap = 0;
+  double* alloc_zeroed(size_t n) {          // returns null when the pool is exhausted (caller zeroes its own buffer)
+    if (!zpool || zpool_off + n > zpool_cap) return nullptr;
+    double* p = zpool + zpool_off;
+    zpool_off += n;
+    return p;
+  }
 };
 
 // launch helper: counts launches, surfaces configuration errors immediately

@@ -342,7 +342,7 @@ void finalize(Handle& h, int which) {
 // A contraction.  e.stats_out (optional, [N][8][2], zeroed here) receives the GroupNorm sums of the output: from the
 // kernel's own epilogue where it has one, else from a statistics pass over the stored tensor.
 static void conv(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y) {
-  if (e.stats_out) zero_async(c, e.stats_out, (size_t)y.n * 16 * sizeof(double));
+  // e.stats_out comes from stats16(): already zero
   if (c.tc && conv3_supported(x1, x2, w, e)) { conv3(c, x1, x2, w, e, y); return; }
   if (c.tc && conv_tc_supported(x1, x2, w, e)) { conv_tc(c, x1, x2, w, e, y); return; }
   ConvEpi e2 = e;
@@ -352,12 +352,11 @@ static void conv(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi
   if (e.stats_out) gn_stats(c, y, nullptr, 8, e.stats_out);
 }
 
-// first conv of a network (1..3 fp32 input planes).  stats (nullable, [N][8][2]): GroupNorm sums of y, zeroed here.
+// first conv of a network (1..3 fp32 input planes).  stats (nullable, [N][8][2], zero on entry): GroupNorm sums of y.
 // Returns false when the statistics were not produced (the caller then runs a statistics pass).
 static bool conv_first(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, Tens& y, double* stats = nullptr) {
   if (conv_smallcin2_supported(x1, x2, w)) {
     const bool st = stats && conv_smallcin2_stats_supported(x1);
-    if (st) zero_async(c, stats, (size_t)y.n * 16 * sizeof(double));
     conv_smallcin2(c, x1, x2, w, y, st ? stats : nullptr);
     return st;
   }
@@ -367,10 +366,14 @@ static bool conv_first(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, Tens& y
 }
 
 static double* new_sums(Ctx& c, int n, int groups) {
-  double* s = c.allocd((size_t)n * groups * 2);
-  zero_async(c, s, (size_t)n * groups * 2 * sizeof(double));
+  const size_t cnt = (size_t)n * groups * 2;
+  if (double* z = c.alloc_zeroed(cnt)) return z;
+  double* s = c.allocd(cnt);
+  zero_async(c, s, cnt * sizeof(double));
   return s;
 }
+// zeroed [n][8][2] GroupNorm sums for a producer's epilogue
+static double* stats16(Ctx& c, int n) { return new_sums(c, n, 8); }
 
 // An activation tensor together with the GroupNorm sums of its 8 channel groups ([N][8][2] doubles; null = unknown).
 // Producers fill them in their epilogues so that the consuming GroupNorm (HYB:264,269,288,354) needs no pass of its own.
@@ -389,7 +392,7 @@ static double* concat_stats(Ctx& c, const TS& x1, const TS* x2, int groups) {
     return s;
   }
   if (x1.st && x2->st && groups == 8 && x1.t.c == x2->t.c) {
-    double* s = c.allocd((size_t)B * 16);
+    double* s = c.allocd((size_t)B * 16);   // fully overwritten
     gn_merge_stats(c, x1.st, x2->st, s, B);      // groups 0..3 = pairs of x1's groups, 4..7 = pairs of x2's
     return s;
   }
@@ -401,14 +404,14 @@ static double* concat_stats(Ctx& c, const TS& x1, const TS* x2, int groups) {
 static void resblock(Ctx& c, UNetW& u, ResW& r, const TS& x1, const TS* x2, const float* temb, int temb_bstride, TS& out) {
   // `out.t` is allocated by the caller; out.st is allocated here (it must outlive this block's scratch)
   const int B = x1.t.n, H = x1.t.h, W = x1.t.w;
-  out.st = c.allocd((size_t)B * 16);
+  out.st = stats16(c, B);
   const size_t mk = c.a->mark();
   const Tens* x2t = x2 ? &x2->t : nullptr;
   double* s1 = concat_stats(c, x1, x2, u.groups);
   Tens a1 = c.alloc(B, H, W, r.cin);
   gn_act(c, x1.t, x2t, u.groups, s1, r.g1, r.b1, 1e-5f, ACT_SILU, a1);
   Tens hm = c.alloc(B, H, W, r.cout);
-  double* s2 = c.allocd((size_t)B * 16);
+  double* s2 = stats16(c, B);
   ConvEpi e1;
   e1.chan_add = temb + r.temb_off; e1.chan_add_bstride = temb_bstride;
   e1.stats_out = s2;
@@ -436,7 +439,7 @@ static void attention(Ctx& c, const Tens& qkv, int heads, Tens& o) {
 
 static void attnblock(Ctx& c, UNetW& u, AttnW& a, const TS& x, TS& out) {
   const int B = x.t.n, H = x.t.h, W = x.t.w;
-  out.st = c.allocd((size_t)B * 16);
+  out.st = stats16(c, B);
   const size_t mk = c.a->mark();
   double* s = concat_stats(c, x, nullptr, u.groups);
   Tens xn = c.alloc(B, H, W, a.c);
@@ -464,12 +467,18 @@ struct UNetOut {           // what the fused out_conv kernel does with eps
 static void unet_eval(Ctx& c, UNetW& u, const float* x, const float* cond, const float* temb, int temb_bstride, int B, int H, int W,
                       const UNetOut& o) {
   const size_t mk0 = c.a->mark();
+  {   // every GroupNorm-sum buffer of this evaluation comes out of one pre-zeroed pool (one memset node)
+    const size_t cnt = (size_t)96 * B * 16;
+    c.zpool = c.allocd(cnt);
+    c.zpool_off = 0; c.zpool_cap = cnt;
+    zero_async(c, c.zpool, cnt * sizeof(double));
+  }
   Tens xin; xin.p = (void*)x; xin.n = B; xin.h = H; xin.w = W; xin.c = 1; xin.dt = DT_F32;
   Tens cin = xin; cin.p = (void*)cond;
   TS h;
   h.t = c.alloc(B, H, W, u.mc);
   {
-    double* st = c.allocd((size_t)B * 16);
+    double* st = stats16(c, B);
     if (conv_first(c, xin, &cin, u.in_conv, h.t, st)) h.st = st;   // cat([x, condition]) never materialised
   }
   std::vector<TS> skips;
@@ -489,7 +498,7 @@ static void unet_eval(Ctx& c, UNetW& u, const float* x, const float* cond, const
       ConvW& d = u.down[L.idx];
       TS out;
       out.t = c.alloc(B, (h.t.h + 2 - 3) / 2 + 1, (h.t.w + 2 - 3) / 2 + 1, d.cout);
-      out.st = c.allocd((size_t)B * 16);
+      out.st = stats16(c, B);
       ConvEpi e;
       e.stats_out = out.st;
       conv(c, h.t, nullptr, d, e, out.t);
@@ -536,7 +545,7 @@ static void unet_eval(Ctx& c, UNetW& u, const float* x, const float* cond, const
       ConvW& up = u.up[L.idx];
       TS out;
       out.t = c.alloc(B, h.t.h, h.t.w, up.cout);
-      out.st = c.allocd((size_t)B * 16);
+      out.st = stats16(c, B);
       ConvEpi e;
       e.stats_out = out.st;
       conv(c, h.t, nullptr, up, e, out.t);
@@ -550,6 +559,7 @@ static void unet_eval(Ctx& c, UNetW& u, const float* x, const float* cond, const
   a.gn_sums = s; a.groups = u.groups; a.gamma = u.og; a.beta = u.ob; a.eps = 1e-5f; a.act_in = ACT_SILU;
   a.mode = o.mode; a.y = o.y; a.x_cur = o.x_cur; a.x_next = o.x_next; a.c1 = o.c1; a.c2 = o.c2;
   conv_cout1(c, a);
+  c.zpool = nullptr; c.zpool_cap = c.zpool_off = 0;
   c.a->release(mk0);
 }
 
@@ -659,6 +669,12 @@ static Tens cgg(Ctx& c, CGG& L, const Tens& x1, const Tens* x2) {
 static void router_forward(Ctx& c, RouterW& r, const float* x, float* mask, int B, int H, int W, int sanitize) {
   XRD_REQUIRE(H % 4 == 0 && W % 4 == 0, "router: H and W must be multiples of 4 (got %dx%d)", H, W);
   const size_t mk0 = c.a->mark();
+  {   // every GroupNorm-sum buffer of this evaluation comes out of one pre-zeroed pool (one memset node)
+    const size_t cnt = (size_t)96 * B * 16;
+    c.zpool = c.allocd(cnt);
+    c.zpool_off = 0; c.zpool_cap = cnt;
+    zero_async(c, c.zpool, cnt * sizeof(double));
+  }
   Tens xin; xin.p = (void*)x; xin.n = B; xin.h = H; xin.w = W; xin.c = 1; xin.dt = DT_F32;
   Tens e1 = cgg(c, r.enc1, xin, nullptr);
   Tens e2 = cgg(c, r.enc2, e1, nullptr);
@@ -673,6 +689,7 @@ static void router_forward(Ctx& c, RouterW& r, const float* x, float* mask, int 
   Cout1Args a;
   a.x = d2; a.k = 1; a.w = r.out_w; a.bias = r.out_b; a.mode = 2; a.sanitize = sanitize; a.y = mask;
   conv_cout1(c, a);
+  c.zpool = nullptr; c.zpool_cap = c.zpool_off = 0;
   c.a->release(mk0);
 }
 
@@ -685,6 +702,7 @@ static void fusion_forward(Ctx& c, FusionW& f, const float* naf, const float* di
   Cout1Args a;
   a.x = a2; a.k = 1; a.w = f.out_w; a.bias = f.out_b; a.mode = 0; a.y = out;
   conv_cout1(c, a);
+  c.zpool = nullptr; c.zpool_cap = c.zpool_off = 0;
   c.a->release(mk0);
 }
 
