@@ -114,6 +114,15 @@ CONV_CASES_HALO_CAT = [   # same kernel over a virtual concat of the two channel
 ]
 
 
+CONV_CASES_1X1 = [   # persistent 1x1 GEMM (conv1.cu): res_conv / qkv / proj shapes, ragged pixel counts, several tiles per CTA
+    (2, 192, 8, 8, 576, 1, 1, 0), (1, 192, 16, 16, 192, 1, 1, 0), (1, 96, 24, 40, 48, 1, 1, 0), (3, 48, 16, 16, 96, 1, 1, 0),
+    (1, 384, 8, 24, 192, 1, 1, 0), (1, 288, 9, 7, 144, 1, 1, 0), (2, 144, 64, 128, 144, 1, 1, 0), (1, 96, 200, 160, 96, 1, 1, 0),
+]
+CONV_CASES_1X1_CAT = [(1, 384, 16, 16, 192, 1, 1, 0), (1, 192, 32, 32, 96, 1, 1, 0), (1, 96, 24, 40, 48, 1, 1, 0), (1, 288, 16, 24, 144, 1, 1, 0),
+                      (1, 192, 16, 16, 48, 1, 1, 0)]
+CONV_CASES_1X1_STATS = [(2, 192, 16, 16, 192, 1, 1, 0), (1, 96, 32, 32, 48, 1, 1, 0), (3, 144, 16, 24, 144, 1, 1, 0), (2, 48, 64, 64, 96, 1, 1, 0)]
+
+
 def check_conv_stats(mode, impl, cases, seed=5):
     """GroupNorm partial sums from the conv epilogue vs the sums of the (fp64) reference output."""
     g = torch.Generator(device="cpu").manual_seed(seed)
@@ -325,6 +334,10 @@ CHECKS = {
     "conv_halo_cat_fp16": lambda: check_conv("fp16", 3, CONV_CASES_HALO_CAT),
     "conv_tc_cat_fp16": lambda: check_conv("fp16", 4, CONV_CASES_HALO_CAT),
     "conv_halo_stats_fp16": lambda: check_conv_stats("fp16", 2, CONV_CASES_HALO),
+    "conv1_fp16": lambda: check_conv("fp16", 5, CONV_CASES_1X1),
+    "conv1_bf16": lambda: check_conv("bf16", 5, CONV_CASES_1X1),
+    "conv1_cat_fp16": lambda: check_conv("fp16", 6, CONV_CASES_1X1_CAT),
+    "conv1_stats_fp16": lambda: check_conv_stats("fp16", 5, CONV_CASES_1X1_STATS),
     "attention_tc_bf16": lambda: check_attention("bf16", 1),
     "attention_tc_fp16": lambda: check_attention("fp16", 1),
     "nafnet_fp32": lambda: check_nafnet("fp32"),
