@@ -515,8 +515,8 @@ XRD_EXPORT int xrd_op_conv2d_stats(xrd_handle* H, int impl, const float* x, cons
     const DType dt = mode_dtype(H->h.mode);
     // impl: 0 CUDA cores, 1 tcgen05 per-tap, 2 tcgen05 persistent halo (conv3), 3 = conv3 over a virtual concat of the two
     // channel halves of x (B must be 1 so that each half is a contiguous NCHW block), 4 = per-tap kernel over the same concat,
-    // 5 = persistent 1x1 GEMM (conv1), 6 = conv1 over the concat
-    const bool split = impl == 3 || impl == 4 || impl == 6;
+    // 5 = persistent 1x1 GEMM (conv1), 6 = conv1 over the concat, 7 = 64-wide 3x3 kernel (conv3w), 8 = conv3w over the concat
+    const bool split = impl == 3 || impl == 4 || impl == 6 || impl == 8;
     if (split) XRD_REQUIRE(B == 1 && Cin % 32 == 0, "split-input conv hook needs B == 1 and Cin %% 32 == 0");
     if (impl >= 1) {
       XRD_REQUIRE(dt != DT_F32, "the tcgen05 kernels need a 16-bit mode");
@@ -538,6 +538,10 @@ XRD_EXPORT int xrd_op_conv2d_stats(xrd_handle* H, int impl, const float* x, cons
           e.stats_out = st;
           zero_async(cc, st, (size_t)yo.n * 16 * sizeof(double));
           conv3(cc, xi, split ? &xj : nullptr, H->op_w, e, yy);
+        } else if (impl == 7 || impl == 8) {
+          e.stats_out = st;
+          zero_async(cc, st, (size_t)yo.n * 16 * sizeof(double));
+          conv3w(cc, xi, split ? &xj : nullptr, H->op_w, e, yy);
         } else if (impl == 5 || impl == 6) {
           if (conv1_supported(xi, split ? &xj : nullptr, H->op_w, [&] { ConvEpi t; t.stats_out = st; return t; }())) {
             e.stats_out = st;
@@ -549,7 +553,7 @@ XRD_EXPORT int xrd_op_conv2d_stats(xrd_handle* H, int impl, const float* x, cons
         else conv_simt(cc, xi, nullptr, H->op_w, e, yy);
       };
       run(c);
-      if (!c.dry && stats && (impl == 2 || impl == 3 || impl == 5 || impl == 6)) XRD_CUDA(cudaMemcpyAsync(stats, st, (size_t)B * 16 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      if (!c.dry && stats && (impl == 2 || impl == 3 || impl >= 5)) XRD_CUDA(cudaMemcpyAsync(stats, st, (size_t)B * 16 * sizeof(double), cudaMemcpyDeviceToDevice, s));
       nhwc_to_nchw(c, yo, y);
       if (!c.dry) {
         H->h.last_op = run;

@@ -344,6 +344,7 @@ void finalize(Handle& h, int which) {
 static void conv(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y) {
   // e.stats_out comes from stats16(): already zero
   if (c.tc && conv3_supported(x1, x2, w, e)) { conv3(c, x1, x2, w, e, y); return; }
+  if (c.tc && conv3w_supported(x1, x2, w, e)) { conv3w(c, x1, x2, w, e, y); return; }
   if (c.tc && conv1_supported(x1, x2, w, e)) { conv1(c, x1, x2, w, e, y); return; }
   if (c.tc && conv_tc_supported(x1, x2, w, e)) { conv_tc(c, x1, x2, w, e, y); return; }
   ConvEpi e2 = e;

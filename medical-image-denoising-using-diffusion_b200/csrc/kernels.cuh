@@ -39,6 +39,9 @@ bool conv_tc_stats_supported(const ConvW& w);   // can the epilogue emit GroupNo
 // persistent halo-reusing variant for 3x3/s1/p1 on maps whose width is a multiple of 128 (conv3.cu)
 bool conv3_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e);
 void conv3(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y);
+// 3x3/s1/p1 on maps exactly 64 pixels wide (conv3w.cu): three column-shifted copies, 4-row tiles, Cout in {144,192}
+bool conv3w_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e);
+void conv3w(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y);
 // persistent 1x1 GEMM with resident weights (conv1.cu): res_conv / qkv / proj of the UNet
 bool conv1_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e);
 void conv1(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y);

@@ -123,6 +123,13 @@ CONV_CASES_1X1_CAT = [(1, 384, 16, 16, 192, 1, 1, 0), (1, 192, 32, 32, 96, 1, 1,
 CONV_CASES_1X1_STATS = [(2, 192, 16, 16, 192, 1, 1, 0), (1, 96, 32, 32, 48, 1, 1, 0), (3, 144, 16, 24, 144, 1, 1, 0), (2, 48, 64, 64, 96, 1, 1, 0)]
 
 
+CONV_CASES_W64 = [   # 3x3/s1/p1 on 64-wide maps (conv3w.cu)
+    (2, 192, 8, 64, 192, 3, 1, 1), (1, 144, 12, 64, 144, 3, 1, 1), (1, 384, 4, 64, 192, 3, 1, 1), (3, 144, 16, 64, 192, 3, 1, 1),
+    (1, 288, 8, 64, 144, 3, 1, 1), (1, 192, 64, 64, 192, 3, 1, 1),
+]
+CONV_CASES_W64_CAT = [(1, 384, 8, 64, 192, 3, 1, 1), (1, 288, 12, 64, 144, 3, 1, 1), (1, 384, 4, 64, 144, 3, 1, 1)]
+
+
 def check_conv_stats(mode, impl, cases, seed=5):
     """GroupNorm partial sums from the conv epilogue vs the sums of the (fp64) reference output."""
     g = torch.Generator(device="cpu").manual_seed(seed)
@@ -334,6 +341,10 @@ CHECKS = {
     "conv_halo_cat_fp16": lambda: check_conv("fp16", 3, CONV_CASES_HALO_CAT),
     "conv_tc_cat_fp16": lambda: check_conv("fp16", 4, CONV_CASES_HALO_CAT),
     "conv_halo_stats_fp16": lambda: check_conv_stats("fp16", 2, CONV_CASES_HALO),
+    "conv3w_fp16": lambda: check_conv("fp16", 7, CONV_CASES_W64),
+    "conv3w_bf16": lambda: check_conv("bf16", 7, CONV_CASES_W64),
+    "conv3w_cat_fp16": lambda: check_conv("fp16", 8, CONV_CASES_W64_CAT),
+    "conv3w_stats_fp16": lambda: check_conv_stats("fp16", 7, CONV_CASES_W64),
     "conv1_fp16": lambda: check_conv("fp16", 5, CONV_CASES_1X1),
     "conv1_bf16": lambda: check_conv("bf16", 5, CONV_CASES_1X1),
     "conv1_cat_fp16": lambda: check_conv("fp16", 6, CONV_CASES_1X1_CAT),

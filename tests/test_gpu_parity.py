@@ -47,6 +47,18 @@ def test_conv_tcgen05_halo_persistent():
         assert e < 2e-3, (k, e)
 
 
+def test_conv_tcgen05_64_wide():
+    # 3x3 on 64-pixel-wide maps (conv3w.cu, the UNet's lowest level): plain, concat and statistics variants
+    for k, e in G.check_conv("fp16", 7, G.CONV_CASES_W64).items():
+        assert e < 6e-4, (k, e)
+    for k, e in G.check_conv("bf16", 7, G.CONV_CASES_W64).items():
+        assert e < 5e-3, (k, e)
+    for k, e in G.check_conv("fp16", 8, G.CONV_CASES_W64_CAT).items():
+        assert e < 6e-4, (k, e)
+    for k, e in G.check_conv_stats("fp16", 7, G.CONV_CASES_W64).items():
+        assert e < 2e-3, (k, e)
+
+
 def test_conv_tcgen05_1x1_persistent():
     # persistent 1x1 GEMM (conv1.cu): res_conv (HYB:274), qkv / proj (HYB:289-290); plain, concat and statistics variants
     for k, e in G.check_conv("fp16", 5, G.CONV_CASES_1X1).items():
