@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 
 GF_PER_IMAGE_512 = 21383.0      # algorithmic 2*MAC of the reference op list, hybrid DDIM-50 @512^2
 UNET_CONV_GF_512 = 347.34       # conv FLOPs of one UNet evaluation @512^2 per image
+NCU_TOP_KERNEL_DRAM_BYTES = 403016448 + 353474560   # profiles/r01_ncu_hot_kernels.csv, k_conv3<half,48,...> per launch
 
 
 def peaks():
@@ -154,6 +155,7 @@ def conv_roofline(model, dev, batch, size):
               (1, 384, 144, s // 8, 3, 1), (1, 288, 144, s // 8, 3, 1), (6, 192, 576, s // 8, 1, 1), (6, 192, 192, s // 8, 1, 1),
               (1, 48, 48, s, 3, 2), (1, 96, 96, s // 2, 3, 2), (1, 144, 144, s // 4, 3, 2)]
     tot_ms, tot_fl, launches = 0.0, 0.0, 0
+    per_kernel = {}
     ms = C.c_float()
     for cnt, ci, co, hh, k, st in layers:
         x = torch.randn(batch, ci, hh, hh, device=dev)
@@ -161,18 +163,29 @@ def conv_roofline(model, dev, batch, size):
         b = torch.zeros(co, device=dev)
         ho = (hh + 2 * (k // 2) - k) // st + 1
         y = torch.empty(batch, co, ho, ho, device=dev)
-        # same dispatch as the engine: the persistent halo kernel (conv3.cu) where it applies, else the per-tap kernel
-        impl = 2 if (k == 3 and st == 1 and hh % 128 == 0 and co in (48, 96, 144)) else 1
+        # same dispatch as the engine (engine.cu conv()): conv3 (W % 128 == 0), conv3w (W == 64), conv1 (1x1), else per-tap
+        if k == 3 and st == 1 and hh % 128 == 0 and co in (48, 96, 144):
+            impl, kern = 2, "k_conv3"
+        elif k == 3 and st == 1 and hh == 64 and co in (144, 192):
+            impl, kern = 7, "k_conv3w"
+        elif k == 1 and st == 1:
+            impl, kern = 5, "k_conv1"
+        else:
+            impl, kern = 1, "k_conv_tc"
         _lib.check(lib.xrd_op_conv2d(h, impl, C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()),
                                      C.c_void_p(y.data_ptr()), batch, ci, hh, hh, co, k, st, k // 2, None))
         _lib.check(lib.xrd_op_time_last(h, 5, C.byref(ms), None))
         tot_ms += cnt * ms.value
-        tot_fl += cnt * 2.0 * batch * ho * ho * co * ci * k * k
+        fl = cnt * 2.0 * batch * ho * ho * co * ci * k * k
+        tot_fl += fl
         launches += cnt
+        per = per_kernel.setdefault(kern, [0.0, 0.0, 0])
+        per[0] += fl; per[1] += cnt * ms.value; per[2] += cnt
         del x, w, y
     lib.xrd_destroy(h)
     torch.cuda.empty_cache()
-    return tot_fl / tot_ms / 1e9, tot_ms, launches, tot_fl
+    by_kernel = {k: {"tflops": v[0] / v[1] / 1e9, "ms_per_eval": v[1], "launches_per_eval": v[2]} for k, v in per_kernel.items()}
+    return tot_fl / tot_ms / 1e9, tot_ms, launches, tot_fl, by_kernel
 
 
 def main():
@@ -274,7 +287,7 @@ def main():
     ips = world * B * args.steps / (ms / 1000.0)
     ips_e2e = world * B * args.steps / (ms_e2e / 1000.0)
     scale = (S / 512.0) ** 2
-    conv_tf, conv_ms, conv_launches, conv_fl = conv_roofline(model, dev, B, S) if args.mode != "fp32" else (0.0, 0.0, 0, 0.0)
+    conv_tf, conv_ms, conv_launches, conv_fl, conv_by = conv_roofline(model, dev, B, S) if args.mode != "fp32" else (0.0, 0.0, 0, 0.0, {})
     step_tf = ips / world * GF_PER_IMAGE_512 * scale / 1000.0
     line = {
         "metric": "denoised images/sec at 512x512 (hybrid, DDIM-50)", "value": ips, "unit": "images/s", "n_gpus": world,
@@ -286,9 +299,13 @@ def main():
                    "parallelism": f"image-sharded x{world}, output all_gather only"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": B * S * S * 4, "d2h_bytes_per_step": B * S * S * 4},
-        "roofline": {"bound": "tensor", "kernel": "k_conv3 + k_conv_tc (tcgen05 implicit-GEMM convolutions), all UNet conv shapes of one evaluation, launch weighted",
+        "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convolutions (k_conv3, k_conv3w, k_conv1, k_conv_tc): every conv layer shape of one UNet evaluation, "
+                               "each timed live with CUDA events through the C-ABI op hook, launch weighted",
                      "achieved": conv_tf, "peak": pk["burst"], "unit": "TFLOP/s", "frac": conv_tf / pk["burst"] if pk["burst"] else None,
-                     "peak_kind": f"bf16 dense burst, {pk['src']}", "traffic": None,
+                     "peak_kind": f"bf16 dense burst, {pk['src']}",
+                     # dram__bytes_read.sum + dram__bytes_write.sum of the top launch (k_conv3 48->48 @512^2 x16) from the committed
+                     # ncu --set full capture (profiles/r01_ncu_hot_kernels.csv); its algorithmic bytes are 2 x 403 MB
+                     "traffic": NCU_TOP_KERNEL_DRAM_BYTES if (B == 16 and S == 512) else None, "by_kernel": conv_by,
                      "flops_per_eval": conv_fl, "ms_per_eval_isolated": conv_ms, "launches_per_eval": conv_launches},
         "roofline_step": {"bound": "tensor", "achieved": step_tf, "peak": pk["sustained"], "unit": "TFLOP/s",
                           "frac": step_tf / pk["sustained"], "note": "images/s x 21383 GF algorithmic per image, of sustained measured peak"},
