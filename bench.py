@@ -215,6 +215,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"       # NCCL's version banner goes to stdout; this program prints ONE JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     import xrd_b200
