@@ -515,8 +515,12 @@ XRD_EXPORT int xrd_op_conv2d_stats(xrd_handle* H, int impl, const float* x, cons
     const DType dt = mode_dtype(H->h.mode);
     // impl: 0 CUDA cores, 1 tcgen05 per-tap, 2 tcgen05 persistent halo (conv3), 3 = conv3 over a virtual concat of the two
     // channel halves of x (B must be 1 so that each half is a contiguous NCHW block), 4 = per-tap kernel over the same concat,
-    // 5 = persistent 1x1 GEMM (conv1), 6 = conv1 over the concat, 7 = 64-wide 3x3 kernel (conv3w), 8 = conv3w over the concat
-    const bool split = impl == 3 || impl == 4 || impl == 6 || impl == 8;
+    // 5 = persistent 1x1 GEMM (conv1), 6 = conv1 over the concat, 7 = 64-wide 3x3 kernel (conv3w), 8 = conv3w over the concat,
+    // 11 = row-ring kernel (conv3r), 12 = conv3r with GroupNorm(8) + SiLU of the input applied inside the kernel,
+    // 9 / 10 = conv3 (single source / concat) with GroupNorm(8) + SiLU of the input applied inside the kernel; affine parameters
+    // gamma[c] = 1 + 0.01*(c % 7), beta[c] = 0.02*(c % 5) - 0.03
+    const bool split = impl == 3 || impl == 4 || impl == 6 || impl == 8 || impl == 10;
+    const bool fuse_gn = impl == 9 || impl == 10 || impl == 12;
     if (split) XRD_REQUIRE(B == 1 && Cin % 32 == 0, "split-input conv hook needs B == 1 and Cin %% 32 == 0");
     if (impl >= 1) {
       XRD_REQUIRE(dt != DT_F32, "the tcgen05 kernels need a 16-bit mode");
@@ -529,12 +533,34 @@ XRD_EXPORT int xrd_op_conv2d_stats(xrd_handle* H, int impl, const float* x, cons
       Tens xj = split ? c.alloc(B, Hh, W, Cin / 2) : Tens();
       Tens yo = c.alloc(B, Ho, Wo, Cout);
       double* st = c.allocd((size_t)B * 16);
+      double* gsum = fuse_gn ? c.allocd((size_t)B * 16) : nullptr;
+      float2* gcoef = fuse_gn ? (float2*)c.a->alloc((size_t)B * Cin * sizeof(float2)) : nullptr;
+      float* gaff = fuse_gn ? c.allocf((size_t)2 * Cin) : nullptr;
       nchw_to_nhwc(c, x, xi);
       if (split) nchw_to_nhwc(c, x + (size_t)(Cin / 2) * Hh * W, xj);
-      auto run = [H, xi, xj, yo, st, impl, split](Ctx& cc) mutable {
+      if (fuse_gn && !c.dry) {
+        std::vector<float> aff(2 * (size_t)Cin);
+        for (int ch = 0; ch < Cin; ++ch) { aff[ch] = 1.0f + 0.01f * (float)(ch % 7); aff[Cin + ch] = 0.02f * (float)(ch % 5) - 0.03f; }
+        XRD_CUDA(cudaMemcpyAsync(gaff, aff.data(), aff.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+        XRD_CUDA(cudaStreamSynchronize(s));
+      }
+      auto run = [H, xi, xj, yo, st, impl, split, fuse_gn, gsum, gcoef, gaff, Cin](Ctx& cc) mutable {
         Tens yy = yo;
         ConvEpi e;
-        if (impl == 2 || impl == 3) {
+        if (fuse_gn) {
+          zero_async(cc, gsum, (size_t)yo.n * 16 * sizeof(double));
+          gn_stats(cc, xi, split ? &xj : nullptr, 8, gsum);
+          gn_coef(cc, gsum, gaff, gaff + Cin, 1e-5f, yo.n, Cin, 8, xi.h * xi.w, gcoef);
+          e.in_coef = gcoef; e.in_act = ACT_SILU;
+          e.stats_out = st;
+          zero_async(cc, st, (size_t)yo.n * 16 * sizeof(double));
+          if (impl == 12) conv3r(cc, xi, H->op_w, e, yy);
+          else conv3(cc, xi, split ? &xj : nullptr, H->op_w, e, yy);
+        } else if (impl == 11) {
+          e.stats_out = st;
+          zero_async(cc, st, (size_t)yo.n * 16 * sizeof(double));
+          conv3r(cc, xi, H->op_w, e, yy);
+        } else if (impl == 2 || impl == 3) {
           e.stats_out = st;
           zero_async(cc, st, (size_t)yo.n * 16 * sizeof(double));
           conv3(cc, xi, split ? &xj : nullptr, H->op_w, e, yy);

@@ -44,10 +44,12 @@ struct Conv3P {
   const void* resid;
   void* y;
   double* stats;            // optional [nimg][8][2] (sum, sum of squares) of the stored output, 8 channel groups
+  const float2* in_coef;    // GN variant: [nimg][c0+c1] (0.5*scale, 0.5*shift) of the GroupNorm + SiLU applied to the input in shared memory
   long long* prof;          // optional clock64 trace of block 0
 };
 
 constexpr int kC3Threads = 320;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kC3ThreadsGN = 448;  // + warps 10..13: GroupNorm + SiLU applied in place to every landed activation stage
 constexpr int kC3Pitch = 136;   // smem pixels per halo row: 130 used (128 + one halo column each side); 136*128 B keeps rows 1024-aligned
 constexpr int kC3Box = 130;
 
@@ -105,8 +107,8 @@ __device__ __forceinline__ void c3_issue_chunk(uint64_t adesc0, uint64_t bdesc0,
   }
 }
 
-template <typename T, int COUT, int TH, int NACC, bool WRES>
-__global__ void __launch_bounds__(kC3Threads, 1)
+template <typename T, int COUT, int TH, int NACC, bool WRES, bool GN>
+__global__ void __launch_bounds__(GN ? kC3ThreadsGN : kC3Threads, 1)
 k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB,
         const Conv3P p) {
   constexpr uint32_t A_BYTES = (uint32_t)(((TH + 2) * kC3Pitch * 128 + 1023) & ~1023);
@@ -132,7 +134,8 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   uint64_t* w_full = bars + 8;        // [1] resident weights
   uint64_t* b_full = bars + 9;        // [16]
   uint64_t* b_empty = b_full + 16;    // [16]
-  uint32_t* tmem_slot = (uint32_t*)(b_empty + 16);
+  uint64_t* a_ready = b_empty + 16;   // [2] GN variant: stage transformed in place, ready for the tensor core
+  uint32_t* tmem_slot = (uint32_t*)(a_ready + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -143,6 +146,7 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1);
       tc::mbar_init(&acc_full[s], 1); tc::mbar_init(&acc_empty[s], 256);
+      tc::mbar_init(&a_ready[s], 128);
     }
     tc::mbar_init(w_full, 1);
     for (int s = 0; s < 16; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
@@ -226,7 +230,7 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       const uint32_t acc0 = tmem_base + (uint32_t)(ab * TH * COUT);
       for (int c = 0; c < p.nchunk; ++c, ++ai) {
         const int st = ai & 1;
-        tc::mbar_wait(&a_full[st], (ai >> 1) & 1);
+        tc::mbar_wait(GN ? &a_ready[st] : &a_full[st], (ai >> 1) & 1);
         tc::tc_fence_after();
         if (c == 0 && lane == 0) C3PROF(ti, 3);
         const bool second = c >= p.nchunk0;
@@ -261,6 +265,73 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         }
       }
       if (lane == 0) C3PROF(ti, 4);
+    }
+  } else if (GN && warp >= 10) {
+    // ===================== input transform (warps 10..13): a = SiLU(GroupNorm(x)) in place, HYB:264-265 / 269-270 =====================
+    // Thread = (16-byte channel chunk j of the stage's valid channels, pixel lane).  The stage is K-major with the 128B
+    // swizzle TMA applied: logical chunk j of buffer pixel sp sits at physical chunk j ^ (sp & 7).  Pixels outside the
+    // image stay zero (the convolution pads the ACTIVATED tensor); the stage's channel tail is never read by the MMAs.
+    const int tt = threadIdx.x - 320;
+    uint32_t ai = 0;
+    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+      int r = t;
+      const int txi = r % p.tiles_w; r /= p.tiles_w;
+      const int tyi = r % p.tiles_h;
+      const int img = r / p.tiles_h;
+      const int w0 = txi * 128 - 1, h0 = tyi * TH - 1;
+      for (int c = 0; c < p.nchunk; ++c, ++ai) {
+        const int st = ai & 1;
+        const bool second = c >= p.nchunk0;
+        const int cl = second ? c - p.nchunk0 : c;
+        const int nvc = min(64, (second ? p.c1 : p.c0) - cl * 64) >> 3;        // valid 8-channel chunks: 2, 4, 6 or 8
+        const int npl = 128 / nvc;
+        const int j = tt % nvc, plane = tt / nvc;
+        float sc[8], sh[8];
+        if (plane < npl) {
+          const float2* cf = p.in_coef + (size_t)img * (p.c0 + p.c1) + (second ? p.c0 : 0) + cl * 64 + j * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const float2 v = __ldg(cf + i); sc[i] = v.x; sh[i] = v.y; }
+        }
+        tc::mbar_wait(&a_full[st], (ai >> 1) & 1);
+        if (plane < npl) {
+          const uint32_t sbase = tc::smem_u32(sA + (size_t)st * A_BYTES);
+          // four pixels per iteration: the chain LDS -> FMA -> MUFU.TANH -> FMA -> STS is ~280 cycles long, a single pixel
+          // in flight per thread made the transform (not the tensor core) the critical path of the tile
+          constexpr int U = 4;
+          for (int pix0 = plane; pix0 < (TH + 2) * kC3Box; pix0 += U * npl) {
+            uint32_t addr[U];
+            bool ok[U];
+            uint4 q[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int pix = pix0 + u * npl;
+              const int rr = pix / kC3Box, cc = pix - rr * kC3Box;
+              const int ih = h0 + rr, iw = w0 + cc;
+              ok[u] = pix < (TH + 2) * kC3Box && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+              const int sp = rr * kC3Pitch + cc;
+              addr[u] = sbase + (uint32_t)sp * 128u + (uint32_t)((j ^ (sp & 7)) << 4);
+              if (ok[u]) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q[u].x), "=r"(q[u].y), "=r"(q[u].z), "=r"(q[u].w) : "r"(addr[u]));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (!ok[u]) continue;
+              float v[8];
+              unpack8<T>(q[u], v);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float h = fmaf(v[i], sc[i], sh[i]);          // 0.5 * GroupNorm(x)
+                float th;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+                v[i] = fmaf(h, th, h);                              // x*sigmoid(x) = h*tanh(h) + h with h = x/2
+              }
+              q[u].x = tc::pack2<T>(v[0], v[1]); q[u].y = tc::pack2<T>(v[2], v[3]); q[u].z = tc::pack2<T>(v[4], v[5]); q[u].w = tc::pack2<T>(v[6], v[7]);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr[u]), "r"(q[u].x), "r"(q[u].y), "r"(q[u].z), "r"(q[u].w) : "memory");
+            }
+          }
+        }
+        tc::fence_async_smem();                        // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        tc::mbar_arrive(&a_ready[st]);
+      }
     }
   } else {
     // ===================== epilogue (warps 2..9, two groups of four) =====================
@@ -410,6 +481,7 @@ bool conv3_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvE
   if (!(w.cout == 48 || w.cout == 96 || w.cout == 144)) return false;
   if (x1.w % 128 != 0) return false;
   if (e.in_scale || e.out_scale || e.act != ACT_NONE) return false;
+  if (e.in_coef && e.in_act != ACT_SILU) return false;
   return true;
 }
 
@@ -423,7 +495,7 @@ C3Cfg c3_plan(int cout, int nkb) {
   c.th = 2;
   c.nacc = cout <= 96 ? 2 : 1;
   const size_t a = (((size_t)(c.th + 2) * kC3Pitch * 128 + 1023) & ~(size_t)1023);
-  const size_t f = 2 * a + 8 * cout * 4 + (9 + 32) * 8 + 64;
+  const size_t f = 2 * a + 8 * cout * 4 + (11 + 32) * 8 + 64;
   const size_t bb = (size_t)cout * 128;
   c.wres = f + (size_t)nkb * bb <= budget;
   if (c3_env("XRD_C3_WRES", 1) == 0) c.wres = false;
@@ -440,10 +512,12 @@ template <typename T, int COUT, int TH, int NACC, bool WRES>
 void c3_launch(Ctx& c, int grid, size_t smem, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const Conv3P& p) {
   static bool attr = false;
   if (!attr) {
-    XRD_CUDA(cudaFuncSetAttribute(k_conv3<T, COUT, TH, NACC, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    XRD_CUDA(cudaFuncSetAttribute(k_conv3<T, COUT, TH, NACC, WRES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    XRD_CUDA(cudaFuncSetAttribute(k_conv3<T, COUT, TH, NACC, WRES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  XRD_LAUNCH(c, (k_conv3<T, COUT, TH, NACC, WRES>), grid, kC3Threads, smem, a0, a1, b, p);
+  if (p.in_coef) XRD_LAUNCH(c, (k_conv3<T, COUT, TH, NACC, WRES, true>), grid, kC3ThreadsGN, smem, a0, a1, b, p);
+  else XRD_LAUNCH(c, (k_conv3<T, COUT, TH, NACC, WRES, false>), grid, kC3Threads, smem, a0, a1, b, p);
 }
 
 template <typename T>
@@ -499,6 +573,7 @@ void conv3(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, T
   p.chan_add = e.chan_add; p.chan_add_bstride = e.chan_add_bstride;
   p.resid = e.resid.p; p.y = y.p;
   p.stats = e.stats_out;
+  p.in_coef = e.in_coef;
   p.prof = nullptr;
   static long long* prof_buf = nullptr;
   const int want_prof = c3_env("XRD_C3_PROF", 0);

@@ -3,6 +3,8 @@
 #include <functional>
 #include "engine.cuh"
 
+#include <stdlib.h>
+
 #include <math.h>
 #include <string.h>
 #include <algorithm>
@@ -36,7 +38,7 @@ static void free_convw_tc(ConvW& w) {
 
 void Handle::free_owned() {
   drop_graphs();
-  auto fr = [](ResW& r) { free_convw_tc(r.c1); free_convw_tc(r.c2); free_convw_tc(r.rc); };
+  auto fr = [](ResW& r) { free_convw_tc(r.c1); free_convw_tc(r.c2); free_convw_tc(r.rc); free_convw_tc(r.c1s); };
   for (auto& r : unet.res) fr(r);
   for (auto& a : unet.attn) { free_convw_tc(a.qkv); free_convw_tc(a.proj); }
   for (auto& d : unet.down) free_convw_tc(d);
@@ -339,10 +341,16 @@ void finalize(Handle& h, int which) {
 // ------------------------------------------------------------------------------------------------
 // network building blocks
 // ------------------------------------------------------------------------------------------------
+static const bool g_fuse_gn = !(getenv("XRD_FUSE_GN") && atoi(getenv("XRD_FUSE_GN")) == 0);
+static const bool g_fuse_gn_conv3 = getenv("XRD_FUSE_GN_CONV3") && atoi(getenv("XRD_FUSE_GN_CONV3")) != 0;
+
 // A contraction.  e.stats_out (optional, [N][8][2], zeroed here) receives the GroupNorm sums of the output: from the
 // kernel's own epilogue where it has one, else from a statistics pass over the stored tensor.
 static void conv(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y) {
   // e.stats_out comes from stats16(): already zero
+  // row-ring kernel: measured faster than the halo kernel from 256 columns up (1.06x activation fetch instead of 2x), slower
+  // at 128 (too few 32-row work items per SM)
+  if (c.tc && x1.w >= 256 && conv3r_supported(x1, x2, w, e)) { conv3r(c, x1, w, e, y); return; }
   if (c.tc && conv3_supported(x1, x2, w, e)) { conv3(c, x1, x2, w, e, y); return; }
   if (c.tc && conv3w_supported(x1, x2, w, e)) { conv3w(c, x1, x2, w, e, y); return; }
   if (c.tc && conv1_supported(x1, x2, w, e)) { conv1(c, x1, x2, w, e, y); return; }
@@ -410,16 +418,38 @@ static void resblock(Ctx& c, UNetW& u, ResW& r, const TS& x1, const TS* x2, cons
   const size_t mk = c.a->mark();
   const Tens* x2t = x2 ? &x2->t : nullptr;
   double* s1 = concat_stats(c, x1, x2, u.groups);
-  Tens a1 = c.alloc(B, H, W, r.cin);
-  gn_act(c, x1.t, x2t, u.groups, s1, r.g1, r.b1, 1e-5f, ACT_SILU, a1);
   Tens hm = c.alloc(B, H, W, r.cout);
   double* s2 = stats16(c, B);
   ConvEpi e1;
   e1.chan_add = temb + r.temb_off; e1.chan_add_bstride = temb_bstride;
   e1.stats_out = s2;
-  conv(c, a1, nullptr, r.c1, e1, hm);
-  Tens a2 = c.alloc(B, H, W, r.cout);
-  gn_act(c, hm, nullptr, u.groups, s2, r.g2, r.b2, 1e-5f, ACT_SILU, a2);
+  // GroupNorm + SiLU of the input applied inside the conv (on the landed shared-memory stage) where the kernel can:
+  // the activated tensor -- and for the up path the concatenated one -- is then never written to HBM.
+  auto fused_in = [&](const Tens& a, const Tens* b, ConvW& w, const ConvEpi& e, const double* sums, const float* g, const float* bt,
+                      Tens& y) -> bool {
+    ConvEpi pe = e;
+    pe.in_coef = reinterpret_cast<const float2*>(sums);      // non-null probe
+    pe.in_act = ACT_SILU;
+    if (!c.tc || !g_fuse_gn) return false;
+    // the row-ring kernel transforms every row once under a deep ring; in the 2-stage halo kernel the transform sits on
+    // the load -> MMA critical path (measured: slower than the stand-alone pass), so conv3 only fuses on request
+    // measured (tools/gn_fuse_time.py, batch 16): 48->48 @512^2 fused 430 us vs 295 + 172 us separate; at 256^2 it is a wash
+    const bool ring = a.w >= 512 && conv3r_supported(a, b, w, pe);
+    const bool halo = !ring && g_fuse_gn_conv3 && conv3_supported(a, b, w, pe) && !(b && (!w.wtc[a.dt] || w.tc_c1 != a.c));
+    if (!ring && !halo) return false;
+    const int ct = a.c + (b ? b->c : 0);
+    float2* cf = (float2*)c.a->alloc((size_t)B * ct * sizeof(float2));
+    gn_coef(c, sums, g, bt, 1e-5f, B, ct, u.groups, H * W, cf);
+    pe.in_coef = cf;
+    if (ring) conv3r(c, a, w, pe, y); else conv3(c, a, b, w, pe, y);
+    return true;
+  };
+  ConvW& w1 = x2 ? r.c1s : r.c1;
+  if (!fused_in(x1.t, x2t, w1, e1, s1, r.g1, r.b1, hm)) {
+    Tens a1 = c.alloc(B, H, W, r.cin);
+    gn_act(c, x1.t, x2t, u.groups, s1, r.g1, r.b1, 1e-5f, ACT_SILU, a1);
+    conv(c, a1, nullptr, r.c1, e1, hm);
+  }
   ConvEpi e2;
   if (r.has_rc) {
     Tens rr = c.alloc(B, H, W, r.cout);
@@ -430,7 +460,11 @@ static void resblock(Ctx& c, UNetW& u, ResW& r, const TS& x1, const TS* x2, cons
     e2.resid = x1.t;
   }
   e2.stats_out = out.st;
-  conv(c, a2, nullptr, r.c2, e2, out.t);
+  if (!fused_in(hm, nullptr, r.c2, e2, s2, r.g2, r.b2, out.t)) {
+    Tens a2 = c.alloc(B, H, W, r.cout);
+    gn_act(c, hm, nullptr, u.groups, s2, r.g2, r.b2, 1e-5f, ACT_SILU, a2);
+    conv(c, a2, nullptr, r.c2, e2, out.t);
+  }
   c.a->release(mk);
 }
 
@@ -772,7 +806,13 @@ void prepack_tc(Handle& h, DType dt) {
     for (auto& L : u.ups) if (L.kind == U_RES) cat[L.idx] = 1;
     for (size_t i = 0; i < u.res.size(); ++i) {
       ResW& r = u.res[i];
-      pk(r.c1, r.cin);                                   // conv1 reads the materialised GN output (one source)
+      pk(r.c1, r.cin);                                   // conv1 reads the materialised GN output (one source) ...
+      if (cat[i]) {                                      // ... or, GroupNorm fused into the conv, the two concat sources directly
+        r.c1s = r.c1;
+        for (int k = 0; k < 3; ++k) r.c1s.wtc[k] = nullptr;
+        r.c1s.tc_c1 = -1;
+        pk(r.c1s, r.cin / 2);
+      }
       pk(r.c2, r.cout);
       if (r.has_rc) pk(r.rc, cat[i] ? r.cin / 2 : r.cin);
     }

@@ -22,6 +22,8 @@ struct ResW {
   bool has_rc = false;
   const float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;
   ConvW c1, c2, rc;
+  ConvW c1s;                 // conv1 again, tensor-core packing split at cin/2: reads a concatenated input as two sources
+                             // (same fp32 weights; used when GroupNorm+SiLU is applied inside the conv, so no concat tensor exists)
 };
 struct AttnW {
   int c = 0;

@@ -27,6 +27,9 @@ struct ConvEpi {
   Tens resid;                       // optional residual with the output's layout
   int act = ACT_NONE;
   double* stats_out = nullptr;      // optional [N][8][2] += (sum, sum of squares) of the stored output over 8 channel groups
+  // GroupNorm + activation of the INPUT applied inside the kernel (conv3 only): [N][cin] (0.5*scale, 0.5*shift) from gn_coef()
+  const float2* in_coef = nullptr;
+  int in_act = ACT_NONE;
 };
 
 // --- contractions ---------------------------------------------------------
@@ -39,6 +42,9 @@ bool conv_tc_stats_supported(const ConvW& w);   // can the epilogue emit GroupNo
 // persistent halo-reusing variant for 3x3/s1/p1 on maps whose width is a multiple of 128 (conv3.cu)
 bool conv3_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e);
 void conv3(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y);
+// row-ring 3x3/s1/p1 for Cin <= 64, Cout in {48,96}, W % 128 == 0 (conv3r.cu); honours ConvEpi::in_coef (GroupNorm+SiLU of the input)
+bool conv3r_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e);
+void conv3r(Ctx& c, const Tens& x, ConvW& w, const ConvEpi& e, Tens& y);
 // 3x3/s1/p1 on maps exactly 64 pixels wide (conv3w.cu): three column-shifted copies, 4-row tiles, Cout in {144,192}
 bool conv3w_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e);
 void conv3w(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y);
@@ -67,6 +73,8 @@ void gn_stats(Ctx& c, const Tens& x1, const Tens* x2, int groups, double* sums);
 void gn_act(Ctx& c, const Tens& x1, const Tens* x2, int groups, const double* sums, const float* gamma,
             const float* beta, float eps, int act, Tens& y);
 void zero_async(Ctx& c, void* p, size_t bytes);
+// coef[n][c] = 0.5 * (rstd*gamma[c], beta[c] - mean*rstd*gamma[c]) for GroupNorm(groups, C) with the given sums ([N][groups][2])
+void gn_coef(Ctx& c, const double* sums, const float* gamma, const float* beta, float eps, int N, int C, int groups, int HW, float2* coef);
 // out[n][g] = a[n][2g] + a[n][2g+1] (g < 4), b[n][2(g-4)] + b[n][2(g-4)+1] (g >= 4): sums of GroupNorm(8, 2C) over [a | b]
 void gn_merge_stats(Ctx& c, const double* a, const double* b, double* out, int N);
 void upsample2x(Ctx& c, const Tens& x, Tens& y);       // bilinear, align_corners=False, exact 2x

@@ -116,6 +116,23 @@ void gn_merge_stats(Ctx& c, const double* a, const double* b, double* out, int N
   XRD_LAUNCH(c, k_gn_merge_stats, cdiv(N * 16, 128), 128, 0, a, b, out, N);
 }
 
+__global__ void k_gn_coef(const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int N,
+                          int C, int groups, int HW, float2* __restrict__ coef) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, ch = i - n * C, cpg = C / groups, g = ch / cpg;
+  const double cnt = (double)cpg * HW;
+  const double m = sums[((int64_t)n * groups + g) * 2] / cnt;
+  double var = sums[((int64_t)n * groups + g) * 2 + 1] / cnt - m * m;
+  if (var < 0) var = 0;
+  const float a = (float)(1.0 / sqrt(var + (double)eps)) * gamma[ch];
+  coef[i] = make_float2(0.5f * a, 0.5f * (beta[ch] - (float)m * a));
+}
+
+void gn_coef(Ctx& c, const double* sums, const float* gamma, const float* beta, float eps, int N, int C, int groups, int HW, float2* coef) {
+  XRD_LAUNCH(c, k_gn_coef, cdiv(N * C, 128), 128, 0, sums, gamma, beta, eps, N, C, groups, HW, coef);
+}
+
 void gn_stats(Ctx& c, const Tens& x1, const Tens* x2, int groups, double* sums) {
   const int c1 = x1.c, c2 = x2 ? x2->c : 0, ctot = c1 + c2;
   const int VN = (int)(16 / dsize(x1.dt));

@@ -179,6 +179,13 @@ template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat
   for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
 }
 
+// 32-byte global store (sm_100: STG.E.ENL2.256): one whole sector per instruction.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z),
+               "r"(b.w)
+               : "memory");
+}
+
 }  // namespace tc
 
 // ---- host: tensor-map encoding through the runtime's driver entry point (no -lcuda) -------------

@@ -123,11 +123,39 @@ CONV_CASES_1X1_CAT = [(1, 384, 16, 16, 192, 1, 1, 0), (1, 192, 32, 32, 96, 1, 1,
 CONV_CASES_1X1_STATS = [(2, 192, 16, 16, 192, 1, 1, 0), (1, 96, 32, 32, 48, 1, 1, 0), (3, 144, 16, 24, 144, 1, 1, 0), (2, 48, 64, 64, 96, 1, 1, 0)]
 
 
+CONV_CASES_RING = [   # row-ring kernel (conv3r.cu): Cin <= 64, Cout in {48, 96}; ragged segment (H % 32 != 0), several items per CTA
+    (1, 48, 8, 128, 48, 3, 1, 1), (2, 48, 40, 256, 48, 3, 1, 1), (1, 48, 33, 128, 96, 3, 1, 1), (1, 64, 70, 128, 48, 3, 1, 1),
+    (1, 32, 5, 256, 96, 3, 1, 1), (3, 48, 64, 512, 48, 3, 1, 1), (1, 16, 3, 128, 48, 3, 1, 1), (2, 48, 200, 512, 48, 3, 1, 1),
+]
 CONV_CASES_W64 = [   # 3x3/s1/p1 on 64-wide maps (conv3w.cu)
     (2, 192, 8, 64, 192, 3, 1, 1), (1, 144, 12, 64, 144, 3, 1, 1), (1, 384, 4, 64, 192, 3, 1, 1), (3, 144, 16, 64, 192, 3, 1, 1),
     (1, 288, 8, 64, 144, 3, 1, 1), (1, 192, 64, 64, 192, 3, 1, 1),
 ]
 CONV_CASES_W64_CAT = [(1, 384, 8, 64, 192, 3, 1, 1), (1, 288, 12, 64, 144, 3, 1, 1), (1, 384, 4, 64, 144, 3, 1, 1)]
+
+
+def check_conv_fused_gn(mode, impl, cases, seed=9):
+    """conv3 with GroupNorm(8)+SiLU of its input applied inside the kernel (hook impl 9 / 10, fixed affine parameters)
+    vs F.conv2d(F.silu(F.group_norm(x))) in fp64 on the rounded operands.  Error relative to max|ref|."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    oh = OpHandle(mode)
+    out = {}
+    dt = torch.bfloat16 if mode == "bf16" else torch.float16
+    try:
+        for (B, Cin, H, W, Cout, k, s, p) in cases:
+            x = (torch.randn(B, Cin, H, W, generator=g) * 1.5 + 0.3).to(DEV)
+            w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(DEV)
+            b = torch.randn(Cout, generator=g).to(DEV)
+            ch = torch.arange(Cin, device=DEV)
+            gamma = (1.0 + 0.01 * (ch % 7)).double()
+            beta = (0.02 * (ch % 5) - 0.03).double()
+            a = F.silu(F.group_norm(x.to(dt).double(), 8, gamma, beta, 1e-5))
+            ref = F.conv2d(a.to(dt).double(), w.to(dt).double(), b.double(), stride=s, padding=p).float()
+            y = oh.conv2d(x, w, b, k, s, p, impl)
+            out[f"{B}x{Cin}x{H}x{W}->{Cout}"] = _rel(y, ref)
+    finally:
+        oh.close()
+    return out
 
 
 def check_conv_stats(mode, impl, cases, seed=5):
@@ -341,6 +369,13 @@ CHECKS = {
     "conv_halo_cat_fp16": lambda: check_conv("fp16", 3, CONV_CASES_HALO_CAT),
     "conv_tc_cat_fp16": lambda: check_conv("fp16", 4, CONV_CASES_HALO_CAT),
     "conv_halo_stats_fp16": lambda: check_conv_stats("fp16", 2, CONV_CASES_HALO),
+    "conv_halo_gn_fp16": lambda: check_conv_fused_gn("fp16", 9, CONV_CASES_HALO),
+    "conv_halo_gn_cat_fp16": lambda: check_conv_fused_gn("fp16", 10, CONV_CASES_HALO_CAT),
+    "conv_halo_gn_bf16": lambda: check_conv_fused_gn("bf16", 9, CONV_CASES_HALO),
+    "conv3r_fp16": lambda: check_conv("fp16", 11, CONV_CASES_RING),
+    "conv3r_bf16": lambda: check_conv("bf16", 11, CONV_CASES_RING),
+    "conv3r_gn_fp16": lambda: check_conv_fused_gn("fp16", 12, CONV_CASES_RING),
+    "conv3r_stats_fp16": lambda: check_conv_stats("fp16", 11, CONV_CASES_RING),
     "conv3w_fp16": lambda: check_conv("fp16", 7, CONV_CASES_W64),
     "conv3w_bf16": lambda: check_conv("bf16", 7, CONV_CASES_W64),
     "conv3w_cat_fp16": lambda: check_conv("fp16", 8, CONV_CASES_W64_CAT),

@@ -47,6 +47,29 @@ def test_conv_tcgen05_halo_persistent():
         assert e < 2e-3, (k, e)
 
 
+def test_conv_tcgen05_fused_groupnorm_silu_input():
+    # GroupNorm(8) + SiLU (HYB:264-265, 269-270) applied to the landed shared-memory stage inside conv3, single source and
+    # virtual concat; the activation is rounded to the operand format exactly as the stand-alone pass stored it
+    for k, e in G.check_conv_fused_gn("fp16", 9, G.CONV_CASES_HALO).items():
+        assert e < 1.5e-3, (k, e)
+    for k, e in G.check_conv_fused_gn("fp16", 10, G.CONV_CASES_HALO_CAT).items():
+        assert e < 1.5e-3, (k, e)
+    for k, e in G.check_conv_fused_gn("bf16", 9, G.CONV_CASES_HALO).items():
+        assert e < 1e-2, (k, e)
+
+
+def test_conv_tcgen05_row_ring():
+    # row-ring kernel (conv3r.cu) for the 48-channel full-resolution layers: plain, statistics, fused GroupNorm+SiLU input
+    for k, e in G.check_conv("fp16", 11, G.CONV_CASES_RING).items():
+        assert e < 6e-4, (k, e)
+    for k, e in G.check_conv("bf16", 11, G.CONV_CASES_RING).items():
+        assert e < 5e-3, (k, e)
+    for k, e in G.check_conv_stats("fp16", 11, G.CONV_CASES_RING).items():
+        assert e < 2e-3, (k, e)
+    for k, e in G.check_conv_fused_gn("fp16", 12, G.CONV_CASES_RING).items():
+        assert e < 1.5e-3, (k, e)
+
+
 def test_conv_tcgen05_64_wide():
     # 3x3 on 64-pixel-wide maps (conv3w.cu, the UNet's lowest level): plain, concat and statistics variants
     for k, e in G.check_conv("fp16", 7, G.CONV_CASES_W64).items():
