@@ -214,6 +214,7 @@ k_conv1(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
 #pragma unroll
       for (int cb = 0; cb < NBLK; ++cb) {
         uint32_t v[48];
+        uint4 pk_even;
         c1_tmem_ld16(tacc + (uint32_t)(cb * 48), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
         c1_tmem_ld16(tacc + (uint32_t)(cb * 48 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
         c1_tmem_ld16(tacc + (uint32_t)(cb * 48 + 32), *reinterpret_cast<uint32_t(*)[16]>(&v[32]));
@@ -249,7 +250,7 @@ k_conv1(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           uint4 pk;
           pk.x = tc::pack2<T>(r8[0], r8[1]); pk.y = tc::pack2<T>(r8[2], r8[3]);
           pk.z = tc::pack2<T>(r8[4], r8[5]); pk.w = tc::pack2<T>(r8[6], r8[7]);
-          if (ok) *reinterpret_cast<uint4*>(yp + pix * p.ldc + n0 + co) = pk;
+          if (h8 & 1) { if (ok) tc::st_global_v8(yp + pix * p.ldc + n0 + co - 8, pk_even, pk); } else pk_even = pk;   // 32-byte sector stores
         }
         if (has_next) {
 #pragma unroll

@@ -44,6 +44,7 @@ struct Conv3P {
   const void* resid;
   void* y;
   double* stats;            // optional [nimg][8][2] (sum, sum of squares) of the stored output, 8 channel groups
+  const void* wsw;          // pre-swizzled weight blocks for 1-D bulk loads (null: tensor-map loads)
   const float2* in_coef;    // GN variant: [nimg][c0+c1] (0.5*scale, 0.5*shift) of the GroupNorm + SiLU applied to the input in shared memory
   long long* prof;          // optional clock64 trace of block 0
 };
@@ -202,7 +203,8 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
             for (int tap = 0; tap < 9; ++tap) {
               tc::mbar_wait(&b_empty[wslot], wphase ^ 1);
               tc::mbar_expect_tx(&b_full[wslot], B_BYTES);
-              tc::tma_load_3d(sB + (size_t)wslot * B_BYTES, &tmB, &b_full[wslot], 0, 0, c * 9 + tap);
+              if (p.wsw) tc::bulk_load_1d(sB + (size_t)wslot * B_BYTES, (const char*)p.wsw + (size_t)(c * 9 + tap) * B_BYTES, B_BYTES, &b_full[wslot]);
+              else tc::tma_load_3d(sB + (size_t)wslot * B_BYTES, &tmB, &b_full[wslot], 0, 0, c * 9 + tap);
               if (++wslot == (uint32_t)p.nb) { wslot = 0; wphase ^= 1; }
             }
           }
@@ -406,6 +408,7 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
 #pragma unroll
           for (int cb = 0; cb < NBLK; ++cb) {
             uint32_t v[48];
+            uint4 pk_even;
             if (!(p.dbg & 8)) {
               tmem_ld16_nowait(tacc + (uint32_t)(cb * 48), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
               tmem_ld16_nowait(tacc + (uint32_t)(cb * 48 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
@@ -445,7 +448,8 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
               uint4 pk;
               pk.x = tc::pack2<T>(r8[0], r8[1]); pk.y = tc::pack2<T>(r8[2], r8[3]);
               pk.z = tc::pack2<T>(r8[4], r8[5]); pk.w = tc::pack2<T>(r8[6], r8[7]);
-              if (row_ok && !(p.dbg & 1)) *reinterpret_cast<uint4*>(yp + opix * COUT + co) = pk;
+              // two 16-byte halves -> one 32-byte store of a whole sector
+              if (h8 & 1) { if (row_ok && !(p.dbg & 1)) tc::st_global_v8(yp + opix * COUT + co - 8, pk_even, pk); } else pk_even = pk;
             }
             if (has_next) {
 #pragma unroll
@@ -574,6 +578,7 @@ void conv3(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, T
   p.resid = e.resid.p; p.y = y.p;
   p.stats = e.stats_out;
   p.in_coef = e.in_coef;
+  p.wsw = c3_env("XRD_WBULK", 1) ? w.wtc_swz(x1.dt) : nullptr;
   p.prof = nullptr;
   static long long* prof_buf = nullptr;
   const int want_prof = c3_env("XRD_C3_PROF", 0);

@@ -33,6 +33,7 @@ struct Conv3WP {
   const void* resid;
   void* y;
   double* stats;
+  const void* wsw;          // pre-swizzled weight blocks for 1-D bulk loads (null: tensor-map loads)
 };
 
 constexpr int kW3Threads = 320;
@@ -148,7 +149,8 @@ k_conv3w(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
             for (int dy = 0; dy < 3; ++dy) {
               tc::mbar_wait(&b_empty[ws], wph ^ 1);
               tc::mbar_expect_tx(&b_full[ws], B_BYTES);
-              tc::tma_load_3d(sB + (size_t)ws * B_BYTES, &tmB, &b_full[ws], 0, 0, c * 9 + dy * 3 + dx);
+              if (p.wsw) tc::bulk_load_1d(sB + (size_t)ws * B_BYTES, (const char*)p.wsw + (size_t)(c * 9 + dy * 3 + dx) * B_BYTES, B_BYTES, &b_full[ws]);
+              else tc::tma_load_3d(sB + (size_t)ws * B_BYTES, &tmB, &b_full[ws], 0, 0, c * 9 + dy * 3 + dx);
               if (++ws == (uint32_t)p.nb) { ws = 0; wph ^= 1; }
             }
           }
@@ -245,6 +247,7 @@ k_conv3w(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
 #pragma unroll
       for (int cb = 0; cb < NBLK; ++cb) {
         uint32_t v[48];
+        uint4 pk_even;
         w3_tmem_ld16(tacc + (uint32_t)(cb * 48), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
         w3_tmem_ld16(tacc + (uint32_t)(cb * 48 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
         w3_tmem_ld16(tacc + (uint32_t)(cb * 48 + 32), *reinterpret_cast<uint32_t(*)[16]>(&v[32]));
@@ -280,7 +283,7 @@ k_conv3w(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
           uint4 pk;
           pk.x = tc::pack2<T>(r8[0], r8[1]); pk.y = tc::pack2<T>(r8[2], r8[3]);
           pk.z = tc::pack2<T>(r8[4], r8[5]); pk.w = tc::pack2<T>(r8[6], r8[7]);
-          *reinterpret_cast<uint4*>(yp + pix * COUT + co) = pk;
+          if (h8 & 1) tc::st_global_v8(yp + pix * COUT + co - 8, pk_even, pk); else pk_even = pk;   // 32-byte sector stores
         }
         if (has_next) {
 #pragma unroll
@@ -335,6 +338,7 @@ void conv3w(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, 
   p.chan_add = e.chan_add; p.chan_add_bstride = e.chan_add_bstride;
   p.resid = e.resid.p; p.y = y.p;
   p.stats = e.stats_out;
+  p.wsw = (getenv("XRD_WBULK") && atoi(getenv("XRD_WBULK")) == 0) ? nullptr : w.wtc_swz(x1.dt);
 
   auto encode_act = [&](CUtensorMap* m, const Tens& x) {
     const cuuint64_t dims[4] = {(cuuint64_t)x.c, (cuuint64_t)x.w, (cuuint64_t)x.h, (cuuint64_t)x.n};

@@ -312,6 +312,12 @@ __global__ void k_pack_tc(const float* __restrict__ w /*[ntaps][cin][cout]*/, T*
       v = w[((int64_t)tap * cin + ci) * cout + n];
     }
     stf<T>(out + i, v);
+    // second copy, pre-swizzled exactly as TMA's 128B swizzle would place the block in (1024-aligned) shared memory: the
+    // 16-byte chunk index is XORed with the row index mod 8.  A streamed weight block can then be fetched with ONE 1-D bulk
+    // copy instead of one TMA request per 128-byte row (the TMA request rate, ~6.4 cycles per row per SM, bounds the
+    // streamed-weight convolutions).
+    const int64_t blk = (int64_t)kb * npad * 64;
+    stf<T>(out + total + blk + (int64_t)n * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7)), v);
   }
 }
 
@@ -327,7 +333,7 @@ void conv_tc_pack(cudaStream_t s, ConvW& w, DType dt, int c1) {
       if (w.wtc[i]) { cudaFree(w.wtc[i]); w.wtc[i] = nullptr; }
   }
   size_t bytes = (size_t)nkb * npad * 64 * 2;
-  XRD_CUDA(cudaMalloc(&w.wtc[dt], bytes));
+  XRD_CUDA(cudaMalloc(&w.wtc[dt], 2 * bytes));     // plain copy (tensor-map loads) + pre-swizzled copy (1-D bulk loads)
   w.tc_c1 = c1; w.tc_nkb = nkb; w.tc_npad = npad;
   int64_t total = (int64_t)nkb * npad * 64;
   int blocks = (int)std::min<int64_t>(cdiv64(total, 256), 148 * 16);

@@ -38,6 +38,7 @@ static void free_convw_tc(ConvW& w) {
 
 void Handle::free_owned() {
   drop_graphs();
+  free_convw_tc(unet.in_conv_g);
   auto fr = [](ResW& r) { free_convw_tc(r.c1); free_convw_tc(r.c2); free_convw_tc(r.rc); free_convw_tc(r.c1s); };
   for (auto& r : unet.res) fr(r);
   for (auto& a : unet.attn) { free_convw_tc(a.qkv); free_convw_tc(a.proj); }
@@ -131,6 +132,14 @@ static void finalize_unet(Handle& h) {
 
   {  // in_conv: (mc, 2, 3, 3)
     u.in_conv = make_conv(h, p + "in_conv", mc, 2, 3, 1, 1);
+    // the same weights as a [32 x mc] GEMM operand: row k = tap*2 + channel for k < 18 (exactly the [tap][cin][cout] layout
+    // of in_conv.w), rows 18..31 zero
+    u.in_conv_g = ConvW();
+    u.in_conv_g.kh = u.in_conv_g.kw = 1; u.in_conv_g.stride = 1; u.in_conv_g.pad = 0; u.in_conv_g.cin = 32; u.in_conv_g.cout = mc;
+    u.in_conv_g.w = h.dalloc_f((size_t)32 * mc);
+    XRD_CUDA(cudaMemset(u.in_conv_g.w, 0, (size_t)32 * mc * sizeof(float)));
+    XRD_CUDA(cudaMemcpy(u.in_conv_g.w, u.in_conv.w, (size_t)18 * mc * sizeof(float), cudaMemcpyDeviceToDevice));
+    u.in_conv_g.bias = u.in_conv.bias;
   }
   int ch = mc, li = 0;
   for (int lvl = 0; lvl < levels; ++lvl) {
@@ -515,7 +524,20 @@ static void unet_eval(Ctx& c, UNetW& u, const float* x, const float* cond, const
   h.t = c.alloc(B, H, W, u.mc);
   {
     double* st = stats16(c, B);
-    if (conv_first(c, xin, &cin, u.in_conv, h.t, st)) h.st = st;   // cat([x, condition]) never materialised
+    ConvEpi e0;
+    e0.stats_out = st;
+    Tens col;
+    col.n = B; col.h = H; col.w = W; col.c = 32; col.dt = c.adt;
+    if (c.tc && u.in_conv_g.w && conv1_supported(col, nullptr, u.in_conv_g, e0)) {
+      // tensor-core first conv: 16-bit im2col rows [pixel][9 taps x (x, cond) | zero pad] (64 B each), then the persistent
+      // 1x1 GEMM with GroupNorm sums in its epilogue.  cat([x, condition]) is still never materialised.
+      col = c.alloc(B, H, W, 32);
+      im2col_3x3_2ch(c, x, cond, col);
+      conv1(c, col, nullptr, u.in_conv_g, e0, h.t);
+      h.st = st;
+    } else if (conv_first(c, xin, &cin, u.in_conv, h.t, st)) {
+      h.st = st;                                         // cat([x, condition]) never materialised
+    }
   }
   std::vector<TS> skips;
   for (const ULayer& L : u.downs) {
@@ -819,6 +841,7 @@ void prepack_tc(Handle& h, DType dt) {
     for (auto& a : u.attn) { pk(a.qkv, a.c); pk(a.proj, a.c); }
     for (auto& d : u.down) pk(d, d.cin);
     for (auto& w : u.up) pk(w, w.cin);
+    pk(u.in_conv_g, 32);
   }
   NafW& n = h.naf;
   if (n.ready) {

@@ -37,6 +37,7 @@ struct UNetW {
   bool ready = false;
   int mc = 0, groups = 8, heads = 2;
   ConvW in_conv;
+  ConvW in_conv_g;           // in_conv as a 1x1 GEMM over the im2col matrix [pixels][32] (18 real columns): tensor-core first conv
   std::vector<ResW> res;     // downs..., mid1, mid2, ups... in creation order
   std::vector<AttnW> attn;
   std::vector<ConvW> down, up;

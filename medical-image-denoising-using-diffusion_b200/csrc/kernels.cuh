@@ -17,6 +17,8 @@ struct ConvW {
   int tc_c1 = -1;          // channel split the tc packing was built for (source-1 channels)
   int tc_nkb = 0;          // number of 64-wide K blocks
   int tc_npad = 0;         // cout rounded up to a multiple of 16
+  // pre-swizzled second copy of the packing (same shape), for 1-D bulk loads of whole K blocks
+  const void* wtc_swz(DType dt) const { return (const char*)wtc[dt] + (size_t)tc_nkb * tc_npad * 128; }
 };
 
 struct ConvEpi {
@@ -77,6 +79,8 @@ void zero_async(Ctx& c, void* p, size_t bytes);
 void gn_coef(Ctx& c, const double* sums, const float* gamma, const float* beta, float eps, int N, int C, int groups, int HW, float2* coef);
 // out[n][g] = a[n][2g] + a[n][2g+1] (g < 4), b[n][2(g-4)] + b[n][2(g-4)+1] (g >= 4): sums of GroupNorm(8, 2C) over [a | b]
 void gn_merge_stats(Ctx& c, const double* a, const double* b, double* out, int N);
+// col[n,h,w, 0..31] = 3x3 neighbourhood (zero padded) of the two fp32 planes a, b: column tap*2 + {0: a, 1: b}, columns 18..31 zero
+void im2col_3x3_2ch(Ctx& c, const float* a, const float* b, Tens& col);
 void upsample2x(Ctx& c, const Tens& x, Tens& y);       // bilinear, align_corners=False, exact 2x
 // same, 16 bytes per access, fused with the GroupNorm sums of y (stats nullable, [N][8][2], zeroed by the caller)
 void upsample2x_stats(Ctx& c, const Tens& x, Tens& y, double* stats);

@@ -306,7 +306,47 @@ __global__ void __launch_bounds__(288) k_upsample2x_stats(const T* __restrict__ 
   }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) k_im2col_3x3_2ch(const float* __restrict__ a, const float* __restrict__ b, T* __restrict__ col, int N, int H,
+                                                        int W) {
+  const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (int64_t)N * H * W) return;
+  const int ow = (int)(pix % W), oh = (int)((pix / W) % H);
+  const int64_t base = pix - (int64_t)oh * W - ow;        // first pixel of this image
+  float v[32];
+#pragma unroll
+  for (int i = 18; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ih = oh + ky - 1, iw = ow + kx - 1;
+      const bool in = ih >= 0 && ih < H && iw >= 0 && iw < W;
+      const int64_t ip = base + (int64_t)ih * W + iw;
+      v[(ky * 3 + kx) * 2 + 0] = in ? __ldg(a + ip) : 0.f;
+      v[(ky * 3 + kx) * 2 + 1] = in ? __ldg(b + ip) : 0.f;
+    }
+  }
+  T* dst = col + pix * 32;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = v[j * 8 + i];
+    st8f<T>(dst + j * 8, o);
+  }
+}
+
 }  // namespace
+
+void im2col_3x3_2ch(Ctx& c, const float* a, const float* b, Tens& col) {
+  XRD_REQUIRE(col.c == 32 && col.dt != DT_F32, "im2col_3x3_2ch: 32 16-bit columns expected");
+  const int64_t total = (int64_t)col.n * col.h * col.w;
+  if (col.dt == DT_BF16)
+    XRD_LAUNCH(c, (k_im2col_3x3_2ch<__nv_bfloat16>), (int)cdiv64(total, 256), 256, 0, a, b, (__nv_bfloat16*)col.p, col.n, col.h, col.w);
+  else
+    XRD_LAUNCH(c, (k_im2col_3x3_2ch<__half>), (int)cdiv64(total, 256), 256, 0, a, b, (__half*)col.p, col.n, col.h, col.w);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // host side
