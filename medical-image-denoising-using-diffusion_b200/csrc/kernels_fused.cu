@@ -186,21 +186,22 @@ __global__ void __launch_bounds__(288) k_gn_act2(const TI* __restrict__ x1, cons
   TO* dst = y + (int64_t)n * HW * ctot + c;
   const int p0 = blockIdx.x * pix_per_block, p1 = min(p0 + pix_per_block, HW);
   int pp = p0 + lane;
-  for (; pp + ppi < p1; pp += 2 * ppi) {
-    float a[VN], b[VN];
-    ldv<TI>(src + (int64_t)pp * cs, a);
-    ldv<TI>(src + (int64_t)(pp + ppi) * cs, b);
+  for (; pp + 3 * ppi < p1; pp += 4 * ppi) {       // four independent 16-byte loads in flight per thread
+    float a[4][VN];
 #pragma unroll
-    for (int i = 0; i < VN; ++i) {
-      const float ta = fmaf(a[i], sc[i], sh[i]), tb = fmaf(b[i], sc[i], sh[i]);
-      a[i] = FAST ? act_fast(ta, act) : act_apply(ta, act);
-      b[i] = FAST ? act_fast(tb, act) : act_apply(tb, act);
-    }
+    for (int u = 0; u < 4; ++u) ldv<TI>(src + (int64_t)(pp + u * ppi) * cs, a[u]);
 #pragma unroll
-    for (int i = 0; i < VN; i += 4) {
-      float o4[4] = {a[i], a[i + 1], a[i + 2], a[i + 3]}, q4[4] = {b[i], b[i + 1], b[i + 2], b[i + 3]};
-      st4<TO>(dst + (int64_t)pp * ctot + i, o4);
-      st4<TO>(dst + (int64_t)(pp + ppi) * ctot + i, q4);
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        const float t = fmaf(a[u][i], sc[i], sh[i]);
+        a[u][i] = FAST ? act_fast(t, act) : act_apply(t, act);
+      }
+#pragma unroll
+      for (int i = 0; i < VN; i += 4) {
+        float o4[4] = {a[u][i], a[u][i + 1], a[u][i + 2], a[u][i + 3]};
+        st4<TO>(dst + (int64_t)(pp + u * ppi) * ctot + i, o4);
+      }
     }
   }
   for (; pp < p1; pp += ppi) {
