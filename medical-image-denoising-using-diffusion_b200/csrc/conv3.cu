@@ -37,6 +37,7 @@ struct Conv3P {
   int c0, c1;               // channels of the two sources (c1 = 0: single source)
   int nchunk0, nchunk;      // 64-channel chunks of source 0 / of both
   int nb;                   // weight ring slots when streaming
+  int nres;                 // streaming variant: the first nres K blocks are nevertheless resident (after the ring in shared memory)
   int dbg;
   int rowload;              // 1: one TMA instruction per halo row instead of one per (TH+2)-row box
   const float* bias;
@@ -81,14 +82,19 @@ template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& 
 // All MMAs of one 64-channel chunk: 9 taps x TH rows x KS k-steps, every descriptor a compile-time offset.
 template <int COUT, int TH, int KS, bool WRES>
 __device__ __forceinline__ void c3_issue_chunk(uint64_t adesc0, uint64_t bdesc0, uint32_t sB_addr, uint64_t* b_full, uint64_t* b_empty,
-                                               uint32_t& wslot, uint32_t& wphase, int nb, uint32_t acc0, uint32_t idesc, uint32_t not_first) {
+                                               uint32_t& wslot, uint32_t& wphase, int nb, int kb0, int nres, uint32_t acc0, uint32_t idesc,
+                                               uint32_t not_first) {
   constexpr uint32_t B_BYTES = COUT * 128;
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
     uint64_t bdesc;
+    bool streamed = false;
     if (WRES) {
       bdesc = bdesc0 + (uint64_t)(tap * (B_BYTES >> 4));
+    } else if (kb0 + tap < nres) {        // partially resident: block kb lives behind the ring
+      bdesc = tc::umma_desc_sw128(sB_addr + (uint32_t)(nb + kb0 + tap) * B_BYTES);
     } else {
+      streamed = true;
       tc::mbar_wait(&b_full[wslot], wphase);
       tc::tc_fence_after();
       bdesc = tc::umma_desc_sw128(sB_addr + wslot * B_BYTES);
@@ -101,7 +107,7 @@ __device__ __forceinline__ void c3_issue_chunk(uint64_t adesc0, uint64_t bdesc0,
         tc::umma_f16(acc0 + (uint32_t)(s * COUT), adesc0 + (uint64_t)(((s + dy) * kC3Pitch + dx) * 8 + k * 2), bdesc + (uint64_t)(k * 2), idesc,
                      (tap == 0 && k == 0) ? not_first : 1u);
     }
-    if (!WRES) {
+    if (streamed) {
       tc::umma_commit(&b_empty[wslot]);
       if (++wslot == (uint32_t)nb) { wslot = 0; wphase ^= 1; }
     }
@@ -123,7 +129,7 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int nkb = p.nchunk * 9;
-  const int nbslots = WRES ? nkb : p.nb;
+  const int nbslots = WRES ? nkb : p.nb + p.nres;
   uint8_t* sA = smem;                                       // [2][A_BYTES]
   uint8_t* sB = sA + 2 * (size_t)A_BYTES;                   // [nbslots][B_BYTES]
   float* s_badd = (float*)(sB + (size_t)nbslots * B_BYTES);   // [8 warps][COUT] bias + time-embedding row of the current image
@@ -170,9 +176,14 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
 
   if (warp == 0) {
     // ===================== TMA producer (one elected lane issues; the warp stays converged) =====================
-    if (WRES && tc::elect_one()) {
-      tc::mbar_expect_tx(w_full, (uint32_t)nkb * B_BYTES);
-      for (int kb = 0; kb < nkb; ++kb) tc::tma_load_3d(sB + (size_t)kb * B_BYTES, &tmB, w_full, 0, 0, kb);
+    if (tc::elect_one()) {
+      if (WRES) {
+        tc::mbar_expect_tx(w_full, (uint32_t)nkb * B_BYTES);
+        for (int kb = 0; kb < nkb; ++kb) tc::tma_load_3d(sB + (size_t)kb * B_BYTES, &tmB, w_full, 0, 0, kb);
+      } else if (p.nres > 0) {
+        tc::mbar_expect_tx(w_full, (uint32_t)p.nres * B_BYTES);
+        for (int kb = 0; kb < p.nres; ++kb) tc::tma_load_3d(sB + (size_t)(p.nb + kb) * B_BYTES, &tmB, w_full, 0, 0, kb);
+      }
     }
     __syncwarp();
     uint32_t ai = 0, wslot = 0, wphase = 0;
@@ -201,6 +212,7 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           }
           if (!WRES) {
             for (int tap = 0; tap < 9; ++tap) {
+              if (c * 9 + tap < p.nres) continue;          // resident block
               tc::mbar_wait(&b_empty[wslot], wphase ^ 1);
               tc::mbar_expect_tx(&b_full[wslot], B_BYTES);
               if (p.wsw) tc::bulk_load_1d(sB + (size_t)wslot * B_BYTES, (const char*)p.wsw + (size_t)(c * 9 + tap) * B_BYTES, B_BYTES, &b_full[wslot]);
@@ -218,7 +230,7 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (WRES) tc::mbar_wait(w_full, 0);
+    if (WRES || p.nres > 0) tc::mbar_wait(w_full, 0);
     const uint32_t idesc = tc::umma_idesc(128, COUT, tc::umma_fmt<T>());
     const uint32_t sB_addr = tc::smem_u32(sB);
     uint32_t ai = 0, ti = 0, wslot = 0, wphase = 0;
@@ -245,13 +257,14 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           const uint32_t nf = c ? 1u : 0u;
           if (!(p.dbg & 2)) {
             switch (ks) {
-              case 4: c3_issue_chunk<COUT, TH, 4, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, p.nb, acc0, idesc, nf); break;
-              case 3: c3_issue_chunk<COUT, TH, 3, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, p.nb, acc0, idesc, nf); break;
-              case 2: c3_issue_chunk<COUT, TH, 2, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, p.nb, acc0, idesc, nf); break;
-              default: c3_issue_chunk<COUT, TH, 1, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, p.nb, acc0, idesc, nf); break;
+              case 4: c3_issue_chunk<COUT, TH, 4, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, p.nb, c * 9, p.nres, acc0, idesc, nf); break;
+              case 3: c3_issue_chunk<COUT, TH, 3, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, p.nb, c * 9, p.nres, acc0, idesc, nf); break;
+              case 2: c3_issue_chunk<COUT, TH, 2, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, p.nb, c * 9, p.nres, acc0, idesc, nf); break;
+              default: c3_issue_chunk<COUT, TH, 1, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, p.nb, c * 9, p.nres, acc0, idesc, nf); break;
             }
           } else if (!WRES) {   // experiment: consume the weight ring without issuing MMAs
             for (int tap = 0; tap < 9; ++tap) {
+              if (c * 9 + tap < p.nres) continue;
               tc::mbar_wait(&b_full[wslot], wphase);
               tc::mbar_arrive(&b_empty[wslot]);
               if (++wslot == (uint32_t)p.nb) { wslot = 0; wphase ^= 1; }
@@ -490,7 +503,7 @@ bool conv3_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvE
 }
 
 namespace {
-struct C3Cfg { int th, nacc; bool wres; int nb; size_t smem; };
+struct C3Cfg { int th, nacc; bool wres; int nb, nres; size_t smem; };
 
 // shared-memory plan: two A stages + weights (resident or ring) + per-warp bias rows + barriers
 C3Cfg c3_plan(int cout, int nkb) {
@@ -503,12 +516,23 @@ C3Cfg c3_plan(int cout, int nkb) {
   const size_t bb = (size_t)cout * 128;
   c.wres = f + (size_t)nkb * bb <= budget;
   if (c3_env("XRD_C3_WRES", 1) == 0) c.wres = false;
-  c.nb = 0;
+  c.nb = 0; c.nres = 0;
   if (!c.wres) {
-    c.nb = (int)std::min<size_t>(12, (budget - f) / bb);
-    XRD_REQUIRE(c.nb >= 2, "conv3: shared memory budget exceeded (cout=%d)", cout);
+    const int fit = (int)((budget - f) / bb);          // weight blocks that fit beside the two activation stages
+    XRD_REQUIRE(fit >= 2, "conv3: shared memory budget exceeded (cout=%d)", cout);
+    // Default: a deep ring, nothing resident.  Keeping the first blocks resident behind a short ring (XRD_C3_PARTIAL=1) cuts
+    // the streamed bytes per tile by up to 40 % but measured no faster (96->96 @256^2: 238 vs 220 us; 96->48 @512^2: 637 vs
+    // 658 us): these layers are not bound by weight bytes alone, and the shorter ring costs more than the bytes save.
+    if (c3_env("XRD_C3_PARTIAL", 0)) {
+      c.nb = std::min(fit, c3_env("XRD_C3_RING", 4));
+      c.nres = std::min(nkb - 1, fit - c.nb);
+    } else {
+      c.nb = std::min(fit, 12);
+      c.nres = 0;
+    }
+    if (c.nres < 0) c.nres = 0;
   }
-  c.smem = 1024 + f + (size_t)(c.wres ? nkb : c.nb) * bb;
+  c.smem = 1024 + f + (size_t)(c.wres ? nkb : c.nb + c.nres) * bb;
   return c;
 }
 
@@ -567,7 +591,7 @@ void conv3(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, T
   const int nkb = p.nchunk * 9;
   XRD_REQUIRE(nkb == w.tc_nkb && w.tc_npad == w.cout, "conv3: packed weights out of date");
   const C3Cfg g = c3_plan(w.cout, nkb);
-  p.nb = g.nb;
+  p.nb = g.nb; p.nres = g.nres;
   p.tiles_w = x1.w / 128;
   p.tiles_h = cdiv(x1.h, g.th);
   p.ntiles = p.tiles_w * p.tiles_h * x1.n;
