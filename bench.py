@@ -153,7 +153,12 @@ def conv_roofline(model, dev, batch, size):
               (1, 144, 144, s // 4, 3, 1), (1, 192, 96, s // 4, 3, 1), (1, 288, 96, s // 4, 3, 1), (2, 144, 144, s // 8, 3, 1),
               (1, 144, 192, s // 8, 3, 1), (10, 192, 192, s // 8, 3, 1), (3, 384, 192, s // 8, 3, 1), (1, 192, 192, s // 8, 3, 1),
               (1, 384, 144, s // 8, 3, 1), (1, 288, 144, s // 8, 3, 1), (6, 192, 576, s // 8, 1, 1), (6, 192, 192, s // 8, 1, 1),
-              (1, 48, 48, s, 3, 2), (1, 96, 96, s // 2, 3, 2), (1, 144, 144, s // 4, 3, 2)]
+              (1, 48, 48, s, 3, 2), (1, 96, 96, s // 2, 3, 2), (1, 144, 144, s // 4, 3, 2),
+              # the 15 res_conv 1x1s (every ResidualBlock whose channel count changes)
+              (1, 48, 96, s // 2, 1, 1), (1, 96, 144, s // 4, 1, 1), (1, 144, 192, s // 8, 1, 1), (3, 384, 192, s // 8, 1, 1),
+              (1, 384, 144, s // 8, 1, 1), (1, 288, 144, s // 8, 1, 1), (1, 288, 144, s // 4, 1, 1), (1, 288, 96, s // 4, 1, 1),
+              (1, 192, 96, s // 4, 1, 1), (1, 192, 96, s // 2, 1, 1), (1, 192, 48, s // 2, 1, 1), (1, 96, 48, s // 2, 1, 1),
+              (1, 96, 48, s, 1, 1)]
     tot_ms, tot_fl, launches = 0.0, 0.0, 0
     per_kernel = {}
     ms = C.c_float()
@@ -163,8 +168,11 @@ def conv_roofline(model, dev, batch, size):
         b = torch.zeros(co, device=dev)
         ho = (hh + 2 * (k // 2) - k) // st + 1
         y = torch.empty(batch, co, ho, ho, device=dev)
-        # same dispatch as the engine (engine.cu conv()): conv3 (W % 128 == 0), conv3w (W == 64), conv1 (1x1), else per-tap
-        if k == 3 and st == 1 and hh % 128 == 0 and co in (48, 96, 144):
+        # same dispatch as the engine (engine.cu conv()): conv3r (<= 64 input channels, W >= 256), conv3 (W % 128 == 0), conv3w (W == 64),
+        # conv1 (1x1), else per-tap.  (In the network the conv3r layers of the 512-wide level additionally apply GroupNorm+SiLU in place.)
+        if k == 3 and st == 1 and hh % 128 == 0 and hh >= 256 and ci <= 64 and co in (48, 96):
+            impl, kern = 11, "k_conv3r"
+        elif k == 3 and st == 1 and hh % 128 == 0 and co in (48, 96, 144):
             impl, kern = 2, "k_conv3"
         elif k == 3 and st == 1 and hh == 64 and co in (144, 192):
             impl, kern = 7, "k_conv3w"
@@ -301,7 +309,7 @@ def main():
                    "parallelism": f"image-sharded x{world}, output all_gather only"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": B * S * S * 4, "d2h_bytes_per_step": B * S * S * 4},
-        "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convolutions (k_conv3, k_conv3w, k_conv1, k_conv_tc): every conv layer shape of one UNet evaluation, "
+        "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convolutions (k_conv3, k_conv3r, k_conv3w, k_conv1, k_conv_tc): every conv layer shape of one UNet evaluation, "
                                "each timed live with CUDA events through the C-ABI op hook, launch weighted",
                      "achieved": conv_tf, "peak": pk["burst"], "unit": "TFLOP/s", "frac": conv_tf / pk["burst"] if pk["burst"] else None,
                      "peak_kind": f"bf16 dense burst, {pk['src']}",

@@ -508,29 +508,38 @@ struct C3Cfg { int th, nacc; bool wres; int nb, nres; size_t smem; };
 // shared-memory plan: two A stages + weights (resident or ring) + per-warp bias rows + barriers
 C3Cfg c3_plan(int cout, int nkb) {
   const size_t budget = 227 * 1024 - 1024 /*alignment slack*/;
+  const size_t bb = (size_t)cout * 128;
+  auto fixed = [&](int th) {
+    const size_t a = (((size_t)(th + 2) * kC3Pitch * 128 + 1023) & ~(size_t)1023);
+    return 2 * a + 8 * cout * 4 + (11 + 32) * 8 + 64;
+  };
   C3Cfg c{};
   c.th = 2;
   c.nacc = cout <= 96 ? 2 : 1;
-  const size_t a = (((size_t)(c.th + 2) * kC3Pitch * 128 + 1023) & ~(size_t)1023);
-  const size_t f = 2 * a + 8 * cout * 4 + (11 + 32) * 8 + 64;
-  const size_t bb = (size_t)cout * 128;
+  size_t f = fixed(c.th);
   c.wres = f + (size_t)nkb * bb <= budget;
   if (c3_env("XRD_C3_WRES", 1) == 0) c.wres = false;
   c.nb = 0; c.nres = 0;
   if (!c.wres) {
+    // Streamed weights: measured (tools/probes/smem_contention_probe.cu) every SM ingests at most ~30 B/clk into shared memory,
+    // chip load or not, and the TMA fill does not slow the MMAs down; a streamed-weight tile is therefore bound by
+    // (weight bytes + halo bytes) / 30 B/clk.  Taller tiles amortise the weight pass over more rows:
+    //   cout 48: 4 rows, still double-buffered accumulators (2*4*48 = 384 columns): 96->48 @512^2 x16 measured 607 vs 750 us
+    //   cout 96: 3 rows would need a single accumulator set (288 columns): measured slower (254 vs 239 us), kept at 2 rows
+    const int tall = c3_env("XRD_C3_TALL", 1);
+    if (tall && cout == 48) { c.th = 4; c.nacc = 2; }
+    else if (tall >= 2 && cout == 96) { c.th = 3; c.nacc = 1; }
+    f = fixed(c.th);
     const int fit = (int)((budget - f) / bb);          // weight blocks that fit beside the two activation stages
     XRD_REQUIRE(fit >= 2, "conv3: shared memory budget exceeded (cout=%d)", cout);
-    // Default: a deep ring, nothing resident.  Keeping the first blocks resident behind a short ring (XRD_C3_PARTIAL=1) cuts
-    // the streamed bytes per tile by up to 40 % but measured no faster (96->96 @256^2: 238 vs 220 us; 96->48 @512^2: 637 vs
-    // 658 us): these layers are not bound by weight bytes alone, and the shorter ring costs more than the bytes save.
+    // A deep ring, nothing resident.  Keeping the first blocks resident behind a short ring (XRD_C3_PARTIAL=1) measured no
+    // faster: the shorter ring costs what the saved bytes gain.
     if (c3_env("XRD_C3_PARTIAL", 0)) {
       c.nb = std::min(fit, c3_env("XRD_C3_RING", 4));
-      c.nres = std::min(nkb - 1, fit - c.nb);
+      c.nres = std::max(0, std::min(nkb - 1, fit - c.nb));
     } else {
       c.nb = std::min(fit, 12);
-      c.nres = 0;
     }
-    if (c.nres < 0) c.nres = 0;
   }
   c.smem = 1024 + f + (size_t)(c.wres ? nkb : c.nb + c.nres) * bb;
   return c;
@@ -553,9 +562,11 @@ void c3_dispatch(Ctx& c, int cout, const C3Cfg& g, int grid, const CUtensorMap& 
                  const Conv3P& p) {
   if (cout == 48) {
     if (g.wres) c3_launch<T, 48, 2, 2, true>(c, grid, g.smem, a0, a1, b, p);
+    else if (g.th == 4) c3_launch<T, 48, 4, 2, false>(c, grid, g.smem, a0, a1, b, p);
     else c3_launch<T, 48, 2, 2, false>(c, grid, g.smem, a0, a1, b, p);
   } else if (cout == 96) {
     if (g.wres) c3_launch<T, 96, 2, 2, true>(c, grid, g.smem, a0, a1, b, p);
+    else if (g.th == 3) c3_launch<T, 96, 3, 1, false>(c, grid, g.smem, a0, a1, b, p);
     else c3_launch<T, 96, 2, 2, false>(c, grid, g.smem, a0, a1, b, p);
   } else {
     if (g.wres) c3_launch<T, 144, 2, 1, true>(c, grid, g.smem, a0, a1, b, p);

@@ -9,8 +9,8 @@ for (cin, hw, cout, impl) in [(96, 256, 96, 2), (96, 512, 48, 2), (192, 256, 96,
     fl = 2.0 * B * hw * hw * cin * cout * 9
     r = []
     for wb in ("0", "1"):
-        os.environ["XRD_C3_PARTIAL"] = wb
+        os.environ["XRD_C3_TALL"] = wb
         oh = OpHandle("fp16"); oh.conv2d(x, w, b, 3, 1, 1, impl); ms = oh.time_last(10); oh.close()
         r.append(ms)
-    print(f"{cin}->{cout} @{hw} impl={impl}: streamed weights {r[0]*1e3:.1f} us, partially resident {r[1]*1e3:.1f} us ({fl/r[1]/1e9:.0f} TF/s)", flush=True)
+    print(f"{cin}->{cout} @{hw} impl={impl}: 2-row tiles {r[0]*1e3:.1f} us, tall tiles {r[1]*1e3:.1f} us ({fl/r[1]/1e9:.0f} TF/s)", flush=True)
     del x, w
