@@ -168,6 +168,18 @@ int xrd_fusion(xrd_handle* h, const float* naf, const float* diff, const float* 
 int xrd_hybrid(xrd_handle* h, const float* noisy, int inference_steps, float* out,
                float* naf_out, float* diff_out, float* mask_out, int B, int H, int W, void* stream);
 
+/* ---- overlap tiling for images larger than the networks' native field (BASELINE.json configs[4]:
+ * 1024x1024 through 512x512 tiles with halos).  The reference has no tiling; the caller these serve is
+ * the resize-to-512 step of RUN:197-201, which they make unnecessary.  Definition:
+ * origins o_k = min(k*(tile-2*halo), L-tile), n = ceil((L-tile)/(tile-2*halo))+1 per axis; a tile's weight
+ * ramps linearly over 2*halo pixels towards each interior edge; pixel = sum(w*v)/sum(w) over the covering
+ * tiles.  Tile t of image b lives at tiles[((b*ny+ty)*nx+tx)*tile*tile], so the tile stack is itself a
+ * (B*ny*nx,1,tile,tile) batch for xrd_hybrid / xrd_ddim_denoise.  fp32, bit-reproducible. */
+/* Host only: tile counts and (nullable) origin lists, each with room for `cap` entries. */
+int xrd_tiles_plan(int H, int W, int tile, int halo, int* ny, int* nx, int* oy, int* ox, int cap);
+int xrd_tiles_extract(const float* img, float* tiles, int B, int H, int W, int tile, int halo, void* stream);
+int xrd_tiles_blend(const float* tiles, float* img, int B, int H, int W, int tile, int halo, void* stream);
+
 /* ---- kernel-level hooks (tests and micro-benchmarks only; no reference counterpart) ----
  * NCHW float32 device tensors in and out; the library converts to its internal NHWC storage
  * of the handle's current mode, runs ONE op through the same kernel the networks use, and

@@ -19,6 +19,11 @@ void run_nafnet(Ctx& c, Handle& h, const float* inp, float* out, int B, int H, i
 void run_router(Ctx& c, Handle& h, const float* x, float* mask, int B, int H, int W, int sanitize);
 void run_fusion(Ctx& c, Handle& h, const float* naf, const float* diff, const float* mask, float* out, int B, int H, int W);
 void prepack_tc(Handle& h, DType dt);
+void tiles_check(int B, int H, int W, int T, int halo);
+void tiles_extract(Ctx& c, const float* img, float* tiles, int B, int H, int W, int T, int halo);
+void tiles_blend(Ctx& c, const float* tiles, float* img, int B, int H, int W, int T, int halo);
+int tiles_count_host(int L, int T, int halo);
+int tiles_origin_host(int k, int L, int T, int halo);
 }  // namespace xrd
 
 using namespace xrd;
@@ -519,6 +524,8 @@ XRD_EXPORT int xrd_op_conv2d_stats(xrd_handle* H, int impl, const float* x, cons
     // 11 = row-ring kernel (conv3r), 12 = conv3r with GroupNorm(8) + SiLU of the input applied inside the kernel,
     // 9 / 10 = conv3 (single source / concat) with GroupNorm(8) + SiLU of the input applied inside the kernel; affine parameters
     // gamma[c] = 1 + 0.01*(c % 7), beta[c] = 0.02*(c % 5) - 0.03
+    // 13 = conv1 with the NAFBlock FFN epilogue (HYB:165-169): y = SimpleGate(conv(x) + bias) * bias[:Cout/2] + x  (Cin == Cout/2),
+    // 14 = conv1 with the scaled-residual epilogue (HYB:161): y = (conv(x) + bias) * bias + x  (Cin == Cout); bias doubles as the scale
     const bool split = impl == 3 || impl == 4 || impl == 6 || impl == 8 || impl == 10;
     const bool fuse_gn = impl == 9 || impl == 10 || impl == 12;
     if (split) XRD_REQUIRE(B == 1 && Cin % 32 == 0, "split-input conv hook needs B == 1 and Cin %% 32 == 0");
@@ -531,7 +538,9 @@ XRD_EXPORT int xrd_op_conv2d_stats(xrd_handle* H, int impl, const float* x, cons
     with_arena(H, s, keyf("opconv", H, B, Hh, W, Cin, Cout, k, stride * 8 + pad, impl), [&](Ctx& c) {
       Tens xi = c.alloc(B, Hh, W, split ? Cin / 2 : Cin);
       Tens xj = split ? c.alloc(B, Hh, W, Cin / 2) : Tens();
-      Tens yo = c.alloc(B, Ho, Wo, Cout);
+      if (impl == 13) XRD_REQUIRE(bias && Cin * 2 == Cout && k == 1, "hook 13 needs a bias, k == 1 and Cin == Cout/2");
+      if (impl == 14) XRD_REQUIRE(bias && Cin == Cout && k == 1, "hook 14 needs a bias, k == 1 and Cin == Cout");
+      Tens yo = c.alloc(B, Ho, Wo, impl == 13 ? Cout / 2 : Cout);
       double* st = c.allocd((size_t)B * 16);
       double* gsum = fuse_gn ? c.allocd((size_t)B * 16) : nullptr;
       float2* gcoef = fuse_gn ? (float2*)c.a->alloc((size_t)B * Cin * sizeof(float2)) : nullptr;
@@ -574,6 +583,12 @@ XRD_EXPORT int xrd_op_conv2d_stats(xrd_handle* H, int impl, const float* x, cons
             zero_async(cc, st, (size_t)yo.n * 16 * sizeof(double));
           }
           conv1(cc, xi, split ? &xj : nullptr, H->op_w, e, yy);
+        }
+        else if (impl == 13 || impl == 14) {
+          e.gate = impl == 13;
+          e.out_scale = H->op_w.bias;
+          e.resid = xi;
+          conv1(cc, xi, nullptr, H->op_w, e, yy);
         }
         else if (impl == 1 || impl == 4) conv_tc(cc, xi, split ? &xj : nullptr, H->op_w, e, yy);
         else conv_simt(cc, xi, nullptr, H->op_w, e, yy);
@@ -671,5 +686,36 @@ XRD_EXPORT int xrd_op_time_last(xrd_handle* H, int iters, float* ms_per_launch, 
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *ms_per_launch = ms / (float)iters;
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// overlap tiling (BASELINE configs[4]); no handle: the kernels need a stream only
+XRD_EXPORT int xrd_tiles_plan(int H, int W, int tile, int halo, int* ny, int* nx, int* oy, int* ox, int cap) {
+  return guarded([&] {
+    tiles_check(1, H, W, tile, halo);
+    const int cy = tiles_count_host(H, tile, halo), cx = tiles_count_host(W, tile, halo);
+    if (ny) *ny = cy;
+    if (nx) *nx = cx;
+    if (oy) { XRD_REQUIRE(cap >= cy, "origin buffer too small (%d < %d)", cap, cy); for (int k = 0; k < cy; ++k) oy[k] = tiles_origin_host(k, H, tile, halo); }
+    if (ox) { XRD_REQUIRE(cap >= cx, "origin buffer too small (%d < %d)", cap, cx); for (int k = 0; k < cx; ++k) ox[k] = tiles_origin_host(k, W, tile, halo); }
+  });
+}
+
+XRD_EXPORT int xrd_tiles_extract(const float* img, float* tiles, int B, int H, int W, int tile, int halo, void* stream) {
+  return guarded([&] {
+    XRD_REQUIRE(img && tiles, "null argument");
+    Ctx c;
+    c.s = (cudaStream_t)stream;
+    tiles_extract(c, img, tiles, B, H, W, tile, halo);
+  });
+}
+
+XRD_EXPORT int xrd_tiles_blend(const float* tiles, float* img, int B, int H, int W, int tile, int halo, void* stream) {
+  return guarded([&] {
+    XRD_REQUIRE(img && tiles, "null argument");
+    Ctx c;
+    c.s = (cudaStream_t)stream;
+    tiles_blend(c, tiles, img, B, H, W, tile, halo);
   });
 }

@@ -12,6 +12,10 @@
 //   * the MMA issue loop uses compile-time descriptor offsets (see conv3.cu);
 //   * epilogue: + bias, + residual (prefetched), optional GroupNorm sums of the output, 16-byte stores of whole
 //     sectors; an output wider than 192 channels is covered by blockIdx.y (qkv: 3 slices of 192).
+// The same kernel serves the NAFBlock 1x1 convolutions (HYB:152-169; channel counts 32..1024, powers of two): slices of
+// 32/64/128/256 output channels drained in 32-column blocks, the per-channel beta/gamma scale of HYB:161,169 in the
+// epilogue, and for conv4 (C -> 2C, 2C <= 256) SimpleGate (HYB:119-121: first half x second half) applied to the
+// accumulator row before it is stored, so the 2C-channel tensor never reaches HBM.
 #include "kernels.cuh"
 #include "tc_common.cuh"
 
@@ -30,6 +34,7 @@ struct Conv1P {
   int nchunk0, nchunk;      // 64-channel chunks of source 0 / of both
   int ldc;                  // output channels per pixel (row stride of Y and of the residual)
   const float* bias;
+  const float* out_scale;   // optional per-output-channel factor on (acc + bias)
   const void* resid;
   void* y;
   double* stats;            // optional [nimg][8][2]; requires ldc == COUT and hw % 128 == 0
@@ -66,22 +71,25 @@ __device__ __forceinline__ void c1_issue(uint32_t acc, uint64_t adesc, uint64_t 
   for (int k = 0; k < KS; ++k) tc::umma_f16(acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, k == 0 ? not_first : 1u);
 }
 
-template <typename T, int COUT>
+template <typename T, int COUT, bool GATE>
 __global__ void __launch_bounds__(kC1Threads, 1)
 k_conv1(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB,
         const Conv1P p) {
   constexpr uint32_t B_BYTES = COUT * 128;                 // one 64-channel K block of the weight slice
-  constexpr int CPG = COUT / 8;
-  constexpr int NBLK = COUT / 48;
-  constexpr uint32_t TMEM_COLS = 2 * COUT <= 128 ? 128 : (2 * COUT <= 256 ? 256 : 512);
-  static_assert(COUT % 48 == 0 && 2 * COUT <= 512, "two accumulators must fit TMEM");
+  constexpr int OC = GATE ? COUT / 2 : COUT;               // channels stored per pixel by this CTA
+  constexpr int EB = (OC % 48 == 0) ? 48 : 32;             // epilogue block: columns drained per TMEM round trip
+  constexpr int CPG = OC / 8;
+  constexpr int NBLK = OC / EB;
+  constexpr uint32_t TMEM_COLS = 2 * COUT <= 64 ? 64 : (2 * COUT <= 128 ? 128 : (2 * COUT <= 256 ? 256 : 512));
+  static_assert(OC % EB == 0 && COUT % 16 == 0 && COUT <= 256 && 2 * COUT <= 512, "two accumulators must fit TMEM");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                        // [kC1Stages][16 KB]
   uint8_t* sB = sA + (size_t)kC1Stages * kC1ATile;           // [nchunk][B_BYTES] resident weight slice
   float* s_bias = (float*)(sB + (size_t)p.nchunk * B_BYTES); // [COUT]
-  uint64_t* bars = (uint64_t*)(s_bias + COUT);
+  float* s_scale = s_bias + COUT;                            // [COUT]
+  uint64_t* bars = (uint64_t*)(s_scale + COUT);
   uint64_t* a_full = bars;                   // [kC1Stages]
   uint64_t* a_empty = bars + kC1Stages;      // [kC1Stages]
   uint64_t* acc_full = bars + 2 * kC1Stages; // [2]
@@ -90,7 +98,7 @@ k_conv1(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * COUT;           // first output channel of this CTA's slice
+  const int n0 = blockIdx.y * COUT;           // first output channel of this CTA's slice (GATE: a single slice)
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmA0);
@@ -105,7 +113,10 @@ k_conv1(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     tc::tmem_alloc(tmem_slot, TMEM_COLS);
     tc::tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_bias[i] = p.bias ? p.bias[n0 + i] : 0.f;
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
+    s_bias[i] = p.bias ? p.bias[n0 + i] : 0.f;
+    s_scale[i] = (p.out_scale && i < OC) ? p.out_scale[n0 + i] : 1.f;
+  }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -203,36 +214,51 @@ k_conv1(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         const int img = (int)(((int64_t)t * 128) / p.hw);
         if (img != cur_img) { flush_stats(cur_img); cur_img = img; }
       }
-      uint4 rcur[6], rnext[6];
+      uint4 rcur[EB / 8], rnext[EB / 8];
       if (rp && ok) {
 #pragma unroll
-        for (int j = 0; j < 6; ++j) rcur[j] = __ldg(reinterpret_cast<const uint4*>(rp + pix * p.ldc + n0) + j);
+        for (int j = 0; j < EB / 8; ++j) rcur[j] = __ldg(reinterpret_cast<const uint4*>(rp + pix * p.ldc + n0) + j);
       }
       tc::mbar_wait(&acc_full[grp], use & 1);
       tc::tc_fence_after();
       const uint32_t tacc = (uint32_t)(grp * COUT) + ((uint32_t)(quad * 32) << 16);
 #pragma unroll
       for (int cb = 0; cb < NBLK; ++cb) {
-        uint32_t v[48];
+        uint32_t v[EB], v2[GATE ? EB : 1];
         uint4 pk_even;
-        c1_tmem_ld16(tacc + (uint32_t)(cb * 48), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-        c1_tmem_ld16(tacc + (uint32_t)(cb * 48 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-        c1_tmem_ld16(tacc + (uint32_t)(cb * 48 + 32), *reinterpret_cast<uint32_t(*)[16]>(&v[32]));
+#pragma unroll
+        for (int j = 0; j < EB / 16; ++j) c1_tmem_ld16(tacc + (uint32_t)(cb * EB + j * 16), *reinterpret_cast<uint32_t(*)[16]>(&v[j * 16]));
+        if (GATE) {
+#pragma unroll
+          for (int j = 0; j < EB / 16; ++j)
+            c1_tmem_ld16(tacc + (uint32_t)(OC + cb * EB + j * 16), *reinterpret_cast<uint32_t(*)[16]>(&v2[GATE ? j * 16 : 0]));
+        }
         const bool has_next = rp && ok && cb + 1 < NBLK;
         if (has_next) {
 #pragma unroll
-          for (int j = 0; j < 6; ++j) rnext[j] = __ldg(reinterpret_cast<const uint4*>(rp + pix * p.ldc + n0 + (cb + 1) * 48) + j);
+          for (int j = 0; j < EB / 8; ++j) rnext[j] = __ldg(reinterpret_cast<const uint4*>(rp + pix * p.ldc + n0 + (cb + 1) * EB) + j);
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int h8 = 0; h8 < 6; ++h8) {
-          const int co = cb * 48 + h8 * 8;
+        for (int h8 = 0; h8 < EB / 8; ++h8) {
+          const int co = cb * EB + h8 * 8;
           const float4 b0 = *reinterpret_cast<const float4*>(s_bias + co), b1 = *reinterpret_cast<const float4*>(s_bias + co + 4);
           float r8[8];
           r8[0] = __uint_as_float(v[h8 * 8 + 0]) + b0.x; r8[1] = __uint_as_float(v[h8 * 8 + 1]) + b0.y;
           r8[2] = __uint_as_float(v[h8 * 8 + 2]) + b0.z; r8[3] = __uint_as_float(v[h8 * 8 + 3]) + b0.w;
           r8[4] = __uint_as_float(v[h8 * 8 + 4]) + b1.x; r8[5] = __uint_as_float(v[h8 * 8 + 5]) + b1.y;
           r8[6] = __uint_as_float(v[h8 * 8 + 6]) + b1.z; r8[7] = __uint_as_float(v[h8 * 8 + 7]) + b1.w;
+          if (GATE) {                                    // SimpleGate: channel co times channel OC + co (HYB:119-121)
+            const float4 g0 = *reinterpret_cast<const float4*>(s_bias + OC + co), g1 = *reinterpret_cast<const float4*>(s_bias + OC + co + 4);
+            r8[0] *= __uint_as_float(v2[GATE ? h8 * 8 + 0 : 0]) + g0.x; r8[1] *= __uint_as_float(v2[GATE ? h8 * 8 + 1 : 0]) + g0.y;
+            r8[2] *= __uint_as_float(v2[GATE ? h8 * 8 + 2 : 0]) + g0.z; r8[3] *= __uint_as_float(v2[GATE ? h8 * 8 + 3 : 0]) + g0.w;
+            r8[4] *= __uint_as_float(v2[GATE ? h8 * 8 + 4 : 0]) + g1.x; r8[5] *= __uint_as_float(v2[GATE ? h8 * 8 + 5 : 0]) + g1.y;
+            r8[6] *= __uint_as_float(v2[GATE ? h8 * 8 + 6 : 0]) + g1.z; r8[7] *= __uint_as_float(v2[GATE ? h8 * 8 + 7 : 0]) + g1.w;
+          }
+          if (p.out_scale) {
+            const float4 s0 = *reinterpret_cast<const float4*>(s_scale + co), s1 = *reinterpret_cast<const float4*>(s_scale + co + 4);
+            r8[0] *= s0.x; r8[1] *= s0.y; r8[2] *= s0.z; r8[3] *= s0.w; r8[4] *= s1.x; r8[5] *= s1.y; r8[6] *= s1.z; r8[7] *= s1.w;
+          }
           if (rp && ok) {
             float q8[8];
             c1_unpack8<T>(rcur[h8], q8);
@@ -250,11 +276,11 @@ k_conv1(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           uint4 pk;
           pk.x = tc::pack2<T>(r8[0], r8[1]); pk.y = tc::pack2<T>(r8[2], r8[3]);
           pk.z = tc::pack2<T>(r8[4], r8[5]); pk.w = tc::pack2<T>(r8[6], r8[7]);
-          if (h8 & 1) { if (ok) tc::st_global_v8(yp + pix * p.ldc + n0 + co - 8, pk_even, pk); } else pk_even = pk;   // 32-byte sector stores
+          if (h8 & 1) { if (ok) tc::st_global_v8(yp + pix * p.ldc + (GATE ? 0 : n0) + co - 8, pk_even, pk); } else pk_even = pk;   // 32-byte sector stores
         }
         if (has_next) {
 #pragma unroll
-          for (int j = 0; j < 6; ++j) rcur[j] = rnext[j];
+          for (int j = 0; j < EB / 8; ++j) rcur[j] = rnext[j];
         }
       }
       tc::tc_fence_before();
@@ -269,31 +295,45 @@ k_conv1(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   }
 }
 
+// output channels per CTA slice: the UNet's multiples of 48 (<= 192) or NAFNet's powers of two (<= 256), weight slice resident
+static int c1_slice(int cout, int nchunk, bool gate) {
+  auto fits = [&](int sl) {
+    return 1024 + (size_t)kC1Stages * kC1ATile + (size_t)nchunk * sl * 128 + (size_t)sl * 8 + 256 <= (size_t)227 * 1024;
+  };
+  if (gate) return (cout == 64 || cout == 128 || cout == 256) && fits(cout) ? cout : 0;
+  if (cout % 48 == 0) {
+    const int sl = cout <= 192 ? cout : 192;
+    return (sl == 48 || sl == 96 || sl == 144 || sl == 192) && cout % sl == 0 && fits(sl) ? sl : 0;
+  }
+  for (int sl : {256, 128, 64, 32})
+    if (cout % sl == 0 && fits(sl)) return sl;
+  return 0;
+}
+
 bool conv1_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e) {
   static const int enabled = getenv("XRD_CONV1") ? atoi(getenv("XRD_CONV1")) : 1;
   if (!enabled) return false;
   if (x1.dt == DT_F32) return false;
   if (!(w.kh == 1 && w.kw == 1 && w.stride == 1 && w.pad == 0) || w.d2s) return false;
   if (x1.c % 16 != 0 || (x2 && x2->c % 16 != 0)) return false;
-  if (e.in_scale || e.out_scale || e.chan_add || e.act != ACT_NONE) return false;
-  const int slice = w.cout <= 192 ? w.cout : 192;
-  if (!(slice == 48 || slice == 96 || slice == 144 || slice == 192) || w.cout % slice != 0) return false;
+  if (e.in_scale || e.chan_add || e.act != ACT_NONE || e.in_coef) return false;
   const int nchunk = (x1.c + 63) / 64 + (x2 ? (x2->c + 63) / 64 : 0);
-  const size_t smem = 1024 + (size_t)kC1Stages * kC1ATile + (size_t)nchunk * slice * 128 + slice * 4 + 256;
-  if (smem > 227 * 1024) return false;
-  if (e.stats_out && (w.cout != slice || ((int64_t)x1.h * x1.w) % 128 != 0)) return false;
+  const int slice = c1_slice(w.cout, nchunk, e.gate);
+  if (!slice) return false;
+  if (e.stats_out && (e.gate || w.cout != slice || ((int64_t)x1.h * x1.w) % 128 != 0)) return false;
   return true;
 }
 
 void conv1(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y) {
   XRD_REQUIRE(conv1_supported(x1, x2, w, e), "conv1: unsupported configuration");
   const int c0 = x1.c, c1 = x2 ? x2->c : 0;
-  XRD_REQUIRE(c0 + c1 == w.cin && y.n == x1.n && y.h == x1.h && y.w == x1.w && y.c == w.cout && y.dt == x1.dt, "conv1: shape mismatch");
+  XRD_REQUIRE(c0 + c1 == w.cin && y.n == x1.n && y.h == x1.h && y.w == x1.w && y.c == (e.gate ? w.cout / 2 : w.cout) && y.dt == x1.dt,
+              "conv1: shape mismatch");
   if (x2) XRD_REQUIRE(x2->n == x1.n && x2->h == x1.h && x2->w == x1.w && x2->dt == x1.dt, "conv1: source mismatch");
   if (e.resid.p) XRD_REQUIRE(e.resid.dt == y.dt && e.resid.numel() == y.numel(), "conv1: residual mismatch");
   if (c.dry) return;
   if (!w.wtc[x1.dt] || w.tc_c1 != c0) conv_tc_pack(c.s, w, x1.dt, c0);
-  const int slice = w.cout <= 192 ? w.cout : 192;
+  const int slice = c1_slice(w.cout, (c0 + 63) / 64 + (c1 + 63) / 64, e.gate);
   Conv1P p;
   p.npix = (int64_t)x1.n * x1.h * x1.w;
   p.hw = x1.h * x1.w;
@@ -302,8 +342,9 @@ void conv1(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, T
   p.nchunk0 = (c0 + 63) / 64;
   p.nchunk = p.nchunk0 + (c1 + 63) / 64;
   XRD_REQUIRE(p.nchunk == w.tc_nkb, "conv1: packed weights out of date");
-  p.ldc = w.cout;
+  p.ldc = y.c;
   p.bias = w.bias;
+  p.out_scale = e.out_scale;
   p.resid = e.resid.p; p.y = y.p;
   p.stats = e.stats_out;
 
@@ -328,7 +369,7 @@ void conv1(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, T
                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) fail(XRD_ERR_CUDA, "cuTensorMapEncodeTiled(conv1 weights) failed: %d", (int)r);
   }
-  const size_t smem = 1024 + (size_t)kC1Stages * kC1ATile + (size_t)p.nchunk * slice * 128 + slice * 4 + 256;
+  const size_t smem = 1024 + (size_t)kC1Stages * kC1ATile + (size_t)p.nchunk * slice * 128 + (size_t)slice * 8 + 256;
   static int nsm = 0;
   if (!nsm) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
   const int nslices = w.cout / slice;
@@ -345,15 +386,24 @@ void conv1(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, T
     }
     XRD_LAUNCH(c, kern, grid, kC1Threads, smem, tmA0, tmA1, tmB, p);
   };
-  if (x1.dt == DT_BF16) {
-    using T = __nv_bfloat16;
-    if (slice == 48) launch(k_conv1<T, 48>); else if (slice == 96) launch(k_conv1<T, 96>);
-    else if (slice == 144) launch(k_conv1<T, 144>); else launch(k_conv1<T, 192>);
-  } else {
-    using T = __half;
-    if (slice == 48) launch(k_conv1<T, 48>); else if (slice == 96) launch(k_conv1<T, 96>);
-    else if (slice == 144) launch(k_conv1<T, 144>); else launch(k_conv1<T, 192>);
-  }
+  auto pick = [&](auto tag) {
+    using T = decltype(tag);
+    if (e.gate) {
+      if (slice == 64) launch(k_conv1<T, 64, true>); else if (slice == 128) launch(k_conv1<T, 128, true>); else launch(k_conv1<T, 256, true>);
+      return;
+    }
+    switch (slice) {
+      case 48: launch(k_conv1<T, 48, false>); break;
+      case 96: launch(k_conv1<T, 96, false>); break;
+      case 144: launch(k_conv1<T, 144, false>); break;
+      case 192: launch(k_conv1<T, 192, false>); break;
+      case 32: launch(k_conv1<T, 32, false>); break;
+      case 64: launch(k_conv1<T, 64, false>); break;
+      case 128: launch(k_conv1<T, 128, false>); break;
+      default: launch(k_conv1<T, 256, false>); break;
+    }
+  };
+  if (x1.dt == DT_BF16) pick(__nv_bfloat16()); else pick(__half());
 }
 
 }  // namespace xrd

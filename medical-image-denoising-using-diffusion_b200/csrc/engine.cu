@@ -363,6 +363,7 @@ static void conv(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi
   if (c.tc && conv3_supported(x1, x2, w, e)) { conv3(c, x1, x2, w, e, y); return; }
   if (c.tc && conv3w_supported(x1, x2, w, e)) { conv3w(c, x1, x2, w, e, y); return; }
   if (c.tc && conv1_supported(x1, x2, w, e)) { conv1(c, x1, x2, w, e, y); return; }
+  XRD_REQUIRE(!e.gate, "conv: the fused SimpleGate epilogue exists in conv1 only (caller must check conv1_supported)");
   if (c.tc && conv_tc_supported(x1, x2, w, e)) { conv_tc(c, x1, x2, w, e, y); return; }
   ConvEpi e2 = e;
   e2.stats_out = nullptr;
@@ -645,8 +646,14 @@ static void nafblock(Ctx& c, NafBlockW& b, const Tens& x, Tens& out) {
   }
   conv(c, g, nullptr, b.c3, e3, y);
   layernorm(c, y, b.n2w, b.n2b, 1e-6f, t);
-  conv(c, t, nullptr, b.c4, ConvEpi(), u);
-  simple_gate(c, u, g);
+  ConvEpi e4;
+  e4.gate = true;                               // SimpleGate in the GEMM epilogue where the 2C-wide row fits one accumulator
+  if (c.tc && conv1_supported(t, nullptr, b.c4, e4)) {
+    conv(c, t, nullptr, b.c4, e4, g);
+  } else {
+    conv(c, t, nullptr, b.c4, ConvEpi(), u);
+    simple_gate(c, u, g);
+  }
   ConvEpi e5;
   e5.out_scale = b.gamma; e5.resid = y;
   conv(c, g, nullptr, b.c5, e5, out);

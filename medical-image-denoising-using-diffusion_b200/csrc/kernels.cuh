@@ -29,6 +29,7 @@ struct ConvEpi {
   Tens resid;                       // optional residual with the output's layout
   int act = ACT_NONE;
   double* stats_out = nullptr;      // optional [N][8][2] += (sum, sum of squares) of the stored output over 8 channel groups
+  bool gate = false;                // SimpleGate on the output row (HYB:119-121): y has cout/2 channels (conv1 only)
   // GroupNorm + activation of the INPUT applied inside the kernel (conv3 only): [N][cin] (0.5*scale, 0.5*shift) from gn_coef()
   const float2* in_coef = nullptr;
   int in_act = ACT_NONE;

@@ -1,0 +1,213 @@
+// kernels_naf.cu -- bandwidth-oriented versions of the NAFBlock's HBM-bound passes for 16-bit NHWC storage
+// (LayerNorm2d HYB:108-115, depthwise 3x3 + SimpleGate + pool HYB:155-157).  Same arithmetic as the generic kernels in
+// kernels_simt.cu (fp32 math, two-pass variance, value-as-stored pooling); what changes is the memory access: 16-byte
+// loads/stores and several independent pixels in flight per thread, because the generic versions (8-byte accesses, one
+// pixel in flight) were latency-bound at 10-48 % of the HBM copy rate (profiles/README.md section 6).
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace xrd {
+
+// ---------------------------------------------------------------------------------------------------------------
+// LayerNorm over the channels of each pixel.  lpp lanes share a pixel, each lane owns NV 16-byte chunks (8 channels each):
+// chunk j of lane `sub` covers channels (j*lpp + sub)*8..+8.  U pixels per thread are loaded before any is reduced.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int NV, int U>
+__global__ void __launch_bounds__(256) k_layernorm16(const T* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+                                                     float eps, T* __restrict__ y, int64_t npix, int C, int lpp) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % lpp, psub = lane / lpp;
+  const int ppw = 32 / lpp;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float invC = 1.0f / (float)C;
+  float gg[NV][8], bb[NV][8];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c0 = (j * lpp + sub) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { gg[j][i] = __ldg(g + c0 + i); bb[j][i] = __ldg(b + c0 + i); }
+  }
+  for (int64_t p0 = warp * (ppw * U); p0 < npix; p0 += nwarps * (ppw * U)) {
+    uint4 q[U][NV];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t pix = p0 + u * ppw + psub;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        if (pix < npix) q[u][j] = __ldg(reinterpret_cast<const uint4*>(x + pix * C + (j * lpp + sub) * 8));
+        else q[u][j] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t pix = p0 + u * ppw + psub;
+      float v[NV][8];
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        tc::unpack8<T>(q[u][j], v[j]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[j][i];
+      }
+      for (int o = lpp >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * invC;
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = v[j][i] - mean; ss = fmaf(d, d, ss); }
+      for (int o = lpp >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rstd = 1.0f / sqrtf(ss * invC + eps);
+      if (pix < npix) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          float o8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o8[i] = (v[j][i] - mean) * rstd * gg[j][i] + bb[j][i];
+          uint4 pk;
+          pk.x = tc::pack2<T>(o8[0], o8[1]); pk.y = tc::pack2<T>(o8[2], o8[3]);
+          pk.z = tc::pack2<T>(o8[4], o8[5]); pk.w = tc::pack2<T>(o8[6], o8[7]);
+          *reinterpret_cast<uint4*>(y + pix * C + (j * lpp + sub) * 8) = pk;
+        }
+      }
+    }
+  }
+}
+
+bool layernorm16_supported(const Tens& x, const Tens& y) {
+  static const int enabled = getenv("XRD_LN16") ? atoi(getenv("XRD_LN16")) : 1;
+  if (!enabled || x.dt == DT_F32 || y.dt != x.dt) return false;
+  const int chunks = x.c / 8;
+  if (x.c % 8 != 0 || chunks < 1) return false;
+  if (chunks <= 32) return (chunks & (chunks - 1)) == 0;          // 8..256 channels: one chunk per lane, lpp = chunks
+  return chunks == 64;                                             // 512 channels: two chunks per lane
+}
+
+void layernorm16(Ctx& c, const Tens& x, const float* g, const float* b, float eps, Tens& y) {
+  XRD_REQUIRE(layernorm16_supported(x, y) && y.numel() == x.numel() && y.c == x.c, "layernorm16: unsupported configuration");
+  const int chunks = x.c / 8;
+  const int nv = chunks > 32 ? 2 : 1;
+  const int lpp = chunks / nv;
+  const int64_t npix = (int64_t)x.n * x.h * x.w;
+  const int U = nv == 2 ? 2 : 4;
+  const int64_t per_block = (int64_t)(32 / lpp) * U * 8;
+  const int bx = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv64(npix, per_block), 148 * 8));
+  if (x.dt == DT_F16) {
+    using T = __half;
+    if (nv == 2) XRD_LAUNCH(c, (k_layernorm16<T, 2, 2>), bx, 256, 0, (const T*)x.p, g, b, eps, (T*)y.p, npix, x.c, lpp);
+    else XRD_LAUNCH(c, (k_layernorm16<T, 1, 4>), bx, 256, 0, (const T*)x.p, g, b, eps, (T*)y.p, npix, x.c, lpp);
+  } else {
+    using T = __nv_bfloat16;
+    if (nv == 2) XRD_LAUNCH(c, (k_layernorm16<T, 2, 2>), bx, 256, 0, (const T*)x.p, g, b, eps, (T*)y.p, npix, x.c, lpp);
+    else XRD_LAUNCH(c, (k_layernorm16<T, 1, 4>), bx, 256, 0, (const T*)x.p, g, b, eps, (T*)y.p, npix, x.c, lpp);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// depthwise 3x3 (2C channels) + SimpleGate + global-average-pool partial sums, C in {32, 64, 128}.
+//   thread = (pixel column x, 8 consecutive channels of the 2C-channel tensor); it walks down a strip of rows.
+//   Each loaded row (pixels x-1, x, x+1: three 16-byte loads) is unpacked once and feeds the three output rows it
+//   touches (ky = 2, 1, 0) held as running accumulators, so every input element is loaded 3x (L1 hits) instead of 9x and
+//   converted once.  The 72 weights of the thread's 8 channels live in registers.  Lanes l and l ^ nq hold channel c
+//   and channel C + c of the same pixel: one shuffle exchange forms the gate product; the lower lane stores 16 bytes.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256, 2) k_dwconv_gate_pool16(const T* __restrict__ u, const float* __restrict__ w9,
+                                                               const float* __restrict__ bias, T* __restrict__ g, float* __restrict__ pool,
+                                                               int H, int W, int C, int rows_per_block) {
+  extern __shared__ float s_pool[];  // [C]
+  const int nq = C >> 3;                       // 8-channel chunks per half: 4, 8 or 16
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ppw = 32 / (2 * nq);               // pixels per warp
+  const int q = lane & (nq - 1);
+  const int half = (lane / nq) & 1;
+  const int x = (blockIdx.x * 8 + warp) * ppw + lane / (2 * nq);
+  const int n = blockIdx.z;
+  const int y0 = blockIdx.y * rows_per_block;
+  const int y1 = min(y0 + rows_per_block, H);
+  const int C2 = 2 * C;
+  const int cb = half * C + q * 8;             // first of this thread's 8 channels in the 2C-channel tensor
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_pool[i] = 0.f;
+  __syncthreads();
+
+  float w[9][8], bs[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w9 + t * C2 + cb)), b = __ldg(reinterpret_cast<const float4*>(w9 + t * C2 + cb + 4));
+    w[t][0] = a.x; w[t][1] = a.y; w[t][2] = a.z; w[t][3] = a.w; w[t][4] = b.x; w[t][5] = b.y; w[t][6] = b.z; w[t][7] = b.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bs[i] = __ldg(bias + cb + i);
+
+  const bool xin = x < W;
+  const T* base = u + (int64_t)n * H * W * C2 + cb;
+  auto load_row = [&](int r, uint4 (&d)[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int xx = x + k - 1;
+      if (xin && r >= 0 && r < H && xx >= 0 && xx < W) d[k] = __ldg(reinterpret_cast<const uint4*>(base + ((int64_t)r * W + xx) * C2));
+      else d[k] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  float a0[8], a1[8], a2[8], ps[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a0[i] = bs[i]; a1[i] = bs[i]; a2[i] = bs[i]; ps[i] = 0.f; }
+  uint4 cur[3], nxt[3];
+  load_row(y0 - 1, cur);
+  for (int r = y0 - 1; r <= y1; ++r) {
+    if (r < y1) load_row(r + 1, nxt);           // next row in flight while this one is consumed
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float v[8];
+      tc::unpack8<T>(cur[k], v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        a0[i] = fmaf(v[i], w[6 + k][i], a0[i]);   // output row r-1 sees this row through ky = 2
+        a1[i] = fmaf(v[i], w[3 + k][i], a1[i]);   // output row r   through ky = 1
+        a2[i] = fmaf(v[i], w[k][i], a2[i]);       // output row r+1 through ky = 0
+      }
+    }
+    // output row r-1 is complete
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = a0[i] * __shfl_xor_sync(0xffffffffu, a0[i], nq);
+    if (r - 1 >= y0 && xin && half == 0) {
+      uint4 pk;
+      pk.x = tc::pack2<T>(o[0], o[1]); pk.y = tc::pack2<T>(o[2], o[3]); pk.z = tc::pack2<T>(o[4], o[5]); pk.w = tc::pack2<T>(o[6], o[7]);
+      *reinterpret_cast<uint4*>(g + (((int64_t)n * H + (r - 1)) * W + x) * C + q * 8) = pk;
+      float st[8];
+      tc::unpack8<T>(pk, st);                    // the pool must see what the next layer sees: the value as stored
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ps[i] += st[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a0[i] = a1[i]; a1[i] = a2[i]; a2[i] = bs[i]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cur[k] = nxt[k];
+  }
+  if (half == 0 && xin) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&s_pool[q * 8 + i], ps[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&pool[(int64_t)n * C + i], s_pool[i]);
+}
+
+bool dwconv_gate_pool16_supported(const Tens& u, const Tens& g) {
+  static const int enabled = getenv("XRD_DW16") ? atoi(getenv("XRD_DW16")) : 1;
+  if (!enabled || u.dt == DT_F32 || g.dt != u.dt) return false;
+  return g.c == 32 || g.c == 64 || g.c == 128;
+}
+
+void dwconv_gate_pool16(Ctx& c, const Tens& u, const float* w9, const float* bias, Tens& g, float* pool) {
+  const int C = g.c;
+  XRD_REQUIRE(dwconv_gate_pool16_supported(u, g) && u.c == 2 * C && g.n == u.n && g.h == u.h && g.w == u.w, "dwconv_gate_pool16: shape");
+  const int ppb = 8 * (32 / (2 * (C / 8)));          // pixel columns per block
+  const int rows = u.h >= 256 ? 32 : 16;
+  dim3 grid(cdiv(u.w, ppb), cdiv(u.h, rows), u.n);
+  if (u.dt == DT_F16) XRD_LAUNCH(c, (k_dwconv_gate_pool16<__half>), grid, 256, C * sizeof(float), (const __half*)u.p, w9, bias, (__half*)g.p, pool, u.h, u.w, C, rows);
+  else XRD_LAUNCH(c, (k_dwconv_gate_pool16<__nv_bfloat16>), grid, 256, C * sizeof(float), (const __nv_bfloat16*)u.p, w9, bias, (__nv_bfloat16*)g.p, pool, u.h, u.w, C, rows);
+}
+
+}  // namespace xrd

@@ -419,7 +419,11 @@ __global__ void __launch_bounds__(256) k_layernorm(const TI* __restrict__ x, con
   }
 }
 
+bool layernorm16_supported(const Tens& x, const Tens& y);
+void layernorm16(Ctx& c, const Tens& x, const float* g, const float* b, float eps, Tens& y);
+
 void layernorm(Ctx& c, const Tens& x, const float* g, const float* b, float eps, Tens& y) {
+  if (layernorm16_supported(x, y)) { layernorm16(c, x, g, b, eps, y); return; }
   const int C = x.c, Q = C / 4;
   XRD_REQUIRE(C % 4 == 0 && y.numel() == x.numel() && y.c == C, "layernorm: shape");
   int lpp = 1;
@@ -497,7 +501,11 @@ __global__ void __launch_bounds__(256) k_dwconv_gate_pool(const T* __restrict__ 
   for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&pool[(int64_t)n * C + i], s_pool[i]);
 }
 
+bool dwconv_gate_pool16_supported(const Tens& u, const Tens& g);
+void dwconv_gate_pool16(Ctx& c, const Tens& u, const float* w9, const float* bias, Tens& g, float* pool);
+
 void dwconv_gate_pool(Ctx& c, const Tens& u, const float* w9, const float* bias, Tens& g, float* pool) {
+  if (dwconv_gate_pool16_supported(u, g)) { dwconv_gate_pool16(c, u, w9, bias, g, pool); return; }
   const int C = g.c;
   XRD_REQUIRE(u.c == 2 * C && C % 4 == 0 && C / 4 <= 256 && g.n == u.n && g.h == u.h && g.w == u.w && g.dt == u.dt,
               "dwconv_gate_pool: shape");

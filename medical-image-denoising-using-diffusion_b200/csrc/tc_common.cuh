@@ -172,6 +172,17 @@ template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) 
   __half2 v = __floats2half2_rn(sat_h(a), sat_h(b));
   return *reinterpret_cast<uint32_t*>(&v);
 }
+template <typename T> __device__ __forceinline__ void unpack8(const uint4& t, float (&v)[8]);
+template <> __device__ __forceinline__ void unpack8<__half>(const uint4& t, float (&v)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& t, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
 template <typename T> __device__ __forceinline__ void ld8(const T* p, float (&v)[8]);
 template <> __device__ __forceinline__ void ld8<__half>(const __half* p, float (&v)[8]) {
   uint4 t = __ldg(reinterpret_cast<const uint4*>(p));

@@ -419,3 +419,50 @@ def synthetic_xray(batch: int, height: int, width: int, seed: int = 7) -> Tuple[
     clean = 0.2 + 0.6 * (clean - mn) / (mx - mn + 1e-12)
     noisy = torch.clamp(clean * (1 + 0.2 * torch.randn(clean.shape, generator=g)), 0, 1)
     return clean.contiguous(), noisy.contiguous()
+
+
+# --------------------------------------------------------------------------
+# Overlap tiling (BASELINE configs[4]).  No reference counterpart: this is the DEFINITION the CUDA kernels in
+# csrc/tiles.cu are checked against (bit-exact; fp32 numpy, same operation order, no fused multiply-add).
+# --------------------------------------------------------------------------
+def tile_origins(length: int, tile: int, halo: int) -> List[int]:
+    if length == tile:
+        return [0]
+    stride = tile - 2 * halo
+    n = -(-(length - tile) // stride) + 1
+    return [min(k * stride, length - tile) for k in range(n)]
+
+
+def tile_weights(k: int, n: int, tile: int, halo: int):
+    import numpy as np
+    r = max(1, 2 * halo)
+    i = np.arange(tile)
+    m = np.full(tile, r)
+    if k != 0:
+        m = np.minimum(m, i + 1)
+    if k != n - 1:
+        m = np.minimum(m, tile - i)
+    return m.astype(np.float32) / np.float32(r)
+
+
+def extract_tiles(img: Tensor, tile: int, halo: int) -> Tensor:
+    b, _, h, w = img.shape
+    oy, ox = tile_origins(h, tile, halo), tile_origins(w, tile, halo)
+    out = [img[i:i + 1, :, y:y + tile, x:x + tile] for i in range(b) for y in oy for x in ox]
+    return torch.cat(out, 0).contiguous()
+
+
+def blend_tiles(tiles: Tensor, batch: int, height: int, width: int, tile: int, halo: int) -> Tensor:
+    import numpy as np
+    oy, ox = tile_origins(height, tile, halo), tile_origins(width, tile, halo)
+    t = tiles.detach().cpu().numpy().astype(np.float32).reshape(batch, len(oy), len(ox), tile, tile)
+    num = np.zeros((batch, height, width), np.float32)
+    den = np.zeros((height, width), np.float32)
+    for iy, y in enumerate(oy):
+        wy = tile_weights(iy, len(oy), tile, halo)
+        for ix, x in enumerate(ox):
+            w = (wy[:, None] * tile_weights(ix, len(ox), tile, halo)[None, :]).astype(np.float32)
+            num[:, y:y + tile, x:x + tile] = num[:, y:y + tile, x:x + tile] + (w[None] * t[:, iy, ix]).astype(np.float32)
+            den[y:y + tile, x:x + tile] = den[y:y + tile, x:x + tile] + w
+    return torch.from_numpy((num / den[None]).astype(np.float32))[:, None]
+

@@ -118,6 +118,14 @@ CONV_CASES_1X1 = [   # persistent 1x1 GEMM (conv1.cu): res_conv / qkv / proj sha
     (2, 192, 8, 8, 576, 1, 1, 0), (1, 192, 16, 16, 192, 1, 1, 0), (1, 96, 24, 40, 48, 1, 1, 0), (3, 48, 16, 16, 96, 1, 1, 0),
     (1, 384, 8, 24, 192, 1, 1, 0), (1, 288, 9, 7, 144, 1, 1, 0), (2, 144, 64, 128, 144, 1, 1, 0), (1, 96, 200, 160, 96, 1, 1, 0),
 ]
+CONV_CASES_1X1_POW2 = [   # the NAFBlock 1x1 shapes (HYB:152-169): powers of two, slices of 32..256, up to 1024 outputs / 512 inputs
+    (1, 32, 24, 40, 64, 1, 1, 0), (2, 32, 16, 16, 32, 1, 1, 0), (1, 64, 16, 24, 128, 1, 1, 0), (1, 128, 16, 16, 256, 1, 1, 0),
+    (1, 256, 8, 24, 512, 1, 1, 0), (1, 512, 8, 8, 1024, 1, 1, 0), (2, 512, 8, 8, 512, 1, 1, 0), (1, 256, 9, 7, 256, 1, 1, 0),
+    (1, 128, 16, 16, 64, 1, 1, 0), (3, 64, 70, 30, 64, 1, 1, 0),
+]
+CONV_CASES_1X1_GATE = [(1, 32, 24, 40, 64, 1, 1, 0), (2, 64, 16, 24, 128, 1, 1, 0), (1, 128, 9, 7, 256, 1, 1, 0), (3, 32, 64, 64, 64, 1, 1, 0)]
+CONV_CASES_1X1_SCALE = [(1, 32, 24, 40, 32, 1, 1, 0), (2, 64, 16, 24, 64, 1, 1, 0), (1, 256, 9, 7, 256, 1, 1, 0), (1, 512, 8, 8, 512, 1, 1, 0),
+                        (1, 96, 16, 16, 96, 1, 1, 0)]
 CONV_CASES_1X1_CAT = [(1, 384, 16, 16, 192, 1, 1, 0), (1, 192, 32, 32, 96, 1, 1, 0), (1, 96, 24, 40, 48, 1, 1, 0), (1, 288, 16, 24, 144, 1, 1, 0),
                       (1, 192, 16, 16, 48, 1, 1, 0)]
 CONV_CASES_1X1_STATS = [(2, 192, 16, 16, 192, 1, 1, 0), (1, 96, 32, 32, 48, 1, 1, 0), (3, 144, 16, 24, 144, 1, 1, 0), (2, 48, 64, 64, 96, 1, 1, 0)]
@@ -197,6 +205,33 @@ def check_conv(mode, impl, cases, seed=0):
             ref = F.conv2d(xr.double(), wr.double(), b.double(), stride=s, padding=p).float()
             y = oh.conv2d(x, w, b, k, s, p, impl)
             out[f"{B}x{Cin}x{H}x{W}->{Cout} k{k}s{s}p{p}"] = _rel(y, ref)
+    finally:
+        oh.close()
+    return out
+
+
+def check_conv1_naf_epilogues(mode, seed=3):
+    """conv1's NAFBlock epilogues: hook 13 = SimpleGate (first half x second half, HYB:119-121) * gamma + input (HYB:165-169),
+    hook 14 = (conv + bias) * beta + input (HYB:161); the bias vector doubles as the per-channel scale."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    oh = OpHandle(mode)
+    dt = torch.bfloat16 if mode == "bf16" else torch.float16
+    out = {}
+    try:
+        for impl, cases in ((13, CONV_CASES_1X1_GATE), (14, CONV_CASES_1X1_SCALE)):
+            for (B, Cin, H, W, Cout, k, s, p) in cases:
+                x = torch.randn(B, Cin, H, W, generator=g).to(DEV)
+                w = (torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5).to(DEV)
+                b = torch.randn(Cout, generator=g).to(DEV)
+                xr = x.to(dt).double()
+                t = F.conv2d(xr, w.to(dt).double(), b.double())
+                if impl == 13:
+                    t = t[:, :Cout // 2] * t[:, Cout // 2:]
+                ref = (t * b[:t.shape[1]].double().view(1, -1, 1, 1) + xr).float()
+                y = torch.empty_like(ref)
+                _lib.check(oh.lib.xrd_op_conv2d(oh.h, impl, _p(x), _p(w), _p(b), _p(y), B, Cin, H, W, Cout, 1, 1, 0, None))
+                torch.cuda.synchronize()
+                out[f"hook{impl} {B}x{Cin}x{H}x{W}->{Cout}"] = _rel(y, ref)
     finally:
         oh.close()
     return out
@@ -382,6 +417,8 @@ CHECKS = {
     "conv3w_stats_fp16": lambda: check_conv_stats("fp16", 7, CONV_CASES_W64),
     "conv1_fp16": lambda: check_conv("fp16", 5, CONV_CASES_1X1),
     "conv1_bf16": lambda: check_conv("bf16", 5, CONV_CASES_1X1),
+    "conv1_pow2_fp16": lambda: check_conv("fp16", 5, CONV_CASES_1X1_POW2),
+    "conv1_naf_epilogues_fp16": lambda: check_conv1_naf_epilogues("fp16"),
     "conv1_cat_fp16": lambda: check_conv("fp16", 6, CONV_CASES_1X1_CAT),
     "conv1_stats_fp16": lambda: check_conv_stats("fp16", 5, CONV_CASES_1X1_STATS),
     "attention_tc_bf16": lambda: check_attention("bf16", 1),

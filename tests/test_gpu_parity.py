@@ -94,6 +94,19 @@ def test_conv_tcgen05_1x1_persistent():
         assert e < 2e-3, (k, e)
 
 
+def test_conv_tcgen05_1x1_nafblock_shapes_and_epilogues():
+    # the same kernel on the NAFBlock 1x1 shapes (powers of two, 32..1024 channels) and its two NAFBlock epilogues:
+    # SimpleGate * gamma + y (HYB:165-169) and (conv + bias) * beta + inp (HYB:161)
+    for k, e in G.check_conv("fp16", 5, G.CONV_CASES_1X1_POW2).items():
+        assert e < 6e-4, (k, e)
+    for k, e in G.check_conv("bf16", 5, G.CONV_CASES_1X1_POW2).items():
+        assert e < 5e-3, (k, e)
+    for k, e in G.check_conv1_naf_epilogues("fp16").items():
+        assert e < 1e-3, (k, e)
+    for k, e in G.check_conv1_naf_epilogues("bf16").items():
+        assert e < 8e-3, (k, e)
+
+
 def test_groupnorm_act():
     for k, e in G.check_groupnorm("fp32").items():
         assert e < 5e-6, (k, e)

@@ -13,7 +13,7 @@ from oracle import xrd_oracle as O  # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-what = sys.argv[4] if len(sys.argv) > 4 else "hybrid"      # "hybrid" | "ddim" (sampler loop only)
+what = sys.argv[4] if len(sys.argv) > 4 else "hybrid"      # "hybrid" | "ddim" (sampler loop only) | "naf" | "router"
 torch.manual_seed(1234)
 m = xrd_b200.HybridDenoisingRouter({}, {}, inference_diffusion_steps=steps).eval()
 O.randomize_identity_params(m.state_dict(), 99)
@@ -23,6 +23,10 @@ m.diffusion_unet.use_cuda_graph = m.use_cuda_graph
 if what == "ddim":
     _w, _steps = m.diffusion_wrapper, steps
     m = lambda x: _w.denoise(x, _steps)   # noqa: E731
+elif what == "naf":
+    m = m.nafnet
+elif what == "router":
+    m = m.router
 _, noisy = O.synthetic_xray(B, S, S, seed=7)
 x = noisy.cuda()
 for _ in range(2):
