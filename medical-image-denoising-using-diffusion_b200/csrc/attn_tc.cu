@@ -16,6 +16,7 @@
 #include "tc_common.cuh"
 
 #include <stdlib.h>
+#include <type_traits>
 
 namespace xrd {
 
@@ -24,7 +25,7 @@ struct AttnTcP {
   int nkv;                 // number of 64-key tiles
   int nchunk;              // 64-channel chunks of the head dim (1 or 2)
   float scale_log2e;       // d^-0.5 * log2(e)
-  uint32_t idesc_qk, idesc_pv;
+  int ahead;               // key tiles Q K^T runs ahead of P V: 1 or 2
   void* out;
 };
 
@@ -94,9 +95,13 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <typename T, int DC>   // DC = ceil(d / 32): 32-column chunks of the output row
+template <typename T, int D16>   // head dim d = 16 * D16 (compile time: the MMA issue loop must not carry runtime predicates)
 __global__ void __launch_bounds__(kAttThreads, 1)
 k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnTcP p) {
+  constexpr int D = 16 * D16;
+  constexpr int DC = (D + 31) / 32;                          // 32-column chunks of the output row
+  constexpr int NCH = (D + 63) / 64;                         // 64-channel chunks of the head dim
+  constexpr int KS0 = (D < 64 ? D : 64) / 16, KS1 = D > 64 ? (D - 64) / 16 : 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   // layout: Q [2 q-tiles][2 chunks] | P [2 q-tiles][2 buffers] | K ring [kRing][2 chunks] | V ring [kRing][2 chunks] | barriers
@@ -114,8 +119,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
   uint64_t* s_free = s_full + 4;
   uint64_t* p_full = s_free + 4;
   uint64_t* p_free = p_full + 4;
-  uint64_t* o_done = p_free + 4;            // [2] one phase per P V (parity waits are only valid one phase back)
-  uint64_t* o_final = o_done + 2;           // [2] completes once, after the last P V
+  uint64_t* o_final = p_free + 4;           // [2] completes once, after the last P V
   uint32_t* tmem_slot = (uint32_t*)(o_final + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -133,7 +137,6 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_free[s], 128);
       tc::mbar_init(&p_full[s], 128); tc::mbar_init(&p_free[s], 1);
     }
-    tc::mbar_init(&o_done[0], 1); tc::mbar_init(&o_done[1], 1);
     tc::mbar_init(&o_final[0], 1); tc::mbar_init(&o_final[1], 1);
     tc::fence_barrier_init();
   }
@@ -144,84 +147,115 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // One CTA per SM (shared memory) and this is its only allocation: the allocator returns column 0.  Treating the base as the
+  // constant 0 keeps every tcgen05.mma operand in uniform registers (no R2UR per instruction in the issue loop).
+  if (*tmem_slot != 0u) {
+    if (threadIdx.x == 0) printf("libxrd: attn_tc expects TMEM base 0, got %u\n", *tmem_slot);
+    __trap();
+  }
+  constexpr uint32_t tmem_base = 0u;
   // TMEM columns: S[t][b] at t*128 + b*64 (64 wide), O[t] at 256 + t*128 (d <= 128 wide)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (tc::elect_one()) {
-      tc::mbar_expect_tx(q_full, (uint32_t)(2 * p.nchunk) * kTile);
+      tc::mbar_expect_tx(q_full, (uint32_t)(2 * NCH) * kTile);
       for (int t = 0; t < 2; ++t)
-        for (int c = 0; c < p.nchunk; ++c) tc::tma_load_3d(sQ + (t * 2 + c) * kTile, &tmQ, q_full, qoff + 64 * c, q0 + t * 128, img);
+        for (int c = 0; c < NCH; ++c) tc::tma_load_3d(sQ + (t * 2 + c) * kTile, &tmQ, q_full, qoff + 64 * c, q0 + t * 128, img);
       uint32_t slot = 0, phase = 0;
       for (int j = 0; j < p.nkv; ++j) {
         tc::mbar_wait(&k_empty[slot], phase ^ 1);
-        tc::mbar_expect_tx(&k_full[slot], (uint32_t)p.nchunk * kKvTile);
-        for (int c = 0; c < p.nchunk; ++c) tc::tma_load_3d(sK + (slot * 2 + c) * kKvTile, &tmKV, &k_full[slot], koff + 64 * c, j * 64, img);
+        tc::mbar_expect_tx(&k_full[slot], (uint32_t)NCH * kKvTile);
+        for (int c = 0; c < NCH; ++c) tc::tma_load_3d(sK + (slot * 2 + c) * kKvTile, &tmKV, &k_full[slot], koff + 64 * c, j * 64, img);
         tc::mbar_wait(&v_empty[slot], phase ^ 1);
-        tc::mbar_expect_tx(&v_full[slot], (uint32_t)p.nchunk * kKvTile);
-        for (int c = 0; c < p.nchunk; ++c) tc::tma_load_3d(sV + (slot * 2 + c) * kKvTile, &tmKV, &v_full[slot], voff + 64 * c, j * 64, img);
+        tc::mbar_expect_tx(&v_full[slot], (uint32_t)NCH * kKvTile);
+        for (int c = 0; c < NCH; ++c) tc::tma_load_3d(sV + (slot * 2 + c) * kKvTile, &tmKV, &v_full[slot], voff + 64 * c, j * 64, img);
         if (++slot == kRing) { slot = 0; phase ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer (one elected lane; the warp stays converged) =====================
-    // order per step j: Q K^T of tile j for both Q tiles (S is double buffered, so this runs under the softmax of
-    // tile j-1), then P V of tile j-1 as soon as its P tiles are published.
-    const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK), aPb = tc::smem_u32(sP), aV = tc::smem_u32(sV);
-    const int ks0 = min(64, p.d) >> 4, ks1 = p.nchunk > 1 ? (min(64, p.d - 64) >> 4) : 0;
+    // per step j: P V of tile j for both Q tiles as soon as its P tiles are published, then Q K^T of tile j+2.
+    // The ncu source view of the previous version showed this warp, not the softmax warps, on the critical path: ~135 cycles per
+    // MMA, i.e. ~14 instructions (R2UR moves, runtime k-step predicates, per-MMA constant loads) retired at the single-thread rate
+    // of one per ~4-8 cycles, while the softmax warps sat in the S-ready wait for 47 % of their time.  Now: everything that
+    // varies is a 64-bit descriptor base computed once per block of 8-12 MMAs, every per-MMA offset is a compile-time constant,
+    // the head dim and both instruction descriptors are template constants, and one elect block covers both Q tiles.
+    constexpr uint32_t IDESC_QK = tc::umma_idesc(128, 64, tc::umma_fmt<T>());
+    constexpr uint32_t IDESC_PV = tc::umma_idesc(128, D, tc::umma_fmt<T>()) | (1u << 16);     // B (V) is MN-major
+    const uint64_t dQ = tc::umma_desc_sw128(tc::smem_u32(sQ));           // + t * (2 * kTile >> 4)
+    const uint64_t dK = tc::umma_desc_sw128(tc::smem_u32(sK));           // + slot * (2 * kKvTile >> 4)
+    const uint64_t dP = tc::umma_desc_sw128(tc::smem_u32(sP));           // + (t * 2 + b) * (kTile >> 4)
+    const uint64_t dV = umma_desc_mn_sw128(tc::smem_u32(sV), kKvTile);   // + slot * (2 * kKvTile >> 4)
     uint32_t kslot = 0, kphase = 0, vslot = 0, vphase = 0;
     auto issue_pv = [&](int j) {      // O_t (+)= P_t,j V_j for both Q tiles
       const int b = j & 1, u = j >> 1;
       tc::mbar_wait(&v_full[vslot], vphase);
-      for (int t = 0; t < 2; ++t) {
-        tc::mbar_wait(&p_full[t * 2 + b], u & 1);
-        tc::tc_fence_after();
-        if (tc::elect_one()) {
-          // one base descriptor per operand tile, compile-time offsets per k-step (a descriptor rebuilt per MMA costs the
-          // issuing thread ~100 cycles of dependent integer work + R2UR moves, more than the MMA itself)
-          const uint64_t aD = tc::umma_desc_sw128(aPb + (uint32_t)(t * 2 + b) * kTile);
-          const uint64_t bD = umma_desc_mn_sw128(aV + vslot * 2 * kKvTile, kKvTile);
-          const uint32_t tO = tmem_base + 256u + (uint32_t)t * 128u;
+      tc::mbar_wait(&p_full[b], u & 1);
+      tc::mbar_wait(&p_full[2 + b], u & 1);
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+        const uint64_t bD = dV + (uint64_t)(vslot * (2 * kKvTile >> 4));
+        const uint64_t aD0 = dP + (uint64_t)(b * (kTile >> 4));
+        const uint32_t acc0 = j ? 1u : 0u;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const uint64_t aD = aD0 + (uint64_t)(t * 2 * (kTile >> 4));
 #pragma unroll
           for (int k = 0; k < 4; ++k)     // 4 x 16 keys: +32 B in the K-major P tile, +2048 B (16 key rows) in the MN-major V tile
-            tc::umma_f16(tO, aD + (uint64_t)(k * 2), bD + (uint64_t)(k * (2048 >> 4)), p.idesc_pv, (j | k) ? 1u : 0u);
-          tc::umma_commit(&p_free[t * 2 + b]);
-          tc::umma_commit(&o_done[t]);
-          if (j == p.nkv - 1) tc::umma_commit(&o_final[t]);
-          if (t == 1) tc::umma_commit(&v_empty[vslot]);
+            tc::umma_f16(256u + (uint32_t)t * 128u, aD + (uint64_t)(k * 2), bD + (uint64_t)(k * (2048 >> 4)), IDESC_PV, k ? 1u : acc0);
         }
-        __syncwarp();
+        tc::umma_commit(&p_free[b]);
+        tc::umma_commit(&p_free[2 + b]);
+        if (j == p.nkv - 1) { tc::umma_commit(&o_final[0]); tc::umma_commit(&o_final[1]); }
+        tc::umma_commit(&v_empty[vslot]);
       }
+      __syncwarp();
       if (++vslot == kRing) { vslot = 0; vphase ^= 1; }
     };
-    tc::mbar_wait(q_full, 0);
-    for (int j = 0; j < p.nkv; ++j) {
+    auto issue_qk = [&](int j) {      // S_t,j = Q_t K_j^T for both Q tiles
       const int b = j & 1, u = j >> 1;
       tc::mbar_wait(&k_full[kslot], kphase);          // K_j
-      for (int t = 0; t < 2; ++t) {
-        tc::mbar_wait(&s_free[t * 2 + b], (u & 1) ^ 1);         // softmax has drained S_t,j-2 from this TMEM buffer
-        tc::tc_fence_after();
-        if (tc::elect_one()) {
-          const uint64_t aD = tc::umma_desc_sw128(aQ + (uint32_t)t * 2 * kTile);
-          const uint64_t bD = tc::umma_desc_sw128(aK + kslot * 2 * kKvTile);
-          const uint32_t tS = tmem_base + (uint32_t)t * 128u + (uint32_t)b * 64u;
+      tc::mbar_wait(&s_free[b], (u & 1) ^ 1);         // softmax has drained S_t,j-2 from these TMEM buffers
+      tc::mbar_wait(&s_free[2 + b], (u & 1) ^ 1);
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+        const uint64_t bD = dK + (uint64_t)(kslot * (2 * kKvTile >> 4));
+        const uint32_t tS0 = (uint32_t)b * 64u;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (k < ks0) tc::umma_f16(tS, aD + (uint64_t)(k * 2), bD + (uint64_t)(k * 2), p.idesc_qk, k ? 1u : 0u);
+        for (int t = 0; t < 2; ++t) {
+          const uint64_t aD = dQ + (uint64_t)(t * (2 * kTile >> 4));
+          const uint32_t tS = tS0 + (uint32_t)t * 128u;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (k < ks1) tc::umma_f16(tS, aD + (uint64_t)((kTile >> 4) + k * 2), bD + (uint64_t)((kKvTile >> 4) + k * 2), p.idesc_qk, 1u);
+          for (int k = 0; k < KS0; ++k) tc::umma_f16(tS, aD + (uint64_t)(k * 2), bD + (uint64_t)(k * 2), IDESC_QK, k ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < KS1; ++k)
+            tc::umma_f16(tS, aD + (uint64_t)((kTile >> 4) + k * 2), bD + (uint64_t)((kKvTile >> 4) + k * 2), IDESC_QK, 1u);
           tc::umma_commit(&s_full[t * 2 + b]);
-          if (t == 1) tc::umma_commit(&k_empty[kslot]);
         }
-        __syncwarp();
+        tc::umma_commit(&k_empty[kslot]);
       }
+      __syncwarp();
       if (++kslot == kRing) { kslot = 0; kphase ^= 1; }
-      if (j > 0) issue_pv(j - 1);
+    };
+    // Q K^T runs one key tile ahead of P V (S is double buffered).  Two ahead (p.ahead == 2: S_j+2 reuses the TMEM buffer the
+    // softmax of tile j drained at its start) measured 4 % slower: the kernel is bound by the MIO queue the MUFU.EX2 stream,
+    // the P stores and the UTCHMMA issue share, not by S arriving late.
+    tc::mbar_wait(q_full, 0);
+    issue_qk(0);
+    if (p.ahead == 2) {
+      if (p.nkv > 1) issue_qk(1);
+      for (int j = 0; j < p.nkv; ++j) {
+        issue_pv(j);
+        if (j + 2 < p.nkv) issue_qk(j + 2);
+      }
+    } else {
+      for (int j = 0; j < p.nkv; ++j) {
+        if (j + 1 < p.nkv) issue_qk(j + 1);
+        issue_pv(j);
+      }
     }
-    issue_pv(p.nkv - 1);
   } else {
     // ===================== softmax / correction / epilogue (warps 2..9, one query row per thread) =====================
     const int t = (warp - 2) >> 2;                 // Q tile
@@ -233,7 +267,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     float m_run = -INFINITY, l_run = 0.f;
     const int sw = row & 7;
     const uint32_t prow0 = tc::smem_u32(sP) + (uint32_t)(t * 2) * kTile + (uint32_t)row * 128u;
-    for (int j = 0; j < p.nkv; ++j) {
+    auto step = [&](const int j, auto ragged) {
       const int b = j & 1, u = j >> 1;
       tc::mbar_wait(&s_full[t * 2 + b], u & 1);
       tc::tc_fence_after();
@@ -244,8 +278,8 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       tmem_ld_wait();
       tc::tc_fence_before();
       tc::mbar_arrive(&s_free[t * 2 + b]);           // S is in registers: Q K^T of tile j+2 may overwrite this buffer
-      const int kvalid = min(64, p.HW - j * 64);
-      if (kvalid < 64) {
+      if (decltype(ragged)::value) {               // only the last, partial key tile pays for the masking (64 compare + select)
+        const int kvalid = p.HW - j * 64;
 #pragma unroll
         for (int i = 0; i < 64; ++i)
           if (i >= kvalid) v[i] = -INFINITY;
@@ -256,8 +290,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         mx0 = fmaxf(mx0, v[i]); mx1 = fmaxf(mx1, v[i + 1]); mx2 = fmaxf(mx2, v[i + 2]); mx3 = fmaxf(mx3, v[i + 3]);
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      // P V of tile j-2 has consumed P[t][b].  It also means o_done has completed at least j-1 phases, which makes the
-      // parity wait for phase j-1 below (and the one of the epilogue) unambiguous.
+      // P V of tile j-2 has consumed P[t][b]
       tc::mbar_wait(&p_free[t * 2 + b], (u & 1) ^ 1);
       // lazy reference maximum: keep m_run unless this tile would push P above 2^kRescaleLog2
       const bool need = (mx - m_run) * p.scale_log2e > kRescaleLog2;      // true on the first tile (m_run = -inf)
@@ -265,7 +298,9 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         const float m_new = need ? mx : m_run;
         if (j > 0) {
           const float alpha = need ? ex2((m_run - m_new) * p.scale_log2e) : 1.0f;
-          tc::mbar_wait(&o_done[t], (j - 1) & 1);      // P V of tile j-1 has landed in O
+          // P V of tile j-1 has landed in O: it is the event that frees P[t][(j-1)&1], phase (j-1)>>1 of that barrier.  At this
+          // point the barrier has completed either that phase or only the one before, so the parity wait is unambiguous.
+          tc::mbar_wait(&p_free[t * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
           tc::tc_fence_after();
 #pragma unroll
           for (int c = 0; c < DC; ++c) {
@@ -299,7 +334,10 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       tc::fence_async_smem();                       // generic-proxy stores -> visible to the tensor core (async proxy)
       tc::mbar_arrive(&p_full[t * 2 + b]);
       l_run += (rs0 + rs1) + (rs2 + rs3);
-    }
+    };
+    const int nfull = p.HW / 64;                   // full 64-key tiles; at most one partial tile follows
+    for (int j = 0; j < nfull; ++j) step(j, std::false_type());
+    if (nfull < p.nkv) step(nfull, std::true_type());
     // epilogue: O / l -> 16-bit -> out[img, q, head*d + :]
     tc::mbar_wait(&o_final[t], 0);
     tc::tc_fence_after();
@@ -351,9 +389,8 @@ void attention_tc(Ctx& c, const Tens& qkv, int heads, Tens& out) {
   p.nkv = cdiv(HW, 64);
   p.nchunk = cdiv(d, 64);
   p.scale_log2e = (float)((1.0 / sqrt((double)d)) * 1.4426950408889634);
-  const int fmt = qkv.dt == DT_BF16 ? 1 : 0;
-  p.idesc_qk = tc::umma_idesc(128, 64, fmt);
-  p.idesc_pv = tc::umma_idesc(128, d, fmt) | (1u << 16);   // B (V) is MN-major
+  static const int ahead = getenv("XRD_ATT_AHEAD") ? atoi(getenv("XRD_ATT_AHEAD")) : 1;   // measured: 0.327 ms (1) vs 0.340 ms (2) at B=16
+  p.ahead = ahead == 1 ? 1 : 2;
   p.out = out.p;
   alignas(64) CUtensorMap tmQ, tmKV;
   for (int which = 0; which < 2; ++which) {
@@ -368,7 +405,7 @@ void attention_tc(Ctx& c, const Tens& qkv, int heads, Tens& out) {
   }
   const size_t smem = 1024 + (size_t)8 * kTile + (size_t)2 * kRing * 2 * kKvTile + 64 * 8;
   dim3 grid(cdiv(HW, 256), heads, qkv.n);
-  const int dc = cdiv(d, 32);
+  const int dc = d / 16;
 #define XRD_ATT_CASE(TT, DCV)                                                                                             \
   case DCV: {                                                                                                             \
     static bool attr = false;                                                                                             \
@@ -376,9 +413,11 @@ void attention_tc(Ctx& c, const Tens& qkv, int heads, Tens& out) {
     XRD_LAUNCH(c, (k_attn_tc<TT, DCV>), grid, kAttThreads, smem, tmQ, tmKV, p);                                                  \
   } break;
   if (qkv.dt == DT_BF16) {
-    switch (dc) { XRD_ATT_CASE(__nv_bfloat16, 1) XRD_ATT_CASE(__nv_bfloat16, 2) XRD_ATT_CASE(__nv_bfloat16, 3) XRD_ATT_CASE(__nv_bfloat16, 4) }
+    switch (dc) { XRD_ATT_CASE(__nv_bfloat16, 1) XRD_ATT_CASE(__nv_bfloat16, 2) XRD_ATT_CASE(__nv_bfloat16, 3) XRD_ATT_CASE(__nv_bfloat16, 4)
+                  XRD_ATT_CASE(__nv_bfloat16, 5) XRD_ATT_CASE(__nv_bfloat16, 6) XRD_ATT_CASE(__nv_bfloat16, 7) XRD_ATT_CASE(__nv_bfloat16, 8) }
   } else {
-    switch (dc) { XRD_ATT_CASE(__half, 1) XRD_ATT_CASE(__half, 2) XRD_ATT_CASE(__half, 3) XRD_ATT_CASE(__half, 4) }
+    switch (dc) { XRD_ATT_CASE(__half, 1) XRD_ATT_CASE(__half, 2) XRD_ATT_CASE(__half, 3) XRD_ATT_CASE(__half, 4)
+                  XRD_ATT_CASE(__half, 5) XRD_ATT_CASE(__half, 6) XRD_ATT_CASE(__half, 7) XRD_ATT_CASE(__half, 8) }
   }
 #undef XRD_ATT_CASE
 }

@@ -320,6 +320,27 @@ static void finalize_fusion(Handle& h) {
   expect_shape(h.P(p + "out_conv.weight"), p + "out_conv.weight", {1, b / 2, 1, 1});
   f.out_w = h.PD(p + "out_conv.weight");
   f.out_b = h.PD(p + "out_conv.bias");
+  if (b == 48 || b == 96) {
+    const int hb = b / 2;
+    auto padded = [&](const float* src, size_t n_src, size_t n_all) {
+      float* d = h.dalloc_f(n_all);
+      XRD_CUDA(cudaMemset(d, 0, n_all * sizeof(float)));
+      XRD_CUDA(cudaMemcpy(d, src, n_src * sizeof(float), cudaMemcpyDeviceToDevice));
+      return d;
+    };
+    const float* wpad = padded(h.PD(p + "conv2.0.weight"), (size_t)hb * b * 9, (size_t)b * b * 9);   // [cout][cin][3][3]: rows hb.. are zero
+    ConvW cw;
+    cw.kh = cw.kw = 3; cw.stride = 1; cw.pad = 1; cw.cin = b; cw.cout = b;
+    cw.w = h.dalloc_f((size_t)b * b * 9);
+    pack_conv_weight(nullptr, wpad, cw.w, b, b, 3, 3);
+    cw.bias = padded(h.PD(p + "conv2.0.bias"), hb, b);
+    f.conv2p.conv = cw;
+    f.conv2p.g = padded(f.conv2.g, hb, b);
+    f.conv2p.b = padded(f.conv2.b, hb, b);
+    f.conv2p.groups = 8;
+    f.out_wp = padded(f.out_w, hb, b);
+    f.padded = true;
+  }
   f.ready = true;
 }
 
@@ -762,6 +783,27 @@ static void fusion_forward(Ctx& c, FusionW& f, const float* naf, const float* di
   const size_t mk0 = c.a->mark();
   Tens x3 = c.alloc(B, H, W, 3, DT_F32);
   interleave3(c, naf, diff, mask, (float*)x3.p, (int64_t)B * H * W);
+  if (c.tc && c.adt != DT_F32 && f.padded && conv_smallcin2_supported(x3, nullptr, f.conv1.conv)) {
+    // 16-bit modes (HYB:552-557 on the tensor cores): conv1 -> 16-bit, GN+GELU pass, conv2 as a padded cout = base_c tcgen05 conv
+    // whose epilogue emits the GroupNorm sums, GroupNorm + GELU folded into the prologue of the final 1x1
+    const int b = f.conv1.conv.cout;
+    Tens y1 = c.alloc(B, H, W, b);
+    double* s1 = new_sums(c, B, 8);
+    if (!conv_first(c, x3, nullptr, f.conv1.conv, y1, s1)) gn_stats(c, y1, nullptr, 8, s1);
+    Tens a1 = c.alloc(B, H, W, b);
+    gn_act(c, y1, nullptr, 8, s1, f.conv1.g, f.conv1.b, 1e-5f, ACT_GELU, a1);
+    Tens y2 = c.alloc(B, H, W, b);
+    ConvEpi e2;
+    e2.stats_out = new_sums(c, B, 8);
+    conv(c, a1, nullptr, f.conv2p.conv, e2, y2);
+    Cout1Args a;
+    a.x = y2; a.k = 1; a.w = f.out_wp; a.bias = f.out_b; a.mode = 0; a.y = out;
+    a.gn_sums = e2.stats_out; a.groups = 8; a.gamma = f.conv2p.g; a.beta = f.conv2p.b; a.eps = 1e-5f; a.act_in = ACT_GELU;
+    conv_cout1(c, a);
+    c.zpool = nullptr; c.zpool_cap = c.zpool_off = 0;
+    c.a->release(mk0);
+    return;
+  }
   Tens a1 = cgg(c, f.conv1, x3, nullptr);
   Tens a2 = cgg(c, f.conv2, a1, nullptr);
   Cout1Args a;
@@ -860,6 +902,7 @@ void prepack_tc(Handle& h, DType dt) {
     for (auto& w : n.ups) pk(w, w.cin);
     for (auto& w : n.skips) pk(w, w.cin / 2);
   }
+  if (h.fusion.ready && h.fusion.padded) pk(h.fusion.conv2p.conv, h.fusion.conv2p.conv.cin);
   XRD_CUDA(cudaDeviceSynchronize());
 }
 

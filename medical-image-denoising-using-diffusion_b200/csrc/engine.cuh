@@ -85,6 +85,11 @@ struct FusionW {
   CGG conv1, conv2;
   const float* out_w = nullptr;
   const float* out_b = nullptr;
+  // 16-bit modes: conv2 (base_c -> base_c/2) zero-padded to base_c outputs so that it runs on the tcgen05 3x3 kernels;
+  // GroupNorm(4, base_c/2) is the first four groups of GroupNorm(8, base_c) over the padded tensor (same group size)
+  bool padded = false;
+  CGG conv2p;
+  const float* out_wp = nullptr;
 };
 
 struct GraphEntry {

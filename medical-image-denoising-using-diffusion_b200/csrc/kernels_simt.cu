@@ -22,13 +22,19 @@ struct ConvP {
   int act, d2s;
 };
 
-template <typename TI, typename TO>
+// BN = 64: 64 pixels x 64 output channels per block; BN = 32: 128 x 32 (router dec2 64->32 and fusion conv2 48->24 at full
+// resolution wasted half of a 64-wide tile).  Every output is accumulated in the same order (tap-major, channels ascending,
+// one fmaf per term) in both shapes, so the result does not depend on the tile choice.
+template <typename TI, typename TO, int BN>
 __global__ void __launch_bounds__(256) k_conv_simt(ConvP p) {
-  constexpr int BM = 64, BN = 64, BK = 16;
+  constexpr int BM = 4096 / BN, BK = 16;
+  constexpr int TXN = BN / 4;                       // threads across the output channels
+  constexpr int APT = BM * BK / 256;                // A elements per thread per stage: 4 or 8
+  constexpr int BPT = BK * BN / 256;                // B elements per thread per stage: 4 or 2
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN];
   const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
+  const int ty = tid / TXN, tx = tid % TXN;
   const int ctot = p.c1 + p.c2;
   const int64_t npix = (int64_t)p.N * p.Ho * p.Wo;
   const int64_t pix0 = (int64_t)blockIdx.x * BM;
@@ -36,8 +42,8 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvP p) {
   const bool vecA = ((p.c1 & 3) == 0) && ((p.c2 & 3) == 0);
   const bool vecB = (p.Cout & 3) == 0;
 
-  // A-load assignment: one pixel, 4 consecutive channels per thread
-  const int a_pix = tid >> 2, a_k = (tid & 3) * 4;
+  // A-load assignment: one pixel, APT consecutive channels per thread
+  const int a_pix = tid / (BK / APT), a_k = (tid % (BK / APT)) * APT;
   int64_t gp = pix0 + a_pix;
   const bool a_ok = gp < npix;
   int an = 0, aoh = 0, aow = 0;
@@ -47,7 +53,7 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvP p) {
     aoh = r / p.Wo; aow = r - aoh * p.Wo;
   }
   // B-load assignment
-  const int b_k = tid >> 4, b_n = (tid & 15) * 4;
+  const int b_k = tid / (BN / BPT), b_n = (tid % (BN / BPT)) * BPT;
 
   float acc[4][4];
 #pragma unroll
@@ -63,56 +69,70 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvP p) {
     const int64_t ipix = ((int64_t)an * p.H + ih) * p.W + iw;
     for (int c0 = 0; c0 < ctot; c0 += BK) {
       // ---- load A (activations) ----
-      float av[4] = {0.f, 0.f, 0.f, 0.f};
-      const int c = c0 + a_k;
-      if (in_ok && c < ctot) {
-        if (vecA) {
-          if (c < p.c1) {
-            ld4<TI>((const TI*)p.x1 + ipix * p.c1 + c, av);
-            if (p.in_scale) {
-              const float* sc = p.in_scale + (int64_t)an * p.c1 + c;
-              av[0] *= sc[0]; av[1] *= sc[1]; av[2] *= sc[2]; av[3] *= sc[3];
-            }
-          } else {
-            ld4<TI>((const TI*)p.x2 + ipix * p.c2 + (c - p.c1), av);
-          }
-        } else {
+      float av[APT];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            int ci = c + i;
-            if (ci < ctot) {
-              if (ci < p.c1) {
-                float v = ldf<TI>((const TI*)p.x1 + ipix * p.c1 + ci);
-                if (p.in_scale) v *= p.in_scale[(int64_t)an * p.c1 + ci];
-                av[i] = v;
-              } else {
-                av[i] = ldf<TI>((const TI*)p.x2 + ipix * p.c2 + (ci - p.c1));
+      for (int i = 0; i < APT; ++i) av[i] = 0.f;
+#pragma unroll
+      for (int h = 0; h < APT; h += 4) {
+        const int c = c0 + a_k + h;
+        if (in_ok && c < ctot) {
+          if (vecA) {
+            float t4[4];
+            if (c < p.c1) {
+              ld4<TI>((const TI*)p.x1 + ipix * p.c1 + c, t4);
+              if (p.in_scale) {
+                const float* sc = p.in_scale + (int64_t)an * p.c1 + c;
+                t4[0] *= sc[0]; t4[1] *= sc[1]; t4[2] *= sc[2]; t4[3] *= sc[3];
+              }
+            } else {
+              ld4<TI>((const TI*)p.x2 + ipix * p.c2 + (c - p.c1), t4);
+            }
+            av[h] = t4[0]; av[h + 1] = t4[1]; av[h + 2] = t4[2]; av[h + 3] = t4[3];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              int ci = c + i;
+              if (ci < ctot) {
+                if (ci < p.c1) {
+                  float v = ldf<TI>((const TI*)p.x1 + ipix * p.c1 + ci);
+                  if (p.in_scale) v *= p.in_scale[(int64_t)an * p.c1 + ci];
+                  av[h + i] = v;
+                } else {
+                  av[h + i] = ldf<TI>((const TI*)p.x2 + ipix * p.c2 + (ci - p.c1));
+                }
               }
             }
           }
         }
       }
       // ---- load B (weights) ----
-      float bv[4] = {0.f, 0.f, 0.f, 0.f};
+      float bv[BPT];
+#pragma unroll
+      for (int i = 0; i < BPT; ++i) bv[i] = 0.f;
       {
         const int ck = c0 + b_k;
         const int nn = n0 + b_n;
         if (ck < ctot) {
           const float* wp = p.w + ((int64_t)tap * ctot + ck) * p.Cout + nn;
-          if (vecB && nn + 3 < p.Cout) {
+          if (BPT == 4 && vecB && nn + 3 < p.Cout) {
             float4 t = *reinterpret_cast<const float4*>(wp);
-            bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
+            bv[0] = t.x; bv[1] = t.y; bv[BPT - 2] = t.z; bv[BPT - 1] = t.w;
           } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < BPT; ++i)
               if (nn + i < p.Cout) bv[i] = wp[i];
           }
         }
       }
       __syncthreads();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) As[a_k + i][a_pix] = av[i];
-      *reinterpret_cast<float4*>(&Bs[b_k][b_n]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+      for (int i = 0; i < APT; ++i) As[a_k + i][a_pix] = av[i];
+      if (BPT == 4) {
+        *reinterpret_cast<float4*>(&Bs[b_k][b_n]) = make_float4(bv[0], bv[1], bv[BPT - 2], bv[BPT - 1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) Bs[b_k][b_n + i] = bv[i];
+      }
       __syncthreads();
 #pragma unroll
       for (int k = 0; k < BK; ++k) {
@@ -215,8 +235,14 @@ void conv_simt(Ctx& c, const Tens& x1, const Tens* x2, const ConvW& w, const Con
   if (e.resid.p) XRD_REQUIRE(e.resid.dt == y.dt && e.resid.numel() == y.numel(), "conv_simt: residual mismatch");
   p.act = e.act; p.d2s = w.d2s;
   int64_t npix = (int64_t)p.N * p.Ho * p.Wo;
-  dim3 grid((unsigned)cdiv64(npix, 64), (unsigned)cdiv(p.Cout, 64));
-  XRD_DISPATCH(x1.dt, TI, XRD_DISPATCH(y.dt, TO, XRD_LAUNCH(c, (k_conv_simt<TI, TO>), grid, 256, 0, p)));
+  static const int narrow = getenv("XRD_SIMT_BN32") ? atoi(getenv("XRD_SIMT_BN32")) : 1;
+  if (narrow && p.Cout <= 32) {
+    dim3 grid((unsigned)cdiv64(npix, 128), 1);
+    XRD_DISPATCH(x1.dt, TI, XRD_DISPATCH(y.dt, TO, XRD_LAUNCH(c, (k_conv_simt<TI, TO, 32>), grid, 256, 0, p)));
+  } else {
+    dim3 grid((unsigned)cdiv64(npix, 64), (unsigned)cdiv(p.Cout, 64));
+    XRD_DISPATCH(x1.dt, TI, XRD_DISPATCH(y.dt, TO, XRD_LAUNCH(c, (k_conv_simt<TI, TO, 64>), grid, 256, 0, p)));
+  }
 }
 
 // =====================================================================================

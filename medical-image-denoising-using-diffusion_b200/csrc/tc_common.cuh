@@ -146,7 +146,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return d;
 }
 // kind::f16 instruction descriptor: D=f32, A/B = bf16 (fmt 1) or f16 (fmt 0), both K-major
-__host__ __device__ inline uint32_t umma_idesc(int M, int N, int fmt) {
+__host__ __device__ constexpr inline uint32_t umma_idesc(int M, int N, int fmt) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
