@@ -85,6 +85,10 @@ __device__ __forceinline__ void c3_issue_chunk(uint64_t adesc0, uint64_t bdesc0,
                                                uint32_t& wslot, uint32_t& wphase, int nb, int kb0, int nres, uint32_t acc0, uint32_t idesc,
                                                uint32_t not_first) {
   constexpr uint32_t B_BYTES = COUT * 128;
+  // streamed weights: the barrier of tap t+1 is probed BEFORE the MMAs of tap t are issued, so the probe's round trip runs under
+  // them (a wait issued right in front of its MMAs stalls the issue stream, and with it the tensor pipe, for ~57 cycles per tap)
+  bool probed = false;
+  if (!WRES && kb0 >= nres) probed = tc::mbar_test(&b_full[wslot], wphase);
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
     uint64_t bdesc;
@@ -95,10 +99,12 @@ __device__ __forceinline__ void c3_issue_chunk(uint64_t adesc0, uint64_t bdesc0,
       bdesc = tc::umma_desc_sw128(sB_addr + (uint32_t)(nb + kb0 + tap) * B_BYTES);
     } else {
       streamed = true;
-      tc::mbar_wait(&b_full[wslot], wphase);
-      tc::tc_fence_after();
+      tc::mbar_wait_probed(probed, &b_full[wslot], wphase);
       bdesc = tc::umma_desc_sw128(sB_addr + wslot * B_BYTES);
     }
+    uint32_t nslot = wslot + 1, nphase = wphase;
+    if (nslot == (uint32_t)nb) { nslot = 0; nphase ^= 1; }
+    if (streamed && tap < 8) probed = tc::mbar_test(&b_full[nslot], nphase);
     const int dy = tap / 3, dx = tap % 3;
 #pragma unroll
     for (int s = 0; s < TH; ++s) {
@@ -109,7 +115,7 @@ __device__ __forceinline__ void c3_issue_chunk(uint64_t adesc0, uint64_t bdesc0,
     }
     if (streamed) {
       tc::umma_commit(&b_empty[wslot]);
-      if (++wslot == (uint32_t)nb) { wslot = 0; wphase ^= 1; }
+      wslot = nslot; wphase = nphase;
     }
   }
 }
@@ -234,6 +240,8 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     const uint32_t idesc = tc::umma_idesc(128, COUT, tc::umma_fmt<T>());
     const uint32_t sB_addr = tc::smem_u32(sB);
     uint32_t ai = 0, ti = 0, wslot = 0, wphase = 0;
+    uint64_t* const abar = GN ? a_ready : a_full;
+    bool a_probed = false;                                   // result of the early probe of the next stage's barrier
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
       const int ab = NACC == 2 ? (int)(ti & 1) : 0;
       const uint32_t use = NACC == 2 ? (ti >> 1) : ti;       // how many times this accumulator buffer was used before
@@ -244,8 +252,10 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       const uint32_t acc0 = tmem_base + (uint32_t)(ab * TH * COUT);
       for (int c = 0; c < p.nchunk; ++c, ++ai) {
         const int st = ai & 1;
-        tc::mbar_wait(GN ? &a_ready[st] : &a_full[st], (ai >> 1) & 1);
+        tc::mbar_wait_probed(a_probed, &abar[st], (ai >> 1) & 1);
         tc::tc_fence_after();
+        // probe the NEXT stage now: the round trip of the barrier test runs under this chunk's MMAs (tc_common.cuh)
+        a_probed = tc::mbar_test(&abar[(ai + 1) & 1], ((ai + 1) >> 1) & 1);
         if (c == 0 && lane == 0) C3PROF(ti, 3);
         const bool second = c >= p.nchunk0;
         const int cl = second ? c - p.nchunk0 : c;

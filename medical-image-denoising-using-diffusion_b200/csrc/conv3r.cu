@@ -169,21 +169,39 @@ k_conv3r(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       auto slot_of = [&](int i) { const uint32_t t = islot + (uint32_t)i; return t % R; };
       auto phase_of = [&](int i) { const uint32_t t = islot + (uint32_t)i; return (iphase ^ ((t / R) & 1u)); };
       int landed = 0;                      // item rows already waited for
+      bool probed = false;                 // this lane's barrier of the coming iteration was already seen complete (early probe)
       for (int r = 0; r < rows;) {
         const int nrow = (rows - r >= 2) ? 2 : 1;
         if (lane == 0) RPROF(o >> 1, 0);
         const int need = r + nrow + 2 - landed;                    // new input rows this iteration (<= 4)
         if (lane < need) {
           const int i = landed + lane;
-          tc::mbar_wait(GN ? &r_ready[slot_of(i)] : &r_full[slot_of(i)], phase_of(i));
+          tc::mbar_wait_probed(probed, GN ? &r_ready[slot_of(i)] : &r_full[slot_of(i)], phase_of(i));
         } else if (lane >= 8 && lane < 8 + nrow) {
           const uint32_t oo = o + (uint32_t)(lane - 8);
-          tc::mbar_wait(&acc_empty[oo % NA], ((oo / NA) & 1) ^ 1);
+          tc::mbar_wait_probed(probed, &acc_empty[oo % NA], ((oo / NA) & 1) ^ 1);
         }
         __syncwarp();
         landed += need;
         if (lane == 0) RPROF(o >> 1, 7);
         tc::tc_fence_after();
+        // Probe the barriers of the NEXT iteration now, lane by lane as it will wait for them: the probes' round trips run under
+        // the MMAs issued below (a satisfied wait in front of the MMAs idles the tensor pipe for its whole latency, mio_probe.cu).
+        probed = false;
+        {
+          const int r2 = r + nrow;
+          if (r2 < rows) {
+            const int nrow2 = (rows - r2 >= 2) ? 2 : 1;
+            const int need2 = r2 + nrow2 + 2 - landed;
+            if (lane < need2) {
+              const int i = landed + lane;
+              probed = tc::mbar_test(GN ? &r_ready[slot_of(i)] : &r_full[slot_of(i)], phase_of(i));
+            } else if (lane >= 8 && lane < 8 + nrow2) {
+              const uint32_t oo = o + (uint32_t)nrow + (uint32_t)(lane - 8);
+              probed = tc::mbar_test(&acc_empty[oo % NA], ((oo / NA) & 1) ^ 1);
+            }
+          }
+        }
         if (lane == 0) RPROF(o >> 1, 1);
         if (tc::elect_one()) {
           const uint32_t s0 = slot_of(r), s1 = slot_of(r + 1), s2 = slot_of(r + 2), s3 = slot_of(r + 3);

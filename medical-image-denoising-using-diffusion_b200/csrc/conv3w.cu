@@ -65,13 +65,16 @@ template <> __device__ __forceinline__ void w3_unpack8<__nv_bfloat16>(const uint
 // the three vertical taps of one (chunk, dx) copy: 3 weight blocks x 2 accumulators x KS k-steps
 template <int COUT, int KS>
 __device__ __forceinline__ void w3_issue_dx(uint64_t adesc0, uint32_t sB_addr, uint64_t* b_full, uint64_t* b_empty, uint32_t& wslot,
-                                            uint32_t& wphase, int nb, uint32_t idesc, uint32_t not_first) {
+                                            uint32_t& wphase, uint32_t& bprobed, int nb, uint32_t idesc, uint32_t not_first) {
   constexpr uint32_t B_BYTES = COUT * 128;
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy) {
-    tc::mbar_wait(&b_full[wslot], wphase);
-    tc::tc_fence_after();
+    // the barrier of this weight block was probed before the previous block's MMAs were issued (tc_common.cuh: mbar_wait_probed)
+    tc::mbar_wait_probed(bprobed != 0u, &b_full[wslot], wphase);
     const uint64_t bdesc = tc::umma_desc_sw128(sB_addr + wslot * B_BYTES);
+    uint32_t nslot = wslot + 1, nphase = wphase;
+    if (nslot == (uint32_t)nb) { nslot = 0; nphase ^= 1; }
+    bprobed = tc::mbar_test(&b_full[nslot], nphase) ? 1u : 0u;
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
 #pragma unroll
@@ -80,7 +83,7 @@ __device__ __forceinline__ void w3_issue_dx(uint64_t adesc0, uint32_t sB_addr, u
                      (dy == 0 && k == 0) ? not_first : 1u);
     }
     tc::umma_commit(&b_empty[wslot]);
-    if (++wslot == (uint32_t)nb) { wslot = 0; wphase ^= 1; }
+    wslot = nslot; wphase = nphase;
   }
 }
 
@@ -163,6 +166,8 @@ k_conv3w(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
     const uint32_t idesc = tc::umma_idesc(128, COUT, tc::umma_fmt<T>());
     const uint32_t sA_addr = tc::smem_u32(sA), sB_addr = tc::smem_u32(sB);
     uint32_t st = 0, ph = 0, ws = 0, wph = 0, ti = 0;
+    uint32_t bprobed = 0u;                   // early probe of the next weight block's barrier (carried across the issue blocks)
+    bool aprobed = false;                    // early probe of the next activation stage's barrier
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
       tc::mbar_wait(acc_empty, (ti & 1) ^ 1);
       tc::tc_fence_after();
@@ -171,17 +176,20 @@ k_conv3w(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
         const int cl = second ? c - p.nchunk0 : c;
         const int ks = min(64, (second ? p.c1 : p.c0) - cl * 64) >> 4;
         for (int dx = 0; dx < 3; ++dx) {
-          tc::mbar_wait(&a_full[st], ph);
+          tc::mbar_wait_probed(aprobed, &a_full[st], ph);
           tc::tc_fence_after();
+          uint32_t nst = st + 1, nph = ph;
+          if (nst == kW3Stages) { nst = 0; nph ^= 1; }
+          aprobed = tc::mbar_test(&a_full[nst], nph);      // its round trip runs under the MMAs issued below
           uint32_t leader;
           if (tc::elect_one(leader)) {
             const uint64_t adesc0 = tc::umma_desc_sw128(sA_addr + st * kW3ABytes);
             const uint32_t nf = (c | dx) ? 1u : 0u;
             switch (ks) {
-              case 4: w3_issue_dx<COUT, 4>(adesc0, sB_addr, b_full, b_empty, ws, wph, p.nb, idesc, nf); break;
-              case 3: w3_issue_dx<COUT, 3>(adesc0, sB_addr, b_full, b_empty, ws, wph, p.nb, idesc, nf); break;
-              case 2: w3_issue_dx<COUT, 2>(adesc0, sB_addr, b_full, b_empty, ws, wph, p.nb, idesc, nf); break;
-              default: w3_issue_dx<COUT, 1>(adesc0, sB_addr, b_full, b_empty, ws, wph, p.nb, idesc, nf); break;
+              case 4: w3_issue_dx<COUT, 4>(adesc0, sB_addr, b_full, b_empty, ws, wph, bprobed, p.nb, idesc, nf); break;
+              case 3: w3_issue_dx<COUT, 3>(adesc0, sB_addr, b_full, b_empty, ws, wph, bprobed, p.nb, idesc, nf); break;
+              case 2: w3_issue_dx<COUT, 2>(adesc0, sB_addr, b_full, b_empty, ws, wph, bprobed, p.nb, idesc, nf); break;
+              default: w3_issue_dx<COUT, 1>(adesc0, sB_addr, b_full, b_empty, ws, wph, bprobed, p.nb, idesc, nf); break;
             }
             tc::umma_commit(&a_empty[st]);
             if (c == p.nchunk - 1 && dx == 2) tc::umma_commit(acc_full);
@@ -189,7 +197,8 @@ k_conv3w(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
           __syncwarp();
           ws = __shfl_sync(0xffffffffu, ws, leader);
           wph = __shfl_sync(0xffffffffu, wph, leader);
-          if (++st == kW3Stages) { st = 0; ph ^= 1; }
+          bprobed = __shfl_sync(0xffffffffu, bprobed, leader);
+          st = nst; ph = nph;
         }
       }
     }

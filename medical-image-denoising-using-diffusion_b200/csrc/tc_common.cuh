@@ -48,6 +48,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe (mbarrier.test_wait): unlike try_wait it never suspends the thread when the phase is still open.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Finish a wait whose first probe (`first`, an earlier mbar_test on the same barrier/parity) was issued ahead of time.
+// Measured (tools/probes/mio_probe.cu): a satisfied parity wait in front of a tcgen05.mma costs the issuing thread ~57 cycles
+// during which the (shallow) MMA queue drains; probing the NEXT barrier before issuing the current MMAs hides that round trip.
+__device__ __forceinline__ void mbar_wait_probed(bool first, uint64_t* bar, uint32_t parity);
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
@@ -57,6 +73,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+}
+
+__device__ __forceinline__ void mbar_wait_probed(bool first, uint64_t* bar, uint32_t parity) {
+  if (!first) mbar_wait(bar, parity);
 }
 
 // ---- TMA ------------------------------------------------------------------------

@@ -1,0 +1,211 @@
+// mio_probe.cu -- does traffic from other warps of the SM slow down a tcgen05.mma stream?
+// Warp 0 issues the 3x3-conv MMA pattern of conv3r (N=48, 9 taps x 3 k-steps, two accumulators); warps 1..8 ("epilogue
+// stand-ins", two per scheduler) loop over one kind of memory-pipe traffic while it runs:
+//   0 none | 1 ld.shared.v4 broadcast (the bias row) | 2 tcgen05.ld 32x32b.x16 (accumulator drain) | 4 st.global.v8 (output rows)
+//   8 MUFU.EX2 (softmax)                           (bits combine)
+// Build: tools/probes/build.sh
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include "../../medical-image-denoising-using-diffusion_b200/csrc/tc_common.cuh"
+using namespace xrd;
+
+struct P { int rounds; long long* out; float* scratch; volatile int* stop; };
+
+template <int N, int GROUPS, int KS, int NOISE, int DATA = 0>
+__global__ void __launch_bounds__(288, 1) k_probe(P p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  __shared__ volatile int done;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    // DATA: pseudo-random f16 pairs in (-2, 2) (sign + exponent 0x3C/0x38.. + random mantissa); else zeros
+    ((uint32_t*)smem)[i] = DATA ? ((h & 0x83FF83FFu) | 0x38003800u) : 0u;
+  }
+  if (threadIdx.x == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); done = 0; }
+  tc::fence_async_smem();
+  if (warp == 0) { tc::tmem_alloc(&slot, 512); tc::tmem_relinquish(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  if (warp == 0) {
+    const uint32_t idesc = tc::umma_idesc(128, N, 0);
+    const uint64_t adesc0 = tc::umma_desc_sw128(tc::smem_u32(smem));
+    const uint64_t bdesc0 = tc::umma_desc_sw128(tc::smem_u32(smem + 96 * 1024));
+    long long t_done = 0;
+    for (int r = 0; r < p.rounds; ++r) {
+      long long t0 = clock64();
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int g = 0; g < GROUPS; ++g) {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const int arow = ((t / 3) + (g % 2)) * 136 + (t % 3);
+#pragma unroll
+            for (int k = 0; k < KS; ++k)
+              tc::umma_f16((uint32_t)((g % 2) * N), adesc0 + (uint64_t)(arow * 8 + k * 2), bdesc0 + (uint64_t)((t & 1) * N * 8 + k * 2), idesc,
+                           (g >= 2 || t > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        tc::umma_commit(&bar);
+      }
+      __syncwarp();
+      tc::mbar_wait(&bar, r & 1);
+      t_done += clock64() - t0;
+    }
+    if (lane == 0) done = 1;
+    if (lane == 0 && blockIdx.x == 0) p.out[0] = t_done / p.rounds;
+  } else if (NOISE) {
+    const uint32_t taddr = 256u + ((uint32_t)((warp & 3) * 32) << 16);
+    float acc = 0.f;
+    float* dst = p.scratch + ((size_t)blockIdx.x * 288 + threadIdx.x) * 64;
+    const uint32_t sb = tc::smem_u32(smem + 150 * 1024);
+    int it = 0;
+    while (!done) {
+      if (NOISE & 1) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          uint32_t a, b, c, d;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(sb + i * 16));
+          acc += __uint_as_float(a ^ d);
+        }
+      }
+      if (NOISE & 2) {
+        uint32_t v[16];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                         "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                       : "r"(taddr + i * 16));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          acc += __uint_as_float(v[0] ^ v[15]);
+        }
+      }
+      if (NOISE & 4) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const uint4 q = make_uint4(it, i, lane, warp);
+          tc::st_global_v8(dst + ((it + i) & 7) * 8, q, q);
+        }
+      }
+      if (NOISE & 8) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(acc + (float)i)); acc = y * 0.001f; }
+      }
+      ++it;
+    }
+    if (acc == 123.456f) p.out[1] = it;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc::tc_fence_after(); tc::tmem_dealloc(0, 512); }
+}
+
+// bursts of GROUPS*9*KS MMAs followed by NCOMMIT tcgen05.commit to distinct barriers and NWAIT (already satisfied) parity waits;
+// the thread does not wait for the MMAs between bursts: what does one commit / one wait cost the issuing thread?
+template <int N, int GROUPS, int KS, int NCOMMIT, int NWAIT, int MODE = 3>
+__global__ void __launch_bounds__(128, 1) k_commit(P p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bars[16];
+  __shared__ uint64_t done_bar, ready[4];
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 16; ++i) tc::mbar_init(&bars[i], 1);
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&ready[i], 1);
+    tc::mbar_init(&done_bar, 1);
+    tc::fence_barrier_init();
+  }
+  tc::fence_async_smem();
+  if (warp == 0) { tc::tmem_alloc(&slot, 512); tc::tmem_relinquish(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  if (warp == 0) {
+    const uint32_t idesc = tc::umma_idesc(128, N, 0);
+    const uint64_t adesc0 = tc::umma_desc_sw128(tc::smem_u32(smem));
+    const uint64_t bdesc0 = tc::umma_desc_sw128(tc::smem_u32(smem + 96 * 1024));
+    long long t0 = clock64();
+    for (int r = 0; r < p.rounds; ++r) {
+      if (NWAIT) {
+        if (MODE & 1) { if (lane < NWAIT) tc::mbar_wait(&ready[lane], 1); __syncwarp(); }      // fresh barrier, parity 1: satisfied at once
+        if (MODE & 2) tc::tc_fence_after();
+      }
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int g = 0; g < GROUPS; ++g) {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const int arow = ((t / 3) + (g % 2)) * 136 + (t % 3);
+            if (MODE & 4) { tc::mbar_wait(&ready[t & 3], 1); if (MODE & 8) tc::tc_fence_after(); }     // per-tap weight wait (conv3 streamed)
+#pragma unroll
+            for (int k = 0; k < KS; ++k)
+              tc::umma_f16((uint32_t)((g % 2) * N), adesc0 + (uint64_t)(arow * 8 + k * 2), bdesc0 + (uint64_t)((t & 1) * N * 8 + k * 2), idesc,
+                           (t > 0 || k > 0) ? 1u : 0u);
+            if (MODE & 16) tc::umma_commit(&bars[8 + (t & 7)]);                                           // per-tap b_empty commit
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NCOMMIT; ++i) tc::umma_commit(&bars[i]);
+      }
+      __syncwarp();
+    }
+    if (tc::elect_one()) tc::umma_commit(&done_bar);
+    __syncwarp();
+    tc::mbar_wait(&done_bar, 0);
+    long long t1 = clock64();
+    if (lane == 0 && blockIdx.x == 0) p.out[0] = (t1 - t0) / p.rounds;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc::tc_fence_after(); tc::tmem_dealloc(0, 512); }
+}
+
+template <int N, int GROUPS, int KS, int NCOMMIT, int NWAIT, int MODE = 3>
+void run_commit(long long* d) {
+  auto k = k_commit<N, GROUPS, KS, NCOMMIT, NWAIT, MODE>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  P p; p.rounds = 64; p.out = d; p.scratch = nullptr; p.stop = nullptr;
+  k<<<148, 128, 170 * 1024>>>(p);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); exit(1); }
+  long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+  const int nmma = GROUPS * 9 * KS;
+  printf("N=%3d  bursts of %3d MMAs + %d commits + %d waits (wait=%d fence=%d tapwait=%d tapfence=%d tapcommit=%d): %7.0f cycles/burst = %6.1f cycles/MMA\n", N, nmma,
+         NCOMMIT, NWAIT, MODE & 1, (MODE >> 1) & 1, (MODE >> 2) & 1, (MODE >> 3) & 1, (MODE >> 4) & 1, (double)h[0], (double)h[0] / nmma);
+}
+
+template <int N, int GROUPS, int KS, int NOISE, int DATA = 0>
+void run(long long* d, float* scratch) {
+  auto k = k_probe<N, GROUPS, KS, NOISE, DATA>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  P p; p.rounds = 20; p.out = d; p.scratch = scratch; p.stop = nullptr;
+  k<<<148, 288, 170 * 1024>>>(p);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); exit(1); }
+  long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+  const int nmma = GROUPS * 9 * KS;
+  printf("N=%3d  %4d MMAs/burst  %s operands  noise=%2d (lds=%d tmem_ld=%d stg=%d mufu=%d): %7.1f cycles/MMA\n", N, nmma, DATA ? "random" : "zero  ", NOISE,
+         NOISE & 1, (NOISE >> 1) & 1, (NOISE >> 2) & 1, (NOISE >> 3) & 1, (double)h[0] / nmma);
+}
+
+int main() {
+  long long* d; cudaMalloc(&d, 16);
+  run_commit<48, 2, 3, 0, 0>(d); run_commit<48, 2, 3, 1, 0>(d); run_commit<48, 2, 3, 2, 0>(d); run_commit<48, 2, 3, 4, 0>(d); run_commit<48, 2, 3, 6, 0>(d);
+  run_commit<48, 2, 3, 1, 1>(d); run_commit<48, 2, 3, 1, 2>(d); run_commit<48, 2, 3, 1, 4>(d); run_commit<48, 2, 3, 4, 4>(d);
+  run_commit<48, 2, 3, 1, 1, 1>(d); run_commit<48, 2, 3, 1, 1, 2>(d); run_commit<48, 2, 3, 1, 1, 0>(d);
+  run_commit<96, 2, 4, 1, 0, 0>(d); run_commit<96, 2, 4, 1, 1, 4>(d); run_commit<96, 2, 4, 1, 1, 12>(d); run_commit<96, 2, 4, 1, 1, 28>(d); run_commit<96, 2, 4, 1, 1, 16>(d);
+  run_commit<48, 1, 3, 1, 0>(d); run_commit<48, 1, 3, 4, 4>(d); run_commit<96, 1, 4, 1, 0>(d); run_commit<96, 1, 4, 4, 4>(d);
+  float* s; cudaMalloc(&s, (size_t)148 * 288 * 64 * 4);
+  run<48, 8, 3, 0>(d, s); run<48, 8, 3, 1>(d, s); run<48, 8, 3, 2>(d, s); run<48, 8, 3, 4>(d, s); run<48, 8, 3, 7>(d, s); run<48, 8, 3, 8>(d, s);
+  run<48, 8, 3, 0, 1>(d, s); run<48, 8, 3, 7, 1>(d, s); run<48, 2, 3, 0, 0>(d, s); run<48, 2, 3, 0, 1>(d, s); run<48, 2, 3, 7, 1>(d, s);
+  run<96, 8, 4, 0, 1>(d, s); run<96, 2, 4, 0, 1>(d, s); run<96, 2, 4, 7, 1>(d, s);
+  run<96, 8, 4, 0>(d, s); run<96, 8, 4, 1>(d, s); run<96, 8, 4, 2>(d, s); run<96, 8, 4, 4>(d, s); run<96, 8, 4, 7>(d, s); run<96, 8, 4, 8>(d, s);
+  return 0;
+}
