@@ -26,6 +26,7 @@ struct AttnTcP {
   int nchunk;              // 64-channel chunks of the head dim (1 or 2)
   float scale_log2e;       // d^-0.5 * log2(e)
   int ahead;               // key tiles Q K^T runs ahead of P V: 1 or 2
+  int probe;               // probe the next Q K^T block's barriers under the P V MMAs
   void* out;
 };
 
@@ -189,12 +190,20 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     const uint64_t dP = tc::umma_desc_sw128(tc::smem_u32(sP));           // + (t * 2 + b) * (kTile >> 4)
     const uint64_t dV = umma_desc_mn_sw128(tc::smem_u32(sV), kKvTile);   // + slot * (2 * kKvTile >> 4)
     uint32_t kslot = 0, kphase = 0, vslot = 0, vphase = 0;
-    auto issue_pv = [&](int j) {      // O_t (+)= P_t,j V_j for both Q tiles
+    bool qk_probed = false;           // this lane's barrier of the next Q K^T block was already seen complete
+    auto issue_pv = [&](int j, int qk_next) {      // O_t (+)= P_t,j V_j for both Q tiles; qk_next: key tile of the Q K^T block that follows (-1: none)
       const int b = j & 1, u = j >> 1;
-      tc::mbar_wait(&v_full[vslot], vphase);
-      tc::mbar_wait(&p_full[b], u & 1);
-      tc::mbar_wait(&p_full[2 + b], u & 1);
+      {   // the three waits as ONE instruction on three lanes (each wait in front of the MMAs idles the tensor pipe for its latency)
+        uint64_t* const bar = lane == 0 ? &v_full[vslot] : &p_full[(lane == 1 ? 0 : 2) + b];
+        if (lane < 3) tc::mbar_wait(bar, lane == 0 ? vphase : (uint32_t)(u & 1));
+        __syncwarp();
+      }
       tc::tc_fence_after();
+      if (p.probe && qk_next >= 0 && lane < 3) {   // probe the barriers of the next Q K^T block now: the round trip runs under the MMAs below
+        const int bn = qk_next & 1, un = qk_next >> 1;
+        uint64_t* const bar = lane == 0 ? &k_full[kslot] : &s_free[(lane == 1 ? 0 : 2) + bn];
+        qk_probed = tc::mbar_test(bar, lane == 0 ? kphase : (uint32_t)((un & 1) ^ 1));
+      }
       if (tc::elect_one()) {
         const uint64_t bD = dV + (uint64_t)(vslot * (2 * kKvTile >> 4));
         const uint64_t aD0 = dP + (uint64_t)(b * (kTile >> 4));
@@ -216,9 +225,12 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     };
     auto issue_qk = [&](int j) {      // S_t,j = Q_t K_j^T for both Q tiles
       const int b = j & 1, u = j >> 1;
-      tc::mbar_wait(&k_full[kslot], kphase);          // K_j
-      tc::mbar_wait(&s_free[b], (u & 1) ^ 1);         // softmax has drained S_t,j-2 from these TMEM buffers
-      tc::mbar_wait(&s_free[2 + b], (u & 1) ^ 1);
+      {   // K_j landed; softmax has drained S_t,j-2 from these TMEM buffers -- one wait instruction on three lanes
+        uint64_t* const bar = lane == 0 ? &k_full[kslot] : &s_free[(lane == 1 ? 0 : 2) + b];
+        if (lane < 3) tc::mbar_wait_probed(qk_probed, bar, lane == 0 ? kphase : (uint32_t)((u & 1) ^ 1));
+        qk_probed = false;
+        __syncwarp();
+      }
       tc::tc_fence_after();
       if (tc::elect_one()) {
         const uint64_t bD = dK + (uint64_t)(kslot * (2 * kKvTile >> 4));
@@ -247,13 +259,13 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     if (p.ahead == 2) {
       if (p.nkv > 1) issue_qk(1);
       for (int j = 0; j < p.nkv; ++j) {
-        issue_pv(j);
+        issue_pv(j, j + 2 < p.nkv ? j + 2 : -1);
         if (j + 2 < p.nkv) issue_qk(j + 2);
       }
     } else {
       for (int j = 0; j < p.nkv; ++j) {
         if (j + 1 < p.nkv) issue_qk(j + 1);
-        issue_pv(j);
+        issue_pv(j, j + 2 < p.nkv ? j + 2 : -1);
       }
     }
   } else {
@@ -391,6 +403,8 @@ void attention_tc(Ctx& c, const Tens& qkv, int heads, Tens& out) {
   p.scale_log2e = (float)((1.0 / sqrt((double)d)) * 1.4426950408889634);
   static const int ahead = getenv("XRD_ATT_AHEAD") ? atoi(getenv("XRD_ATT_AHEAD")) : 1;   // measured: 0.327 ms (1) vs 0.340 ms (2) at B=16
   p.ahead = ahead == 1 ? 1 : 2;
+  static const int probe = getenv("XRD_ATT_PROBE") ? atoi(getenv("XRD_ATT_PROBE")) : 1;
+  p.probe = probe;
   p.out = out.p;
   alignas(64) CUtensorMap tmQ, tmKV;
   for (int which = 0; which < 2; ++which) {
