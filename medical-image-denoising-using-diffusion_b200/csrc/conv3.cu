@@ -82,13 +82,13 @@ template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& 
 // All MMAs of one 64-channel chunk: 9 taps x TH rows x KS k-steps, every descriptor a compile-time offset.
 template <int COUT, int TH, int KS, bool WRES>
 __device__ __forceinline__ void c3_issue_chunk(uint64_t adesc0, uint64_t bdesc0, uint32_t sB_addr, uint64_t* b_full, uint64_t* b_empty,
-                                               uint32_t& wslot, uint32_t& wphase, int nb, int kb0, int nres, uint32_t acc0, uint32_t idesc,
-                                               uint32_t not_first) {
+                                               uint32_t& wslot, uint32_t& wphase, uint32_t& wprobed, int nb, int kb0, int nres, uint32_t acc0,
+                                               uint32_t idesc, uint32_t not_first) {
   constexpr uint32_t B_BYTES = COUT * 128;
   // streamed weights: the barrier of tap t+1 is probed BEFORE the MMAs of tap t are issued, so the probe's round trip runs under
-  // them (a wait issued right in front of its MMAs stalls the issue stream, and with it the tensor pipe, for ~57 cycles per tap)
-  bool probed = false;
-  if (!WRES && kb0 >= nres) probed = tc::mbar_test(&b_full[wslot], wphase);
+  // them (a wait issued right in front of its MMAs stalls the issue stream, and with it the tensor pipe, for ~57 cycles per tap);
+  // the probe of the next chunk's first tap is carried out of this call in `wprobed`
+  bool probed = wprobed != 0u;
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
     uint64_t bdesc;
@@ -104,7 +104,7 @@ __device__ __forceinline__ void c3_issue_chunk(uint64_t adesc0, uint64_t bdesc0,
     }
     uint32_t nslot = wslot + 1, nphase = wphase;
     if (nslot == (uint32_t)nb) { nslot = 0; nphase ^= 1; }
-    if (streamed && tap < 8) probed = tc::mbar_test(&b_full[nslot], nphase);
+    if (streamed) probed = tc::mbar_test(&b_full[nslot], nphase);
     const int dy = tap / 3, dx = tap % 3;
 #pragma unroll
     for (int s = 0; s < TH; ++s) {
@@ -118,6 +118,7 @@ __device__ __forceinline__ void c3_issue_chunk(uint64_t adesc0, uint64_t bdesc0,
       wslot = nslot; wphase = nphase;
     }
   }
+  wprobed = probed ? 1u : 0u;
 }
 
 template <typename T, int COUT, int TH, int NACC, bool WRES, bool GN>
@@ -242,11 +243,13 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     uint32_t ai = 0, ti = 0, wslot = 0, wphase = 0;
     uint64_t* const abar = GN ? a_ready : a_full;
     bool a_probed = false;                                   // result of the early probe of the next stage's barrier
+    bool acc_probed = false;                                 // ... of the next tile's accumulator-drained barrier
+    uint32_t wprobed = 0u;                                   // ... of the next streamed weight block (leader's value, broadcast)
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
       const int ab = NACC == 2 ? (int)(ti & 1) : 0;
       const uint32_t use = NACC == 2 ? (ti >> 1) : ti;       // how many times this accumulator buffer was used before
       if (lane == 0) C3PROF(ti, 1);
-      tc::mbar_wait(&acc_empty[ab], (use & 1) ^ 1);
+      tc::mbar_wait_probed(acc_probed, &acc_empty[ab], (use & 1) ^ 1);
       tc::tc_fence_after();
       if (lane == 0) C3PROF(ti, 2);
       const uint32_t acc0 = tmem_base + (uint32_t)(ab * TH * COUT);
@@ -256,6 +259,10 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         tc::tc_fence_after();
         // probe the NEXT stage now: the round trip of the barrier test runs under this chunk's MMAs (tc_common.cuh)
         a_probed = tc::mbar_test(&abar[(ai + 1) & 1], ((ai + 1) >> 1) & 1);
+        if (c == p.nchunk - 1) {                               // last chunk of the tile: probe the next tile's accumulator barrier as well
+          const uint32_t tn = ti + 1;
+          acc_probed = tc::mbar_test(&acc_empty[NACC == 2 ? (tn & 1) : 0], ((NACC == 2 ? (tn >> 1) : tn) & 1) ^ 1);
+        }
         if (c == 0 && lane == 0) C3PROF(ti, 3);
         const bool second = c >= p.nchunk0;
         const int cl = second ? c - p.nchunk0 : c;
@@ -267,12 +274,13 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           const uint32_t nf = c ? 1u : 0u;
           if (!(p.dbg & 2)) {
             switch (ks) {
-              case 4: c3_issue_chunk<COUT, TH, 4, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, p.nb, c * 9, p.nres, acc0, idesc, nf); break;
-              case 3: c3_issue_chunk<COUT, TH, 3, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, p.nb, c * 9, p.nres, acc0, idesc, nf); break;
-              case 2: c3_issue_chunk<COUT, TH, 2, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, p.nb, c * 9, p.nres, acc0, idesc, nf); break;
-              default: c3_issue_chunk<COUT, TH, 1, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, p.nb, c * 9, p.nres, acc0, idesc, nf); break;
+              case 4: c3_issue_chunk<COUT, TH, 4, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, wprobed, p.nb, c * 9, p.nres, acc0, idesc, nf); break;
+              case 3: c3_issue_chunk<COUT, TH, 3, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, wprobed, p.nb, c * 9, p.nres, acc0, idesc, nf); break;
+              case 2: c3_issue_chunk<COUT, TH, 2, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, wprobed, p.nb, c * 9, p.nres, acc0, idesc, nf); break;
+              default: c3_issue_chunk<COUT, TH, 1, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, wprobed, p.nb, c * 9, p.nres, acc0, idesc, nf); break;
             }
           } else if (!WRES) {   // experiment: consume the weight ring without issuing MMAs
+            wprobed = 0u;
             for (int tap = 0; tap < 9; ++tap) {
               if (c * 9 + tap < p.nres) continue;
               tc::mbar_wait(&b_full[wslot], wphase);
@@ -287,6 +295,7 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         if (!WRES) {
           wslot = __shfl_sync(0xffffffffu, wslot, leader);
           wphase = __shfl_sync(0xffffffffu, wphase, leader);
+          wprobed = __shfl_sync(0xffffffffu, wprobed, leader);
         }
       }
       if (lane == 0) C3PROF(ti, 4);
