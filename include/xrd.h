@@ -180,6 +180,22 @@ int xrd_tiles_plan(int H, int W, int tile, int halo, int* ny, int* nx, int* oy, 
 int xrd_tiles_extract(const float* img, float* tiles, int B, int H, int W, int tile, int halo, void* stream);
 int xrd_tiles_blend(const float* tiles, float* img, int B, int H, int W, int tile, int halo, void* stream);
 
+/* ---- the pixel work either side of the networks in /denoise, on the GPU and bit-exact with the reference's CPU path ----
+ * Replaces: transforms.Resize((512,512), BICUBIC) on the PIL 'L' image + ToTensor() (RUN:191-201) and
+ * (output_np * 255).astype('uint8') + Image.resize(original_size, Image.BICUBIC) (RUN:143-149).  The arithmetic is Pillow's
+ * 8-bit resampler (libImaging/Resample.c: Keys cubic a=-0.5, antialiased when shrinking, 22-bit fixed point, horizontal then
+ * vertical pass through an 8-bit intermediate).  All buffers are device memory; images are (N, H, W) single-channel uint8.
+ * tmp: N*Hin*Wout bytes, needed when both axes change.  PNG/base64 encoding stays on the host (RUN:147-149). */
+int xrd_resize_bicubic_u8(const uint8_t* src, uint8_t* dst, uint8_t* tmp, int N, int Hin, int Win, int Hout, int Wout,
+                          void* stream);
+/* Host only: the window table of one axis (bounds [out][2] = first input index and count, kk [out][*ksize] weights with
+ * 22 fractional bits); bounds / kk nullable, kk has room for cap_k ints. */
+int xrd_resample_table(int in_size, int out_size, int* ksize, int* bounds, int* kk, int cap_k);
+/* ToTensor(): dst[i] = src[i] / 255 in float32. */
+int xrd_u8_to_unit(const uint8_t* src, float* dst, int64_t n, void* stream);
+/* torch.clamp(x, 0, 1) then (x * 255).astype('uint8'): float32 product, truncation (RUN:110,145). */
+int xrd_unit_to_u8(const float* src, uint8_t* dst, int64_t n, void* stream);
+
 /* ---- kernel-level hooks (tests and micro-benchmarks only; no reference counterpart) ----
  * NCHW float32 device tensors in and out; the library converts to its internal NHWC storage
  * of the handle's current mode, runs ONE op through the same kernel the networks use, and

@@ -14,11 +14,14 @@ from .models import (                                                # noqa: F40
 from .build import build_library                                    # noqa: F401
 from .sharding import shard_bounds, shard_batch, gather_outputs, run_sharded   # noqa: F401
 from .tiling import tile_plan, extract_tiles, blend_tiles, denoise_tiled          # noqa: F401
+from .serving import MicroBatcher                                               # noqa: F401
+from .imageio import resize_bicubic_u8, preprocess_u8, postprocess_u8, resample_table   # noqa: F401
 
 __all__ = [
     "XrdError", "LIB_PATH", "load_library", "build_library",
     "UNetDiffusion", "DiffusionDenoiser", "EnhancedNAFNet", "NoiseAnalyzer", "FusionModule",
     "HybridDenoisingRouter", "ddim_timestep_indices", "native_kernel_launches",
     "shard_bounds", "shard_batch", "gather_outputs", "run_sharded",
-    "tile_plan", "extract_tiles", "blend_tiles", "denoise_tiled",
+    "tile_plan", "extract_tiles", "blend_tiles", "denoise_tiled", "MicroBatcher",
+    "resize_bicubic_u8", "preprocess_u8", "postprocess_u8", "resample_table",
 ]

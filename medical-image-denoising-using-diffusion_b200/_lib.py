@@ -76,6 +76,10 @@ SYMBOLS = {
     "xrd_tiles_plan": (C.c_int, [C.c_int] * 4 + [C.POINTER(C.c_int)] * 4 + [C.c_int]),
     "xrd_tiles_extract": (C.c_int, [_F, _F] + [C.c_int] * 5 + [_P]),
     "xrd_tiles_blend": (C.c_int, [_F, _F] + [C.c_int] * 5 + [_P]),
+    "xrd_resize_bicubic_u8": (C.c_int, [_P, _P, _P] + [C.c_int] * 5 + [_P]),
+    "xrd_resample_table": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]),
+    "xrd_u8_to_unit": (C.c_int, [_P, _F, C.c_int64, _P]),
+    "xrd_unit_to_u8": (C.c_int, [_F, _P, C.c_int64, _P]),
     "xrd_op_conv2d": (C.c_int, [_P, C.c_int, _F, _F, _F, _F] + [C.c_int] * 8 + [_P]),
     "xrd_op_conv2d_stats": (C.c_int, [_P, C.c_int, _F, _F, _F, _F, _P] + [C.c_int] * 8 + [_P]),
     "xrd_op_groupnorm_act": (C.c_int, [_P, _F, _F, _F, _F] + [C.c_int] * 6 + [_P]),

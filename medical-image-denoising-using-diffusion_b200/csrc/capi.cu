@@ -24,6 +24,10 @@ void tiles_extract(Ctx& c, const float* img, float* tiles, int B, int H, int W, 
 void tiles_blend(Ctx& c, const float* tiles, float* img, int B, int H, int W, int T, int halo);
 int tiles_count_host(int L, int T, int halo);
 int tiles_origin_host(int k, int L, int T, int halo);
+void resize_bicubic_u8(Ctx& c, const uint8_t* src, uint8_t* dst, uint8_t* tmp, int N, int Hin, int Win, int Hout, int Wout);
+int resample_table_host(int in_size, int out_size, int* bounds, int* kk, int cap_k);
+void u8_to_unit(Ctx& c, const uint8_t* in, float* out, int64_t n);
+void unit_to_u8(Ctx& c, const float* in, uint8_t* out, int64_t n);
 }  // namespace xrd
 
 using namespace xrd;
@@ -717,5 +721,41 @@ XRD_EXPORT int xrd_tiles_blend(const float* tiles, float* img, int B, int H, int
     Ctx c;
     c.s = (cudaStream_t)stream;
     tiles_blend(c, tiles, img, B, H, W, tile, halo);
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// pre/post-processing of `/denoise` on the GPU (Pillow-exact 8-bit bicubic resampling); no handle
+XRD_EXPORT int xrd_resize_bicubic_u8(const uint8_t* src, uint8_t* dst, uint8_t* tmp, int N, int Hin, int Win, int Hout, int Wout, void* stream) {
+  return guarded([&] {
+    XRD_REQUIRE(src && dst, "null argument");
+    Ctx c;
+    c.s = (cudaStream_t)stream;
+    resize_bicubic_u8(c, src, dst, tmp, N, Hin, Win, Hout, Wout);
+  });
+}
+
+XRD_EXPORT int xrd_resample_table(int in_size, int out_size, int* ksize, int* bounds, int* kk, int cap_k) {
+  return guarded([&] {
+    XRD_REQUIRE(in_size >= 1 && out_size >= 1 && ksize, "bad argument");
+    *ksize = resample_table_host(in_size, out_size, bounds, kk, cap_k);
+  });
+}
+
+XRD_EXPORT int xrd_u8_to_unit(const uint8_t* src, float* dst, int64_t n, void* stream) {
+  return guarded([&] {
+    XRD_REQUIRE(src && dst && n >= 0, "bad argument");
+    Ctx c;
+    c.s = (cudaStream_t)stream;
+    if (n) u8_to_unit(c, src, dst, n);
+  });
+}
+
+XRD_EXPORT int xrd_unit_to_u8(const float* src, uint8_t* dst, int64_t n, void* stream) {
+  return guarded([&] {
+    XRD_REQUIRE(src && dst && n >= 0, "bad argument");
+    Ctx c;
+    c.s = (cudaStream_t)stream;
+    if (n) unit_to_u8(c, src, dst, n);
   });
 }
