@@ -148,13 +148,20 @@ k_conv1(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     const uint32_t idesc = tc::umma_idesc(128, COUT, tc::umma_fmt<T>());
     const uint32_t sA_addr = tc::smem_u32(sA), sB_addr = tc::smem_u32(sB);
     uint32_t st = 0, ph = 0, ti = 0;
+    bool a_probed = false, acc_probed = false;     // early probes of the next stage / next accumulator barrier (tc_common.cuh)
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
       const uint32_t ab = ti & 1, use = ti >> 1;
-      tc::mbar_wait(&acc_empty[ab], (use & 1) ^ 1);
+      tc::mbar_wait_probed(acc_probed, &acc_empty[ab], (use & 1) ^ 1);
       tc::tc_fence_after();
       for (int c = 0; c < p.nchunk; ++c) {
-        tc::mbar_wait(&a_full[st], ph);
+        tc::mbar_wait_probed(a_probed, &a_full[st], ph);
         tc::tc_fence_after();
+        {
+          uint32_t nst = st + 1, nph = ph;
+          if (nst == kC1Stages) { nst = 0; nph ^= 1; }
+          a_probed = tc::mbar_test(&a_full[nst], nph);            // the round trip runs under the MMAs issued below
+          if (c == p.nchunk - 1) acc_probed = tc::mbar_test(&acc_empty[(ti + 1) & 1], (((ti + 1) >> 1) & 1) ^ 1);
+        }
         const bool second = c >= p.nchunk0;
         const int cl = second ? c - p.nchunk0 : c;
         const int ks = min(64, (second ? p.c1 : p.c0) - cl * 64) >> 4;

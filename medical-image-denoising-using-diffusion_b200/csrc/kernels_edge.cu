@@ -9,6 +9,7 @@
 //                      3x3 gather then runs on that 9-plane fp32 tile in shared memory.
 //   * upsample2x_stats: bilinear 2x (align_corners=False, HYB:381-382) fused with the GroupNorm sums of its output.
 #include "kernels.cuh"
+#include <stdlib.h>
 
 namespace xrd {
 
@@ -306,6 +307,74 @@ __global__ void __launch_bounds__(288) k_upsample2x_stats(const T* __restrict__ 
   }
 }
 
+// Same arithmetic, one thread per INPUT pixel and 8 channels: the 2x2 output block of input pixel (i, j) needs the 3x3 input
+// neighbourhood, i.e. 9 loads and conversions for four outputs instead of 16, and the three rows' horizontal interpolations are
+// shared by the two output rows (the per-output kernel above was issue-bound: 2 TB/s).
+template <typename T>
+__global__ void __launch_bounds__(288) k_upsample2x_stats_v2(const T* __restrict__ x, T* __restrict__ y, int H, int W, int C, int pix_per_block,
+                                                             double* __restrict__ stats) {
+  extern __shared__ float sm[];   // [2][C]
+  const int V = C >> 3;
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int ppi = blockDim.x / V;
+  const int slot = threadIdx.x % V, lane = threadIdx.x / V;
+  const int Wo = 2 * W, HW = H * W;
+  const T* xb = x + (int64_t)n * HW * C + slot * 8;
+  T* yb = y + (int64_t)n * 4 * HW * C + slot * 8;
+  float s[8], ss[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(p0 + pix_per_block, HW);
+  for (int pp = p0 + lane; pp < p1; pp += ppi) {
+    const int i = pp / W, j = pp - i * W;
+    const int rr[3] = {max(i - 1, 0), i, min(i + 1, H - 1)};
+    const int cm = max(j - 1, 0), cp = min(j + 1, W - 1);
+    float hl[3][8], hr[3][8];              // per input row: value at output column 2j (weights .25/.75) and 2j+1 (.75/.25)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      float a[8], b[8], d[8];
+      const T* row = xb + (int64_t)rr[r] * W * C;
+      ld8f<T>(row + (int64_t)cm * C, a);
+      ld8f<T>(row + (int64_t)j * C, b);
+      ld8f<T>(row + (int64_t)cp * C, d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        hl[r][k] = a[k] + 0.75f * (b[k] - a[k]);
+        hr[r][k] = b[k] + 0.25f * (d[k] - b[k]);
+      }
+    }
+    float o[8];
+    T* o00 = yb + ((int64_t)(2 * i) * Wo + 2 * j) * C;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {          // (output row parity, output column parity)
+      const int dy = q >> 1, dxp = q & 1;
+      const float fh = dy ? 0.25f : 0.75f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float top = dxp ? hr[dy][k] : hl[dy][k];
+        const float bot = dxp ? hr[dy + 1][k] : hl[dy + 1][k];
+        o[k] = top + fh * (bot - top);
+        s[k] += o[k]; ss[k] = fmaf(o[k], o[k], ss[k]);
+      }
+      st8f<T>(o00 + ((int64_t)dy * Wo + dxp) * C, o);
+    }
+  }
+  if (stats) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { atomicAdd(&sm[slot * 8 + i], s[i]); atomicAdd(&sm[C + slot * 8 + i], ss[i]); }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      const int cpg = C / 8;
+      double a = 0.0, b = 0.0;
+      for (int i = 0; i < cpg; ++i) { a += (double)sm[threadIdx.x * cpg + i]; b += (double)sm[C + threadIdx.x * cpg + i]; }
+      atomicAdd(&stats[((int64_t)n * 8 + threadIdx.x) * 2 + 0], a);
+      atomicAdd(&stats[((int64_t)n * 8 + threadIdx.x) * 2 + 1], b);
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_im2col_3x3_2ch(const float* __restrict__ a, const float* __restrict__ b, T* __restrict__ col, int N, int H,
                                                         int W) {
@@ -402,6 +471,22 @@ void upsample2x_stats(Ctx& c, const Tens& x, Tens& y, double* stats) {
     return;
   }
   const int threads = (288 / V) * V;
+  static const int v2 = getenv("XRD_UPS2") ? atoi(getenv("XRD_UPS2")) : 1;
+  if (v2) {                      // one thread per input pixel: 2x2 outputs from 9 loads
+    const int HWi = x.h * x.w;
+    const int ppi = threads / V;
+    int64_t ppb = cdiv64((int64_t)HWi * x.n, 148 * 8);
+    ppb = std::max<int64_t>(ppb, (int64_t)ppi * 4);
+    ppb = std::min<int64_t>(cdiv64(ppb, ppi) * ppi, HWi);
+    dim3 grid(cdiv(HWi, (int)ppb), x.n);
+    if (x.dt == DT_BF16)
+      XRD_LAUNCH(c, (k_upsample2x_stats_v2<__nv_bfloat16>), grid, threads, 2 * x.c * sizeof(float), (const __nv_bfloat16*)x.p,
+                 (__nv_bfloat16*)y.p, x.h, x.w, x.c, (int)ppb, stats);
+    else
+      XRD_LAUNCH(c, (k_upsample2x_stats_v2<__half>), grid, threads, 2 * x.c * sizeof(float), (const __half*)x.p, (__half*)y.p, x.h, x.w,
+                 x.c, (int)ppb, stats);
+    return;
+  }
   const int HWo = y.h * y.w;
   const int ppi = threads / V;
   int64_t ppb = cdiv64((int64_t)HWo * x.n, 148 * 8);
