@@ -134,7 +134,7 @@ def run_reference(args, rank, world):
                          "sample": f"batch 1 @512x512: {CPU_UNET_EVALS} UNet evals + 1 NAFNet + 1 router + 1 fusion per step, 50*median(t_unet)+rest"},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def conv_roofline(model, dev, batch, size):
@@ -199,7 +199,30 @@ def conv_roofline(model, dev, batch, size):
     return tot_fl / tot_ms / 1e9, tot_ms, launches, tot_fl, by_kernel
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """This program prints ONE JSON line on stdout.  Native libraries write there too (NCCL's version banner at WARN level and
+    above): send file descriptor 1 to stderr for the whole run and keep the real stdout for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
@@ -226,8 +249,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"       # NCCL's version banner goes to stdout; this program prints ONE JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     import xrd_b200
@@ -328,7 +349,7 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"batch 1 @{S}x{S}: {CPU_UNET_EVALS} UNet evals + NAFNet + router + fusion ({spent:.1f} s of CPU work), "
                                           "50*median(t_unet)+rest"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
