@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 GF_PER_IMAGE_512 = 21383.0      # algorithmic 2*MAC of the reference op list, hybrid DDIM-50 @512^2
 UNET_CONV_GF_512 = 347.34       # conv FLOPs of one UNet evaluation @512^2 per image
-NCU_TOP_KERNEL_DRAM_BYTES = 403016448 + 353474560   # profiles/r01_ncu_hot_kernels.csv, k_conv3<half,48,...> per launch
+NCU_TOP_KERNEL_DRAM_BYTES = 807400000 + 375400000   # profiles/r01_ncu_hot_kernels.csv: k_conv3<half,48,4,2> 96->48 @512^2 x16, the longest launch
 
 
 def peaks():
@@ -337,8 +337,8 @@ def main():
                                "each timed live with CUDA events through the C-ABI op hook, launch weighted",
                      "achieved": conv_tf, "peak": pk["burst"], "unit": "TFLOP/s", "frac": conv_tf / pk["burst"] if pk["burst"] else None,
                      "peak_kind": f"bf16 dense burst, {pk['src']}",
-                     # dram__bytes_read.sum + dram__bytes_write.sum of the top launch (k_conv3 48->48 @512^2 x16) from the committed
-                     # ncu --set full capture (profiles/r01_ncu_hot_kernels.csv); its algorithmic bytes are 2 x 403 MB
+                     # dram__bytes_read.sum + dram__bytes_write.sum of the longest launch (k_conv3 96->48 @512^2 x16) from the committed
+                     # ncu --set full capture (profiles/r01_ncu_hot_kernels.csv); its algorithmic bytes are 805 + 403 MB
                      "traffic": NCU_TOP_KERNEL_DRAM_BYTES if (B == 16 and S == 512) else None, "by_kernel": conv_by,
                      "flops_per_eval": conv_fl, "ms_per_eval_isolated": conv_ms, "launches_per_eval": conv_launches},
         "roofline_step": {"bound": "tensor", "achieved": step_tf, "peak": pk["sustained"], "unit": "TFLOP/s",
