@@ -52,7 +52,13 @@ template <> __device__ __forceinline__ void st8f<float>(float* p, const float (&
   *(reinterpret_cast<float4*>(p) + 1) = make_float4(v[4], v[5], v[6], v[7]);
 }
 
-__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// x*sigmoid(x) = h*tanh(h) + h with h = x/2: FMUL, MUFU.TANH, FFMA (the exp + divide form is 6 instructions)
+__device__ __forceinline__ float silu_fast(float v) {
+  const float h = 0.5f * v;
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+  return fmaf(h, th, h);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // conv_smallcin2

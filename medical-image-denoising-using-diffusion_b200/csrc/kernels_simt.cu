@@ -2,6 +2,7 @@
 // memory-bound fused kernel (GroupNorm/LayerNorm/SimpleGate/pool/sampler update),
 // layout helpers and weight packing.  NHWC everywhere; fp32 arithmetic.
 #include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace xrd {
 
@@ -925,8 +926,33 @@ __global__ void k_scale_nc(T* __restrict__ x, const float* __restrict__ scale, i
     st4<T>(x + pix * C + c, v);
   }
 }
+// 16-bit storage, 8 channels (16 bytes) per thread
+template <typename T>
+__global__ void k_scale_nc16(T* __restrict__ x, const float* __restrict__ scale, int64_t hw, int C, int64_t total_o) {
+  const int O = C >> 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_o; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / O;
+    const int c = (int)(i - pix * O) * 8;
+    const int n = (int)(pix / hw);
+    uint4* ptr = reinterpret_cast<uint4*>(x + pix * C + c);
+    const uint4 q = *ptr;
+    float v[8];
+    tc::unpack8<T>(q, v);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + (int64_t)n * C + c)), s1 = __ldg(reinterpret_cast<const float4*>(scale + (int64_t)n * C + c + 4));
+    uint4 o;
+    o.x = tc::pack2<T>(v[0] * s0.x, v[1] * s0.y); o.y = tc::pack2<T>(v[2] * s0.z, v[3] * s0.w);
+    o.z = tc::pack2<T>(v[4] * s1.x, v[5] * s1.y); o.w = tc::pack2<T>(v[6] * s1.z, v[7] * s1.w);
+    *ptr = o;
+  }
+}
 void scale_nc(Ctx& c, Tens& x, const float* scale) {
   XRD_REQUIRE(x.c % 4 == 0, "scale_nc: channels");
+  if (x.dt != DT_F32 && x.c % 8 == 0) {
+    const int64_t to = (int64_t)x.n * x.h * x.w * (x.c / 8);
+    if (x.dt == DT_F16) XRD_LAUNCH(c, (k_scale_nc16<__half>), ew_blocks(to), 256, 0, (__half*)x.p, scale, (int64_t)x.h * x.w, x.c, to);
+    else XRD_LAUNCH(c, (k_scale_nc16<__nv_bfloat16>), ew_blocks(to), 256, 0, (__nv_bfloat16*)x.p, scale, (int64_t)x.h * x.w, x.c, to);
+    return;
+  }
   int64_t tq = (int64_t)x.n * x.h * x.w * (x.c / 4);
   XRD_DISPATCH(x.dt, T, XRD_LAUNCH(c, (k_scale_nc<T>), ew_blocks(tq), 256, 0, (T*)x.p, scale, (int64_t)x.h * x.w, x.c, tq));
 }
