@@ -74,10 +74,10 @@ class ClockSampler(threading.Thread):
 
 def build_model(dev, mode):
     import xrd_b200
-    from oracle import xrd_oracle as O          # only for the shared seeding helper + synthetic inputs
+    import synthetic_data as SY                 # seeded weights/inputs only; the oracle is not imported on the GPU arm
     torch.manual_seed(1234)
     m = xrd_b200.HybridDenoisingRouter({}, {}, inference_diffusion_steps=50).eval()
-    O.randomize_identity_params(m.state_dict(), 99)
+    SY.randomize_identity_params(m.state_dict(), 99)
     m = m.to(dev)
     m.set_native_mode(mode)
     return m
@@ -252,10 +252,10 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     import xrd_b200
-    from oracle import xrd_oracle as O
+    import synthetic_data as SY
     model = build_model(dev, args.mode)
     B, S = args.batch, args.size
-    _, noisy = O.synthetic_xray(B, S, S, seed=7 + rank)
+    _, noisy = SY.synthetic_xray(B, S, S, seed=7 + rank)
     x_dev = noisy.to(dev)
     x_pin = noisy.pin_memory()
     out_pin = torch.empty_like(noisy).pin_memory()

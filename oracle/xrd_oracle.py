@@ -369,56 +369,13 @@ def hybrid_forward(sd: SD, noisy: Tensor, inference_steps: int, noise_steps: int
 
 
 # --------------------------------------------------------------------------
-# seeded weights / inputs shared by the golden generator, the tests and bench
+# seeded weights / inputs: neutral helpers (no reference arithmetic) that live in synthetic_data.py at the repository
+# root so that bench.py's GPU arm can build its workload without importing this file; re-exported for the tests
 # --------------------------------------------------------------------------
-def is_norm_param(key: str) -> bool:
-    """True for the affine parameters of LayerNorm / GroupNorm modules in the
-    reference's state_dict naming."""
-    parts = key.split(".")
-    if len(parts) < 2 or parts[-1] not in ("weight", "bias"):
-        return False
-    owner = parts[-2]
-    if owner in ("norm1", "norm2", "norm"):                      # NAFBlock LayerNorms, attention GroupNorm
-        return True
-    if len(parts) >= 3:
-        grand = parts[-3]
-        if owner == "0" and grand in ("block1", "block2", "out_conv"):   # ResidualBlock / UNet out_conv GroupNorm
-            return True
-        if owner == "1" and grand in ("enc1", "enc2", "enc3", "mid", "dec3", "dec2", "conv1", "conv2"):
-            return True                                              # router / fusion GroupNorms
-    return False
-
-
-def randomize_identity_params(sd: SD, seed: int = 99) -> None:
-    """In place.  At default init every NAFBlock is the identity (beta = gamma
-    = 0, HYB:149-150) and every norm's affine is (1, 0); a broken kernel would
-    pass.  Overwrite them with seeded values."""
-    g = torch.Generator().manual_seed(seed)
-    for k in sorted(sd.keys()):
-        v = sd[k]
-        leaf = k.rsplit(".", 1)[-1]
-        if leaf in ("beta", "gamma"):
-            v.copy_(0.5 * torch.randn(v.shape, generator=g))
-        elif is_norm_param(k):
-            if leaf == "weight":
-                v.copy_(1.0 + 0.2 * torch.randn(v.shape, generator=g))
-            else:
-                v.copy_(0.1 * torch.randn(v.shape, generator=g))
-
-
-def synthetic_xray(batch: int, height: int, width: int, seed: int = 7) -> Tuple[Tensor, Tensor]:
-    """(clean, noisy) synthetic grayscale X-ray-like fields in [0,1], float32
-    (B,1,H,W).  clean = low-pass filtered uniform noise rescaled to [0.2,0.8];
-    noisy = clamp(clean * (1 + 0.2 randn), 0, 1)  (speckle)."""
-    g = torch.Generator().manual_seed(seed)
-    lo_h, lo_w = max(2, height // 16), max(2, width // 16)
-    base = torch.rand(batch, 1, lo_h, lo_w, generator=g)
-    clean = F.interpolate(base, size=(height, width), mode="bicubic", align_corners=False)
-    mn = clean.amin(dim=(2, 3), keepdim=True)
-    mx = clean.amax(dim=(2, 3), keepdim=True)
-    clean = 0.2 + 0.6 * (clean - mn) / (mx - mn + 1e-12)
-    noisy = torch.clamp(clean * (1 + 0.2 * torch.randn(clean.shape, generator=g)), 0, 1)
-    return clean.contiguous(), noisy.contiguous()
+import os as _os
+import sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+from synthetic_data import is_norm_param, randomize_identity_params, synthetic_xray  # noqa: E402,F401
 
 
 # --------------------------------------------------------------------------
