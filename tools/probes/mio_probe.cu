@@ -10,7 +10,7 @@
 #include "../../medical-image-denoising-using-diffusion_b200/csrc/tc_common.cuh"
 using namespace xrd;
 
-struct P { int rounds; long long* out; float* scratch; volatile int* stop; };
+struct P { int rounds; long long* out; float* scratch; volatile int* stop; int rounds_zero; };
 
 template <int N, int GROUPS, int KS, int NOISE, int DATA = 0>
 __global__ void __launch_bounds__(288, 1) k_probe(P p) {
@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(288, 1) k_probe(P p) {
     if (lane == 0) done = 1;
     if (lane == 0 && blockIdx.x == 0) p.out[0] = t_done / p.rounds;
   } else if (NOISE) {
-    const uint32_t taddr = 256u + ((uint32_t)((warp & 3) * 32) << 16);
+    // NOISE bit 4 (16): drain the columns right next to / inside the accumulators the MMA stream is writing (as the real epilogue does)
+    const uint32_t taddr = ((NOISE & 16) ? 48u : 256u) + ((uint32_t)((warp & 3) * 32) << 16);
     float acc = 0.f;
     float* dst = p.scratch + ((size_t)blockIdx.x * 288 + threadIdx.x) * 64;
     const uint32_t sb = tc::smem_u32(smem + 150 * 1024);
@@ -107,7 +108,18 @@ __global__ void __launch_bounds__(288, 1) k_probe(P p) {
 
 // bursts of GROUPS*9*KS MMAs followed by NCOMMIT tcgen05.commit to distinct barriers and NWAIT (already satisfied) parity waits;
 // the thread does not wait for the MMAs between bursts: what does one commit / one wait cost the issuing thread?
-template <int N, int GROUPS, int KS, int NCOMMIT, int NWAIT, int MODE = 3>
+__device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int N, int GROUPS, int KS, int NCOMMIT, int NWAIT, int MODE = 3, int DESC = 0>
 __global__ void __launch_bounds__(128, 1) k_commit(P p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -138,6 +150,10 @@ __global__ void __launch_bounds__(128, 1) k_commit(P p) {
         if (MODE & 2) tc::tc_fence_after();
       }
       if (tc::elect_one()) {
+        // DESC != 0: the bases change every burst (ring slots in the real kernels), so no descriptor can be hoisted out of the loop
+        const uint32_t roff = DESC ? (uint32_t)((r & 1) * p.rounds_zero + (r & 1) * 0) : 0u;
+        const uint64_t ab = adesc0 + (uint64_t)roff * 1088u, bb = bdesc0 + (uint64_t)roff;
+        const uint32_t alo = (uint32_t)ab, ahi = (uint32_t)(ab >> 32), blo = (uint32_t)bb, bhi = (uint32_t)(bb >> 32);
 #pragma unroll
         for (int g = 0; g < GROUPS; ++g) {
 #pragma unroll
@@ -145,9 +161,14 @@ __global__ void __launch_bounds__(128, 1) k_commit(P p) {
             const int arow = ((t / 3) + (g % 2)) * 136 + (t % 3);
             if (MODE & 4) { tc::mbar_wait(&ready[t & 3], 1); if (MODE & 8) tc::tc_fence_after(); }     // per-tap weight wait (conv3 streamed)
 #pragma unroll
-            for (int k = 0; k < KS; ++k)
-              tc::umma_f16((uint32_t)((g % 2) * N), adesc0 + (uint64_t)(arow * 8 + k * 2), bdesc0 + (uint64_t)((t & 1) * N * 8 + k * 2), idesc,
+            for (int k = 0; k < KS; ++k) {
+              if (DESC == 2)
+                umma_f16_lo((uint32_t)((g % 2) * N), alo + (uint32_t)(arow * 8 + k * 2), ahi, blo + (uint32_t)((t & 1) * N * 8 + k * 2), bhi, idesc,
+                            (t > 0 || k > 0) ? 1u : 0u);
+              else
+              tc::umma_f16((uint32_t)((g % 2) * N), ab + (uint64_t)(arow * 8 + k * 2), bb + (uint64_t)((t & 1) * N * 8 + k * 2), idesc,
                            (t > 0 || k > 0) ? 1u : 0u);
+            }
             if (MODE & 16) tc::umma_commit(&bars[8 + (t & 7)]);                                           // per-tap b_empty commit
           }
         }
@@ -167,36 +188,40 @@ __global__ void __launch_bounds__(128, 1) k_commit(P p) {
   if (warp == 0) { tc::tc_fence_after(); tc::tmem_dealloc(0, 512); }
 }
 
-template <int N, int GROUPS, int KS, int NCOMMIT, int NWAIT, int MODE = 3>
+template <int N, int GROUPS, int KS, int NCOMMIT, int NWAIT, int MODE = 3, int DESC = 0>
 void run_commit(long long* d) {
-  auto k = k_commit<N, GROUPS, KS, NCOMMIT, NWAIT, MODE>;
+  auto k = k_commit<N, GROUPS, KS, NCOMMIT, NWAIT, MODE, DESC>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  P p; p.rounds = 64; p.out = d; p.scratch = nullptr; p.stop = nullptr;
+  P p; p.rounds = 64; p.out = d; p.scratch = nullptr; p.stop = nullptr; p.rounds_zero = 0;
   k<<<148, 128, 170 * 1024>>>(p);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); exit(1); }
   long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
   const int nmma = GROUPS * 9 * KS;
-  printf("N=%3d  bursts of %3d MMAs + %d commits + %d waits (wait=%d fence=%d tapwait=%d tapfence=%d tapcommit=%d): %7.0f cycles/burst = %6.1f cycles/MMA\n", N, nmma,
-         NCOMMIT, NWAIT, MODE & 1, (MODE >> 1) & 1, (MODE >> 2) & 1, (MODE >> 3) & 1, (MODE >> 4) & 1, (double)h[0], (double)h[0] / nmma);
+  printf("N=%3d  bursts of %3d MMAs + %d commits + %d waits (wait=%d fence=%d tapwait=%d tapfence=%d tapcommit=%d desc=%d): %7.0f cycles/burst = %6.1f cycles/MMA\n", N, nmma,
+         NCOMMIT, NWAIT, MODE & 1, (MODE >> 1) & 1, (MODE >> 2) & 1, (MODE >> 3) & 1, (MODE >> 4) & 1, DESC, (double)h[0], (double)h[0] / nmma);
 }
 
 template <int N, int GROUPS, int KS, int NOISE, int DATA = 0>
 void run(long long* d, float* scratch) {
   auto k = k_probe<N, GROUPS, KS, NOISE, DATA>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  P p; p.rounds = 20; p.out = d; p.scratch = scratch; p.stop = nullptr;
+  P p; p.rounds = 20; p.out = d; p.scratch = scratch; p.stop = nullptr; p.rounds_zero = 0;
   k<<<148, 288, 170 * 1024>>>(p);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); exit(1); }
   long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
   const int nmma = GROUPS * 9 * KS;
-  printf("N=%3d  %4d MMAs/burst  %s operands  noise=%2d (lds=%d tmem_ld=%d stg=%d mufu=%d): %7.1f cycles/MMA\n", N, nmma, DATA ? "random" : "zero  ", NOISE,
-         NOISE & 1, (NOISE >> 1) & 1, (NOISE >> 2) & 1, (NOISE >> 3) & 1, (double)h[0] / nmma);
+  printf("N=%3d  %4d MMAs/burst  %s operands  noise=%2d (lds=%d tmem_ld=%d stg=%d mufu=%d tmem_ld_on_accumulators=%d): %7.1f cycles/MMA\n", N, nmma, DATA ? "random" : "zero  ", NOISE,
+         NOISE & 1, (NOISE >> 1) & 1, (NOISE >> 2) & 1, (NOISE >> 3) & 1, (NOISE >> 4) & 1, (double)h[0] / nmma);
 }
 
 int main() {
   long long* d; cudaMalloc(&d, 16);
+  // descriptor arithmetic in the issue stream: hoistable (0), 64-bit adds per MMA from a per-burst base (1), 32-bit low-word adds (2)
+  { float* s0; cudaMalloc(&s0, (size_t)148 * 288 * 64 * 4); run<48, 8, 3, 2, 1>(d, s0); run<48, 8, 3, 18, 1>(d, s0); run<96, 8, 4, 2, 1>(d, s0); run<96, 8, 4, 18, 1>(d, s0); cudaFree(s0); }
+  run_commit<48, 2, 3, 1, 0, 0, 0>(d); run_commit<48, 2, 3, 1, 0, 0, 1>(d); run_commit<48, 2, 3, 1, 0, 0, 2>(d);
+  run_commit<96, 2, 4, 1, 0, 0, 0>(d); run_commit<96, 2, 4, 1, 0, 0, 1>(d); run_commit<96, 2, 4, 1, 0, 0, 2>(d);
   run_commit<48, 2, 3, 0, 0>(d); run_commit<48, 2, 3, 1, 0>(d); run_commit<48, 2, 3, 2, 0>(d); run_commit<48, 2, 3, 4, 0>(d); run_commit<48, 2, 3, 6, 0>(d);
   run_commit<48, 2, 3, 1, 1>(d); run_commit<48, 2, 3, 1, 2>(d); run_commit<48, 2, 3, 1, 4>(d); run_commit<48, 2, 3, 4, 4>(d);
   run_commit<48, 2, 3, 1, 1, 1>(d); run_commit<48, 2, 3, 1, 1, 2>(d); run_commit<48, 2, 3, 1, 1, 0>(d);
