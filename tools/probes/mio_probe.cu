@@ -19,7 +19,9 @@ __global__ void __launch_bounds__(288, 1) k_probe(P p) {
   __shared__ uint64_t bar;
   __shared__ uint32_t slot;
   __shared__ volatile int done;
+  __shared__ uint64_t never;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) tc::mbar_init(&never, 1);
   for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) {
     uint32_t h = (uint32_t)i * 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
     // DATA: pseudo-random f16 pairs in (-2, 2) (sign + exponent 0x3C/0x38.. + random mantissa); else zeros
@@ -92,6 +94,12 @@ __global__ void __launch_bounds__(288, 1) k_probe(P p) {
           const uint4 q = make_uint4(it, i, lane, warp);
           tc::st_global_v8(dst + ((it + i) & 7) * 8, q, q);
         }
+      }
+      if (NOISE & 32) {      // spin on a barrier that never completes, as the epilogue warps do while they wait for an accumulator
+        (void)tc::mbar_try_wait(&never, 0);
+      }
+      if (NOISE & 64) {      // the same with the non-suspending probe
+        (void)tc::mbar_test(&never, 0);
       }
       if (NOISE & 8) {
 #pragma unroll
@@ -212,13 +220,14 @@ void run(long long* d, float* scratch) {
   if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); exit(1); }
   long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
   const int nmma = GROUPS * 9 * KS;
-  printf("N=%3d  %4d MMAs/burst  %s operands  noise=%2d (lds=%d tmem_ld=%d stg=%d mufu=%d tmem_ld_on_accumulators=%d): %7.1f cycles/MMA\n", N, nmma, DATA ? "random" : "zero  ", NOISE,
-         NOISE & 1, (NOISE >> 1) & 1, (NOISE >> 2) & 1, (NOISE >> 3) & 1, (NOISE >> 4) & 1, (double)h[0] / nmma);
+  printf("N=%3d  %4d MMAs/burst  %s operands  noise=%2d (lds=%d tmem_ld=%d stg=%d mufu=%d tmem_ld_on_accumulators=%d spin_try_wait=%d spin_test_wait=%d): %7.1f cycles/MMA\n", N, nmma, DATA ? "random" : "zero  ", NOISE,
+         NOISE & 1, (NOISE >> 1) & 1, (NOISE >> 2) & 1, (NOISE >> 3) & 1, (NOISE >> 4) & 1, (NOISE >> 5) & 1, (NOISE >> 6) & 1, (double)h[0] / nmma);
 }
 
 int main() {
   long long* d; cudaMalloc(&d, 16);
   // descriptor arithmetic in the issue stream: hoistable (0), 64-bit adds per MMA from a per-burst base (1), 32-bit low-word adds (2)
+  { float* s0; cudaMalloc(&s0, (size_t)148 * 288 * 64 * 4); run<48, 8, 3, 32, 1>(d, s0); run<48, 8, 3, 64, 1>(d, s0); run<96, 8, 4, 32, 1>(d, s0); run<96, 8, 4, 64, 1>(d, s0); cudaFree(s0); }
   { float* s0; cudaMalloc(&s0, (size_t)148 * 288 * 64 * 4); run<48, 8, 3, 2, 1>(d, s0); run<48, 8, 3, 18, 1>(d, s0); run<96, 8, 4, 2, 1>(d, s0); run<96, 8, 4, 18, 1>(d, s0); cudaFree(s0); }
   run_commit<48, 2, 3, 1, 0, 0, 0>(d); run_commit<48, 2, 3, 1, 0, 0, 1>(d); run_commit<48, 2, 3, 1, 0, 0, 2>(d);
   run_commit<96, 2, 4, 1, 0, 0, 0>(d); run_commit<96, 2, 4, 1, 0, 0, 1>(d); run_commit<96, 2, 4, 1, 0, 0, 2>(d);
