@@ -96,3 +96,48 @@ def test_pure_host_entry_points_without_gpu():
         h = ctypes.c_void_p()
         rc = lib.xrd_create(0, ctypes.byref(cfg), ctypes.byref(h))
         assert rc != 0 and lib.xrd_last_error()          # loud failure, no fallback
+
+
+def test_checkpoints_load_through_the_reference_import_paths(tmp_path):
+    """Checkpoint ingest exactly as run.py does it (RUN:33-73): dict checkpoints read with torch.load(weights_only=False),
+    hyper-parameters riding along, classes imported under the REFERENCE's module paths (compat/ shims), attribute writes
+    after construction.  The checkpoints are written from the drop-in classes, whose keys and shapes equal the reference's
+    (the digest tests above)."""
+    import subprocess
+    import sys
+    torch.manual_seed(3)
+    unet = xrd_b200.UNetDiffusion()
+    naf = xrd_b200.EnhancedNAFNet()
+    hyb = xrd_b200.HybridDenoisingRouter({"width": 32}, {"noise_steps": 50})
+    torch.save({"model_state_dict": unet.state_dict(), "noise_steps": 50, "epoch": 1}, tmp_path / "ddimdiffusion.pth")
+    torch.save({"model_state_dict": naf.state_dict(), "best_psnr": 30.0}, tmp_path / "NafNet.pth")
+    torch.save({"model_state_dict": hyb.state_dict(), "nafnet_params": {"img_channel": 1, "width": 32, "middle_blk_num": 8,
+                "enc_blk_nums": [2, 2, 4, 6], "dec_blk_nums": [2, 2, 2, 2]},
+                "diffusion_params": {"in_channels": 1, "model_channels": 48, "channel_mult": (1, 2, 3, 4), "num_res_blocks": 2,
+                                     "attention_resolutions": (3,), "time_emb_dim": 192, "noise_steps": 50},
+                "best_psnr": 31.0, "best_ssim": 0.9}, tmp_path / "Latest_Hybrid_Denoiser.pth")
+    code = f'''
+import torch
+from DDIM.DDIMModel import UNetDiffusion, DiffusionDenoiser, device          # RUN:13
+from NafNet.NafnetModel import EnhancedNAFNet                                # RUN:14
+from hybrid.hybrid3diffusionspeed import HybridDenoisingRouter              # RUN:16
+d = r"{tmp_path}"
+m = UNetDiffusion(in_channels=1, model_channels=48, channel_mult=(1, 2, 3, 4), num_res_blocks=2, attention_resolutions=(3,),
+                  dropout=0.0, time_emb_dim=192).to(device)
+ck = torch.load(d + "/ddimdiffusion.pth", map_location=device, weights_only=False)
+m.load_state_dict(ck["model_state_dict"]); m.eval()
+w = DiffusionDenoiser(m, noise_steps=ck.get("noise_steps", 50))
+ck = torch.load(d + "/NafNet.pth", map_location=device, weights_only=False)
+n = EnhancedNAFNet(img_channel=1, width=32, middle_blk_num=8, enc_blk_nums=[2, 2, 4, 6], dec_blk_nums=[2, 2, 2, 2]).to(device)
+n.load_state_dict(ck["model_state_dict"]); n.eval()
+ck = torch.load(d + "/Latest_Hybrid_Denoiser.pth", map_location=device, weights_only=False)
+h = HybridDenoisingRouter(nafnet_params=ck["nafnet_params"], diffusion_params=ck["diffusion_params"], inference_diffusion_steps=7).to(device)
+h.load_state_dict(ck["model_state_dict"]); h.eval()
+h.inference_diffusion_steps = 8; h.training_diffusion_steps = 8
+assert w.noise_steps == 50 and h.diffusion_wrapper.noise_steps == 50 and len(h.state_dict()) == 912
+print("loaded", len(m.state_dict()), len(n.state_dict()), len(h.state_dict()))
+'''
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "compat"), ROOT, os.environ.get("PYTHONPATH", "")]))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "loaded" in r.stdout
