@@ -50,6 +50,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     common = flags + ["-Xcompiler", "-fPIC,-fvisibility=hidden", "-I", os.path.join(_ROOT, "include"), "-I", CSRC]
     if verbose:
         common += ["-Xptxas", "-v"]
+    if os.environ.get("XRD_TRACE"):          # in-kernel clock64 traces and experiment switches of conv3 / conv3r (tools/c3_trace.py, c3r_dbg.py)
+        common += ["-DXRD_TRACE"]
     procs = []
     objs = []
     for src in _sources():

@@ -55,7 +55,15 @@ constexpr int kC3ThreadsGN = 448;  // + warps 10..13: GroupNorm + SiLU applied i
 constexpr int kC3Pitch = 136;   // smem pixels per halo row: 130 used (128 + one halo column each side); 136*128 B keeps rows 1024-aligned
 constexpr int kC3Box = 130;
 
+// clock64 trace of block 0 and the bottleneck-experiment switches (XRD_C3_DBG): compiled in only with -DXRD_TRACE -- their
+// predicated stores and tests sit in the MMA issue stream, where every instruction is tensor-pipe idle time (measured: 4-7 %)
+#ifdef XRD_TRACE
+#define XRD_KDBG(m) (p.dbg & (m))
 #define C3PROF(tile, slot) do { if (p.prof && blockIdx.x == 0 && (tile) < 64) p.prof[(tile) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define XRD_KDBG(m) 0
+#define C3PROF(tile, slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -206,7 +214,7 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         if (lane == 0) C3PROF(ai, 0);
         uint32_t leader;
         if (tc::elect_one(leader)) {
-          if ((p.dbg & 4) && ai >= 2) {
+          if (XRD_KDBG(4) && ai >= 2) {
             tc::mbar_arrive(&a_full[st]);
           } else {
             tc::mbar_expect_tx(&a_full[st], (uint32_t)(TH + 2) * kC3Box * 128u);
@@ -272,7 +280,7 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           const uint64_t adesc0 = tc::umma_desc_sw128(tc::smem_u32(sA + (size_t)st * A_BYTES));
           const uint64_t bdesc0 = tc::umma_desc_sw128(sB_addr + (uint32_t)(c * 9) * B_BYTES);
           const uint32_t nf = c ? 1u : 0u;
-          if (!(p.dbg & 2)) {
+          if (!XRD_KDBG(2)) {
             switch (ks) {
               case 4: c3_issue_chunk<COUT, TH, 4, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, wprobed, p.nb, c * 9, p.nres, acc0, idesc, nf); break;
               case 3: c3_issue_chunk<COUT, TH, 3, WRES>(adesc0, bdesc0, sB_addr, b_full, b_empty, wslot, wphase, wprobed, p.nb, c * 9, p.nres, acc0, idesc, nf); break;
@@ -441,7 +449,7 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           for (int cb = 0; cb < NBLK; ++cb) {
             uint32_t v[48];
             uint4 pk_even;
-            if (!(p.dbg & 8)) {
+            if (!XRD_KDBG(8)) {
               tmem_ld16_nowait(tacc + (uint32_t)(cb * 48), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
               tmem_ld16_nowait(tacc + (uint32_t)(cb * 48 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
               tmem_ld16_nowait(tacc + (uint32_t)(cb * 48 + 32), *reinterpret_cast<uint32_t(*)[16]>(&v[32]));
@@ -453,7 +461,7 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
 #pragma unroll
               for (int j = 0; j < 6; ++j) rnext[j] = __ldg(reinterpret_cast<const uint4*>(nsrc) + j);
             }
-            if (!(p.dbg & 8)) tmem_wait_ld();
+            if (!XRD_KDBG(8)) tmem_wait_ld();
 #pragma unroll
             for (int h8 = 0; h8 < 6; ++h8) {
               const int co = cb * 48 + h8 * 8;
@@ -481,7 +489,7 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
               pk.x = tc::pack2<T>(r8[0], r8[1]); pk.y = tc::pack2<T>(r8[2], r8[3]);
               pk.z = tc::pack2<T>(r8[4], r8[5]); pk.w = tc::pack2<T>(r8[6], r8[7]);
               // two 16-byte halves -> one 32-byte store of a whole sector
-              if (h8 & 1) { if (row_ok && !(p.dbg & 1)) tc::st_global_v8(yp + opix * COUT + co - 8, pk_even, pk); } else pk_even = pk;
+              if (h8 & 1) { if (row_ok && !XRD_KDBG(1)) tc::st_global_v8(yp + opix * COUT + co - 8, pk_even, pk); } else pk_even = pk;
             }
             if (has_next) {
 #pragma unroll

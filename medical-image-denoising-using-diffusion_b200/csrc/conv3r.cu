@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 #include <stdlib.h>
 
@@ -35,7 +36,15 @@ struct Conv3RP {
   long long* prof;          // optional clock64 trace of block 0: [64][8]
 };
 
+// clock64 trace of block 0: compiled in only with -DXRD_TRACE (the predicated stores and clock reads sit in the MMA issue stream,
+// where every instruction is tensor-pipe idle time)
+#ifdef XRD_TRACE
+#define XRD_KDBG(m) (p.dbg & (m))          // bottleneck-experiment switches (XRD_C3_DBG / XRD_C3R_DBG), trace builds only
 #define RPROF(idx, slot_) do { if (p.prof && blockIdx.x == 0 && (idx) < 64) p.prof[(idx) * 8 + (slot_)] = clock64(); } while (0)
+#else
+#define XRD_KDBG(m) 0
+#define RPROF(idx, slot_) do { } while (0)
+#endif
 
 constexpr int kRThreads = 320, kRThreadsGN = 448;
 constexpr int kRSeg = 32;                    // output rows per work item
@@ -76,7 +85,7 @@ __device__ __forceinline__ void r3_issue_row(uint64_t a0, uint64_t a1, uint64_t 
   }
 }
 
-template <typename T, int COUT, int R, int NA, bool GN>
+template <typename T, int COUT, int KS, int R, int NA, bool GN>     // KS = input channels / 16: a template constant, no dispatch in the issue stream
 __global__ void __launch_bounds__(GN ? kRThreadsGN : kRThreads, 1)
 k_conv3r(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Conv3RP p) {
   constexpr uint32_t B_BYTES = COUT * 128;
@@ -139,7 +148,7 @@ k_conv3r(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         item(q, img, cb, r0, rows);
         for (int j = 0; j < rows + 2; ++j) {
           tc::mbar_wait(&r_empty[slot], phase ^ 1);
-          if ((p.dbg & 4) && phase) {
+          if (XRD_KDBG(4) && phase) {
             tc::mbar_arrive(&r_full[slot]);
           } else {
             tc::mbar_expect_tx(&r_full[slot], (uint32_t)kRBox * 128u);
@@ -157,7 +166,6 @@ k_conv3r(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     const uint32_t idesc = tc::umma_idesc(128, COUT, tc::umma_fmt<T>());
     const uint32_t sA_addr = tc::smem_u32(sA);
     const uint64_t bdesc0 = tc::umma_desc_sw128(tc::smem_u32(sB));
-    const int ks = p.cin >> 4;
     // Two output rows per iteration: the per-iteration skeleton (barrier waits, fences, commits: ~900 cycles measured) is not
     // hidden by the shallow MMA queue, so it is paid once per 54 MMAs instead of once per 27; the waits themselves run in
     // parallel on different lanes of the (converged) warp.
@@ -208,11 +216,9 @@ k_conv3r(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           const uint64_t d0 = tc::umma_desc_sw128(sA_addr + s0 * kRSlot), d1 = tc::umma_desc_sw128(sA_addr + s1 * kRSlot),
                          d2 = tc::umma_desc_sw128(sA_addr + s2 * kRSlot), d3 = tc::umma_desc_sw128(sA_addr + s3 * kRSlot);
           const uint32_t a0 = o % NA, a1 = (o + 1) % NA;
-          if (!(p.dbg & 2)) switch (ks) {
-            case 4: r3_issue_row<COUT, 4>(d0, d1, d2, bdesc0, a0 * COUT, idesc); if (nrow == 2) r3_issue_row<COUT, 4>(d1, d2, d3, bdesc0, a1 * COUT, idesc); break;
-            case 3: r3_issue_row<COUT, 3>(d0, d1, d2, bdesc0, a0 * COUT, idesc); if (nrow == 2) r3_issue_row<COUT, 3>(d1, d2, d3, bdesc0, a1 * COUT, idesc); break;
-            case 2: r3_issue_row<COUT, 2>(d0, d1, d2, bdesc0, a0 * COUT, idesc); if (nrow == 2) r3_issue_row<COUT, 2>(d1, d2, d3, bdesc0, a1 * COUT, idesc); break;
-            default: r3_issue_row<COUT, 1>(d0, d1, d2, bdesc0, a0 * COUT, idesc); if (nrow == 2) r3_issue_row<COUT, 1>(d1, d2, d3, bdesc0, a1 * COUT, idesc); break;
+          if (!XRD_KDBG(2)) {
+            r3_issue_row<COUT, KS>(d0, d1, d2, bdesc0, a0 * COUT, idesc);
+            if (nrow == 2) r3_issue_row<COUT, KS>(d1, d2, d3, bdesc0, a1 * COUT, idesc);
           }
           tc::umma_commit(&acc_full[a0]);
           if (nrow == 2) tc::umma_commit(&acc_full[a1]);
@@ -387,7 +393,7 @@ k_conv3r(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
             pk.x = tc::pack2<T>(r8[0], r8[1]); pk.y = tc::pack2<T>(r8[2], r8[3]);
             pk.z = tc::pack2<T>(r8[4], r8[5]); pk.w = tc::pack2<T>(r8[6], r8[7]);
             // two 16-byte halves -> one 32-byte store of a whole sector (partial-sector stores doubled the L2 write requests)
-            if (h8 & 1) { if (!(p.dbg & 1)) tc::st_global_v8(yp + pix * COUT + co - 8, pk_even, pk); } else pk_even = pk;
+            if (h8 & 1) { if (!XRD_KDBG(1)) tc::st_global_v8(yp + pix * COUT + co - 8, pk_even, pk); } else pk_even = pk;
           }
           if (has_next) {
 #pragma unroll
@@ -486,15 +492,21 @@ void conv3r(Ctx& c, const Tens& x, ConvW& w, const ConvEpi& e, Tens& y) {
     }
     XRD_LAUNCH(c, kern, grid, gn ? kRThreadsGN : kRThreads, smem, tmA, tmB, p);
   };
-  if (x.dt == DT_BF16) {
-    using T = __nv_bfloat16;
-    if (w.cout == 48) { if (gn) launch(k_conv3r<T, 48, 8, 8, true>); else launch(k_conv3r<T, 48, 8, 8, false>); }
-    else { if (gn) launch(k_conv3r<T, 96, 6, 4, true>); else launch(k_conv3r<T, 96, 6, 4, false>); }
-  } else {
-    using T = __half;
-    if (w.cout == 48) { if (gn) launch(k_conv3r<T, 48, 8, 8, true>); else launch(k_conv3r<T, 48, 8, 8, false>); }
-    else { if (gn) launch(k_conv3r<T, 96, 6, 4, true>); else launch(k_conv3r<T, 96, 6, 4, false>); }
-  }
+  auto pick = [&](auto tag, auto ks_tag) {
+    using T = decltype(tag);
+    constexpr int KS = decltype(ks_tag)::value;
+    if (w.cout == 48) { if (gn) launch(k_conv3r<T, 48, KS, 8, 8, true>); else launch(k_conv3r<T, 48, KS, 8, 8, false>); }
+    else { if (gn) launch(k_conv3r<T, 96, KS, 6, 4, true>); else launch(k_conv3r<T, 96, KS, 6, 4, false>); }
+  };
+  auto pick_ks = [&](auto tag) {
+    switch (x.c >> 4) {
+      case 4: pick(tag, std::integral_constant<int, 4>()); break;
+      case 3: pick(tag, std::integral_constant<int, 3>()); break;
+      case 2: pick(tag, std::integral_constant<int, 2>()); break;
+      default: pick(tag, std::integral_constant<int, 1>()); break;
+    }
+  };
+  if (x.dt == DT_BF16) pick_ks(__nv_bfloat16()); else pick_ks(__half());
   if (want_prof == 2) {
     XRD_CUDA(cudaStreamSynchronize(c.s));
     long long h[64 * 8];
