@@ -1,3 +1,5 @@
+# NOTE: the in-kernel clock64 traces and the XRD_C3_DBG / XRD_C3R_DBG experiment switches exist only in trace builds:
+#   XRD_TRACE=1 XRD_FORCE_BUILD=1 python -c "import __graft_entry__ as g; g.build()"
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,5 +1,8 @@
 """Bottleneck analysis of the persistent halo conv: per-tile clock64 traces of block 0 (stderr) plus timings
 under the XRD_C3_DBG experiment masks.   python tools/halo_prof.py [fp16|bf16]"""
+# NOTE: the in-kernel clock64 traces and the XRD_C3_DBG / XRD_C3R_DBG experiment switches exist only in trace builds:
+#   XRD_TRACE=1 XRD_FORCE_BUILD=1 python -c "import __graft_entry__ as g; g.build()"
+
 import os
 import sys
 
