@@ -33,7 +33,7 @@ def test_conv_tcgen05_f16_and_bf16():
 
 
 def test_conv_tcgen05_halo_persistent():
-    # the persistent halo-reusing 3x3 kernel (conv_halo.cu): same bound as the per-tap kernel
+    # the persistent halo-reusing 3x3 kernel (conv3.cu): same bound as the per-tap kernel
     for k, e in G.check_conv("fp16", 2, G.CONV_CASES_HALO).items():
         assert e < 6e-4, (k, e)
     for k, e in G.check_conv("bf16", 2, G.CONV_CASES_HALO).items():
