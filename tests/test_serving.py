@@ -86,3 +86,39 @@ def test_concurrent_single_image_requests_equal_direct_calls():
         assert sum(mb.batches) == 6 and len(mb.batches) < 6
     for i in range(6):
         assert (outs[i] - direct[i]).abs().max() < 5e-3      # identical up to the GroupNorm atomics' summation order
+
+
+@pytest.mark.gpu
+def test_three_models_from_three_threads_like_run_py():
+    """RUN:85-91: the sampler, NAFNet and the hybrid run concurrently from three OS threads on one GPU, each model object with
+    its own library handle (graph capture is thread-local, handles share nothing).  Results must equal the sequential calls."""
+    import gpu_checks as G
+    from oracle import xrd_oracle as O
+    hyb, _ = G._hybrid("fp16")
+    hyb.inference_diffusion_steps = 8
+    unet, _ = G.seeded_state_dict("unet")
+    unet = unet.to(G.DEV)
+    wrapper = xrd_b200.DiffusionDenoiser(unet, noise_steps=50)
+    naf, _ = G.seeded_state_dict("nafnet")
+    naf = naf.to(G.DEV)
+    _, noisy = O.synthetic_xray(1, 64, 64, seed=29)
+    x = noisy.to(G.DEV)
+    jobs = {"diffusion": lambda: wrapper.denoise(x, inference_steps=8), "nafnet": lambda: naf(x), "hybrid": lambda: hyb(x)}
+    seq = {k: f().clone() for k, f in jobs.items()}
+    for _ in range(3):                                   # first round captures the graphs concurrently, later rounds replay them
+        out, err = {}, {}
+
+        def work(k):
+            try:
+                out[k] = jobs[k]()
+                torch.cuda.synchronize()
+            except Exception as e:  # noqa: BLE001
+                err[k] = e
+        ts = [threading.Thread(target=work, args=(k,)) for k in jobs]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert not err, err
+        for k in jobs:
+            assert (out[k] - seq[k]).abs().max() < 5e-3, k
