@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define XRD_API_VERSION 1
+#define XRD_API_VERSION 2
 #define XRD_MAX_LEVELS 8
 
 typedef struct xrd_handle xrd_handle;
@@ -63,6 +63,7 @@ typedef enum xrd_mode {
  *                  dec_blk_nums)                                      HYB:173-174
  *   NoiseAnalyzer(in_c, out_c, base_c) / FusionModule(in_c,out_c,base_c)  HYB:471,538
  *   DiffusionDenoiser(model, noise_steps, beta_start, beta_end)       HYB:392
+ *   ExpertDenoiser(in_channels, base_channels)                        DirectUNet/DirectUNetModel.py:161
  * The *_prefix strings are prepended to the reference's state_dict keys
  * ("" for a standalone model, "diffusion_unet." etc. inside the hybrid). */
 typedef struct xrd_config {
@@ -95,6 +96,10 @@ typedef struct xrd_config {
   char naf_prefix[64];
   char router_prefix[64];
   char fusion_prefix[64];
+
+  /* ExpertDenoiser(in_channels=1, base_channels) (DirectUNet/DirectUNetModel.py:161; RUN:54) */
+  int32_t expert_base_c;
+  char expert_prefix[64];
 } xrd_config;
 
 /* Fill *cfg with the reference's default constructor arguments. */
@@ -125,7 +130,8 @@ int xrd_set_param(xrd_handle* h, const char* key, const void* data, const int64_
 #define XRD_PART_NAFNET 2
 #define XRD_PART_ROUTER 4
 #define XRD_PART_FUSION 8
-#define XRD_PART_ALL    15
+#define XRD_PART_ALL    15   /* the four parts of HybridDenoisingRouter */
+#define XRD_PART_EXPERT 16   /* ExpertDenoiser (the 4th /denoise output, RUN:52-57,127) */
 int xrd_finalize_weights(xrd_handle* h, int which);
 
 int xrd_set_mode(xrd_handle* h, int mode);
@@ -167,6 +173,21 @@ int xrd_fusion(xrd_handle* h, const float* naf, const float* diff, const float* 
  * naf_out / diff_out / mask_out are nullable (B,1,H,W) taps of the sanitised intermediates. */
 int xrd_hybrid(xrd_handle* h, const float* noisy, int inference_steps, float* out,
                float* naf_out, float* diff_out, float* mask_out, int B, int H, int W, void* stream);
+
+/* Replaces: ExpertDenoiser.forward(x) (DirectUNet/DirectUNetModel.py:232-255; called at RUN:127).  Eval-mode BatchNorm
+ * (running statistics: the state_dict keys *.running_mean / *.running_var) is folded into the bias-free convolution in front
+ * of it when the weights are finalised.  Output is the raw network output (NOT clamped; RUN:128 clamps). */
+int xrd_expert(xrd_handle* h, const float* inp, float* out, int B, int H, int W, void* stream);
+
+/* ---- range audit of the 16-bit activation storage (no reference counterpart) ----
+ * The default mode stores activations as f16 with saturating stores (|v| > 65504 is clipped, never inf).  With the audit
+ * enabled every 16-bit activation tensor the networks produce is scanned right after its producer (the sampler then runs
+ * eagerly, not as a graph): elements sitting at the saturation value, non-finite elements, the largest finite magnitude.
+ * A caller proves with it that a checkpoint's activations stay inside the f16 range -- or sees how often they do not and
+ * switches that model to XRD_MODE_BF16 / XRD_MODE_FP32_CHECK.  xrd_get_range_report synchronises the handle's stream. */
+int xrd_set_range_audit(xrd_handle* h, int enable);
+int xrd_get_range_report(xrd_handle* h, uint64_t* saturated, uint64_t* nonfinite, uint64_t* elements, float* absmax,
+                         uint32_t* tensors, int reset);
 
 /* ---- overlap tiling for images larger than the networks' native field (BASELINE.json configs[4]:
  * 1024x1024 through 512x512 tiles with halos).  The reference has no tiling; the caller these serve is

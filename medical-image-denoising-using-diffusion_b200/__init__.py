@@ -7,7 +7,7 @@ through the alias module ``xrd_b200`` at the repository root.
 """
 from ._lib import XrdError, LIB_PATH, load as load_library          # noqa: F401
 from .models import (                                                # noqa: F401
-    AttentionBlock, DiffusionDenoiser, EnhancedNAFNet, FusionModule, HybridDenoisingRouter,
+    AttentionBlock, DiffusionDenoiser, EnhancedNAFNet, ExpertDenoiser, FusionModule, HybridDenoisingRouter,
     LayerNorm, NAFBlock, NoiseAnalyzer, ResidualBlock, SimpleGate, SinusoidalPositionEmbeddings,
     UNetDiffusion, ddim_timestep_indices, native_kernel_launches,
 )
@@ -19,7 +19,7 @@ from .imageio import resize_bicubic_u8, preprocess_u8, postprocess_u8, resample_
 
 __all__ = [
     "XrdError", "LIB_PATH", "load_library", "build_library",
-    "UNetDiffusion", "DiffusionDenoiser", "EnhancedNAFNet", "NoiseAnalyzer", "FusionModule",
+    "UNetDiffusion", "DiffusionDenoiser", "EnhancedNAFNet", "ExpertDenoiser", "NoiseAnalyzer", "FusionModule",
     "HybridDenoisingRouter", "ddim_timestep_indices", "native_kernel_launches",
     "shard_bounds", "shard_batch", "gather_outputs", "run_sharded",
     "tile_plan", "extract_tiles", "blend_tiles", "denoise_tiled", "MicroBatcher",

@@ -16,6 +16,8 @@ LIB_PATH = os.path.join(_HERE, "libxrd.so")
 XRD_MAX_LEVELS = 8
 MODE_BF16, MODE_FP32_CHECK, MODE_FP16 = 0, 1, 2
 PART_UNET, PART_NAFNET, PART_ROUTER, PART_FUSION, PART_ALL = 1, 2, 4, 8, 15
+PART_EXPERT = 16
+API_VERSION = 2
 
 _I8 = C.c_int32 * XRD_MAX_LEVELS
 
@@ -48,6 +50,8 @@ class XrdConfig(C.Structure):
         ("naf_prefix", C.c_char * 64),
         ("router_prefix", C.c_char * 64),
         ("fusion_prefix", C.c_char * 64),
+        ("expert_base_c", C.c_int32),
+        ("expert_prefix", C.c_char * 64),
     ]
 
 
@@ -73,6 +77,10 @@ SYMBOLS = {
     "xrd_router": (C.c_int, [_P, _F, _F, C.c_int, C.c_int, C.c_int, _P]),
     "xrd_fusion": (C.c_int, [_P, _F, _F, _F, _F, C.c_int, C.c_int, C.c_int, _P]),
     "xrd_hybrid": (C.c_int, [_P, _F, C.c_int, _F, _F, _F, _F, C.c_int, C.c_int, C.c_int, _P]),
+    "xrd_expert": (C.c_int, [_P, _F, _F, C.c_int, C.c_int, C.c_int, _P]),
+    "xrd_set_range_audit": (C.c_int, [_P, C.c_int]),
+    "xrd_get_range_report": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_float),
+                                       C.POINTER(C.c_uint32), C.c_int]),
     "xrd_tiles_plan": (C.c_int, [C.c_int] * 4 + [C.POINTER(C.c_int)] * 4 + [C.c_int]),
     "xrd_tiles_extract": (C.c_int, [_F, _F] + [C.c_int] * 5 + [_P]),
     "xrd_tiles_blend": (C.c_int, [_F, _F] + [C.c_int] * 5 + [_P]),
@@ -89,6 +97,11 @@ SYMBOLS = {
 
 _lib = None
 _lock = threading.Lock()
+
+
+def loaded() -> bool:
+    """True once libxrd.so has been dlopen'ed by this process (never triggers the load)."""
+    return _lib is not None
 
 
 class XrdError(RuntimeError):
@@ -111,7 +124,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)           # AttributeError if the .so lacks a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if lib.xrd_api_version() != 1:
+        if lib.xrd_api_version() != API_VERSION:
             raise XrdError("libxrd.so API version mismatch; rebuild")
         _lib = lib
         return lib

@@ -18,6 +18,7 @@ void run_ddim_loop(Ctx& c, Handle& h, const float* noisy, float* xcur, const flo
 void run_nafnet(Ctx& c, Handle& h, const float* inp, float* out, int B, int H, int W, int sanitize);
 void run_router(Ctx& c, Handle& h, const float* x, float* mask, int B, int H, int W, int sanitize);
 void run_fusion(Ctx& c, Handle& h, const float* naf, const float* diff, const float* mask, float* out, int B, int H, int W);
+void run_expert(Ctx& c, Handle& h, const float* inp, float* out, int B, int H, int W);
 void prepack_tc(Handle& h, DType dt);
 void tiles_check(int B, int H, int W, int T, int halo);
 void tiles_extract(Ctx& c, const float* img, float* tiles, int B, int H, int W, int T, int halo);
@@ -71,6 +72,7 @@ static Ctx make_ctx(xrd_handle* H, cudaStream_t s, bool dry, Arena* a) {
   c.s = s; c.a = a; c.dry = dry;
   c.adt = mode_dtype(H->h.mode);
   c.tc = H->h.mode != XRD_MODE_FP32_CHECK;
+  c.audit = (H->h.audit && !dry) ? H->h.audit_dev : nullptr;
   return c;
 }
 
@@ -151,6 +153,7 @@ XRD_EXPORT void xrd_default_config(xrd_config* c) {
   for (int i = 0; i < 4; ++i) { c->naf_enc_blk_nums[i] = eb[i]; c->naf_dec_blk_nums[i] = db[i]; }
   c->router_base_c = 32; c->fusion_base_c = 48;
   c->noise_steps = 50; c->beta_start = 1e-4f; c->beta_end = 0.02f;
+  c->expert_base_c = 64;
 }
 
 XRD_EXPORT int xrd_api_version(void) { return XRD_API_VERSION; }
@@ -177,11 +180,12 @@ XRD_EXPORT int xrd_create(int device, const xrd_config* cfg, xrd_handle** out) {
     XRD_REQUIRE(cfg->unet_n_levels >= 1 && cfg->unet_n_levels <= XRD_MAX_LEVELS && cfg->naf_n_enc <= XRD_MAX_LEVELS &&
                     cfg->naf_n_dec <= XRD_MAX_LEVELS && cfg->noise_steps >= 1,
                 "invalid configuration");
-    XRD_CUDA(cudaSetDevice(device));
+    DeviceScope dscope(device);
     xrd_handle* H = new xrd_handle();
     H->h.device = device;
     H->h.cfg = *cfg;
     H->h.cfg.unet_prefix[63] = H->h.cfg.naf_prefix[63] = H->h.cfg.router_prefix[63] = H->h.cfg.fusion_prefix[63] = 0;
+    H->h.cfg.expert_prefix[63] = 0;
     XRD_CUDA(cudaStreamCreateWithFlags(&H->cap_stream, cudaStreamNonBlocking));
     *out = H;
   });
@@ -197,6 +201,8 @@ static void free_op_state(xrd_handle* H) {
 
 XRD_EXPORT void xrd_destroy(xrd_handle* H) {
   if (!H) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
   cudaSetDevice(H->h.device);
   cudaDeviceSynchronize();
   free_op_state(H);
@@ -204,7 +210,9 @@ XRD_EXPORT void xrd_destroy(xrd_handle* H) {
   for (auto& kv : H->h.params) cudaFree(kv.second.d);
   if (H->h.arena.base) cudaFree(H->h.arena.base);
   if (H->scratch) cudaFree(H->scratch);
+  if (H->h.audit_dev) cudaFree(H->h.audit_dev);
   if (H->cap_stream) cudaStreamDestroy(H->cap_stream);
+  if (prev >= 0) cudaSetDevice(prev);
   delete H;
 }
 
@@ -212,7 +220,13 @@ XRD_EXPORT int xrd_set_param(xrd_handle* H, const char* key, const void* data, c
   return guarded([&] {
     XRD_REQUIRE(H && key && data && ndim >= 0 && ndim <= 8, "bad argument");
     std::lock_guard<std::mutex> lk(H->h.mu);
-    XRD_CUDA(cudaSetDevice(H->h.device));
+    DeviceScope dscope(H->h.device);
+    // Kernels of this handle still in flight (on a non-blocking stream the blocking copy below does not wait for) may read the
+    // tensor being replaced; and every packed plan / captured graph derived from the old value is now stale: quiesce, then
+    // invalidate, so that a run without xrd_finalize_weights fails loudly instead of mixing new and old weights.
+    if (H->have_last_stream) XRD_CUDA(cudaStreamSynchronize(H->last_stream));
+    H->h.unet.ready = H->h.naf.ready = H->h.router.ready = H->h.fusion.ready = H->h.expert.ready = false;
+    H->h.drop_graphs();
     size_t n = 1;
     std::vector<int64_t> shp;
     for (int i = 0; i < ndim; ++i) { XRD_REQUIRE(shape[i] >= 0, "negative dimension"); n *= (size_t)shape[i]; shp.push_back(shape[i]); }
@@ -231,6 +245,7 @@ XRD_EXPORT int xrd_finalize_weights(xrd_handle* H, int which) {
   return guarded([&] {
     XRD_REQUIRE(H, "null handle");
     std::lock_guard<std::mutex> lk(H->h.mu);
+    DeviceScope dscope(H->h.device);
     finalize(H->h, which);
     H->packed_dt = DT_F32;
   });
@@ -260,6 +275,7 @@ XRD_EXPORT int xrd_unet_eps(xrd_handle* H, const float* x, const float* cond, co
     XRD_REQUIRE(H->h.unet.ready, "UNet weights are not finalised");
     check_unet_shape(H, Hh, W);
     cudaStream_t s = (cudaStream_t)stream;
+    DeviceScope dscope(H->h.device);
     bind_stream(H, s);
     const int mb = micro_batch(B, Hh, W);
     const size_t plane = (size_t)Hh * W;
@@ -306,7 +322,7 @@ static void ddim_chunk(xrd_handle* H, cudaStream_t s, const float* noisy, int in
   const bool traced = eps_trace || xin_trace || teacher_x;
   const std::string key = keyf("ddim", H, nb, Hh, W, inference_steps);
 
-  if (!h.use_graph || traced) {
+  if (!h.use_graph || traced || h.audit) {      // the audit kernels are not part of the captured graph
     with_arena(H, s, key + (traced ? "|eager-trace" : "|eager"), [&](Ctx& c) {
       float* xcur = c.allocf(plane);
       float* temb = c.allocf(ts.size() * (size_t)h.unet.te.total);
@@ -386,6 +402,7 @@ XRD_EXPORT int xrd_ddim_denoise(xrd_handle* H, const float* noisy, int inference
     XRD_REQUIRE(H->h.unet.ready, "UNet weights are not finalised");
     check_unet_shape(H, Hh, W);
     cudaStream_t s = (cudaStream_t)stream;
+    DeviceScope dscope(H->h.device);
     bind_stream(H, s);
     const int mb = micro_batch(B, Hh, W);
     const size_t img = (size_t)Hh * W;
@@ -405,6 +422,7 @@ XRD_EXPORT int xrd_nafnet(xrd_handle* H, const float* inp, float* out, int B, in
     std::lock_guard<std::mutex> lk(H->h.mu);
     XRD_REQUIRE(H->h.naf.ready, "NAFNet weights are not finalised");
     cudaStream_t s = (cudaStream_t)stream;
+    DeviceScope dscope(H->h.device);
     bind_stream(H, s);
     const int mb = micro_batch(B, Hh, W);
     const size_t img = (size_t)Hh * W;
@@ -422,6 +440,7 @@ XRD_EXPORT int xrd_router(xrd_handle* H, const float* x, float* mask, int B, int
     std::lock_guard<std::mutex> lk(H->h.mu);
     XRD_REQUIRE(H->h.router.ready, "router weights are not finalised");
     cudaStream_t s = (cudaStream_t)stream;
+    DeviceScope dscope(H->h.device);
     bind_stream(H, s);
     const int mb = micro_batch(B, Hh, W);
     const size_t img = (size_t)Hh * W;
@@ -440,6 +459,7 @@ XRD_EXPORT int xrd_fusion(xrd_handle* H, const float* naf, const float* diff, co
     std::lock_guard<std::mutex> lk(H->h.mu);
     XRD_REQUIRE(H->h.fusion.ready, "fusion weights are not finalised");
     cudaStream_t s = (cudaStream_t)stream;
+    DeviceScope dscope(H->h.device);
     bind_stream(H, s);
     const int mb = micro_batch(B, Hh, W);
     const size_t img = (size_t)Hh * W;
@@ -448,6 +468,59 @@ XRD_EXPORT int xrd_fusion(xrd_handle* H, const float* naf, const float* diff, co
       with_arena(H, s, keyf("fusion", H, nb, Hh, W),
                  [&](Ctx& c) { run_fusion(c, H->h, naf + b0 * img, diff + b0 * img, mask + b0 * img, out + b0 * img, nb, Hh, W); });
     }
+  });
+}
+
+XRD_EXPORT int xrd_expert(xrd_handle* H, const float* inp, float* out, int B, int Hh, int W, void* stream) {
+  return guarded([&] {
+    XRD_REQUIRE(H && inp && out, "null argument");
+    check_img(B, Hh, W);
+    std::lock_guard<std::mutex> lk(H->h.mu);
+    XRD_REQUIRE(H->h.expert.ready, "ExpertDenoiser weights are not finalised");
+    cudaStream_t s = (cudaStream_t)stream;
+    DeviceScope dscope(H->h.device);
+    bind_stream(H, s);
+    // 128 + 128 channels live at full resolution: a quarter of the sampler's micro-batch bounds the workspace
+    const int mb = std::max(1, micro_batch(B, Hh, W) / 4);
+    const size_t img = (size_t)Hh * W;
+    for (int b0 = 0; b0 < B; b0 += mb) {
+      const int nb = std::min(mb, B - b0);
+      with_arena(H, s, keyf("expert", H, nb, Hh, W), [&](Ctx& c) { run_expert(c, H->h, inp + b0 * img, out + b0 * img, nb, Hh, W); });
+    }
+  });
+}
+
+XRD_EXPORT int xrd_set_range_audit(xrd_handle* H, int enable) {
+  return guarded([&] {
+    XRD_REQUIRE(H, "null handle");
+    std::lock_guard<std::mutex> lk(H->h.mu);
+    DeviceScope dscope(H->h.device);
+    if (enable && !H->h.audit_dev) {
+      XRD_CUDA(cudaMalloc((void**)&H->h.audit_dev, sizeof(RangeAudit)));
+      XRD_CUDA(cudaMemset(H->h.audit_dev, 0, sizeof(RangeAudit)));
+    }
+    H->h.audit = enable != 0;
+  });
+}
+
+XRD_EXPORT int xrd_get_range_report(xrd_handle* H, uint64_t* saturated, uint64_t* nonfinite, uint64_t* elements, float* absmax,
+                                    uint32_t* tensors, int reset) {
+  return guarded([&] {
+    XRD_REQUIRE(H, "null handle");
+    std::lock_guard<std::mutex> lk(H->h.mu);
+    DeviceScope dscope(H->h.device);
+    RangeAudit r;
+    memset(&r, 0, sizeof(r));
+    if (H->h.audit_dev) {
+      if (H->have_last_stream) XRD_CUDA(cudaStreamSynchronize(H->last_stream));
+      XRD_CUDA(cudaMemcpy(&r, H->h.audit_dev, sizeof(r), cudaMemcpyDeviceToHost));
+      if (reset) XRD_CUDA(cudaMemset(H->h.audit_dev, 0, sizeof(RangeAudit)));
+    }
+    if (saturated) *saturated = r.saturated;
+    if (nonfinite) *nonfinite = r.nonfinite;
+    if (elements) *elements = r.elements;
+    if (tensors) *tensors = r.tensors;
+    if (absmax) { float f; memcpy(&f, &r.absmax_bits, 4); *absmax = f; }
   });
 }
 
@@ -462,6 +535,7 @@ XRD_EXPORT int xrd_hybrid(xrd_handle* H, const float* noisy, int inference_steps
     XRD_REQUIRE(h.unet.ready && h.naf.ready && h.router.ready && h.fusion.ready, "hybrid weights are not finalised");
     check_unet_shape(H, Hh, W);
     cudaStream_t s = (cudaStream_t)stream;
+    DeviceScope dscope(H->h.device);
     bind_stream(H, s);
     const int mb = micro_batch(B, Hh, W);
     const size_t img = (size_t)Hh * W;
@@ -510,6 +584,7 @@ XRD_EXPORT int xrd_op_conv2d_stats(xrd_handle* H, int impl, const float* x, cons
     XRD_REQUIRE(H && x && weight && y, "null argument");
     std::lock_guard<std::mutex> lk(H->h.mu);
     cudaStream_t s = (cudaStream_t)stream;
+    DeviceScope dscope(H->h.device);
     bind_stream(H, s);
     XRD_CUDA(cudaStreamSynchronize(s));
     free_op_state(H);
@@ -614,6 +689,7 @@ XRD_EXPORT int xrd_op_groupnorm_act(xrd_handle* H, const float* x, const float* 
     XRD_REQUIRE(H && x && gamma && beta && y, "null argument");
     std::lock_guard<std::mutex> lk(H->h.mu);
     cudaStream_t s = (cudaStream_t)stream;
+    DeviceScope dscope(H->h.device);
     bind_stream(H, s);
     H->h.last_op = nullptr;
     with_arena(H, s, keyf("opgn", H, B, Hh, W, C, groups), [&](Ctx& c) {
@@ -640,6 +716,7 @@ XRD_EXPORT int xrd_op_attention(xrd_handle* H, int impl, const float* qkv, float
     XRD_REQUIRE(H && qkv && out, "null argument");
     std::lock_guard<std::mutex> lk(H->h.mu);
     cudaStream_t s = (cudaStream_t)stream;
+    DeviceScope dscope(H->h.device);
     bind_stream(H, s);
     H->h.last_op = nullptr;
     with_arena(H, s, keyf("opattn", H, B, Hh, W, heads, d, impl), [&](Ctx& c) {
@@ -664,6 +741,7 @@ XRD_EXPORT int xrd_op_time_last(xrd_handle* H, int iters, float* ms_per_launch, 
     std::lock_guard<std::mutex> lk(H->h.mu);
     XRD_REQUIRE((bool)H->h.last_op, "no op to time: call an xrd_op_* function first");
     cudaStream_t s = (cudaStream_t)stream;
+    DeviceScope dscope(H->h.device);
     bind_stream(H, s);
     Arena none;
     Ctx c = make_ctx(H, s, false, &none);
@@ -711,6 +789,7 @@ XRD_EXPORT int xrd_tiles_extract(const float* img, float* tiles, int B, int H, i
     XRD_REQUIRE(img && tiles, "null argument");
     Ctx c;
     c.s = (cudaStream_t)stream;
+    DeviceScope dscope(device_of(img));
     tiles_extract(c, img, tiles, B, H, W, tile, halo);
   });
 }
@@ -720,6 +799,7 @@ XRD_EXPORT int xrd_tiles_blend(const float* tiles, float* img, int B, int H, int
     XRD_REQUIRE(img && tiles, "null argument");
     Ctx c;
     c.s = (cudaStream_t)stream;
+    DeviceScope dscope(device_of(tiles));
     tiles_blend(c, tiles, img, B, H, W, tile, halo);
   });
 }
@@ -731,6 +811,7 @@ XRD_EXPORT int xrd_resize_bicubic_u8(const uint8_t* src, uint8_t* dst, uint8_t* 
     XRD_REQUIRE(src && dst, "null argument");
     Ctx c;
     c.s = (cudaStream_t)stream;
+    DeviceScope dscope(device_of(src));
     resize_bicubic_u8(c, src, dst, tmp, N, Hin, Win, Hout, Wout);
   });
 }
@@ -747,6 +828,7 @@ XRD_EXPORT int xrd_u8_to_unit(const uint8_t* src, float* dst, int64_t n, void* s
     XRD_REQUIRE(src && dst && n >= 0, "bad argument");
     Ctx c;
     c.s = (cudaStream_t)stream;
+    DeviceScope dscope(device_of(src));
     if (n) u8_to_unit(c, src, dst, n);
   });
 }
@@ -756,6 +838,7 @@ XRD_EXPORT int xrd_unit_to_u8(const float* src, uint8_t* dst, int64_t n, void* s
     XRD_REQUIRE(src && dst && n >= 0, "bad argument");
     Ctx c;
     c.s = (cudaStream_t)stream;
+    DeviceScope dscope(device_of(src));
     if (n) unit_to_u8(c, src, dst, n);
   });
 }

@@ -44,6 +44,28 @@ struct Error : public std::runtime_error {
 
 extern std::atomic<uint64_t> g_launches;
 
+// Makes `dev` the calling thread's current device for the lifetime of the object and restores the previous one afterwards
+// (the C entry points must not leave the caller's thread on another device).
+struct DeviceScope {
+  int prev = -1;
+  explicit DeviceScope(int dev) {
+    int cur = -1;
+    XRD_CUDA(cudaGetDevice(&cur));
+    if (cur != dev) { XRD_CUDA(cudaSetDevice(dev)); prev = cur; }
+  }
+  ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
+};
+// device that owns a device pointer (handle-less entry points take the device from their buffers, not from the thread state)
+inline int device_of(const void* p) {
+  cudaPointerAttributes a;
+  XRD_CUDA(cudaPointerGetAttributes(&a, p));
+  if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged)
+    fail(XRD_ERR_INVALID, "pointer %p is not device memory (this library has no CPU path)", p);
+  return a.device;
+}
+
 // ---------------------------------------------------------------- dtypes / tensors
 enum DType : int { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
 inline size_t dsize(DType d) { return d == DT_F32 ? 4 : 2; }
@@ -77,7 +99,17 @@ struct Arena {
   void release(size_t m) { off = m; }
 };
 
+// Range audit of the 16-bit activation tensors (xrd_set_range_audit): device-side counters, one block per handle.
+struct RangeAudit {
+  unsigned long long saturated;   // f16 elements stored at +-65504 (the saturating stores clipped them)
+  unsigned long long nonfinite;   // NaN / inf elements
+  unsigned long long elements;    // elements audited
+  unsigned int absmax_bits;       // max |v| over finite elements (float bits; non-negative floats order like unsigned ints)
+  unsigned int tensors;           // tensors audited
+};
+
 struct Ctx {
+  RangeAudit* audit = nullptr;   // non-null: every 16-bit activation tensor the networks produce is scanned after its producer
   cudaStream_t s = nullptr;
   Arena* a = nullptr;
   bool dry = false;     // planning pass: no launches
@@ -126,7 +158,15 @@ template <typename T> __device__ __forceinline__ void stf(T* p, float v);
 template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 // f16 stores saturate (finite overflow -> +-65504) so that one large activation cannot turn into inf/NaN downstream
-__device__ __forceinline__ float sat_h(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+// torch.clamp semantics: NaN stays NaN (fminf/fmaxf would drop it).  max.NaN / min.NaN are single FMNMX.NAN instructions.
+__device__ __forceinline__ float clamp_nan(float v, float lo, float hi) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "f"(lo));
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(r), "f"(hi));
+  return r;
+}
+// A NaN is preserved (as the reference propagates it to the final nan_to_num, HYB:615-620); +-inf saturates like any overflow.
+__device__ __forceinline__ float sat_h(float v) { return clamp_nan(v, -65504.f, 65504.f); }
 template <> __device__ __forceinline__ void stf<__half>(__half* p, float v) { *p = __float2half_rn(sat_h(v)); }
 
 // 4 consecutive elements (pointer must be aligned to 4 elements)
@@ -176,13 +216,14 @@ template <> __device__ __forceinline__ void st4<__half>(__half* p, const float (
     }                                                              \
   } while (0)
 
-enum Act : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_SIGMOID = 3 };
+enum Act : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_SIGMOID = 3, ACT_RELU = 4 };
 
 __device__ __forceinline__ float act_apply(float v, int act) {
   switch (act) {
     case ACT_SILU: return v / (1.0f + expf(-v));
     case ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
     case ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+    case ACT_RELU: return v < 0.0f ? 0.0f : v;          // NaN stays NaN, like torch.relu
     default: return v;
   }
 }

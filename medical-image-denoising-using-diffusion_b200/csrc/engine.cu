@@ -48,6 +48,9 @@ void Handle::free_owned() {
   for (auto& s : naf.enc) for (auto& b : s) fb(b);
   for (auto& s : naf.dec) for (auto& b : s) fb(b);
   for (auto& b : naf.mid) fb(b);
+  for (ConvW* w : {&expert.inc[0], &expert.inc[1], &expert.down1[0], &expert.down1[1], &expert.down2[0], &expert.down2[1], &expert.bott[0],
+                   &expert.bott[1], &expert.upc2[0], &expert.upc2[1], &expert.upc1[0], &expert.upc1[1], &expert.fin, &expert.up2, &expert.up1})
+    free_convw_tc(*w);
   for (auto& w : naf.downs) free_convw_tc(w);
   for (auto& w : naf.ups) free_convw_tc(w);
   for (auto& w : naf.skips) free_convw_tc(w);
@@ -344,14 +347,60 @@ static void finalize_fusion(Handle& h) {
   f.ready = true;
 }
 
+// Conv2d(cin, cout, 3, padding=1, bias=False) + BatchNorm2d(cout) in eval mode -> one conv with bias (keys q+"N", q+"N+1")
+static ConvW make_conv_bn(Handle& h, const std::string& q, int i, int cout, int cin) {
+  const std::string ck = q + std::to_string(i), bk = q + std::to_string(i + 1);
+  const Param& w = h.P(ck + ".weight");
+  expect_shape(w, ck + ".weight", {cout, cin, 3, 3});
+  for (const char* sfx : {".weight", ".bias", ".running_mean", ".running_var"}) expect_shape(h.P(bk + sfx), bk + sfx, {cout});
+  float* wf = h.dalloc_f((size_t)cout * cin * 9);
+  float* bf = h.dalloc_f(cout);
+  fold_bn_weight(nullptr, w.d, h.PD(bk + ".weight"), h.PD(bk + ".bias"), h.PD(bk + ".running_mean"), h.PD(bk + ".running_var"), 1e-5f, wf, bf,
+                 cout, cin * 9);
+  ConvW c;
+  c.kh = c.kw = 3; c.stride = 1; c.pad = 1; c.cin = cin; c.cout = cout;
+  c.w = h.dalloc_f((size_t)cout * cin * 9);
+  pack_conv_weight(nullptr, wf, c.w, cout, cin, 3, 3);
+  c.bias = bf;
+  return c;
+}
+
+static void finalize_expert(Handle& h) {
+  const std::string p = h.cfg.expert_prefix;
+  const int b = h.cfg.expert_base_c;
+  XRD_REQUIRE(b >= 16 && b % 16 == 0, "ExpertDenoiser: base_channels must be a multiple of 16 (got %d)", b);
+  ExpertW& e = h.expert;
+  e = ExpertW();
+  e.base = b;
+  auto pair = [&](ConvW (&dst)[2], const std::string& q, int cin, int cout) {
+    dst[0] = make_conv_bn(h, q, 0, cout, cin);
+    dst[1] = make_conv_bn(h, q, 3, cout, cout);
+  };
+  pair(e.inc, p + "inc.", 1, b);
+  pair(e.down1, p + "down1.", b, 2 * b);
+  pair(e.down2, p + "down2.", 2 * b, 4 * b);
+  pair(e.bott, p + "bottleneck.", 4 * b, 8 * b);
+  e.up2 = make_convT2(h, p + "up2", 8 * b, 4 * b);
+  pair(e.upc2, p + "upconv2.", 8 * b, 4 * b);
+  e.up1 = make_convT2(h, p + "up1", 4 * b, 2 * b);
+  pair(e.upc1, p + "upconv1.", 4 * b, 2 * b);
+  e.fin = make_conv_bn(h, p + "final.", 0, b, 2 * b);
+  expect_shape(h.P(p + "outc.weight"), p + "outc.weight", {1, b, 1, 1});
+  e.out_w = h.PD(p + "outc.weight");
+  e.out_b = h.PD(p + "outc.bias");
+  e.ready = true;
+}
+
 void finalize(Handle& h, int which) {
   XRD_CUDA(cudaSetDevice(h.device));
   XRD_CUDA(cudaDeviceSynchronize());
   h.free_owned();
+  h.unet.ready = h.naf.ready = h.router.ready = h.fusion.ready = h.expert.ready = false;   // free_owned() released every packed plan
   if (which & XRD_PART_UNET) finalize_unet(h);
   if (which & XRD_PART_NAFNET) finalize_nafnet(h);
   if (which & XRD_PART_ROUTER) finalize_router(h);
   if (which & XRD_PART_FUSION) finalize_fusion(h);
+  if (which & XRD_PART_EXPERT) finalize_expert(h);
   // sampler coefficient tables (float32 like HYB:396-398)
   const int T = h.cfg.noise_steps;
   h.coef1.assign(T, 0.f); h.coef2.assign(T, 0.f);
@@ -376,7 +425,12 @@ static const bool g_fuse_gn_conv3 = getenv("XRD_FUSE_GN_CONV3") && atoi(getenv("
 
 // A contraction.  e.stats_out (optional, [N][8][2], zeroed here) receives the GroupNorm sums of the output: from the
 // kernel's own epilogue where it has one, else from a statistics pass over the stored tensor.
+static void conv_impl(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y);
 static void conv(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y) {
+  conv_impl(c, x1, x2, w, e, y);
+  range_audit(c, y);
+}
+static void conv_impl(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y) {
   // e.stats_out comes from stats16(): already zero
   // row-ring kernel: measured faster than the halo kernel from 256 columns up (1.06x activation fetch instead of 2x), slower
   // at 128 (too few 32-row work items per SM)
@@ -473,12 +527,14 @@ static void resblock(Ctx& c, UNetW& u, ResW& r, const TS& x1, const TS* x2, cons
     gn_coef(c, sums, g, bt, 1e-5f, B, ct, u.groups, H * W, cf);
     pe.in_coef = cf;
     if (ring) conv3r(c, a, w, pe, y); else conv3(c, a, b, w, pe, y);
+    range_audit(c, y);
     return true;
   };
   ConvW& w1 = x2 ? r.c1s : r.c1;
   if (!fused_in(x1.t, x2t, w1, e1, s1, r.g1, r.b1, hm)) {
     Tens a1 = c.alloc(B, H, W, r.cin);
     gn_act(c, x1.t, x2t, u.groups, s1, r.g1, r.b1, 1e-5f, ACT_SILU, a1);
+    range_audit(c, a1);
     conv(c, a1, nullptr, r.c1, e1, hm);
   }
   ConvEpi e2;
@@ -494,6 +550,7 @@ static void resblock(Ctx& c, UNetW& u, ResW& r, const TS& x1, const TS* x2, cons
   if (!fused_in(hm, nullptr, r.c2, e2, s2, r.g2, r.b2, out.t)) {
     Tens a2 = c.alloc(B, H, W, r.cout);
     gn_act(c, hm, nullptr, u.groups, s2, r.g2, r.b2, 1e-5f, ACT_SILU, a2);
+    range_audit(c, a2);
     conv(c, a2, nullptr, r.c2, e2, out.t);
   }
   c.a->release(mk);
@@ -511,10 +568,12 @@ static void attnblock(Ctx& c, UNetW& u, AttnW& a, const TS& x, TS& out) {
   double* s = concat_stats(c, x, nullptr, u.groups);
   Tens xn = c.alloc(B, H, W, a.c);
   gn_act(c, x.t, nullptr, u.groups, s, a.g, a.b, 1e-5f, ACT_NONE, xn);
+  range_audit(c, xn);
   Tens qkv = c.alloc(B, H, W, 3 * a.c);
   conv(c, xn, nullptr, a.qkv, ConvEpi(), qkv);
   Tens o = c.alloc(B, H, W, a.c);
   attention(c, qkv, u.heads, o);
+  range_audit(c, o);
   ConvEpi e;
   e.resid = x.t;
   e.stats_out = out.st;
@@ -557,8 +616,10 @@ static void unet_eval(Ctx& c, UNetW& u, const float* x, const float* cond, const
       im2col_3x3_2ch(c, x, cond, col);
       conv1(c, col, nullptr, u.in_conv_g, e0, h.t);
       h.st = st;
-    } else if (conv_first(c, xin, &cin, u.in_conv, h.t, st)) {
-      h.st = st;                                         // cat([x, condition]) never materialised
+      range_audit(c, h.t);
+    } else {
+      if (conv_first(c, xin, &cin, u.in_conv, h.t, st)) h.st = st;      // cat([x, condition]) never materialised
+      range_audit(c, h.t);
     }
   }
   std::vector<TS> skips;
@@ -608,6 +669,7 @@ static void unet_eval(Ctx& c, UNetW& u, const float* x, const float* cond, const
         xs.t = c.alloc(B, skip.t.h, skip.t.w, h.t.c);
         xs.st = new_sums(c, B, 8);                        // sums of the resized tensor are not those of its source
         upsample2x_stats(c, h.t, xs.t, xs.st);            // F.interpolate(bilinear) 2x (HYB:381-382)
+        range_audit(c, xs.t);
       }
       TS out;
       out.t = c.alloc(B, skip.t.h, skip.t.w, r.cout);
@@ -649,12 +711,14 @@ static void nafblock(Ctx& c, NafBlockW& b, const Tens& x, Tens& out) {
   const int B = x.n, H = x.h, W = x.w, C = b.c;
   Tens t = c.alloc(B, H, W, C);
   layernorm(c, x, b.n1w, b.n1b, 1e-6f, t);
+  range_audit(c, t);
   Tens u = c.alloc(B, H, W, 2 * C);
   conv(c, t, nullptr, b.c1, ConvEpi(), u);
   Tens g = c.alloc(B, H, W, C);
   float* pool = c.allocf((size_t)B * C);
   zero_async(c, pool, (size_t)B * C * 4);
   dwconv_gate_pool(c, u, b.dw, b.dwb, g, pool);
+  range_audit(c, g);
   float* scale = c.allocf((size_t)B * C);
   sca_scale(c, pool, B, C, H * W, b.scaw, b.scab, scale);
   Tens y = c.alloc(B, H, W, C);
@@ -662,11 +726,13 @@ static void nafblock(Ctx& c, NafBlockW& b, const Tens& x, Tens& out) {
   e3.out_scale = b.beta; e3.resid = x;
   if (c.tc && x.dt != DT_F32) {
     scale_nc(c, g, scale);                      // x * sca(x) (HYB:157) ahead of the tensor-core GEMM
+    range_audit(c, g);
   } else {
     e3.in_scale = scale;                        // folded into the A-operand load of the CUDA-core GEMM
   }
   conv(c, g, nullptr, b.c3, e3, y);
   layernorm(c, y, b.n2w, b.n2b, 1e-6f, t);
+  range_audit(c, t);
   ConvEpi e4;
   e4.gate = true;                               // SimpleGate in the GEMM epilogue where the 2C-wide row fits one accumulator
   if (c.tc && conv1_supported(t, nullptr, b.c4, e4)) {
@@ -674,6 +740,7 @@ static void nafblock(Ctx& c, NafBlockW& b, const Tens& x, Tens& out) {
   } else {
     conv(c, t, nullptr, b.c4, ConvEpi(), u);
     simple_gate(c, u, g);
+    range_audit(c, g);
   }
   ConvEpi e5;
   e5.out_scale = b.gamma; e5.resid = y;
@@ -695,6 +762,7 @@ static void nafnet_forward(Ctx& c, NafW& n, const float* inp, float* out, int B,
   Tens xin; xin.p = (void*)ip; xin.n = B; xin.h = Hp; xin.w = Wp; xin.c = 1; xin.dt = DT_F32;
   Tens x = c.alloc(B, Hp, Wp, n.width);
   conv_first(c, xin, nullptr, n.intro, x);
+  range_audit(c, x);
   std::vector<Tens> encs;
   for (size_t s = 0; s < n.enc.size(); ++s) {
     for (auto& b : n.enc[s]) {
@@ -790,8 +858,10 @@ static void fusion_forward(Ctx& c, FusionW& f, const float* naf, const float* di
     Tens y1 = c.alloc(B, H, W, b);
     double* s1 = new_sums(c, B, 8);
     if (!conv_first(c, x3, nullptr, f.conv1.conv, y1, s1)) gn_stats(c, y1, nullptr, 8, s1);
+    range_audit(c, y1);
     Tens a1 = c.alloc(B, H, W, b);
     gn_act(c, y1, nullptr, 8, s1, f.conv1.g, f.conv1.b, 1e-5f, ACT_GELU, a1);
+    range_audit(c, a1);
     Tens y2 = c.alloc(B, H, W, b);
     ConvEpi e2;
     e2.stats_out = new_sums(c, B, 8);
@@ -813,9 +883,47 @@ static void fusion_forward(Ctx& c, FusionW& f, const float* naf, const float* di
   c.a->release(mk0);
 }
 
+// ---------------------------------------------------------------- ExpertDenoiser (DirectUNetModel.py:232-255)
+static void expert_forward(Ctx& c, ExpertW& e, const float* inp, float* out, int B, int H, int W) {
+  XRD_REQUIRE(H % 4 == 0 && W % 4 == 0, "ExpertDenoiser: H and W must be multiples of 4 (got %dx%d)", H, W);
+  const size_t mk0 = c.a->mark();
+  ConvEpi relu;
+  relu.act = ACT_RELU;
+  auto cbr = [&](const Tens& a, const Tens* b, ConvW& w) {       // conv + folded BatchNorm + ReLU
+    Tens y = c.alloc(a.n, a.h, a.w, w.cout);
+    conv(c, a, b, w, relu, y);
+    return y;
+  };
+  Tens xin; xin.p = (void*)inp; xin.n = B; xin.h = H; xin.w = W; xin.c = 1; xin.dt = DT_F32;
+  Tens x1 = c.alloc(B, H, W, e.base);
+  conv_simt(c, xin, nullptr, e.inc[0], relu, x1);                 // 1 -> base from the fp32 plane (CUDA cores: 9 MACs per output)
+  range_audit(c, x1);
+  x1 = cbr(x1, nullptr, e.inc[1]);
+  Tens x2 = cbr(cbr(x1, nullptr, e.down1[0]), nullptr, e.down1[1]);
+  Tens x2p = c.alloc(B, H / 2, W / 2, x2.c);
+  maxpool2x2(c, x2, x2p);
+  Tens x3 = cbr(cbr(x2p, nullptr, e.down2[0]), nullptr, e.down2[1]);
+  Tens x3p = c.alloc(B, H / 4, W / 4, x3.c);
+  maxpool2x2(c, x3, x3p);
+  Tens x4 = cbr(cbr(x3p, nullptr, e.bott[0]), nullptr, e.bott[1]);
+  Tens u2 = c.alloc(B, H / 2, W / 2, e.up2.cout / 4);
+  conv(c, x4, nullptr, e.up2, ConvEpi(), u2);                     // ConvTranspose2d(2,2): GEMM + depth-to-space store
+  Tens d2 = cbr(cbr(u2, &x3, e.upc2[0]), nullptr, e.upc2[1]);     // cat([xd2, x3]) as a two-source contraction
+  Tens u1 = c.alloc(B, H, W, e.up1.cout / 4);
+  conv(c, d2, nullptr, e.up1, ConvEpi(), u1);
+  Tens d1 = cbr(cbr(u1, &x2, e.upc1[0]), nullptr, e.upc1[1]);
+  Tens f = cbr(d1, nullptr, e.fin);
+  Cout1Args a;
+  a.x = f; a.k = 1; a.w = e.out_w; a.bias = e.out_b; a.mode = 0; a.y = out;
+  conv_cout1(c, a);
+  c.a->release(mk0);
+}
+
 // ------------------------------------------------------------------------------------------------
 // exported to capi.cu
 // ------------------------------------------------------------------------------------------------
+void run_expert(Ctx& c, Handle& h, const float* inp, float* out, int B, int H, int W) { expert_forward(c, h.expert, inp, out, B, H, W); }
+
 std::vector<int> ddim_timesteps(int noise_steps, int inference_steps) {
   std::vector<int> t;
   if (inference_steps < 1) inference_steps = 1;
@@ -903,6 +1011,13 @@ void prepack_tc(Handle& h, DType dt) {
     for (auto& w : n.skips) pk(w, w.cin / 2);
   }
   if (h.fusion.ready && h.fusion.padded) pk(h.fusion.conv2p.conv, h.fusion.conv2p.conv.cin);
+  if (h.expert.ready) {
+    ExpertW& e = h.expert;
+    pk(e.inc[1], e.inc[1].cin);
+    for (ConvW* w : {&e.down1[0], &e.down1[1], &e.down2[0], &e.down2[1], &e.bott[0], &e.bott[1], &e.upc2[1], &e.upc1[1], &e.fin, &e.up2, &e.up1}) pk(*w, w->cin);
+    pk(e.upc2[0], e.upc2[0].cin / 2);                      // two sources: [up(x4) | x3]
+    pk(e.upc1[0], e.upc1[0].cin / 2);
+  }
   XRD_CUDA(cudaDeviceSynchronize());
 }
 

@@ -92,6 +92,17 @@ struct FusionW {
   const float* out_wp = nullptr;
 };
 
+// ExpertDenoiser (DirectUNet/DirectUNetModel.py:160-255): Conv3x3(no bias) + BatchNorm2d(eval) + ReLU pairs, MaxPool2d(2),
+// ConvTranspose2d(2,2) ups, 1x1 head.  BatchNorm is folded into the conv weights/bias at pack time.
+struct ExpertW {
+  bool ready = false;
+  int base = 0;
+  ConvW inc[2], down1[2], down2[2], bott[2], upc2[2], upc1[2], fin;
+  ConvW up2, up1;
+  const float* out_w = nullptr;   // outc (1,base,1,1) == [1][base]
+  const float* out_b = nullptr;
+};
+
 struct GraphEntry {
   cudaGraphExec_t exec = nullptr;
   uint64_t kernels = 0;     // kernel nodes per replay (launch accounting)
@@ -105,6 +116,8 @@ struct Handle {
   xrd_config cfg;
   int mode = XRD_MODE_FP16;
   bool use_graph = true;
+  RangeAudit* audit_dev = nullptr;   // device counters of the range audit (allocated on first use)
+  bool audit = false;
   std::mutex mu;
 
   std::unordered_map<std::string, Param> params;
@@ -113,6 +126,7 @@ struct Handle {
   NafW naf;
   RouterW router;
   FusionW fusion;
+  ExpertW expert;
 
   Arena arena;
   std::map<std::string, size_t> plan_cache;      // call signature -> arena bytes

@@ -76,6 +76,8 @@ void gn_stats(Ctx& c, const Tens& x1, const Tens* x2, int groups, double* sums);
 void gn_act(Ctx& c, const Tens& x1, const Tens* x2, int groups, const double* sums, const float* gamma,
             const float* beta, float eps, int act, Tens& y);
 void zero_async(Ctx& c, void* p, size_t bytes);
+// range audit (no-op unless c.audit is set and t is a 16-bit tensor): counts saturated / non-finite elements, tracks max |v|
+void range_audit(Ctx& c, const Tens& t);
 // coef[n][c] = 0.5 * (rstd*gamma[c], beta[c] - mean*rstd*gamma[c]) for GroupNorm(groups, C) with the given sums ([N][groups][2])
 void gn_coef(Ctx& c, const double* sums, const float* gamma, const float* beta, float eps, int N, int C, int groups, int HW, float2* coef);
 // out[n][g] = a[n][2g] + a[n][2g+1] (g < 4), b[n][2(g-4)] + b[n][2(g-4)+1] (g >= 4): sums of GroupNorm(8, 2C) over [a | b]
@@ -92,6 +94,7 @@ void dwconv_gate_pool(Ctx& c, const Tens& u, const float* w9, const float* bias,
 void sca_scale(Ctx& c, const float* pool, int N, int C, int HW, const float* W, const float* b, float* scale);
 
 void simple_gate(Ctx& c, const Tens& u, Tens& g);        // g = u[..., :C] * u[..., C:]
+void maxpool2x2(Ctx& c, const Tens& x, Tens& y);         // nn.MaxPool2d(2): y[n,h,w,c] = max of the 2x2 block (H, W even; NaN propagates)
 void scale_nc(Ctx& c, Tens& x, const float* scale);      // x[n,h,w,c] *= scale[n][c]   (in place)
 void interleave3(Ctx& c, const float* a, const float* b, const float* m, float* y, int64_t n);
 void pad_crop_plane(Ctx& c, const float* src, float* dst, int N, int Hs, int Ws, int Hd, int Wd);
@@ -144,6 +147,10 @@ void pack_convT4_avg_weight(cudaStream_t s, const float* w, float* out, int cin,
 void pack_convT2_weight(cudaStream_t s, const float* w, const float* b, float* out, float* bout, int cin, int cout);
 // 1x1 conv feeding PixelShuffle(2): (4*Cf,Cin,1,1) with q_ref=c*4+i*2+j -> [1][Cin][4*Cf] with q=(i*2+j)*Cf+c
 void pack_pixelshuffle_weight(cudaStream_t s, const float* w, float* out, int cin, int cf);
+// eval-mode BatchNorm2d folded into the bias-free conv in front of it (DirectUNetModel.py:163-165 etc.):
+// wf[co][...] = w[co][...] * g[co]/sqrt(var[co]+eps),  bf[co] = beta[co] - mean[co] * g[co]/sqrt(var[co]+eps)
+void fold_bn_weight(cudaStream_t s, const float* w, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                    float* wf, float* bf, int cout, int per_cout);
 // depthwise (C2,1,3,3) -> [9][C2]
 void pack_dw_weight(cudaStream_t s, const float* w, float* out, int c2);
 

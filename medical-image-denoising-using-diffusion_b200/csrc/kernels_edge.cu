@@ -237,9 +237,9 @@ __global__ void __launch_bounds__(256) k_conv_cout1_v2(Cout1P p) {
     const int64_t oi = ((int64_t)n * p.H + oy) * p.W + ox;
     if (p.mode == 3) {
       if (p.y) p.y[oi] = v;
-      const float e = fminf(fmaxf(v, -5.f), 5.f);
+      const float e = clamp_nan(v, -5.f, 5.f);
       const float xn = p.c1 * (p.x_cur[oi] - p.c2 * e);
-      p.x_next[oi] = fminf(fmaxf(xn, 0.f), 1.f);
+      p.x_next[oi] = clamp_nan(xn, 0.f, 1.f);
       continue;
     }
     if (p.mode == 1) v += p.inp[oi];

@@ -4,6 +4,8 @@
 //   * the single-output-channel 3x3 conv (UNet out_conv + sampler update, NAFNet ending) with the
 //     GroupNorm+SiLU'd input tile staged once in shared memory.
 #include "kernels.cuh"
+#include <type_traits>
+#include <algorithm>
 #include "tc_common.cuh"
 
 namespace xrd {
@@ -433,9 +435,9 @@ __global__ void __launch_bounds__(256) k_conv_cout1_tiled(Cout1T p) {
   const int64_t o = ((int64_t)n * p.H + oy) * p.W + ox;
   if (p.mode == 3) {
     if (p.y) p.y[o] = v;
-    const float e = fminf(fmaxf(v, -5.f), 5.f);
+    const float e = clamp_nan(v, -5.f, 5.f);
     const float xn = p.c1 * (p.x_cur[o] - p.c2 * e);
-    p.x_next[o] = fminf(fmaxf(xn, 0.f), 1.f);
+    p.x_next[o] = clamp_nan(xn, 0.f, 1.f);
     return;
   }
   if (p.mode == 1) v += p.inp[o];
@@ -473,6 +475,50 @@ void conv_cout1(Ctx& c, const Cout1Args& a) {
       XRD_LAUNCH(c, (k_conv_cout1_tiled<__half, true>), grid, 256, smem, p);
     } break;
   }
+}
+
+// ---------------------------------------------------------------- range audit of 16-bit activations
+// The f16 mode stores activations with saturation (common.cuh sat_h): one large value cannot become inf/NaN downstream, but a
+// clipped value is silently wrong.  The audit scans a tensor after its producer and counts elements sitting exactly at the
+// saturation value, non-finite elements, and the largest finite magnitude, so that a caller (tests, a periodic production
+// check) can prove the activations of a checkpoint stay inside the f16 range -- or see exactly how often they do not.
+template <typename T>
+__global__ void k_range_audit(const uint4* __restrict__ x, size_t nvec, RangeAudit* a) {
+  unsigned int sat = 0, bad = 0;
+  float amax = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 t = x[i];
+    const T* h = reinterpret_cast<const T*>(&t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = fabsf(ldf<T>(h + j));
+      if (!(v <= 3.0e38f)) { ++bad; continue; }          // NaN or inf
+      if (sizeof(T) == 2 && std::is_same<T, __half>::value && v >= 65504.f) ++sat;
+      amax = fmaxf(amax, v);
+    }
+  }
+#pragma unroll
+  for (int of = 16; of > 0; of >>= 1) {
+    sat += __shfl_xor_sync(0xffffffffu, sat, of);
+    bad += __shfl_xor_sync(0xffffffffu, bad, of);
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, of));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (sat) atomicAdd(&a->saturated, (unsigned long long)sat);
+    if (bad) atomicAdd(&a->nonfinite, (unsigned long long)bad);
+    atomicMax(&a->absmax_bits, __float_as_uint(amax));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&a->elements, (unsigned long long)nvec * 8ull); atomicAdd(&a->tensors, 1u); }
+}
+
+void range_audit(Ctx& c, const Tens& t) {
+  if (!c.audit || c.dry || t.dt == DT_F32 || !t.p) return;
+  const size_t n = t.numel();
+  if (n == 0 || n % 8 != 0) return;                       // every internal tensor has a multiple of 8 channels
+  const size_t nvec = n / 8;
+  const int grid = (int)std::min<size_t>((nvec + 255) / 256, 148 * 8);
+  if (t.dt == DT_F16) XRD_LAUNCH(c, k_range_audit<__half>, grid, 256, 0, (const uint4*)t.p, nvec, c.audit);
+  else XRD_LAUNCH(c, k_range_audit<__nv_bfloat16>, grid, 256, 0, (const uint4*)t.p, nvec, c.audit);
 }
 
 }  // namespace xrd

@@ -630,9 +630,9 @@ __global__ void __launch_bounds__(128) k_conv_cout1(Cout1P p) {
   const int64_t o = (int64_t)n * HW + pp;
   if (p.mode == 3) {
     if (p.y) p.y[o] = v;                       // raw eps tap (parity trace)
-    float e = fminf(fmaxf(v, -5.f), 5.f);      // clamp(eps,-5,5)
+    float e = clamp_nan(v, -5.f, 5.f);      // clamp(eps,-5,5)
     float xn = p.c1 * (p.x_cur[o] - p.c2 * e);
-    p.x_next[o] = fminf(fmaxf(xn, 0.f), 1.f);
+    p.x_next[o] = clamp_nan(xn, 0.f, 1.f);
     return;
   }
   if (p.mode == 1) v += p.inp[o];
@@ -911,6 +911,37 @@ void simple_gate(Ctx& c, const Tens& u, Tens& g) {
   XRD_DISPATCH(u.dt, T, XRD_LAUNCH(c, (k_simple_gate<T>), ew_blocks(npix * (g.c / 4)), 256, 0, (const T*)u.p, (T*)g.p, npix, g.c));
 }
 
+// nn.MaxPool2d(2) on NHWC, 4 channels per thread.  torch's max_pool2d propagates NaN: so does this (comparison order as ATen's
+// `(val > maxval) || isnan(val)`).
+template <typename T>
+__global__ void k_maxpool2x2(const T* __restrict__ x, T* __restrict__ y, int N, int Ho, int Wo, int C) {
+  const int Q = C >> 2;
+  const int64_t total = (int64_t)N * Ho * Wo * Q;
+  const int W = Wo * 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Q) * 4;
+    int64_t r = i / Q;
+    const int ow = (int)(r % Wo); r /= Wo;
+    const int oh = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    const T* src = x + (((int64_t)n * Ho * 2 + oh * 2) * W + ow * 2) * C + c;
+    float m[4], v[4];
+    ld4<T>(src, m);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      ld4<T>(src + ((int64_t)(k >> 1) * W + (k & 1)) * C, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (v[j] > m[j] || v[j] != v[j]) m[j] = v[j];
+    }
+    st4<T>(y + (((int64_t)n * Ho + oh) * Wo + ow) * C + c, m);
+  }
+}
+void maxpool2x2(Ctx& c, const Tens& x, Tens& y) {
+  XRD_REQUIRE(x.h % 2 == 0 && x.w % 2 == 0 && y.h * 2 == x.h && y.w * 2 == x.w && y.c == x.c && y.n == x.n && y.dt == x.dt && x.c % 4 == 0,
+              "maxpool2x2: shape");
+  XRD_DISPATCH(x.dt, T, XRD_LAUNCH(c, (k_maxpool2x2<T>), ew_blocks((int64_t)y.numel() / 4), 256, 0, (const T*)x.p, (T*)y.p, y.n, y.h, y.w, y.c));
+}
+
 template <typename T>
 __global__ void k_scale_nc(T* __restrict__ x, const float* __restrict__ scale, int64_t hw, int C, int64_t total_q) {
   const int Q = C >> 2;
@@ -999,6 +1030,22 @@ __global__ void k_pack_conv_w(const float* __restrict__ w, float* __restrict__ o
 void pack_conv_weight(cudaStream_t s, const float* w, float* out, int cout, int cin, int kh, int kw) {
   int64_t total = (int64_t)cout * cin * kh * kw;
   k_pack_conv_w<<<ew_blocks(total), 256, 0, s>>>(w, out, cout, cin, kh * kw);
+  XRD_CUDA(cudaPeekAtLastError());
+}
+
+__global__ void k_fold_bn(const float* __restrict__ w, const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ mean,
+                          const float* __restrict__ var, float eps, float* __restrict__ wf, float* __restrict__ bf, int cout, int per) {
+  const int64_t total = (int64_t)cout * per;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i / per);
+    const float sc = g[co] / sqrtf(var[co] + eps);
+    wf[i] = w[i] * sc;
+    if (i % per == 0) bf[co] = b[co] - mean[co] * sc;
+  }
+}
+void fold_bn_weight(cudaStream_t s, const float* w, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                    float* wf, float* bf, int cout, int per_cout) {
+  k_fold_bn<<<ew_blocks((int64_t)cout * per_cout), 256, 0, s>>>(w, gamma, beta, mean, var, eps, wf, bf, cout, per_cout);
   XRD_CUDA(cudaPeekAtLastError());
 }
 

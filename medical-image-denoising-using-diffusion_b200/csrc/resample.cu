@@ -6,13 +6,14 @@
 // (a = -0.5) stretched by max(1, in/out) (antialiasing when shrinking), computed in double, normalised, converted to fixed
 // point with 22 fractional bits (round half away from zero); a horizontal pass then a vertical pass, each accumulating in
 // int32 from 1 << 21 and clipping (sum >> 22) to [0, 255] -- the intermediate image is 8-bit, as in Pillow.
-// The coefficient tables are built on the host in double exactly as Pillow's C does and cached per (in, out) size pair.
+// The coefficient tables are built on the host in double exactly as Pillow's C does and cached per (device, in, out).
 #include "common.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <map>
 #include <mutex>
+#include <tuple>
 #include <vector>
 
 namespace xrd {
@@ -71,21 +72,42 @@ void build_table(int in_size, int out_size, std::vector<int>& bounds, std::vecto
   }
 }
 
+// Device tables are cached per (device, in, out): a table lives on the device it was built on.  The cache is bounded (every
+// upload size of `/denoise` adds a (512 -> W0/H0) pair): least recently used entries are freed -- cudaFree waits for the
+// kernels that may still read them.
 std::mutex g_mu;
-std::map<std::pair<int, int>, Table> g_tables;
+struct Entry { Table t; uint64_t stamp = 0; };
+std::map<std::tuple<int, int, int>, Entry> g_tables;
+uint64_t g_stamp = 0;
+constexpr size_t kMaxTables = 64;
 
-const Table& table_for(int in_size, int out_size) {
+Table table_for(int in_size, int out_size) {
+  int dev = 0;
+  XRD_CUDA(cudaGetDevice(&dev));           // the entry point made the buffers' device current
   std::lock_guard<std::mutex> lk(g_mu);
-  auto it = g_tables.find({in_size, out_size});
-  if (it != g_tables.end()) return it->second;
+  const auto key = std::make_tuple(dev, in_size, out_size);
+  auto it = g_tables.find(key);
+  if (it != g_tables.end()) { it->second.stamp = ++g_stamp; return it->second.t; }
+  if (g_tables.size() >= kMaxTables) {
+    auto old = g_tables.begin();
+    for (auto j = g_tables.begin(); j != g_tables.end(); ++j) if (j->second.stamp < old->second.stamp) old = j;
+    {
+      DeviceScope ds(std::get<0>(old->first));
+      cudaFree(old->second.t.bounds);
+      cudaFree(old->second.t.kk);
+    }
+    g_tables.erase(old);
+  }
   std::vector<int> b, k;
-  Table t;
-  build_table(in_size, out_size, b, k, t.ksize);
-  XRD_CUDA(cudaMalloc((void**)&t.bounds, b.size() * sizeof(int)));
-  XRD_CUDA(cudaMalloc((void**)&t.kk, k.size() * sizeof(int)));
-  XRD_CUDA(cudaMemcpy(t.bounds, b.data(), b.size() * sizeof(int), cudaMemcpyHostToDevice));
-  XRD_CUDA(cudaMemcpy(t.kk, k.data(), k.size() * sizeof(int), cudaMemcpyHostToDevice));
-  return g_tables.emplace(std::make_pair(in_size, out_size), t).first->second;
+  Entry e;
+  build_table(in_size, out_size, b, k, e.t.ksize);
+  XRD_CUDA(cudaMalloc((void**)&e.t.bounds, b.size() * sizeof(int)));
+  XRD_CUDA(cudaMalloc((void**)&e.t.kk, k.size() * sizeof(int)));
+  XRD_CUDA(cudaMemcpy(e.t.bounds, b.data(), b.size() * sizeof(int), cudaMemcpyHostToDevice));
+  XRD_CUDA(cudaMemcpy(e.t.kk, k.data(), k.size() * sizeof(int), cudaMemcpyHostToDevice));
+  e.stamp = ++g_stamp;
+  g_tables.emplace(key, e);
+  return e.t;
 }
 
 __device__ __forceinline__ uint8_t clip8(int v) {
@@ -153,14 +175,14 @@ void resize_bicubic_u8(Ctx& c, const uint8_t* src, uint8_t* dst, uint8_t* tmp, i
   }
   const uint8_t* cur = src;
   if (need_h) {
-    const Table& t = table_for(Win, Wout);
+    const Table t = table_for(Win, Wout);
     uint8_t* o = need_v ? tmp : dst;
     XRD_REQUIRE(o != nullptr, "resize: temporary buffer required");
     XRD_LAUNCH(c, k_resample_h_u8, ew_grid((int64_t)N * Hin * Wout), 256, 0, cur, o, N, Hin, Win, Wout, t.bounds, t.kk, t.ksize);
     cur = o;
   }
   if (need_v) {
-    const Table& t = table_for(Hin, Hout);
+    const Table t = table_for(Hin, Hout);
     XRD_LAUNCH(c, k_resample_v_u8, ew_grid((int64_t)N * Hout * Wout), 256, 0, cur, dst, N, Hin, Hout, Wout, t.bounds, t.kk, t.ksize);
   }
 }

@@ -129,6 +129,8 @@ class _NativeModel(nn.Module):
         object.__setattr__(self, "_xrd_handles", {})
         object.__setattr__(self, "_xrd_lock", threading.Lock())
         object.__setattr__(self, "_xrd_schedule", (50, 1e-4, 0.02))
+        object.__setattr__(self, "_xrd_tensor_cache", None)
+        object.__setattr__(self, "_xrd_audit", False)
         self.native_mode = _default_mode()
         self.use_cuda_graph = True
 
@@ -153,9 +155,68 @@ class _NativeModel(nn.Module):
             object.__setattr__(self, "_xrd_schedule", sched)
 
     # -- handle + weights ---------------------------------------------------
+    def _xrd_tensors(self):
+        """(key, tensor) of every parameter and buffer, cached: walking the module tree (912 tensors for the hybrid)
+        on every forward costs more than a batch-1 UNet evaluation.  The cache is dropped whenever the module tree can
+        have changed (load_state_dict, _apply = .to()/.half()/..., explicit refresh_weights())."""
+        ts = self.__dict__.get("_xrd_tensor_cache")
+        if ts is None:
+            ts = list(self.state_dict(keep_vars=True).items())
+            object.__setattr__(self, "_xrd_tensor_cache", ts)
+        return ts
+
     def _xrd_fingerprint(self, device) -> tuple:
-        return tuple((k, v.data_ptr(), v._version, v.device.index)
-                     for k, v in self.state_dict(keep_vars=True).items())
+        # (storage address, in-place version) per tensor.  Limitation (documented in INTEGRATION.md): an edit made through
+        # ``param.data`` (e.g. an EMA swap with ``p.data.copy_()``) bumps neither -- call refresh_weights() after such edits.
+        return tuple((v.data_ptr(), v._version) for _, v in self._xrd_tensors())
+
+    def refresh_weights(self) -> "_NativeModel":
+        """Force a re-upload and re-pack of the weights on the next call (after edits through ``.data``)."""
+        object.__setattr__(self, "_xrd_tensor_cache", None)
+        with self._xrd_lock:
+            for ent in self._xrd_handles.values():
+                ent["fp"] = None
+        return self
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        object.__setattr__(self, "_xrd_tensor_cache", None)
+        return r
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        object.__setattr__(self, "_xrd_tensor_cache", None)
+        return r
+
+    # -- range audit of the 16-bit activation storage (include/xrd.h: xrd_set_range_audit) ---------------------------
+    def set_range_audit(self, enable: bool = True) -> "_NativeModel":
+        """Scan every 16-bit activation tensor after its producer (saturated f16 stores, non-finite values, max |v|).
+        The sampler then runs eagerly instead of as a CUDA graph; meant for checkpoint qualification and periodic checks."""
+        object.__setattr__(self, "_xrd_audit", bool(enable))
+        return self
+
+    def range_report(self, reset: bool = True) -> dict:
+        """Counters accumulated since the last reset over all devices this model ran on."""
+        lib = _lib.load()
+        tot = dict(saturated=0, nonfinite=0, elements=0, tensors=0, absmax=0.0)
+        with self._xrd_lock:
+            for ent in self._xrd_handles.values():
+                sat, bad, n = C.c_uint64(), C.c_uint64(), C.c_uint64()
+                amax, nt = C.c_float(), C.c_uint32()
+                _lib.check(lib.xrd_get_range_report(ent["h"], C.byref(sat), C.byref(bad), C.byref(n), C.byref(amax), C.byref(nt),
+                                                    1 if reset else 0))
+                tot["saturated"] += sat.value; tot["nonfinite"] += bad.value; tot["elements"] += n.value
+                tot["tensors"] += nt.value; tot["absmax"] = max(tot["absmax"], amax.value)
+        return tot
+
+    def check_range(self, reset: bool = True) -> dict:
+        """range_report() that raises XrdError when any activation saturated the f16 storage or became non-finite."""
+        r = self.range_report(reset)
+        if r["saturated"] or r["nonfinite"]:
+            raise XrdError(f"16-bit activation range exceeded: {r['saturated']} saturated and {r['nonfinite']} non-finite elements "
+                           f"of {r['elements']} audited (max finite |v| = {r['absmax']:.4g}); run this model with "
+                           "set_native_mode('bf16') or 'fp32'")
+        return r
 
     def _xrd_handle(self, device: torch.device):
         lib = _lib.load()
@@ -176,29 +237,42 @@ class _NativeModel(nn.Module):
             fp = self._xrd_fingerprint(device)
             if fp != ent["fp"]:
                 keep = []
-                for key, v in self.state_dict(keep_vars=True).items():
+                for key, v in self._xrd_tensors():
                     t = v.detach()
                     if t.device.type != "cuda" or t.device.index != idx:
                         raise XrdError(f"parameter {key} lives on {t.device}, the input on cuda:{idx}; "
                                        "move the model with .to(device) first")
-                    t = t.to(torch.float32).contiguous()
-                    keep.append(t)
+                    keep.append((key, t.to(torch.float32).contiguous()))
+                # The casts/copies above (and whatever produced the parameters: a GPU-side load_state_dict, .half(), ...) were
+                # enqueued on torch's current stream, possibly a non-blocking side stream that xrd_set_param's blocking
+                # device-to-device copy would NOT wait for: drain it first, then hand the pointers over.
+                torch.cuda.current_stream(idx).synchronize()
+                for key, t in keep:
                     shape = (C.c_int64 * max(1, t.dim()))(*t.shape)
                     _lib.check(lib.xrd_set_param(ent["h"], (self._xrd_prefix + key).encode(),
                                                  C.c_void_p(t.data_ptr()), shape, t.dim(), 1))
-                torch.cuda.current_stream(idx).synchronize()
                 _lib.check(lib.xrd_finalize_weights(ent["h"], self._xrd_parts))
                 del keep
                 ent["fp"] = fp
-            _lib.check(lib.xrd_set_mode(ent["h"], _MODE_NAMES[self.native_mode]))
-            _lib.check(lib.xrd_set_use_graph(ent["h"], 1 if self.use_cuda_graph else 0))
+                ent["mode"] = ent["graph"] = ent["audit"] = None
+            mode, graph, audit = _MODE_NAMES[self.native_mode], 1 if self.use_cuda_graph else 0, 1 if self._xrd_audit else 0
+            if ent.get("mode") != mode:
+                _lib.check(lib.xrd_set_mode(ent["h"], mode)); ent["mode"] = mode
+            if ent.get("graph") != graph:
+                _lib.check(lib.xrd_set_use_graph(ent["h"], graph)); ent["graph"] = graph
+            if ent.get("audit") != audit:
+                _lib.check(lib.xrd_set_range_audit(ent["h"], audit)); ent["audit"] = audit
             return ent["h"]
 
     def __del__(self):
+        # never dlopen from a finaliser: a model that never ran has no handles (bench.py's CPU arm builds such models)
         try:
-            lib = _lib.load()
-            for ent in self._xrd_handles.values():
-                lib.xrd_destroy(ent["h"])
+            handles = self.__dict__.get("_xrd_handles") or {}
+            if handles and _lib.loaded():
+                lib = _lib.load()
+                for ent in handles.values():
+                    lib.xrd_destroy(ent["h"])
+                handles.clear()
         except Exception:
             pass
 
@@ -207,12 +281,14 @@ class _NativeModel(nn.Module):
         d = self.__dict__.copy()
         d["_xrd_handles"] = {}
         d["_xrd_lock"] = None
+        d["_xrd_tensor_cache"] = None
         return d
 
     def __setstate__(self, d):
         self.__dict__.update(d)
         object.__setattr__(self, "_xrd_handles", {})
         object.__setattr__(self, "_xrd_lock", threading.Lock())
+        object.__setattr__(self, "_xrd_tensor_cache", None)
 
 
 def _image_arg(x: torch.Tensor, name: str, channels: int = 1) -> torch.Tensor:
@@ -561,6 +637,58 @@ class HybridDenoisingRouter(_NativeModel):
         if return_parts:
             return out, dict(naf=parts[0], diff=parts[1], mask=parts[2])
         return out
+
+
+# ---------------------------------------------------------------------------
+# ExpertDenoiser (the 4th /denoise output)
+# ---------------------------------------------------------------------------
+def _cbr(in_c, out_c, n=2):
+    layers = []
+    for i in range(n):
+        layers += [nn.Conv2d(in_c if i == 0 else out_c, out_c, 3, padding=1, bias=False), nn.BatchNorm2d(out_c), nn.ReLU(inplace=True)]
+    return nn.Sequential(*layers)
+
+
+class ExpertDenoiser(_NativeModel):
+    """ExpertDenoiser(in_channels, base_channels) -- DirectUNet/DirectUNetModel.py:160-255; constructed at RUN:54 and
+    called at RUN:127.  Conv3x3(bias=False) + BatchNorm2d + ReLU pairs, MaxPool2d(2), ConvTranspose2d(2,2) ups, 1x1 head;
+    same state_dict keys (including the BatchNorm running statistics).  ``forward`` is one xrd_expert call; it is
+    inference-only: BatchNorm always uses its running statistics (the reference calls ``.eval()`` before use, RUN:56)."""
+
+    _xrd_parts = _lib.PART_EXPERT
+
+    def __init__(self, in_channels=1, base_channels=64):
+        super().__init__()
+        self._xrd_init()
+        if in_channels != 1:
+            raise XrdError("ExpertDenoiser: only in_channels=1 (grayscale) is implemented")
+        b = base_channels
+        self._base_c = b
+        self.inc = _cbr(in_channels, b)
+        self.down1 = _cbr(b, 2 * b)
+        self.pool1 = nn.MaxPool2d(2)
+        self.down2 = _cbr(2 * b, 4 * b)
+        self.pool2 = nn.MaxPool2d(2)
+        self.bottleneck = _cbr(4 * b, 8 * b)
+        self.up2 = nn.ConvTranspose2d(8 * b, 4 * b, 2, stride=2)
+        self.upconv2 = _cbr(8 * b, 4 * b)
+        self.up1 = nn.ConvTranspose2d(4 * b, 2 * b, 2, stride=2)
+        self.upconv1 = _cbr(4 * b, 2 * b)
+        self.final = _cbr(2 * b, b, n=1)
+        self.outc = nn.Conv2d(b, in_channels, 1)
+
+    def _xrd_fill_config(self, cfg, prefix=""):
+        cfg.expert_base_c = self._base_c
+        cfg.expert_prefix = prefix.encode()
+
+    @torch.no_grad()
+    def forward(self, x):
+        xx = _image_arg(x, "x")
+        h = self._xrd_handle(xx.device)
+        out = torch.empty_like(xx)
+        B, _, H, W = xx.shape
+        _lib.check(_lib.load().xrd_expert(h, _ptr(xx), _ptr(out), B, H, W, _stream_ptr(xx.device)))
+        return out.to(x.dtype)
 
 
 def native_kernel_launches() -> int:

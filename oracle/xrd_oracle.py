@@ -350,6 +350,36 @@ def fusion_forward(sd: SD, naf: Tensor, diff: Tensor, mask: Tensor, prefix: str 
     return F.conv2d(x, _g(sd, p + "out_conv.weight", dt), _g(sd, p + "out_conv.bias", dt))
 
 
+# --------------------------------------------------------------------------
+# ExpertDenoiser (the 4th /denoise output; RUN:52-57,127)
+# --------------------------------------------------------------------------
+def _cbr(sd: SD, p: str, i: int, x: Tensor) -> Tensor:
+    """Conv2d(3x3, bias=False) -> BatchNorm2d in eval mode (running statistics, eps 1e-5) -> ReLU
+    (DirectUNetModel.py:163-168 and the other Sequential blocks of that class)."""
+    dt = x.dtype
+    y = F.conv2d(x, _g(sd, f"{p}{i}.weight", dt), None, padding=1)
+    b = f"{p}{i + 1}."
+    y = F.batch_norm(y, _g(sd, b + "running_mean", dt), _g(sd, b + "running_var", dt), _g(sd, b + "weight", dt), _g(sd, b + "bias", dt),
+                     training=False, eps=1e-5)
+    return F.relu(y)
+
+
+def expert_forward(sd: SD, x: Tensor, prefix: str = "") -> Tensor:
+    """ExpertDenoiser.forward (DirectUNet/DirectUNetModel.py:232-255)."""
+    p, dt = prefix, x.dtype
+    pair = lambda q, t: _cbr(sd, q, 3, _cbr(sd, q, 0, t))
+    x1 = pair(p + "inc.", x)
+    x2 = pair(p + "down1.", x1)
+    x3 = pair(p + "down2.", F.max_pool2d(x2, 2))
+    x4 = pair(p + "bottleneck.", F.max_pool2d(x3, 2))
+    d2 = F.conv_transpose2d(x4, _g(sd, p + "up2.weight", dt), _g(sd, p + "up2.bias", dt), stride=2)
+    d2 = pair(p + "upconv2.", torch.cat([d2, x3], dim=1))
+    d1 = F.conv_transpose2d(d2, _g(sd, p + "up1.weight", dt), _g(sd, p + "up1.bias", dt), stride=2)
+    d1 = pair(p + "upconv1.", torch.cat([d1, x2], dim=1))
+    d1 = _cbr(sd, p + "final.", 0, d1)
+    return F.conv2d(d1, _g(sd, p + "outc.weight", dt), _g(sd, p + "outc.bias", dt))
+
+
 def _sanitize(x: Tensor) -> Tensor:
     """nan_to_num(nan=0,posinf=1,neginf=0) + clamp(0,1) (HYB:615-616)."""
     return torch.clamp(torch.nan_to_num(x, nan=0.0, posinf=1.0, neginf=0.0), 0, 1)
@@ -375,7 +405,31 @@ def hybrid_forward(sd: SD, noisy: Tensor, inference_steps: int, noise_steps: int
 import os as _os
 import sys as _sys
 _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
-from synthetic_data import is_norm_param, randomize_identity_params, synthetic_xray  # noqa: E402,F401
+from synthetic_data import is_norm_param, randomize_batchnorm_params, randomize_identity_params, synthetic_xray  # noqa: E402,F401
+
+
+def synthetic_state_dict(shapes: Dict[str, Sequence[int]], seed: int = 1234) -> SD:
+    """A seeded state_dict with the given key -> shape table (tests/golden/meta.json: the reference's 912 hybrid keys), for the
+    CPU timing legs of bench.py: the cost of this path does not depend on the values, and building the weights here keeps the
+    reference arm free of any import of the product package.  Conv / linear weights ~ N(0, 1/fan_in), norm weights around
+    1, biases and NAFBlock beta / gamma small (never the identity)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: SD = {}
+    for k in sorted(shapes):
+        shp = tuple(int(v) for v in shapes[k])
+        leaf = k.rsplit(".", 1)[-1]
+        if leaf in ("beta", "gamma"):
+            sd[k] = 0.5 * torch.randn(shp, generator=g)
+        elif len(shp) >= 2:
+            fan_in = 1
+            for v in shp[1:]:
+                fan_in *= v
+            sd[k] = torch.randn(shp, generator=g) / math.sqrt(max(1, fan_in))
+        elif leaf == "weight":
+            sd[k] = 1.0 + 0.2 * torch.randn(shp, generator=g)
+        else:
+            sd[k] = 0.1 * torch.randn(shp, generator=g)
+    return sd
 
 
 # --------------------------------------------------------------------------

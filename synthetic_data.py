@@ -47,6 +47,22 @@ def randomize_identity_params(sd: SD, seed: int = 99) -> None:
                 v.copy_(0.1 * torch.randn(v.shape, generator=g))
 
 
+def randomize_batchnorm_params(sd: SD, seed: int = 99) -> None:
+    """In place.  A fresh BatchNorm2d is (almost) the identity in eval mode (weight 1, bias 0, running_mean 0, running_var 1):
+    a kernel that dropped the BatchNorm folding would pass.  Overwrite affine parameters and running statistics of every
+    BatchNorm in `sd` (recognised by its ``running_mean`` sibling) with seeded values."""
+    g = torch.Generator().manual_seed(seed)
+    for k in sorted(sd.keys()):
+        if not k.endswith(".running_mean"):
+            continue
+        base = k[: -len("running_mean")]
+        n = sd[k].shape
+        sd[base + "weight"].copy_(1.0 + 0.2 * torch.randn(n, generator=g))
+        sd[base + "bias"].copy_(0.1 * torch.randn(n, generator=g))
+        sd[k].copy_(0.1 * torch.randn(n, generator=g))
+        sd[base + "running_var"].copy_(0.5 + torch.rand(n, generator=g))
+
+
 def synthetic_xray(batch: int, height: int, width: int, seed: int = 7) -> Tuple[Tensor, Tensor]:
     """(clean, noisy) synthetic grayscale X-ray-like fields in [0,1], float32
     (B,1,H,W).  clean = low-pass filtered uniform noise rescaled to [0.2,0.8];

@@ -53,9 +53,14 @@ def seeded_state_dict(kind: str):
         m = xrd_b200.UNetDiffusion()
     elif kind == "nafnet":
         m = xrd_b200.EnhancedNAFNet()
+    elif kind in ("expert", "expert32"):
+        m = xrd_b200.ExpertDenoiser(in_channels=1, base_channels=64 if kind == "expert" else 32)
     else:
         raise KeyError(kind)
     m.eval()
     sd = m.state_dict()
-    O.randomize_identity_params(sd, 99)
+    if kind.startswith("expert"):
+        O.randomize_batchnorm_params(sd, 99)
+    else:
+        O.randomize_identity_params(sd, 99)
     return m, sd

@@ -264,7 +264,9 @@ def check_attention(mode, impl):
         # last two cases: peaked softmax whose row maximum keeps growing along the key axis -- exercises the in-TMEM
         # rescale of the running output (the reference maximum is only raised when a tile exceeds it by 2^8)
         for (B, heads, d, H, W, peaked) in [(2, 2, 96, 8, 8, 0), (1, 2, 96, 16, 16, 0), (1, 2, 96, 4, 4, 0), (1, 2, 96, 32, 32, 0),
-                                            (1, 1, 64, 12, 10, 0), (1, 2, 96, 32, 32, 1), (2, 2, 96, 24, 24, 1)]:
+                                            (1, 1, 64, 12, 10, 0), (1, 2, 96, 32, 32, 1), (2, 2, 96, 24, 24, 1),
+                                            # production size of the 512x512 configurations: 64x64 = 4096 tokens (64 key tiles)
+                                            (1, 2, 96, 64, 64, 0), (2, 2, 96, 64, 64, 1)]:
             qkv = torch.randn(B, 3 * heads * d, H, W, generator=g)
             if peaked:
                 ramp = torch.linspace(0.2, 4.0, H * W).reshape(1, 1, H, W)
@@ -391,6 +393,177 @@ def check_hybrid_oracle_128(mode):
     return out
 
 
+# ------------------------------------------------------------------ the benched shapes against the oracle
+_ORACLE_CACHE = {}
+
+
+def _oracle_hybrid_512(steps=2):
+    """O.hybrid_forward at 512x512, batch 1, `steps` sampler steps on this box's CPU (a few seconds), with the eps trace."""
+    key = ("hyb512", steps)
+    if key not in _ORACLE_CACHE:
+        _, sd = seeded_state_dict("hybrid")
+        sd = {k: v.detach().clone() for k, v in sd.items()}
+        _, noisy = O.synthetic_xray(1, 512, 512, seed=31)
+        parts, tr = {}, {}
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        with torch.no_grad():
+            fused = O.hybrid_forward(sd, noisy, steps, 50, parts=parts)
+            O.ddim_denoise(sd, noisy, steps, 50, prefix="diffusion_unet.", trace=tr)
+        _ORACLE_CACHE[key] = dict(noisy=noisy, fused=fused, parts=parts, eps=torch.stack(tr["eps"]), x_in=torch.stack(tr["x_in"]))
+    return _ORACLE_CACHE[key]
+
+
+def check_hybrid_512(mode, steps=2):
+    """BASELINE configs[2]'s image size through the kernels only that size dispatches to (row-ring conv with the in-place
+    GroupNorm+SiLU, 4-row halo tiles, 64-wide conv with 192 outputs, attention over 4096 tokens): hybrid, batch 1,
+    inference_steps=2 (t = 25, 0) against the oracle; per-evaluation eps teacher-forced and free-running."""
+    ref = _oracle_hybrid_512(steps)
+    m, _ = _hybrid(mode)
+    m.inference_diffusion_steps = steps
+    x = ref["noisy"].to(DEV)
+    fused, got = m(x, return_parts=True)
+    out = {k + "_maxabs": float((got[k].cpu() - ref["parts"][k]).abs().max()) for k in ("naf", "diff", "mask")}
+    out["fused_maxabs"] = float((fused.cpu() - ref["fused"]).abs().max())
+    w = m.diffusion_wrapper
+    _, eps_t, _ = w.denoise(x, steps, return_trace=True, teacher_x=ref["x_in"])
+    out["eps_teacher_worst"] = float((eps_t.cpu()[:, :, None] - ref["eps"]).abs().max())
+    y_free, eps_f, _ = w.denoise(x, steps, return_trace=True)
+    out["eps_free_worst"] = float((eps_f.cpu()[:, :, None] - ref["eps"]).abs().max())
+    out["graph_vs_eager_diff"] = float((got["diff"] - torch.clamp(y_free, 0, 1)).abs().max())
+    out["eps_ref_absmax"] = float(ref["eps"].abs().max())
+    out["n_evals"] = int(eps_t.shape[0])
+    return out
+
+
+def check_unet_teacher_256(mode, evals=3):
+    """configs[1]'s image size: per-evaluation eps at 256x256, batch 1, the first `evals` timesteps of DDIM-50, teacher-forced
+    with the oracle's own x (oracle on this box's CPU)."""
+    key = ("unet256", evals)
+    if key not in _ORACLE_CACHE:
+        _, sd = seeded_state_dict("unet")
+        sd = {k: v.detach().clone() for k, v in sd.items()}
+        _, noisy = O.synthetic_xray(1, 256, 256, seed=33)
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        xs, es = [], []
+        x = noisy.clone()
+        _, alpha, alpha_hat = O.ddim_tables(50)
+        with torch.no_grad():
+            for i in O.ddim_timesteps(50, 50)[:evals]:
+                e = O.unet_forward(sd, x, noisy, torch.full((1,), i, dtype=torch.long))
+                xs.append(x.clone()); es.append(e)
+                x = O.ddim_update(x, e, alpha[i], alpha_hat[i])
+        _ORACLE_CACHE[key] = dict(noisy=noisy, x_in=xs, eps=es, ts=O.ddim_timesteps(50, 50)[:evals])
+    ref = _ORACLE_CACHE[key]
+    m, _ = seeded_state_dict("unet")
+    m = m.to(DEV).set_native_mode(mode)
+    out, worst = {}, 0.0
+    for x, e, t in zip(ref["x_in"], ref["eps"], ref["ts"]):
+        got = m(x.to(DEV), ref["noisy"].to(DEV), torch.full((1,), t, dtype=torch.long, device=DEV)).cpu()
+        err = float((got - e).abs().max())
+        out[f"eps@t{t}"] = err
+        worst = max(worst, err)
+    out["eps_worst"] = worst
+    return out
+
+
+def check_modes_agree_512_b16(steps=50):
+    """configs[2] as benched (512x512, batch 16, DDIM-50, the CUDA-graph path with micro-batching): the default f16 mode against
+    the fp32 check mode of the same library, which check_hybrid_512 / the goldens pin to the oracle."""
+    m, _ = _hybrid("fp16")
+    m.inference_diffusion_steps = steps
+    _, noisy = O.synthetic_xray(16, 512, 512, seed=21)
+    x = noisy.to(DEV)
+    y16, p16 = m(x, return_parts=True)
+    m.set_native_mode("fp32")
+    y32, p32 = m(x, return_parts=True)
+    out = {k + "_maxabs": float((p16[k] - p32[k]).abs().max()) for k in ("naf", "diff", "mask")}
+    out["fused_maxabs"] = float((y16 - y32).abs().max())
+    out["diff_at_clamp0_frac"] = float((p32["diff"] == 0).float().mean())
+    return out
+
+
+def check_expert(mode):
+    """ExpertDenoiser against vectors of the unmodified reference class (tests/golden/make_golden_expert.py) and the oracle."""
+    g = load_golden("expert_64_b2.npz")
+    m, sd = seeded_state_dict("expert")
+    m = m.to(DEV).set_native_mode(mode)
+    out = {}
+    out["golden64_b2"] = float((m(g["noisy"].to(DEV)).cpu() - g["out"]).abs().max())
+    out["golden40x56"] = float((m(g["noisy_r"].to(DEV)).cpu() - g["out_r"]).abs().max())
+    m32, _ = seeded_state_dict("expert32")
+    m32 = m32.to(DEV).set_native_mode(mode)
+    out["golden40x56_base32"] = float((m32(g["noisy_r"].to(DEV)).cpu() - g["out_r_base32"]).abs().max())
+    out["ref_absmax"] = float(g["out"].abs().max())
+    # the served shape (RUN:197-201: every upload is resized to 512x512), oracle on this box's CPU
+    _, noisy = O.synthetic_xray(1, 512, 512, seed=35)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    with torch.no_grad():
+        ref = O.expert_forward({k: v.detach().cpu() for k, v in m.state_dict().items()}, noisy)
+    out["oracle512"] = float((m(noisy.to(DEV)).cpu() - ref).abs().max())
+    return out
+
+
+def check_f16_range(mode="fp16"):
+    """The f16 mode's range contract: activations are stored with saturation and the range audit (xrd_set_range_audit) counts
+    every clipped or non-finite element.  (1) seeded weights: nothing saturates and the largest magnitude is far from 65504;
+    (2) a UNet whose first conv is scaled so that the residual stream of level 0 passes 6e4: the audit must report it and
+    check_range() must raise; the fp32 mode of the same weights still matches the oracle."""
+    out = {}
+    m, _ = _hybrid(mode)
+    m.inference_diffusion_steps = 5
+    m.set_range_audit(True)
+    _, noisy = O.synthetic_xray(1, 128, 128, seed=41)
+    m(noisy.to(DEV))
+    r = m.range_report()
+    out.update({"normal_" + k: v for k, v in r.items()})
+    # stressed weights
+    u, sd = seeded_state_dict("unet")
+    with torch.no_grad():
+        u.in_conv.weight.mul_(3.0e5)
+        u.in_conv.bias.mul_(3.0e5)
+    u = u.to(DEV).set_native_mode(mode)
+    u.set_range_audit(True)
+    _, noisy = O.synthetic_xray(1, 64, 64, seed=42)
+    t = torch.full((1,), 25, dtype=torch.long, device=DEV)
+    eps16 = u(noisy.to(DEV), noisy.to(DEV), t).cpu()
+    r = u.range_report(reset=False)
+    out.update({"stress_" + k: v for k, v in r.items()})
+    try:
+        u.check_range()
+        out["stress_raised"] = False
+    except xrd_b200.XrdError:
+        out["stress_raised"] = True
+    u.set_range_audit(False).set_native_mode("fp32")
+    eps32 = u(noisy.to(DEV), noisy.to(DEV), t).cpu()
+    with torch.no_grad():
+        ref = O.unet_forward({k: v.detach().cpu() for k, v in u.state_dict().items()}, noisy, noisy, t.cpu())
+    out["stress_fp32_vs_oracle_rel"] = _rel(eps32, ref)
+    out["stress_f16_vs_oracle_rel"] = _rel(eps16, ref)
+    out["stress_f16_finite"] = bool(torch.isfinite(eps16).all())
+    return out
+
+
+def check_nan_propagation(mode):
+    """A NaN in the input must travel the way it does in the reference: through every network to the final nan_to_num
+    (HYB:615-624), not be laundered into a finite number by a saturating store or an fminf/fmaxf clamp."""
+    m, sd = _hybrid(mode)
+    m.inference_diffusion_steps = 2
+    _, noisy = O.synthetic_xray(1, 64, 64, seed=43)
+    noisy[0, 0, 10, 20] = float("nan")
+    parts = {}
+    with torch.no_grad():
+        ref = O.hybrid_forward(sd, noisy, 2, 50, parts=parts)
+    fused, got = m(noisy.to(DEV), return_parts=True)
+    out = {"ref_" + k + "_zero_frac": float((parts[k] == 0).float().mean()) for k in ("naf", "diff", "mask")}
+    out.update({k + "_zero_frac": float((got[k] == 0).float().mean()) for k in ("naf", "diff", "mask")})
+    out["fused_maxabs"] = float((fused.cpu() - ref).abs().max()) if torch.isfinite(ref).all() else float("nan")
+    out["fused_finite"] = bool(torch.isfinite(fused).all())
+    w = m.diffusion_wrapper
+    _, eps, _ = w.denoise(noisy.to(DEV), 2, return_trace=True)
+    out["eps_nan_frac"] = float(torch.isnan(eps).float().mean())
+    return out
+
+
 CHECKS = {
     "conv_simt_fp32": lambda: check_conv("fp32", 0, CONV_CASES_SIMT),
     "conv_simt_bf16": lambda: check_conv("bf16", 0, CONV_CASES_SIMT),
@@ -436,6 +609,18 @@ CHECKS = {
     "hybrid_fp16": lambda: check_hybrid("fp16"),
     "hybrid128_fp32": lambda: check_hybrid_oracle_128("fp32"),
     "hybrid128_bf16": lambda: check_hybrid_oracle_128("bf16"),
+    "hybrid512_fp32": lambda: check_hybrid_512("fp32"),
+    "hybrid512_fp16": lambda: check_hybrid_512("fp16"),
+    "hybrid512_bf16": lambda: check_hybrid_512("bf16"),
+    "unet256_fp32": lambda: check_unet_teacher_256("fp32"),
+    "unet256_fp16": lambda: check_unet_teacher_256("fp16"),
+    "modes_512_b16": lambda: check_modes_agree_512_b16(),
+    "expert_fp32": lambda: check_expert("fp32"),
+    "expert_fp16": lambda: check_expert("fp16"),
+    "expert_bf16": lambda: check_expert("bf16"),
+    "f16_range": lambda: check_f16_range(),
+    "nan_fp16": lambda: check_nan_propagation("fp16"),
+    "nan_fp32": lambda: check_nan_propagation("fp32"),
 }
 
 if __name__ == "__main__":

@@ -2,8 +2,12 @@
 versus the reference-pinned oracle / golden vectors.  Tolerances, as BASELINE.json's north star states them:
    fp32 check mode   : 1e-4 max-abs on per-step eps, final image, NAFNet, fused output; mask quantised bit-exact
    16-bit tensor mode: 1e-2 max-abs on per-step eps and final image (default mode = f16 operands)
-   bf16 operands     : reported and bounded at 6e-2 -- single-pass bf16 operands cannot reach 1e-2 on this
-                       network (PyTorch's own bf16 autocast sits at 3-4.6e-2); see DESIGN.md.
+                       -- including at the benched 512x512 size (oracle run on the box's CPU) and, for batch 16 / DDIM-50 as
+                       benched, against the fp32 check mode; the f16 range is covered by the range-audit tests.
+   bf16 operands     : OUT OF CONTRACT.  Single-pass bf16 operands cannot reach 1e-2 on this network (PyTorch's own bf16
+                       autocast sits at 3-4.6e-2 against its fp32); the mode stays selectable for checkpoints whose
+                       activations leave the f16 range and is tested against its MEASURED bound (6e-2), which is not the
+                       north star's tolerance.  The tolerance the north star states is met by the default f16 mode.
 """
 import pytest
 import torch
@@ -14,7 +18,7 @@ pytestmark = pytest.mark.gpu
 
 TOL_FP32 = 1e-4
 TOL_16 = 1e-2
-TOL_BF16 = 6e-2
+TOL_BF16 = 6e-2      # measured bound of the out-of-contract bf16 mode (see the module docstring); NOT the 1e-2 contract
 
 
 # ------------------------------------------------------------------ kernels
@@ -194,6 +198,72 @@ def test_bf16_operands_bounded():
     assert r["eps_worst"] < TOL_BF16, r
     r = G.check_hybrid("bf16")
     assert max(r["naf_maxabs"], r["diff_maxabs"], r["fused_maxabs"]) < TOL_BF16, r
+
+
+# ------------------------------------------------------------------ the benched sizes against the oracle
+def test_fp32_hybrid_512_vs_oracle():
+    """512x512 (BASELINE configs[2]'s size), batch 1, inference_steps=2: the width-dependent dispatch against the oracle."""
+    r = G.check_hybrid_512("fp32")
+    assert r["n_evals"] == 2
+    assert max(r["naf_maxabs"], r["diff_maxabs"], r["fused_maxabs"], r["eps_teacher_worst"], r["eps_free_worst"]) < TOL_FP32, r
+    assert r["mask_maxabs"] < 2e-6, r
+
+
+def test_f16_hybrid_512_vs_oracle():
+    """Same in the default tensor-core mode: here the 512-only kernels run (row-ring conv with in-place GroupNorm+SiLU, 4-row
+    halo tiles, conv3w with 192 outputs, attention over 4096 tokens)."""
+    r = G.check_hybrid_512("fp16")
+    assert max(r["naf_maxabs"], r["diff_maxabs"], r["fused_maxabs"], r["eps_teacher_worst"], r["eps_free_worst"]) < TOL_16, r
+    assert r["mask_maxabs"] < 2e-6 and r["graph_vs_eager_diff"] < 5e-3, r
+
+
+def test_unet_256_teacher_forced_vs_oracle():
+    """BASELINE configs[1]'s size: per-evaluation eps at 256x256 against the oracle, both modes."""
+    r = G.check_unet_teacher_256("fp32")
+    assert r["eps_worst"] < TOL_FP32, r
+    r = G.check_unet_teacher_256("fp16")
+    assert r["eps_worst"] < TOL_16, r
+
+
+def test_f16_vs_fp32_mode_at_the_benched_configuration():
+    """configs[2] exactly as bench.py runs it (512x512, batch 16, DDIM-50, graph replay): f16 against the fp32 check mode."""
+    r = G.check_modes_agree_512_b16()
+    assert max(r["naf_maxabs"], r["diff_maxabs"], r["fused_maxabs"]) < TOL_16, r
+    assert r["mask_maxabs"] < 1e-6, r
+
+
+def test_bf16_512_bounded():
+    r = G.check_hybrid_512("bf16")
+    assert max(r["naf_maxabs"], r["diff_maxabs"], r["fused_maxabs"], r["eps_teacher_worst"]) < TOL_BF16, r
+
+
+# ------------------------------------------------------------------ f16 range contract, NaN semantics
+def test_f16_range_audit_normal_and_stressed_weights():
+    r = G.check_f16_range()
+    # seeded weights: every 16-bit activation tensor audited, none clipped, none non-finite, > 8x head-room to 65504
+    assert r["normal_tensors"] > 500 and r["normal_saturated"] == 0 and r["normal_nonfinite"] == 0 and r["normal_absmax"] < 8192, r
+    # residual stream driven past the f16 range: reported, loudly
+    assert r["stress_saturated"] > 0 and r["stress_raised"] and r["stress_absmax"] >= 65504, r
+    assert r["stress_f16_finite"], r                       # saturating stores: clipped, never inf
+    assert r["stress_fp32_vs_oracle_rel"] < 1e-4, r        # the check mode is unaffected
+
+
+def test_nan_travels_to_nan_to_num_like_the_reference():
+    for mode in ("fp32", "fp16"):
+        r = G.check_nan_propagation(mode)
+        assert r["eps_nan_frac"] == 1.0, (mode, r)         # GroupNorm statistics spread the NaN over the whole image
+        for k in ("naf", "diff", "mask"):
+            assert r[k + "_zero_frac"] == r["ref_" + k + "_zero_frac"] == 1.0, (mode, r)
+        assert r["fused_finite"] and r["fused_maxabs"] < (TOL_FP32 if mode == "fp32" else TOL_16), (mode, r)
+
+
+# ------------------------------------------------------------------ ExpertDenoiser (SURVEY 8f item 3)
+def test_expert_denoiser_fp32_and_f16():
+    r = G.check_expert("fp32")
+    assert max(r["golden64_b2"], r["golden40x56"], r["golden40x56_base32"], r["oracle512"]) < TOL_FP32, r
+    r = G.check_expert("fp16")
+    # random-init outputs are small (|out| ~ 0.08): bound the f16 error relative to that, well inside the 1e-2 absolute contract
+    assert max(r["golden64_b2"], r["golden40x56"], r["golden40x56_base32"], r["oracle512"]) < 2e-3, r
 
 
 # ------------------------------------------------------------------ edge cases / boundary behaviour

@@ -82,7 +82,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"libxrd.so does not export {name}"
     assert declared == set(xrd_b200._lib.SYMBOLS), "ctypes table and header disagree"
-    assert xrd_b200.load_library().xrd_api_version() == 1
+    assert xrd_b200.load_library().xrd_api_version() == xrd_b200._lib.API_VERSION == 2
 
 
 def test_pure_host_entry_points_without_gpu():
@@ -111,6 +111,7 @@ def test_checkpoints_load_through_the_reference_import_paths(tmp_path):
     hyb = xrd_b200.HybridDenoisingRouter({"width": 32}, {"noise_steps": 50})
     torch.save({"model_state_dict": unet.state_dict(), "noise_steps": 50, "epoch": 1}, tmp_path / "ddimdiffusion.pth")
     torch.save({"model_state_dict": naf.state_dict(), "best_psnr": 30.0}, tmp_path / "NafNet.pth")
+    torch.save({"model_state_dict": xrd_b200.ExpertDenoiser(1, 64).state_dict(), "epoch": 3}, tmp_path / "DirectUNet.pth")
     torch.save({"model_state_dict": hyb.state_dict(), "nafnet_params": {"img_channel": 1, "width": 32, "middle_blk_num": 8,
                 "enc_blk_nums": [2, 2, 4, 6], "dec_blk_nums": [2, 2, 2, 2]},
                 "diffusion_params": {"in_channels": 1, "model_channels": 48, "channel_mult": (1, 2, 3, 4), "num_res_blocks": 2,
@@ -120,8 +121,13 @@ def test_checkpoints_load_through_the_reference_import_paths(tmp_path):
 import torch
 from DDIM.DDIMModel import UNetDiffusion, DiffusionDenoiser, device          # RUN:13
 from NafNet.NafnetModel import EnhancedNAFNet                                # RUN:14
+from DirectUNet.DirectUNetModel import ExpertDenoiser                        # RUN:15
 from hybrid.hybrid3diffusionspeed import HybridDenoisingRouter              # RUN:16
 d = r"{tmp_path}"
+ck = torch.load(d + "/DirectUNet.pth", map_location=device, weights_only=False)
+e = ExpertDenoiser(in_channels=1, base_channels=64).to(device)              # RUN:54
+e.load_state_dict(ck["model_state_dict"]); e.eval()
+assert len(e.state_dict()) == 84
 m = UNetDiffusion(in_channels=1, model_channels=48, channel_mult=(1, 2, 3, 4), num_res_blocks=2, attention_resolutions=(3,),
                   dropout=0.0, time_emb_dim=192).to(device)
 ck = torch.load(d + "/ddimdiffusion.pth", map_location=device, weights_only=False)
@@ -141,3 +147,32 @@ print("loaded", len(m.state_dict()), len(n.state_dict()), len(h.state_dict()))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "loaded" in r.stdout
+
+
+def test_model_that_never_ran_does_not_load_the_library():
+    """bench.py's CPU reference arm builds drop-in models only for their seeded state_dict; garbage-collecting them must not
+    dlopen libxrd.so (it would show up as native code loaded in an arm that runs none)."""
+    import subprocess
+    import sys
+    code = (
+        "import gc, xrd_b200\n"
+        "m = xrd_b200.HybridDenoisingRouter({}, {}); sd = m.state_dict(); del m; gc.collect()\n"
+        "e = xrd_b200.ExpertDenoiser(); del e; gc.collect()\n"
+        "assert not xrd_b200._lib.loaded()\n"
+        "assert 'libxrd' not in open('/proc/self/maps').read()\n"
+        "print('clean')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert r.returncode == 0 and "clean" in r.stdout, r.stderr[-2000:]
+
+
+def test_ddim_shim_defaults_follow_their_reference_files():
+    """DDIM/DDIMModel.py's sampler defaults to 25 steps (DDIM:269), the hybrid file's copy to 10 (HYB:401)."""
+    import inspect
+    import subprocess
+    import sys
+    assert inspect.signature(xrd_b200.DiffusionDenoiser.denoise).parameters["inference_steps"].default == 10
+    code = ("import inspect\nfrom DDIM.DDIMModel import DiffusionDenoiser\n"
+            "print(inspect.signature(DiffusionDenoiser.denoise).parameters['inference_steps'].default)\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "compat"), ROOT, os.environ.get("PYTHONPATH", "")]))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip() == "25", r.stderr[-2000:]

@@ -86,3 +86,31 @@ def test_fp64_oracle_agrees(golden, hyb):
     t = torch.full((2,), 49, dtype=torch.long)
     eps = O.unet_forward(hyb, g["x_in"][0].double(), g["noisy"].double(), t, prefix="diffusion_unet.")
     assert (eps.float() - g["eps"][0]).abs().max() < 5e-5
+
+
+# ------------------------------------------------------------------ ExpertDenoiser
+def test_expert_oracle_matches_reference(golden):
+    g = golden("expert_64_b2.npz")
+    _, sd = seeded_state_dict("expert")
+    for x, want in ((g["noisy"], g["out"]), (g["noisy_r"], g["out_r"])):
+        out = O.expert_forward(sd, x)
+        assert out.shape == want.shape
+        assert (out - want).abs().max() < TOL
+    _, sd32 = seeded_state_dict("expert32")
+    assert (O.expert_forward(sd32, g["noisy_r"]) - g["out_r_base32"]).abs().max() < TOL
+
+
+def test_expert_state_dict_keys_and_seeded_init_equal_the_reference():
+    import json
+    import os
+    import xrd_b200
+    from conftest import GOLDEN
+    meta = json.load(open(os.path.join(GOLDEN, "meta_expert.json")))
+    torch.manual_seed(1234)
+    m = xrd_b200.ExpertDenoiser(in_channels=1, base_channels=64)
+    sd = m.state_dict()
+    assert {k: list(v.shape) for k, v in sd.items()} == meta["expert_keys"]      # incl. running stats and num_batches_tracked
+    for k, (shape, s1, s2) in meta["expert_init_digest"].items():
+        d = sd[k].double()
+        assert list(sd[k].shape) == shape
+        assert abs(float(d.sum()) - s1) <= 1e-9 * max(1.0, abs(s1)) and abs(float((d * d).sum()) - s2) <= 1e-9 * max(1.0, abs(s2)), k
