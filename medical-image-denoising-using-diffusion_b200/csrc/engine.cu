@@ -422,6 +422,13 @@ void finalize(Handle& h, int which) {
 // ------------------------------------------------------------------------------------------------
 static const bool g_fuse_gn = !(getenv("XRD_FUSE_GN") && atoi(getenv("XRD_FUSE_GN")) == 0);
 static const bool g_fuse_gn_conv3 = getenv("XRD_FUSE_GN_CONV3") && atoi(getenv("XRD_FUSE_GN_CONV3")) != 0;
+// N-stacked row-ring kernel (conv3s.cu): narrowest map it takes over, and where GroupNorm+SiLU is applied inside it
+// (0 never, 1 one-chunk inputs only, 2 also two-chunk inputs, whose row ring is only three rows deep)
+static const int g_c3s_minw = getenv("XRD_C3S_MINW") ? atoi(getenv("XRD_C3S_MINW")) : 128;
+static const int g_c3s_gn = getenv("XRD_C3S_GN") ? atoi(getenv("XRD_C3S_GN")) : 2;
+static bool use_conv3s(const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e) {
+  return x1.w >= g_c3s_minw && conv3s_supported(x1, x2, w, e);
+}
 
 // A contraction.  e.stats_out (optional, [N][8][2], zeroed here) receives the GroupNorm sums of the output: from the
 // kernel's own epilogue where it has one, else from a statistics pass over the stored tensor.
@@ -434,6 +441,7 @@ static void conv_impl(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const Co
   // e.stats_out comes from stats16(): already zero
   // row-ring kernel: measured faster than the halo kernel from 256 columns up (1.06x activation fetch instead of 2x), slower
   // at 128 (too few 32-row work items per SM)
+  if (c.tc && use_conv3s(x1, x2, w, e)) { conv3s(c, x1, x2, w, e, y); return; }
   if (c.tc && x1.w >= 256 && conv3r_supported(x1, x2, w, e)) { conv3r(c, x1, w, e, y); return; }
   if (c.tc && conv3_supported(x1, x2, w, e)) { conv3(c, x1, x2, w, e, y); return; }
   if (c.tc && conv3w_supported(x1, x2, w, e)) { conv3w(c, x1, x2, w, e, y); return; }
@@ -519,14 +527,16 @@ static void resblock(Ctx& c, UNetW& u, ResW& r, const TS& x1, const TS* x2, cons
     // the row-ring kernel transforms every row once under a deep ring; in the 2-stage halo kernel the transform sits on
     // the load -> MMA critical path (measured: slower than the stand-alone pass), so conv3 only fuses on request
     // measured (tools/gn_fuse_time.py, batch 16): 48->48 @512^2 fused 430 us vs 295 + 172 us separate; at 256^2 it is a wash
-    const bool ring = a.w >= 512 && conv3r_supported(a, b, w, pe);
-    const bool halo = !ring && g_fuse_gn_conv3 && conv3_supported(a, b, w, pe) && !(b && (!w.wtc[a.dt] || w.tc_c1 != a.c));
-    if (!ring && !halo) return false;
+    const bool two_chunks = b != nullptr || a.c > 64;
+    const bool stack = g_c3s_gn >= (two_chunks ? 2 : 1) && use_conv3s(a, b, w, pe) && !(b && (!w.wtc[a.dt] || w.tc_c1 != a.c));
+    const bool ring = !stack && a.w >= 512 && conv3r_supported(a, b, w, pe);
+    const bool halo = !stack && !ring && g_fuse_gn_conv3 && conv3_supported(a, b, w, pe) && !(b && (!w.wtc[a.dt] || w.tc_c1 != a.c));
+    if (!stack && !ring && !halo) return false;
     const int ct = a.c + (b ? b->c : 0);
     float2* cf = (float2*)c.a->alloc((size_t)B * ct * sizeof(float2));
     gn_coef(c, sums, g, bt, 1e-5f, B, ct, u.groups, H * W, cf);
     pe.in_coef = cf;
-    if (ring) conv3r(c, a, w, pe, y); else conv3(c, a, b, w, pe, y);
+    if (stack) conv3s(c, a, b, w, pe, y); else if (ring) conv3r(c, a, w, pe, y); else conv3(c, a, b, w, pe, y);
     range_audit(c, y);
     return true;
   };

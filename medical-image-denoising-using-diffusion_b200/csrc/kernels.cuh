@@ -48,6 +48,10 @@ void conv3(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, T
 // row-ring 3x3/s1/p1 for Cin <= 64, Cout in {48,96}, W % 128 == 0 (conv3r.cu); honours ConvEpi::in_coef (GroupNorm+SiLU of the input)
 bool conv3r_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e);
 void conv3r(Ctx& c, const Tens& x, ConvW& w, const ConvEpi& e, Tens& y);
+// N-stacked row-ring 3x3/s1/p1 (conv3s.cu): the three vertical taps share one N=144 MMA per input row; Cout in {48,96} as slices of
+// 48, input = one tensor of <= 128 channels or a virtual concat of two <= 64-channel tensors; honours ConvEpi::in_coef
+bool conv3s_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e);
+void conv3s(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y);
 // 3x3/s1/p1 on maps exactly 64 pixels wide (conv3w.cu): three column-shifted copies, 4-row tiles, Cout in {144,192}
 bool conv3w_supported(const Tens& x1, const Tens* x2, const ConvW& w, const ConvEpi& e);
 void conv3w(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, Tens& y);

@@ -135,6 +135,16 @@ CONV_CASES_RING = [   # row-ring kernel (conv3r.cu): Cin <= 64, Cout in {48, 96}
     (1, 48, 8, 128, 48, 3, 1, 1), (2, 48, 40, 256, 48, 3, 1, 1), (1, 48, 33, 128, 96, 3, 1, 1), (1, 64, 70, 128, 48, 3, 1, 1),
     (1, 32, 5, 256, 96, 3, 1, 1), (3, 48, 64, 512, 48, 3, 1, 1), (1, 16, 3, 128, 48, 3, 1, 1), (2, 48, 200, 512, 48, 3, 1, 1),
 ]
+CONV_CASES_STACK = [   # N-stacked row-ring kernel (conv3s.cu): one chunk (16..64 channels), 64 + tail, Cout 48 / 96 (two slices);
+    # ragged segments (H % 32 != 0, H = 1, 2, 3), several items per CTA, accumulator-ring wrap (> 10 output rows per CTA)
+    (1, 48, 8, 128, 48, 3, 1, 1), (2, 48, 40, 256, 48, 3, 1, 1), (1, 48, 33, 128, 96, 3, 1, 1), (1, 64, 70, 128, 48, 3, 1, 1),
+    (1, 32, 5, 256, 96, 3, 1, 1), (3, 48, 64, 512, 48, 3, 1, 1), (1, 16, 3, 128, 48, 3, 1, 1), (2, 48, 200, 512, 48, 3, 1, 1),
+    (1, 96, 37, 128, 48, 3, 1, 1), (2, 96, 64, 256, 96, 3, 1, 1), (1, 96, 1, 128, 96, 3, 1, 1), (1, 48, 2, 128, 48, 3, 1, 1),
+    (1, 96, 130, 256, 48, 3, 1, 1), (16, 48, 64, 128, 48, 3, 1, 1),
+]
+CONV_CASES_STACK_CAT = [   # virtual concat of two 48-channel tensors (HYB:383), Cout 48 / 96
+    (1, 96, 7, 128, 48, 3, 1, 1), (1, 96, 40, 256, 96, 3, 1, 1), (2, 96, 33, 128, 48, 3, 1, 1), (1, 96, 70, 512, 48, 3, 1, 1),
+]
 CONV_CASES_W64 = [   # 3x3/s1/p1 on 64-wide maps (conv3w.cu)
     (2, 192, 8, 64, 192, 3, 1, 1), (1, 144, 12, 64, 144, 3, 1, 1), (1, 384, 4, 64, 192, 3, 1, 1), (3, 144, 16, 64, 192, 3, 1, 1),
     (1, 288, 8, 64, 144, 3, 1, 1), (1, 192, 64, 64, 192, 3, 1, 1),
@@ -584,6 +594,13 @@ CHECKS = {
     "conv3r_bf16": lambda: check_conv("bf16", 11, CONV_CASES_RING),
     "conv3r_gn_fp16": lambda: check_conv_fused_gn("fp16", 12, CONV_CASES_RING),
     "conv3r_stats_fp16": lambda: check_conv_stats("fp16", 11, CONV_CASES_RING),
+    "conv3s_fp16": lambda: check_conv("fp16", 15, CONV_CASES_STACK),
+    "conv3s_bf16": lambda: check_conv("bf16", 15, CONV_CASES_STACK),
+    "conv3s_cat_fp16": lambda: check_conv("fp16", 17, CONV_CASES_STACK_CAT),
+    "conv3s_stats_fp16": lambda: check_conv_stats("fp16", 15, CONV_CASES_STACK),
+    "conv3s_cat_stats_fp16": lambda: check_conv_stats("fp16", 17, CONV_CASES_STACK_CAT),
+    "conv3s_gn_fp16": lambda: check_conv_fused_gn("fp16", 16, CONV_CASES_STACK),
+    "conv3s_gn_cat_fp16": lambda: check_conv_fused_gn("fp16", 18, CONV_CASES_STACK_CAT),
     "conv3w_fp16": lambda: check_conv("fp16", 7, CONV_CASES_W64),
     "conv3w_bf16": lambda: check_conv("bf16", 7, CONV_CASES_W64),
     "conv3w_cat_fp16": lambda: check_conv("fp16", 8, CONV_CASES_W64_CAT),

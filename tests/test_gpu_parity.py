@@ -74,6 +74,26 @@ def test_conv_tcgen05_row_ring():
         assert e < 1.5e-3, (k, e)
 
 
+def test_conv_tcgen05_stacked_row_ring():
+    # N-stacked row-ring kernel (conv3s.cu): plain, two output slices, 64 + tail chunk, virtual concat, statistics, fused GroupNorm+SiLU
+    for k, e in G.check_conv("fp16", 15, G.CONV_CASES_STACK).items():
+        assert e < 6e-4, (k, e)
+    for k, e in G.check_conv("bf16", 15, G.CONV_CASES_STACK).items():
+        assert e < 5e-3, (k, e)
+    for k, e in G.check_conv("fp16", 17, G.CONV_CASES_STACK_CAT).items():
+        assert e < 6e-4, (k, e)
+    for k, e in G.check_conv_stats("fp16", 15, G.CONV_CASES_STACK).items():
+        assert e < 2e-3, (k, e)
+    for k, e in G.check_conv_stats("fp16", 17, G.CONV_CASES_STACK_CAT).items():
+        assert e < 2e-3, (k, e)
+    for k, e in G.check_conv_fused_gn("fp16", 16, G.CONV_CASES_STACK).items():
+        assert e < 1.5e-3, (k, e)
+    for k, e in G.check_conv_fused_gn("fp16", 18, G.CONV_CASES_STACK_CAT).items():
+        assert e < 1.5e-3, (k, e)
+    for k, e in G.check_conv_fused_gn("bf16", 16, G.CONV_CASES_STACK).items():
+        assert e < 1e-2, (k, e)
+
+
 def test_conv_tcgen05_64_wide():
     # 3x3 on 64-pixel-wide maps (conv3w.cu, the UNet's lowest level): plain, concat and statistics variants
     for k, e in G.check_conv("fp16", 7, G.CONV_CASES_W64).items():
