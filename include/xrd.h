@@ -134,6 +134,14 @@ int xrd_set_param(xrd_handle* h, const char* key, const void* data, const int64_
 #define XRD_PART_EXPERT 16   /* ExpertDenoiser (the 4th /denoise output, RUN:52-57,127) */
 int xrd_finalize_weights(xrd_handle* h, int which);
 
+/* Weight blob (checkpoint ingest of RUN:37-73).  xrd_export_weights serialises every tensor the handle received
+ * through xrd_set_param (key, shape, float32 data) into one relocatable host buffer: call with buf = NULL to get *need, then
+ * with a buffer of that size.  xrd_import_weights replaces the per-key xrd_set_param loop (912 calls and copies for the hybrid)
+ * by ONE allocation and ONE host-to-device copy; xrd_finalize_weights must follow.  The format carries no code (unlike the
+ * reference's torch.load(weights_only=False) pickles) and is validated field by field. */
+int xrd_export_weights(xrd_handle* h, void* buf, uint64_t cap, uint64_t* need);
+int xrd_import_weights(xrd_handle* h, const void* blob, uint64_t bytes);
+
 int xrd_set_mode(xrd_handle* h, int mode);
 int xrd_get_mode(xrd_handle* h);
 /* 0 = plain stream launches, 1 (default) = the sampler loop is captured into one CUDA graph

@@ -67,6 +67,8 @@ SYMBOLS = {
     "xrd_destroy": (None, [_P]),
     "xrd_set_param": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int, C.c_int]),
     "xrd_finalize_weights": (C.c_int, [_P, C.c_int]),
+    "xrd_export_weights": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "xrd_import_weights": (C.c_int, [_P, _P, C.c_uint64]),
     "xrd_set_mode": (C.c_int, [_P, C.c_int]),
     "xrd_get_mode": (C.c_int, [_P]),
     "xrd_set_use_graph": (C.c_int, [_P, C.c_int]),

@@ -207,7 +207,8 @@ XRD_EXPORT void xrd_destroy(xrd_handle* H) {
   cudaDeviceSynchronize();
   free_op_state(H);
   H->h.free_owned();
-  for (auto& kv : H->h.params) cudaFree(kv.second.d);
+  for (auto& kv : H->h.params) if (!kv.second.in_slab) cudaFree(kv.second.d);
+  if (H->h.slab) cudaFree(H->h.slab);
   if (H->h.arena.base) cudaFree(H->h.arena.base);
   if (H->scratch) cudaFree(H->scratch);
   if (H->h.audit_dev) cudaFree(H->h.audit_dev);
@@ -233,11 +234,115 @@ XRD_EXPORT int xrd_set_param(xrd_handle* H, const char* key, const void* data, c
     Param& p = H->h.params[key];
     if (p.n != n || !p.d) {
       // weights referenced by packed plans may be replaced: invalidate plans first
-      if (p.d) { XRD_CUDA(cudaDeviceSynchronize()); cudaFree(p.d); p.d = nullptr; }
+      if (p.d && !p.in_slab) { XRD_CUDA(cudaDeviceSynchronize()); cudaFree(p.d); }
+      p.d = nullptr; p.in_slab = false;
       XRD_CUDA(cudaMalloc((void**)&p.d, std::max<size_t>(n * 4, 16)));
     }
     p.n = n; p.shape = shp;
     XRD_CUDA(cudaMemcpy(p.d, data, n * 4, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  });
+}
+
+// ---- weight blob: every state_dict tensor of a handle in one relocatable buffer ---------------------------
+// layout: "XRDW0001" | u64 count | u64 payload_offset | u64 payload_floats | entries | pad | payload (float32)
+//         entry = u32 key_len | key | u32 ndim | i64 dims[ndim] | u64 offset_in_floats      (tensors start at multiples of 64 floats)
+namespace {
+struct BlobWriter {
+  char* p; uint64_t cap, off = 0;
+  void put(const void* src, size_t n) { if (p && off + n <= cap) memcpy(p + off, src, n); off += n; }
+  template <typename V> void val(V v) { put(&v, sizeof(V)); }
+};
+struct BlobReader {
+  const char* p; uint64_t n, off = 0;
+  void get(void* dst, size_t k) { XRD_REQUIRE(off + k <= n, "weight blob truncated"); memcpy(dst, p + off, k); off += k; }
+  template <typename V> V val() { V v; get(&v, sizeof(V)); return v; }
+};
+}  // namespace
+
+XRD_EXPORT int xrd_export_weights(xrd_handle* H, void* buf, uint64_t cap, uint64_t* need) {
+  return guarded([&] {
+    XRD_REQUIRE(H && need, "null argument");
+    std::lock_guard<std::mutex> lk(H->h.mu);
+    DeviceScope dscope(H->h.device);
+    std::vector<std::string> keys;
+    for (auto& kv : H->h.params) keys.push_back(kv.first);
+    std::sort(keys.begin(), keys.end());
+    uint64_t hdr = 8 + 3 * 8, floats = 0;
+    for (auto& k : keys) {
+      const Param& p = H->h.params[k];
+      hdr += 4 + k.size() + 4 + 8 * p.shape.size() + 8;
+      floats += (p.n + 63) & ~(uint64_t)63;
+    }
+    const uint64_t pay = (hdr + 255) & ~(uint64_t)255;
+    *need = pay + floats * 4;
+    if (!buf || cap < *need) return;                       // size query
+    if (H->have_last_stream) XRD_CUDA(cudaStreamSynchronize(H->last_stream));
+    BlobWriter w{(char*)buf, cap};
+    w.put("XRDW0001", 8);
+    w.val<uint64_t>(keys.size()); w.val<uint64_t>(pay); w.val<uint64_t>(floats);
+    uint64_t o = 0;
+    for (auto& k : keys) {
+      const Param& p = H->h.params[k];
+      w.val<uint32_t>((uint32_t)k.size()); w.put(k.data(), k.size());
+      w.val<uint32_t>((uint32_t)p.shape.size());
+      for (auto d : p.shape) w.val<int64_t>(d);
+      w.val<uint64_t>(o);
+      o += (p.n + 63) & ~(uint64_t)63;
+    }
+    memset((char*)buf + w.off, 0, pay - w.off);
+    o = 0;
+    for (auto& k : keys) {
+      const Param& p = H->h.params[k];
+      const uint64_t span = (p.n + 63) & ~(uint64_t)63;
+      float* dst = (float*)((char*)buf + pay) + o;
+      XRD_CUDA(cudaMemcpy(dst, p.d, p.n * 4, cudaMemcpyDeviceToHost));
+      for (uint64_t i = p.n; i < span; ++i) dst[i] = 0.f;
+      o += span;
+    }
+  });
+}
+
+XRD_EXPORT int xrd_import_weights(xrd_handle* H, const void* blob, uint64_t bytes) {
+  return guarded([&] {
+    XRD_REQUIRE(H && blob, "null argument");
+    std::lock_guard<std::mutex> lk(H->h.mu);
+    DeviceScope dscope(H->h.device);
+    BlobReader r{(const char*)blob, bytes};
+    char magic[8];
+    r.get(magic, 8);
+    XRD_REQUIRE(memcmp(magic, "XRDW0001", 8) == 0, "not a libxrd weight blob");
+    const uint64_t count = r.val<uint64_t>(), pay = r.val<uint64_t>(), floats = r.val<uint64_t>();
+    XRD_REQUIRE(pay <= bytes && floats <= (bytes - pay) / 4 && count < (1u << 20), "weight blob header out of range");
+    struct Ent { std::string key; std::vector<int64_t> shape; uint64_t off, n; };
+    std::vector<Ent> ents(count);
+    for (auto& e : ents) {
+      const uint32_t kl = r.val<uint32_t>();
+      XRD_REQUIRE(kl < 4096, "weight blob: key too long");
+      e.key.resize(kl);
+      r.get(&e.key[0], kl);
+      const uint32_t nd = r.val<uint32_t>();
+      XRD_REQUIRE(nd <= 8, "weight blob: too many dimensions");
+      e.n = 1;
+      for (uint32_t i = 0; i < nd; ++i) { const int64_t d = r.val<int64_t>(); XRD_REQUIRE(d >= 0, "weight blob: negative dimension"); e.shape.push_back(d); e.n *= (uint64_t)d; }
+      e.off = r.val<uint64_t>();
+      XRD_REQUIRE(e.off <= floats && e.n <= floats - e.off, "weight blob: tensor '%s' outside the payload", e.key.c_str());
+    }
+    // quiesce and invalidate exactly as xrd_set_param does, then swap the whole parameter set
+    XRD_CUDA(cudaDeviceSynchronize());
+    H->h.unet.ready = H->h.naf.ready = H->h.router.ready = H->h.fusion.ready = H->h.expert.ready = false;
+    H->h.drop_graphs();
+    float* slab = nullptr;
+    XRD_CUDA(cudaMalloc((void**)&slab, std::max<uint64_t>(floats * 4, 16)));
+    cudaError_t ce = cudaMemcpy(slab, (const char*)blob + pay, floats * 4, cudaMemcpyHostToDevice);     // ONE copy for all tensors
+    if (ce != cudaSuccess) { cudaFree(slab); fail(XRD_ERR_CUDA, "weight blob upload failed: %s", cudaGetErrorString(ce)); }
+    for (auto& kv : H->h.params) if (!kv.second.in_slab && kv.second.d) cudaFree(kv.second.d);
+    H->h.params.clear();
+    if (H->h.slab) cudaFree(H->h.slab);
+    H->h.slab = slab;
+    for (auto& e : ents) {
+      Param& p = H->h.params[e.key];
+      p.shape = e.shape; p.n = e.n; p.d = slab + e.off; p.in_slab = true;
+    }
   });
 }
 

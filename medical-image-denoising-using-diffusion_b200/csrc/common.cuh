@@ -167,7 +167,20 @@ __device__ __forceinline__ float clamp_nan(float v, float lo, float hi) {
 }
 // A NaN is preserved (as the reference propagates it to the final nan_to_num, HYB:615-620); +-inf saturates like any overflow.
 __device__ __forceinline__ float sat_h(float v) { return clamp_nan(v, -65504.f, 65504.f); }
-template <> __device__ __forceinline__ void stf<__half>(__half* p, float v) { *p = __float2half_rn(sat_h(v)); }
+// The saturating f16 conversions as ONE instruction each (F2FP.SATFINITE): round to nearest, |v| > 65504 (inf included) -> +-65504,
+// NaN -> NaN.  (The first version clamped with two FMNMX per element before the conversion: a quarter of the instructions of the
+// tensor-core kernels' epilogues, which ncu showed to be as loaded as the MMA issue thread.)
+__device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ __half f2h_sat(float v) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  return __ushort_as_half(r);
+}
+template <> __device__ __forceinline__ void stf<__half>(__half* p, float v) { *p = f2h_sat(v); }
 
 // 4 consecutive elements (pointer must be aligned to 4 elements)
 template <typename T> __device__ __forceinline__ void ld4(const T* p, float (&v)[4]);
@@ -199,10 +212,9 @@ template <> __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p,
   *reinterpret_cast<uint2*>(p) = t;
 }
 template <> __device__ __forceinline__ void st4<__half>(__half* p, const float (&v)[4]) {
-  __half2 a = __floats2half2_rn(sat_h(v[0]), sat_h(v[1])), b = __floats2half2_rn(sat_h(v[2]), sat_h(v[3]));
   uint2 t;
-  t.x = *reinterpret_cast<uint32_t*>(&a);
-  t.y = *reinterpret_cast<uint32_t*>(&b);
+  t.x = pack_h2_sat(v[0], v[1]);
+  t.y = pack_h2_sat(v[2], v[3]);
   *reinterpret_cast<uint2*>(p) = t;
 }
 

@@ -33,7 +33,7 @@ namespace xrd {
 
 struct Conv3SP {
   int H, W, nimg;
-  int ncb, nseg, seg, nitems;   // column blocks per row, row segments per image, rows per segment, work items (per slice)
+  int ncb, nseg, nbig, nitems;  // column blocks per row, row segments per image (the first nbig of kSegBig rows, the rest of kSegSmall), work items per slice
   int cout_total;               // 48 * slices
   int c0, c1;                   // channels of chunk 0 / chunk 1 (0: single chunk)
   int two_src;                  // chunk 1 is the second tensor (tmA1, channel 0) instead of channels 64.. of the first
@@ -45,10 +45,12 @@ struct Conv3SP {
   const float2* in_coef;        // GN variant: [nimg][c0 + c1] (0.5*scale, 0.5*shift)
 };
 
-constexpr int kSThreads = 320, kSThreadsGN = 448;
+constexpr int kSThreads = 352, kSThreadsGN = 480;   // warp 0 TMA, 1 + 10 MMA issuers (ping-pong), 2..9 epilogue, 11..14 input transform (GN)
+constexpr int kSWarpB = 10;                         // the second MMA-issuing warp
 constexpr int kSBox = 130;                   // pixels fetched per row (128 + halo column each side)
 constexpr uint32_t kSSlot = 136 * 128;       // one chunk of one row: 17 KB keeps every row 1024-byte aligned
 constexpr int kSNB = 10;                     // accumulator blocks (48 columns each) in the TMEM ring
+constexpr int kSegBig = 40, kSegSmall = 10;  // output rows per work item: multiples of kSNB, so every item starts at ring block 0
 constexpr uint32_t kSBlk = 48 * 128;         // one weight block: 48 output channels x 64 input channels, 16 bit
 constexpr uint32_t kSBlk16 = kSBlk >> 4;
 
@@ -61,63 +63,135 @@ __device__ __forceinline__ void s3_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) 
       : "memory");
 }
 
-// All MMAs of one landed input row.  a_base: descriptor of the row's chunk-0 slot; b_base: descriptor of the resident weights
-// ([chunk][dx][block][48][64]); t0: TMEM ring block of the row's first output, n: number of outputs (1..3), fb: first weight block
-// of the stack (0: dy=+1 ... 2: dy=-1), fresh: the LAST output block is touched for the first time (overwrite, do not accumulate).
-template <int KS0, int KS1>
-__device__ __forceinline__ void c3s_issue_row(uint64_t a_base, uint64_t b_base, uint32_t t0, int n, int fb, bool fresh, uint32_t id48) {
-  // instruction descriptors for N = 48 / 96 / 144 differ only in the N field (bits 17..22, N >> 3): selected arithmetically so
-  // that nothing is indexed in local memory from the issue stream
-  auto idn = [&](int nn) { return id48 + ((uint32_t)(nn - 1) * (48u >> 3) << 17); };
-  // first k-step, block by block (each with its own accumulate flag)
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    if (i < n) {
-      uint32_t tb = t0 + (uint32_t)i;
-      if (tb >= (uint32_t)kSNB) tb -= (uint32_t)kSNB;
-      tc::umma_f16(tb * 48u, a_base, b_base + (uint64_t)((fb + i) * kSBlk16), id48, (fresh && i == n - 1) ? 0u : 1u);
-    }
+// All MMAs of one landed input row of a SEG-row work item.  J (the row's index inside the item, 0 .. SEG+1) and SEG are literal
+// at every call site, so after inlining every quantity below is a compile-time constant: which outputs the row feeds
+// (J-2 .. J clipped to the item), which weight blocks of the stack those are, which ring blocks of TMEM (items always start at
+// block 0: SEG is a multiple of the ring length), where a run of blocks wraps around the ring end and has to be split into two
+// MMAs, and which block is touched for the first time.  The issue thread executes nothing but descriptor additions and MMAs.
+// (ncu source view of the first, runtime-parameterised version: ~250 scalar instructions per row in the single issuing
+// thread, 1335 cycles per row against 700 cycles of MMA work -- the issue thread, not the tensor pipe or HBM, was the bound.)
+// `baton` (nullable): arrived on just before the last horizontal tap of the row is issued -- the other issuing warp may then start
+// its burst; its MMAs interleave with the last few of this row, which is harmless: every block this row touches has had its
+// first (overwriting) MMA long before, and accumulation order does not matter.
+template <int KS0, int KS1, int J, int SEG>
+__device__ __forceinline__ void c3s_issue_row(uint64_t a_base, uint64_t b_base, uint32_t id48, uint64_t* baton) {
+  constexpr int LO = J - 2 < 0 ? 0 : J - 2, HI = J > SEG - 1 ? SEG - 1 : J, N = HI - LO + 1;
+  constexpr int FB = 2 - (J - LO);             // first weight block of the stack: 0 = dy +1 ... 2 = dy -1
+  constexpr bool FRESH = J <= SEG - 1;         // output J exists: its block is overwritten by this row's first MMA
+  constexpr int T0 = LO % kSNB;
+  auto idn = [&](int nn) { return id48 + ((uint32_t)((nn - 1) * 6) << 17); };      // N field = N >> 3 at bit 17
+  // first k-step: the accumulating blocks (one or two pieces), then the fresh block on its own
+  {
+    constexpr int NA = FRESH ? N - 1 : N;
+    constexpr int A1 = NA < kSNB - T0 ? NA : kSNB - T0;
+    if (A1 > 0) tc::umma_f16((uint32_t)(T0 * 48), a_base, b_base + (uint64_t)(FB * kSBlk16), idn(A1), 1u);
+    if (NA - A1 > 0) tc::umma_f16(0u, a_base, b_base + (uint64_t)((FB + A1) * kSBlk16), idn(NA - A1), 1u);
+    if (FRESH) tc::umma_f16((uint32_t)(((T0 + N - 1) % kSNB) * 48), a_base, b_base + (uint64_t)((FB + N - 1) * kSBlk16), id48, 0u);
   }
-  // the other k-steps: one N = 48*n MMA, or two when the block run wraps around the ring end
-  const int n1 = min(n, kSNB - (int)t0);
-  const uint32_t d1 = t0 * 48u;
-  const uint64_t b1 = b_base + (uint64_t)(fb * kSBlk16);
-  if (n1 == n) {
-    const uint32_t id = idn(n);
+  constexpr int P1 = N < kSNB - T0 ? N : kSNB - T0;
 #pragma unroll
-    for (int c = 0; c < (KS1 ? 2 : 1); ++c) {
+  for (int c = 0; c < (KS1 ? 2 : 1); ++c) {
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
+    for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-        for (int k = 0; k < (c ? KS1 : KS0); ++k) {
-          if (c == 0 && dx == 0 && k == 0) continue;
-          tc::umma_f16(d1, a_base + (uint64_t)(c * (kSSlot >> 4) + dx * 8 + k * 2), b1 + (uint64_t)((c * 9 + dx * 3) * kSBlk16 + k * 2), id, 1u);
-        }
-      }
-    }
-  } else {
-    const uint32_t id1 = idn(n1), id2 = idn(n - n1);
-    const uint64_t b2 = b1 + (uint64_t)(n1 * kSBlk16);
-#pragma unroll
-    for (int c = 0; c < (KS1 ? 2 : 1); ++c) {
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-#pragma unroll
-        for (int k = 0; k < (c ? KS1 : KS0); ++k) {
-          if (c == 0 && dx == 0 && k == 0) continue;
-          const uint64_t ao = a_base + (uint64_t)(c * (kSSlot >> 4) + dx * 8 + k * 2);
-          const uint64_t bo = (uint64_t)((c * 9 + dx * 3) * kSBlk16 + k * 2);
-          tc::umma_f16(d1, ao, b1 + bo, id1, 1u);
-          tc::umma_f16(0u, ao, b2 + bo, id2, 1u);
-        }
+      for (int k = 0; k < (c ? KS1 : KS0); ++k) {
+        if (c == 0 && dx == 0 && k == 0) continue;
+        if (c == (KS1 ? 1 : 0) && dx == 2 && k == 0 && baton) { tc::tc_fence_before(); tc::mbar_arrive(baton); }
+        const uint64_t ao = a_base + (uint64_t)(c * (kSSlot >> 4) + dx * 8 + k * 2);
+        const uint64_t bo = b_base + (uint64_t)((c * 9 + dx * 3 + FB) * kSBlk16 + k * 2);
+        tc::umma_f16((uint32_t)(T0 * 48), ao, bo, idn(P1), 1u);
+        if (N - P1 > 0) tc::umma_f16(0u, ao, bo + (uint64_t)(P1 * kSBlk16), idn(N - P1), 1u);
       }
     }
   }
 }
 
-// KS0 / KS1: 16-channel k-steps of chunk 0 / chunk 1 (KS1 = 0: one chunk); R: ring rows; G: input rows per issue iteration;
-// NSL: output slices of 48 (1 or 2); GN: GroupNorm + SiLU applied to the landed rows
-template <typename T, int KS0, int KS1, int R, int G, int NSL, bool GN>
+// MMA-warp state that survives from row to row: everything else about a row is a compile-time constant
+struct C3SState {
+  uint32_t sl;     // ring slot of the next input row
+  uint32_t rph;    // bit s: phase of r_full / r_ready[s] the next use of slot s waits for
+  uint32_t accb;   // how many times every accumulator block was used before this item (only the parity matters)
+  uint32_t k;      // running iteration number: iteration k belongs to issuing warp k & 1
+};
+struct C3SBars { uint64_t *rbar, *r_empty, *acc_full, *acc_empty, *baton; };
+
+// One issue iteration = the two landed input rows J, J+1 (pattern indices; see c3s_issue_row) of a work item; `dec` = use index
+// of the accumulator blocks of outputs J, J+1 within the item (the decade of the output row).
+// Two warps issue alternately (`my` = 0 / 1): while one is blocked feeding its burst into the (shallow) MMA queue, the other runs
+// the barrier waits and the address arithmetic of the next iteration, so the tensor pipe does not idle through them (ncu of
+// the single-issuer version: ~1800 cycles of burst and ~2000 cycles of waits / warp synchronisation / set-up per iteration).
+// Both warps walk every iteration and keep the same state; only the owner waits, issues and commits.
+template <int KS0, int KS1, int R, int J, int SEG>
+__device__ __forceinline__ void c3s_iteration(C3SState& st, const C3SBars& b, uint32_t dec, uint64_t adesc0, uint64_t bdesc0, uint32_t id48,
+                                              uint32_t row16, int lane, uint32_t my) {
+  const uint32_t s0 = st.sl, s1 = (st.sl + 1 == (uint32_t)R) ? 0u : st.sl + 1;
+  if ((st.k & 1u) == my) {
+    // lanes 0 / 1: the two input rows have landed (and are transformed); lanes 8 / 9: the accumulator blocks the rows touch for the
+    // first time (outputs J, J+1, when they exist) have been drained by the epilogue; lane 2: the other warp has issued its burst
+    // A parity wait can only tell "the current phase" from "the one before": with a ring of fewer than four rows this iteration
+    // shares a slot with the previous one (the other warp's), and probing that slot's barrier before the other warp's wait has
+    // been satisfied would succeed on the WRONG phase.  There the baton (passed after the other warp's waits) is taken first.
+    if (R < 4) {
+      if (lane == 2 && st.k > 0u) tc::mbar_wait(&b.baton[my], ((st.k >> 1) & 1u) ^ (my ? 0u : 1u));
+      __syncwarp();
+    }
+    if (lane < 2) {
+      const uint32_t sx = lane ? s1 : s0;
+      tc::mbar_wait(&b.rbar[sx], (st.rph >> sx) & 1u);
+    } else if (lane >= 8 && lane < 10 && J + (lane - 8) < SEG) {
+      const int o = J + (lane - 8);
+      tc::mbar_wait(&b.acc_empty[o % kSNB], ((st.accb + dec) & 1u) ^ 1u);
+    } else if (R >= 4 && lane == 2 && st.k > 0u) {
+      tc::mbar_wait(&b.baton[my], ((st.k >> 1) & 1u) ^ (my ? 0u : 1u));
+    }
+    __syncwarp();
+    tc::tc_fence_after();
+    if (tc::elect_one()) {
+      // opaque copy of the weight descriptor: without it the compiler hoists every `bdesc0 + constant` of the unrolled bursts out
+      // of the item loop into VECTOR registers and moves them back (R2UR) in front of each MMA
+      uint64_t bd = bdesc0;
+      asm volatile("" : "+l"(bd));
+      const uint64_t a0 = adesc0 + (uint64_t)(s0 * row16), a1 = adesc0 + (uint64_t)(s1 * row16);
+      c3s_issue_row<KS0, KS1, J, SEG>(a0, bd, id48, nullptr);
+      if (J < SEG) tc::umma_commit(&b.acc_full[J % kSNB]);               // output J: its first row is in (arrival 1 of 2)
+      if (J >= 2) tc::umma_commit(&b.acc_full[(J - 2) % kSNB]);          // output J-2: its last row is in (arrival 2 of 2)
+      tc::umma_commit(&b.r_empty[s0]);                                   // the input row is not needed again
+      c3s_issue_row<KS0, KS1, J + 1, SEG>(a1, bd, id48, &b.baton[my ^ 1u]);
+      if (J + 1 < SEG) tc::umma_commit(&b.acc_full[(J + 1) % kSNB]);
+      if (J >= 1) tc::umma_commit(&b.acc_full[(J - 1) % kSNB]);
+      tc::umma_commit(&b.r_empty[s1]);
+    }
+    __syncwarp();
+  }
+  st.rph ^= (1u << s0) | (1u << s1);
+  st.sl = (s1 + 1 == (uint32_t)R) ? 0u : s1 + 1;
+  st.k += 1u;
+}
+
+// A work item of `seg` output rows (kSegBig or kSegSmall): rows 0, 1 (top edge), the interior rows decade by decade (the five
+// iterations of a decade have the same patterns in every decade), rows seg, seg+1 (bottom edge: they feed the outputs seg-2,
+// seg-1 = ring blocks 8, 9 only, whatever the length of the item -- the pattern of rows 10, 11 of a 10-row item).
+template <int KS0, int KS1, int R>
+__device__ __forceinline__ void c3s_run_item(C3SState& st, const C3SBars& b, int seg, uint64_t adesc0, uint64_t bdesc0, uint32_t id48,
+                                             uint32_t row16, int lane, uint32_t my) {
+  constexpr int INT = 1000;      // "long enough": rows 2 .. 11 of such an item are interior rows
+  c3s_iteration<KS0, KS1, R, 0, INT>(st, b, 0u, adesc0, bdesc0, id48, row16, lane, my);
+  for (int m = 0; m * kSNB + 2 < seg; ++m) {
+    const uint32_t um = (uint32_t)m;
+    c3s_iteration<KS0, KS1, R, 2, INT>(st, b, um, adesc0, bdesc0, id48, row16, lane, my);
+    c3s_iteration<KS0, KS1, R, 4, INT>(st, b, um, adesc0, bdesc0, id48, row16, lane, my);
+    c3s_iteration<KS0, KS1, R, 6, INT>(st, b, um, adesc0, bdesc0, id48, row16, lane, my);
+    c3s_iteration<KS0, KS1, R, 8, INT>(st, b, um, adesc0, bdesc0, id48, row16, lane, my);
+    if (m * kSNB + 10 < seg) c3s_iteration<KS0, KS1, R, 10, INT>(st, b, um + 1u, adesc0, bdesc0, id48, row16, lane, my);
+  }
+  c3s_iteration<KS0, KS1, R, kSNB, kSNB>(st, b, 0u, adesc0, bdesc0, id48, row16, lane, my);
+  st.accb += (uint32_t)(seg / kSNB);
+}
+
+// KS0 / KS1: 16-channel k-steps of chunk 0 / chunk 1 (KS1 = 0: one chunk); R: ring rows; NSL: output slices of 48 (1 or 2);
+// GN: GroupNorm + SiLU applied to the landed rows.  Work items are segments of kSegBig or kSegSmall output rows (both multiples
+// of the accumulator ring, with an even number of input rows): the MMA warp walks them two input rows per iteration.
+template <typename T, int KS0, int KS1, int R, int NSL, bool GN>
 __global__ void __launch_bounds__(GN ? kSThreadsGN : kSThreads, 1)
 k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB,
          const Conv3SP p) {
@@ -126,7 +200,7 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
   constexpr int CPG = (48 * NSL) / 8;                       // channels per GroupNorm group of the WHOLE output (8 groups)
   constexpr int GPS = 8 / NSL;                              // groups per slice
   constexpr uint32_t ROW_BYTES = NCH * kSSlot;
-  static_assert(G >= 1 && G <= 4 && G < R, "rows per iteration must leave the producer a free slot");
+  static_assert(R >= 3, "two rows per iteration must leave the producer a free slot");
   static_assert(NSL == 1 || NSL == 2, "48 or 96 output channels");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -141,7 +215,8 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
   uint64_t* acc_full = bars + 3 * R;       // [NB]
   uint64_t* acc_empty = acc_full + kSNB;   // [NB]
   uint64_t* w_full = acc_empty + kSNB;
-  uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
+  uint64_t* baton = w_full + 1;            // [2]  baton[w]: the other issuing warp has issued (almost all of) its burst, warp w may issue
+  uint32_t* tmem_slot = (uint32_t*)(baton + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = NSL == 1 ? 0 : (int)(blockIdx.x % NSL);
@@ -152,7 +227,9 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
     tc::tma_prefetch_desc(&tmA1);
     tc::tma_prefetch_desc(&tmB);
     for (int s = 0; s < R; ++s) { tc::mbar_init(&r_full[s], 1); tc::mbar_init(&r_ready[s], 128); tc::mbar_init(&r_empty[s], 1); }
-    for (int s = 0; s < kSNB; ++s) { tc::mbar_init(&acc_full[s], 1); tc::mbar_init(&acc_empty[s], 128); }
+    // acc_full: two arrivals per use -- a commit of the warp that issued the output's first row and one of the warp that issued its last
+    for (int s = 0; s < kSNB; ++s) { tc::mbar_init(&acc_full[s], 2); tc::mbar_init(&acc_empty[s], 128); }
+    tc::mbar_init(&baton[0], 1); tc::mbar_init(&baton[1], 1);
     tc::mbar_init(w_full, 1);
     tc::fence_barrier_init();
   }
@@ -168,12 +245,15 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
     __trap();
   }
 
-  // item q -> (image, column block, row segment)
+  // item q -> (image, column block, first row, rows of the segment).  Every item spans a FULL segment (kSegBig or kSegSmall
+  // rows) even when the image ends inside it: the rows past the end are zero-filled by TMA, multiplied like any other row and
+  // dropped by the epilogue, so that ring slots, accumulator blocks and barrier phases stay in step with the compile-time
+  // pattern of the MMA warp (at most 9 of them per image column).
   auto item = [&](int q, int& img, int& cb, int& r0, int& rows) {
     const int sg = q % p.nseg; q /= p.nseg;
     cb = q % p.ncb; img = q / p.ncb;
-    r0 = sg * p.seg;
-    rows = min(p.seg, p.H - r0);
+    if (sg < p.nbig) { r0 = sg * kSegBig; rows = kSegBig; }
+    else { r0 = p.nbig * kSegBig + (sg - p.nbig) * kSegSmall; rows = kSegSmall; }
   };
 
   if (warp == 0) {
@@ -203,74 +283,25 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == kSWarpB) {
+    // ===================== MMA issuers (two warps, alternating iterations) =====================
+    const uint32_t my = warp == 1 ? 0u : 1u;
     tc::mbar_wait(w_full, 0);
     const uint32_t id48 = tc::umma_idesc(128, 48, tc::umma_fmt<T>());
-    const uint32_t sA_addr = tc::smem_u32(sA);
+    const uint64_t adesc0 = tc::umma_desc_sw128(tc::smem_u32(sA));
     const uint64_t bdesc0 = tc::umma_desc_sw128(tc::smem_u32(sB));
-    uint32_t islot = 0, iphase = 0;        // ring position of the first input row of the current item
-    uint32_t q0 = 0;                       // running output-row counter at the start of the item (accumulator ring)
-    uint64_t* const rbar = GN ? r_ready : r_full;
+    C3SState st{0u, 0u, 0u, 0u};
+    const C3SBars bs{GN ? r_ready : r_full, r_empty, acc_full, acc_empty, baton};
     for (int q = wi; q < p.nitems; q += nw) {
       int img, cb, r0, rows;
       item(q, img, cb, r0, rows);
-      const int nin = rows + 2;
-      auto slot_of = [&](int i) { const uint32_t t = islot + (uint32_t)i; return t % R; };
-      auto phase_of = [&](int i) { const uint32_t t = islot + (uint32_t)i; return (iphase ^ ((t / R) & 1u)); };
-      bool probed = false;                 // this lane's barrier of the coming iteration was already seen complete (early probe)
-      for (int j = 0; j < nin; j += G) {
-        const int ng = min(G, nin - j);
-        // lanes 0..ng-1: input row j+lane landed (and transformed); lanes 8..8+ng-1: the accumulator block that row j+lane-8
-        // touches for the first time (output row j+lane-8, if it exists) has been drained by the epilogue
-        if (lane < ng) {
-          tc::mbar_wait_probed(probed, &rbar[slot_of(j + lane)], phase_of(j + lane));
-        } else if (lane >= 8 && lane < 8 + ng && j + lane - 8 < rows) {
-          const uint32_t oo = q0 + (uint32_t)(j + lane - 8);
-          tc::mbar_wait_probed(probed, &acc_empty[oo % kSNB], ((oo / kSNB) & 1) ^ 1);
-        }
-        __syncwarp();
-        tc::tc_fence_after();
-        // probe the barriers of the NEXT iteration now: the probes' round trips run under the MMAs issued below
-        probed = false;
-        {
-          const int j2 = j + G;
-          if (j2 < nin) {
-            const int ng2 = min(G, nin - j2);
-            if (lane < ng2) {
-              probed = tc::mbar_test(&rbar[slot_of(j2 + lane)], phase_of(j2 + lane));
-            } else if (lane >= 8 && lane < 8 + ng2 && j2 + lane - 8 < rows) {
-              const uint32_t oo = q0 + (uint32_t)(j2 + lane - 8);
-              probed = tc::mbar_test(&acc_empty[oo % kSNB], ((oo / kSNB) & 1) ^ 1);
-            }
-          }
-        }
-        if (tc::elect_one()) {
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            if (g < ng) {
-              const int jj = j + g;
-              const int lo = max(0, jj - 2), hi = min(rows - 1, jj);
-              const uint32_t sl = slot_of(jj);
-              const uint64_t a_base = tc::umma_desc_sw128(sA_addr + sl * ROW_BYTES);
-              c3s_issue_row<KS0, KS1>(a_base, bdesc0, (q0 + (uint32_t)lo) % kSNB, hi - lo + 1, 2 - (jj - lo), jj <= rows - 1, id48);
-              if (jj >= 2) tc::umma_commit(&acc_full[(q0 + (uint32_t)(jj - 2)) % kSNB]);    // output row jj-2 is complete
-              tc::umma_commit(&r_empty[sl]);                                               // the input row is not needed again
-            }
-          }
-        }
-        __syncwarp();
-      }
-      const uint32_t t = islot + (uint32_t)nin;
-      iphase ^= (t / R) & 1u;
-      islot = t % R;
-      q0 += (uint32_t)rows;
+      c3s_run_item<KS0, KS1, R>(st, bs, rows, adesc0, bdesc0, id48, ROW_BYTES >> 4, lane, my);
     }
-  } else if (GN && warp >= 10) {
+  } else if (GN && warp >= 11) {
     // ===================== input transform (warps 10..13): a = SiLU(GroupNorm(x)) in place, once per landed row =====================
     // thread = (16-byte chunk j of the valid channels, pixel lane); logical chunk j of ring pixel sp sits at physical
     // chunk j ^ (sp & 7) (128B swizzle on absolute addresses; slots are 1024-aligned).  Out-of-image pixels stay zero.
-    const int tt = threadIdx.x - 320;
+    const int tt = threadIdx.x - 352;
     float sc[NCH][8], sh[NCH][8];
     int cur_img = -1;
     uint32_t slot = 0, phase = 0;
@@ -341,27 +372,30 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
     T* yp = (T*)p.y + slice * 48;
     const T* rp = p.resid ? (const T*)p.resid + slice * 48 : nullptr;
     float* badd = s_badd + (warp - 2) * COUT;
-    float gs[GPS + 1], gq[GPS + 1];          // this slice's GroupNorm groups (+1: a slice of 144 outputs would straddle; unused here)
+    // GroupNorm partial sums of this thread's pixels, two lanes per group (even / odd channel of each pair: CPG is even)
+    float2 gs[GPS], gq[GPS];
 #pragma unroll
-    for (int g = 0; g < GPS; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
+    for (int g = 0; g < GPS; ++g) { gs[g] = make_float2(0.f, 0.f); gq[g] = make_float2(0.f, 0.f); }
     auto flush_stats = [&](int img) {
       if (!p.stats || img < 0) return;
+      float s1[GPS], s2[GPS];
 #pragma unroll
       for (int g = 0; g < GPS; ++g) {
+        s1[g] = gs[g].x + gs[g].y; s2[g] = gq[g].x + gq[g].y;
 #pragma unroll
         for (int of = 16; of > 0; of >>= 1) {
-          gs[g] += __shfl_xor_sync(0xffffffffu, gs[g], of);
-          gq[g] += __shfl_xor_sync(0xffffffffu, gq[g], of);
+          s1[g] += __shfl_xor_sync(0xffffffffu, s1[g], of);
+          s2[g] += __shfl_xor_sync(0xffffffffu, s2[g], of);
         }
       }
       if (lane < 2 * GPS) {
         float v = 0.f;
 #pragma unroll
-        for (int g = 0; g < GPS; ++g) { if (lane == 2 * g) v = gs[g]; if (lane == 2 * g + 1) v = gq[g]; }
+        for (int g = 0; g < GPS; ++g) { if (lane == 2 * g) v = s1[g]; if (lane == 2 * g + 1) v = s2[g]; }
         atomicAdd(p.stats + (size_t)img * 16 + slice * 2 * GPS + lane, (double)v);
       }
 #pragma unroll
-      for (int g = 0; g < GPS; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
+      for (int g = 0; g < GPS; ++g) { gs[g] = make_float2(0.f, 0.f); gq[g] = make_float2(0.f, 0.f); }
     };
     uint32_t o = 0;
     int cur_img = -1;
@@ -380,9 +414,10 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
       for (int r = 0; r < rows; ++r, ++o) {
         if ((int)(o & 1) != grp) continue;
         const uint32_t a = o % kSNB, use = o / kSNB;
+        const bool row_ok = r0 + r < p.H;                    // rows past the image end (last segment) are computed and dropped
         const int64_t pix = ((int64_t)img * p.H + r0 + r) * p.W + cb * 128 + quad * 32 + lane;
         uint4 rcur[6];
-        if (rp) {
+        if (rp && row_ok) {
 #pragma unroll
           for (int j = 0; j < 6; ++j) rcur[j] = __ldg(reinterpret_cast<const uint4*>(rp + pix * CT) + j);
         }
@@ -398,32 +433,31 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
         // the block is in registers: hand it back to the MMA warp before the arithmetic and the stores
         tc::tc_fence_before();
         tc::mbar_arrive(&acc_empty[a]);
+        if (!row_ok) continue;
 #pragma unroll
         for (int h8 = 0; h8 < 6; ++h8) {
           const int co = h8 * 8;
           const float4 b0 = *reinterpret_cast<const float4*>(badd + co), b1 = *reinterpret_cast<const float4*>(badd + co + 4);
-          float r8[8];
-          r8[0] = __uint_as_float(v[h8 * 8 + 0]) + b0.x; r8[1] = __uint_as_float(v[h8 * 8 + 1]) + b0.y;
-          r8[2] = __uint_as_float(v[h8 * 8 + 2]) + b0.z; r8[3] = __uint_as_float(v[h8 * 8 + 3]) + b0.w;
-          r8[4] = __uint_as_float(v[h8 * 8 + 4]) + b1.x; r8[5] = __uint_as_float(v[h8 * 8 + 5]) + b1.y;
-          r8[6] = __uint_as_float(v[h8 * 8 + 6]) + b1.z; r8[7] = __uint_as_float(v[h8 * 8 + 7]) + b1.w;
+          float2 r2[4];
+          r2[0] = tc::fadd2(make_float2(__uint_as_float(v[co + 0]), __uint_as_float(v[co + 1])), make_float2(b0.x, b0.y));
+          r2[1] = tc::fadd2(make_float2(__uint_as_float(v[co + 2]), __uint_as_float(v[co + 3])), make_float2(b0.z, b0.w));
+          r2[2] = tc::fadd2(make_float2(__uint_as_float(v[co + 4]), __uint_as_float(v[co + 5])), make_float2(b1.x, b1.y));
+          r2[3] = tc::fadd2(make_float2(__uint_as_float(v[co + 6]), __uint_as_float(v[co + 7])), make_float2(b1.z, b1.w));
           if (rp) {
-            float q8[8];
-            tc::unpack8<T>(rcur[h8], q8);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) r8[j] += q8[j];
+            r2[0] = tc::fadd2(r2[0], tc::unpack2<T>(rcur[h8].x)); r2[1] = tc::fadd2(r2[1], tc::unpack2<T>(rcur[h8].y));
+            r2[2] = tc::fadd2(r2[2], tc::unpack2<T>(rcur[h8].z)); r2[3] = tc::fadd2(r2[3], tc::unpack2<T>(rcur[h8].w));
           }
           if (p.stats) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int g = (co + j) / CPG;
-              gs[g] += r8[j];
-              gq[g] = fmaf(r8[j], r8[j], gq[g]);
+            for (int j = 0; j < 4; ++j) {
+              const int g = (co + 2 * j) / CPG;               // both channels of a pair lie in the same group (CPG is even)
+              gs[g] = tc::fadd2(gs[g], r2[j]);
+              gq[g] = tc::ffma2(r2[j], r2[j], gq[g]);
             }
           }
           uint4 pk;
-          pk.x = tc::pack2<T>(r8[0], r8[1]); pk.y = tc::pack2<T>(r8[2], r8[3]);
-          pk.z = tc::pack2<T>(r8[4], r8[5]); pk.w = tc::pack2<T>(r8[6], r8[7]);
+          pk.x = tc::pack2<T>(r2[0].x, r2[0].y); pk.y = tc::pack2<T>(r2[1].x, r2[1].y);
+          pk.z = tc::pack2<T>(r2[2].x, r2[2].y); pk.w = tc::pack2<T>(r2[3].x, r2[3].y);
           // two 16-byte halves -> one 32-byte store of a whole sector
           if (h8 & 1) tc::st_global_v8(yp + pix * CT + co - 8, pk_even, pk); else pk_even = pk;
         }
@@ -489,15 +523,14 @@ void conv3s(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, 
   static int nsm = 0;
   if (!nsm) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
   p.ncb = x1.w / 128;
-  // rows per work item: 32 unless that leaves SMs without work (small maps): then the largest of 16 / 8 that fills them
+  // segments: as many 40-row items as fit, 10-row items for the rest of the image -- or 10-row items only when the long ones
+  // would leave SMs without work (small maps, batch 1)
   const int workers = std::max(1, nsm / nsl);
-  int seg = c3s_env("XRD_C3S_SEG", 0);
-  if (seg <= 0) {
-    seg = 32;
-    while (seg > 8 && (int64_t)p.ncb * cdiv(x1.h, seg) * x1.n < 2 * workers) seg >>= 1;
-  }
-  p.seg = seg;
-  p.nseg = cdiv(x1.h, seg);
+  auto nsmall = [&](int nbig) { return cdiv(x1.h - nbig * kSegBig, kSegSmall); };
+  int nbig = x1.h / kSegBig;
+  if (c3s_env("XRD_C3S_SMALL", 0) || (int64_t)p.ncb * (nbig + nsmall(nbig)) * x1.n < 2 * (int64_t)workers) nbig = 0;
+  p.nbig = nbig;
+  p.nseg = nbig + nsmall(nbig);
   p.nitems = p.ncb * p.nseg * x1.n;
   p.bias = w.bias;
   p.chan_add = e.chan_add; p.chan_add_bstride = e.chan_add_bstride;
@@ -527,7 +560,7 @@ void conv3s(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, 
     if (r != CUDA_SUCCESS) fail(XRD_ERR_CUDA, "cuTensorMapEncodeTiled(conv3s weights) failed: %d", (int)r);
   }
   const int R = nch == 1 ? 8 : 3;
-  const size_t smem = 1024 + (size_t)R * nch * kSSlot + (size_t)nch * 9 * kSBlk + 8 * 48 * 4 + (3 * R + 2 * kSNB + 1) * 8 + 64;
+  const size_t smem = 1024 + (size_t)R * nch * kSSlot + (size_t)nch * 9 * kSBlk + 8 * 48 * 4 + (3 * R + 2 * kSNB + 3) * 8 + 64;
   int grid = std::min(p.nitems * nsl, (nsm / nsl) * nsl);
   grid = std::max(nsl, (grid / nsl) * nsl);
   const bool gn = e.in_coef != nullptr;
@@ -546,14 +579,14 @@ void conv3s(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, 
   };
   auto pick = [&](auto tag) {
     using T = decltype(tag);
-#define C3S_CASE(K0, K1, RR, GG, NS)                                                                                   \
+#define C3S_CASE(K0, K1, RR, NS)                                                                                       \
     if (k0 == K0 && k1 == K1 && nsl == NS) {                                                                           \
-      if (gn) launch(k_conv3s<T, K0, K1, RR, GG, NS, true>); else launch(k_conv3s<T, K0, K1, RR, GG, NS, false>);       \
+      if (gn) launch(k_conv3s<T, K0, K1, RR, NS, true>); else launch(k_conv3s<T, K0, K1, RR, NS, false>);               \
       return;                                                                                                          \
     }
-    C3S_CASE(1, 0, 8, 4, 1) C3S_CASE(2, 0, 8, 4, 1) C3S_CASE(3, 0, 8, 4, 1) C3S_CASE(4, 0, 8, 4, 1)
-    C3S_CASE(3, 3, 3, 2, 1) C3S_CASE(4, 2, 3, 2, 1)
-    C3S_CASE(3, 0, 8, 4, 2) C3S_CASE(3, 3, 3, 2, 2) C3S_CASE(4, 2, 3, 2, 2)
+    C3S_CASE(1, 0, 8, 1) C3S_CASE(2, 0, 8, 1) C3S_CASE(3, 0, 8, 1) C3S_CASE(4, 0, 8, 1)
+    C3S_CASE(3, 3, 3, 1) C3S_CASE(4, 2, 3, 1)
+    C3S_CASE(3, 0, 8, 2) C3S_CASE(3, 3, 3, 2) C3S_CASE(4, 2, 3, 2)
 #undef C3S_CASE
     fail(XRD_ERR_INVALID, "conv3s: no kernel for k-steps (%d,%d), %d slices", k0, k1, nsl);
   };

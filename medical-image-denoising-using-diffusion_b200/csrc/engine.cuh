@@ -15,6 +15,7 @@ struct Param {
   std::vector<int64_t> shape;
   float* d = nullptr;
   size_t n = 0;
+  bool in_slab = false;     // d points into Handle::slab (xrd_import_weights): not freed on its own
 };
 
 struct ResW {
@@ -121,6 +122,7 @@ struct Handle {
   std::mutex mu;
 
   std::unordered_map<std::string, Param> params;
+  float* slab = nullptr;          // one allocation holding every tensor of an imported weight blob
   std::vector<void*> owned;       // packed weights etc. freed on refinalize / destroy
   UNetW unet;
   NafW naf;

@@ -36,10 +36,9 @@ template <> __device__ __forceinline__ void ld8f<float>(const float* p, float (&
 }
 template <typename T> __device__ __forceinline__ void st8f(T* p, const float (&v)[8]);
 template <> __device__ __forceinline__ void st8f<__half>(__half* p, const float (&v)[8]) {
-  __half2 h[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(sat_h(v[2 * i]), sat_h(v[2 * i + 1]));
-  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<uint4*>(h);
+  uint4 h;
+  h.x = pack_h2_sat(v[0], v[1]); h.y = pack_h2_sat(v[2], v[3]); h.z = pack_h2_sat(v[4], v[5]); h.w = pack_h2_sat(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = h;
 }
 template <> __device__ __forceinline__ void st8f<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
   __nv_bfloat162 h[4];

@@ -189,8 +189,7 @@ template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, fl
   return *reinterpret_cast<uint32_t*>(&v);
 }
 template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
-  __half2 v = __floats2half2_rn(sat_h(a), sat_h(b));
-  return *reinterpret_cast<uint32_t*>(&v);
+  return pack_h2_sat(a, b);
 }
 template <typename T> __device__ __forceinline__ void unpack8(const uint4& t, float (&v)[8]);
 template <> __device__ __forceinline__ void unpack8<__half>(const uint4& t, float (&v)[8]) {
@@ -216,6 +215,24 @@ template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat
 #pragma unroll
   for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
 }
+
+// Packed fp32 pairs (sm_100: FADD2 / FFMA2 / FMUL2 process two fp32 values per instruction): the epilogues' bias / residual adds and
+// GroupNorm partial sums are element-wise over channel pairs, so half the arithmetic instructions disappear.
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 r;
+  asm("{.reg .b64 x, y, z; mov.b64 x, {%2, %3}; mov.b64 y, {%4, %5}; add.rn.f32x2 z, x, y; mov.b64 {%0, %1}, z;}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{.reg .b64 x, y, w, z; mov.b64 x, {%2, %3}; mov.b64 y, {%4, %5}; mov.b64 w, {%6, %7}; fma.rn.f32x2 z, x, y, w; mov.b64 {%0, %1}, z;}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t u);
+template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u)); }
 
 // 32-byte global store (sm_100: STG.E.ENL2.256): one whole sector per instruction.  `p` must be 32-byte aligned.
 __device__ __forceinline__ void st_global_v8(void* p, const uint4& a, const uint4& b) {

@@ -264,6 +264,89 @@ class _NativeModel(nn.Module):
                 _lib.check(lib.xrd_set_range_audit(ent["h"], audit)); ent["audit"] = audit
             return ent["h"]
 
+    # -- weight blob (include/xrd.h: xrd_export_weights / xrd_import_weights) ------------------------
+    def save_weight_blob(self, path: str, device=None) -> int:
+        """Write every state_dict tensor (key, shape, float32 data) as ONE relocatable file: the checkpoint format of this
+        library.  Unlike the reference's ``torch.load(weights_only=False)`` checkpoints (RUN:37,45,53,60) it carries no
+        code.  The model must live on a CUDA device (the blob is exported from the library's copy of the weights)."""
+        dev = torch.device(device) if device is not None else next(iter(self.state_dict().values())).device
+        h = self._xrd_handle(dev)
+        lib = _lib.load()
+        need = C.c_uint64(0)
+        _lib.check(lib.xrd_export_weights(h, None, 0, C.byref(need)))
+        buf = (C.c_char * need.value)()
+        _lib.check(lib.xrd_export_weights(h, buf, need.value, C.byref(need)))
+        with open(path, "wb") as f:
+            f.write(bytes(buf))
+        return int(need.value)
+
+    def load_weight_blob(self, path: str, device=None) -> "_NativeModel":
+        """Checkpoint ingest without unpickling: the file is read once, its payload goes to the GPU in ONE copy
+        (xrd_import_weights) and is packed for the kernels; the module's own parameters / buffers are filled from the same
+        buffer, so ``state_dict()`` stays truthful.  Replaces torch.load + load_state_dict + the per-tensor upload."""
+        import struct
+        import numpy as np
+        dev = torch.device(device) if device is not None else next(iter(self.state_dict().values())).device
+        if dev.type != "cuda":
+            raise XrdError("load_weight_blob needs the model on a CUDA device (move it with .to(device) first)")
+        raw = np.fromfile(path, dtype=np.uint8)
+        mv = memoryview(raw)
+        if len(raw) < 32 or bytes(mv[:8]) != b"XRDW0001":
+            raise XrdError(f"{path} is not a libxrd weight blob")
+        count, pay, floats = struct.unpack_from("<QQQ", mv, 8)
+        if pay + 4 * floats > len(raw) or count > (1 << 20):
+            raise XrdError(f"{path}: truncated or corrupt weight blob")
+        off, ents = 32, {}
+        try:
+            for _ in range(count):
+                (kl,) = struct.unpack_from("<I", mv, off); off += 4
+                key = bytes(mv[off:off + kl]).decode(); off += kl
+                (nd,) = struct.unpack_from("<I", mv, off); off += 4
+                shape = struct.unpack_from(f"<{nd}q", mv, off); off += 8 * nd
+                (o,) = struct.unpack_from("<Q", mv, off); off += 8
+                if nd > 8 or o > floats:
+                    raise XrdError(f"{path}: corrupt weight blob entry {key!r}")
+                ents[key] = (shape, o)
+        except (struct.error, UnicodeDecodeError) as e:
+            raise XrdError(f"{path}: corrupt weight blob header ({e})") from None
+        own = dict(self._xrd_tensors())
+        pre = self._xrd_prefix
+        missing = [k for k in own if pre + k not in ents]
+        extra = [k for k in ents if not (k.startswith(pre) and k[len(pre):] in own)]
+        if missing or extra:
+            raise XrdError(f"weight blob does not match this model: missing {missing[:3]}, unexpected {extra[:3]}")
+        payload = torch.from_numpy(raw[pay:pay + 4 * floats].view(np.float32))
+        with torch.no_grad():
+            for k, v in own.items():
+                shape, o = ents[pre + k]
+                if tuple(shape) != tuple(v.shape):
+                    raise XrdError(f"weight blob: {k} has shape {tuple(shape)}, the model needs {tuple(v.shape)}")
+                v.copy_(payload[o:o + int(v.numel())].reshape(v.shape).to(v.dtype))
+        ent = self._xrd_handle_raw(dev)
+        lib = _lib.load()
+        torch.cuda.current_stream(dev).synchronize()
+        _lib.check(lib.xrd_import_weights(ent["h"], C.c_void_p(raw.ctypes.data), len(raw)))
+        _lib.check(lib.xrd_finalize_weights(ent["h"], self._xrd_parts))
+        ent["fp"] = self._xrd_fingerprint(dev)
+        ent["mode"] = ent["graph"] = ent["audit"] = None
+        return self
+
+    def _xrd_handle_raw(self, device: torch.device) -> dict:
+        """The handle entry of a device, created if needed, WITHOUT uploading the module's parameters."""
+        lib = _lib.load()
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        with self._xrd_lock:
+            ent = self._xrd_handles.get(idx)
+            if ent is None:
+                cfg = _lib.default_config()
+                self._xrd_fill_config(cfg)
+                cfg.noise_steps, cfg.beta_start, cfg.beta_end = self._xrd_schedule
+                h = C.c_void_p()
+                _lib.check(lib.xrd_create(idx, C.byref(cfg), C.byref(h)))
+                ent = {"h": h, "fp": None}
+                self._xrd_handles[idx] = ent
+            return ent
+
     def __del__(self):
         # never dlopen from a finaliser: a model that never ran has no handles (bench.py's CPU arm builds such models)
         try:

@@ -298,7 +298,7 @@ def ddim_denoise(sd: SD, noisy: Tensor, inference_steps: int, noise_steps: int =
     for n, i in enumerate(ddim_timesteps(noise_steps, inference_steps)):
         if teacher_x is not None:
             x = teacher_x[n].to(dt)
-        t = torch.full((x.shape[0],), i, dtype=torch.long)
+        t = torch.full((x.shape[0],), i, dtype=torch.long, device=x.device)
         eps = unet_forward(sd, x, noisy, t, cfg, prefix)
         if trace is not None:
             trace.setdefault("x_in", []).append(x.clone())

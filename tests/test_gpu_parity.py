@@ -317,6 +317,37 @@ def test_state_dict_reload_repacks_weights():
     assert (y1 - ref).abs().max() < TOL_FP32 and (y1 - y0).abs().max() > 1e-3
 
 
+def test_weight_blob_roundtrip(tmp_path):
+    """export the weights of a loaded model as one relocatable blob, ingest it into a FRESH model (different
+    random init) with one host-to-device copy, and get bit-identical results and an identical state_dict."""
+    import xrd_b200
+    from oracle import xrd_oracle as O
+    m, _ = G.seeded_state_dict("nafnet")
+    m = m.to(G.DEV).set_native_mode("fp32")
+    _, noisy = O.synthetic_xray(1, 64, 64, seed=3)
+    y0 = m(noisy.to(G.DEV))
+    path = str(tmp_path / "naf.xrdw")
+    nbytes = m.save_weight_blob(path)
+    assert nbytes > 4 * sum(v.numel() for v in m.state_dict().values())
+    torch.manual_seed(777)
+    m2 = xrd_b200.EnhancedNAFNet().to(G.DEV).eval().set_native_mode("fp32")
+    m2.load_weight_blob(path)
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert torch.equal(m2(noisy.to(G.DEV)), y0)
+    e, _ = G.seeded_state_dict("expert")                       # buffers (running statistics, int64 counters) travel too
+    e = e.to(G.DEV).set_native_mode("fp32")
+    ye = e(noisy.to(G.DEV))
+    pe = str(tmp_path / "expert.xrdw")
+    e.save_weight_blob(pe)
+    e2 = xrd_b200.ExpertDenoiser().to(G.DEV).eval().set_native_mode("fp32").load_weight_blob(pe)
+    assert torch.equal(e2(noisy.to(G.DEV)), ye) and e2.state_dict()["inc.1.num_batches_tracked"].dtype == torch.int64
+    with open(pe, "r+b") as f:                                 # a corrupted blob is an error, not undefined behaviour
+        f.seek(8); f.write(b"\xff" * 8)
+    with pytest.raises(xrd_b200.XrdError):
+        xrd_b200.ExpertDenoiser().to(G.DEV).load_weight_blob(pe)
+
+
 def test_full_size_properties_config3():
     """BASELINE configs[2] size (512x512, batch 16, DDIM-50): too large for the CPU oracle in test time, so
     check size-independent properties: per-image independence of the batch, determinism of the graph replay,
