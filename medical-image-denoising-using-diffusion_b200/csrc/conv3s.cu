@@ -33,7 +33,7 @@ namespace xrd {
 
 struct Conv3SP {
   int H, W, nimg;
-  int ncb, nseg, nbig, nitems;  // column blocks per row, row segments per image (the first nbig of kSegBig rows, the rest of kSegSmall), work items per slice
+  int ncb, dpc, ndec;           // column blocks per row, decades (kSNB output rows) per image column, decades in total (per slice)
   int cout_total;               // 48 * slices
   int c0, c1;                   // channels of chunk 0 / chunk 1 (0: single chunk)
   int two_src;                  // chunk 1 is the second tensor (tmA1, channel 0) instead of channels 64.. of the first
@@ -45,12 +45,25 @@ struct Conv3SP {
   const float2* in_coef;        // GN variant: [nimg][c0 + c1] (0.5*scale, 0.5*shift)
 };
 
-constexpr int kSThreads = 352, kSThreadsGN = 480;   // warp 0 TMA, 1 + 10 MMA issuers (ping-pong), 2..9 epilogue, 11..14 input transform (GN)
-constexpr int kSWarpB = 10;                         // the second MMA-issuing warp
+// Warp roles, aligned to warpgroups so that each role gets its own register budget (setmaxnreg):
+//   warpgroup 0: warp 0 TMA producer, warps 1 + 2 MMA issuers (ping-pong), warp 3 idle        -> 56 registers
+//   warpgroups 1, 2: the two epilogue groups (warps 4..7, 8..11; warp % 4 = its TMEM lane quarter) -> 184 (GN) / 216
+//   warpgroups 3, 4 (GN variant only): input transform, warps 12..15 take the even landed rows, 16..19 the odd ones -> 72
+//     (ncu of the version with ONE transform warpgroup: its warps were busy 90 % of the time, 2150 cycles per row against 1160
+//     of the plain kernel -- the transform, not the tensor pipe, paced the kernel)
+// (the first version had 11 / 15 warps under one budget: the GN variant's 480 threads left 128 registers per thread and its
+// epilogue spilled; ptxas -v of that version: 88 bytes of spill stores, 320 of spill loads.)
+constexpr int kSThreads = 384, kSThreadsGN = 640;
+constexpr int kSWarpB = 2;                          // the second MMA-issuing warp
+constexpr int kSRegLow = 56, kSRegLowGN = 40, kSRegXf = 64, kSRegEpiGN = 152, kSRegEpi = 216;
+// The pool setmaxnreg draws from is what the CTA was LAUNCHED with (threads x registers per thread), not the whole register file:
+// GN variant 640 x 96 = 480 x 128 >= (40 + 2 * 152 + 2 * 64) x 128; plain 384 x 168 = 504 x 128 >= (56 + 2 * 216) x 128.  An inc beyond the
+// pool never returns (first 640-thread version: 48 + 2*160 + 2*72 = 512 units against 480 -- the second epilogue group hung).
+static_assert(kSRegLowGN + 2 * kSRegEpiGN + 2 * kSRegXf <= (kSThreadsGN * 96) / 128, "GN variant: setmaxnreg budget exceeds the launch allocation");
+static_assert(kSRegLow + 2 * kSRegEpi <= (kSThreads * 168) / 128, "plain variant: setmaxnreg budget exceeds the launch allocation");
 constexpr int kSBox = 130;                   // pixels fetched per row (128 + halo column each side)
 constexpr uint32_t kSSlot = 136 * 128;       // one chunk of one row: 17 KB keeps every row 1024-byte aligned
 constexpr int kSNB = 10;                     // accumulator blocks (48 columns each) in the TMEM ring
-constexpr int kSegBig = 40, kSegSmall = 10;  // output rows per work item: multiples of kSNB, so every item starts at ring block 0
 constexpr uint32_t kSBlk = 48 * 128;         // one weight block: 48 output channels x 64 input channels, 16 bit
 constexpr uint32_t kSBlk16 = kSBlk >> 4;
 
@@ -121,7 +134,7 @@ struct C3SBars { uint64_t *rbar, *r_empty, *acc_full, *acc_empty, *baton; };
 // the barrier waits and the address arithmetic of the next iteration, so the tensor pipe does not idle through them (ncu of
 // the single-issuer version: ~1800 cycles of burst and ~2000 cycles of waits / warp synchronisation / set-up per iteration).
 // Both warps walk every iteration and keep the same state; only the owner waits, issues and commits.
-template <int KS0, int KS1, int R, int J, int SEG>
+template <int KS0, int KS1, int R, int J, int SEG, bool SPLIT>
 __device__ __forceinline__ void c3s_iteration(C3SState& st, const C3SBars& b, uint32_t dec, uint64_t adesc0, uint64_t bdesc0, uint32_t id48,
                                               uint32_t row16, int lane, uint32_t my) {
   const uint32_t s0 = st.sl, s1 = (st.sl + 1 == (uint32_t)R) ? 0u : st.sl + 1;
@@ -135,7 +148,11 @@ __device__ __forceinline__ void c3s_iteration(C3SState& st, const C3SBars& b, ui
       if (lane == 2 && st.k > 0u) tc::mbar_wait(&b.baton[my], ((st.k >> 1) & 1u) ^ (my ? 0u : 1u));
       __syncwarp();
     }
-    if (lane < 2) {
+    // SPLIT (shallow ring + input transform: the two-chunk GN variants): the ring cannot hold the two rows of the NEXT iteration
+    // while this one runs, so the second row is waited for only after the first has been issued and its load + transform overlap
+    // the first row's MMAs (both waits up front: 3700 cycles per row measured, 96->48 @512 574 us; split: 489 us).  Without a
+    // transform the split costs more than it hides (plain 96->48 @512: 370 us up front, 426 us split).
+    if (lane < (SPLIT ? 1 : 2)) {
       const uint32_t sx = lane ? s1 : s0;
       tc::mbar_wait(&b.rbar[sx], (st.rph >> sx) & 1u);
     } else if (lane >= 8 && lane < 10 && J + (lane - 8) < SEG) {
@@ -146,16 +163,25 @@ __device__ __forceinline__ void c3s_iteration(C3SState& st, const C3SBars& b, ui
     }
     __syncwarp();
     tc::tc_fence_after();
-    if (tc::elect_one()) {
-      // opaque copy of the weight descriptor: without it the compiler hoists every `bdesc0 + constant` of the unrolled bursts out
-      // of the item loop into VECTOR registers and moves them back (R2UR) in front of each MMA
-      uint64_t bd = bdesc0;
-      asm volatile("" : "+l"(bd));
-      const uint64_t a0 = adesc0 + (uint64_t)(s0 * row16), a1 = adesc0 + (uint64_t)(s1 * row16);
+    // opaque copy of the weight descriptor: without it the compiler hoists every `bdesc0 + constant` of the unrolled bursts out
+    // of the item loop into VECTOR registers and moves them back (R2UR) in front of each MMA
+    uint64_t bd = bdesc0;
+    asm volatile("" : "+l"(bd));
+    const uint64_t a0 = adesc0 + (uint64_t)(s0 * row16), a1 = adesc0 + (uint64_t)(s1 * row16);
+    const bool leader = tc::elect_one();       // ONE thread issues and commits both rows (a commit covers the issuing thread's MMAs)
+    if (leader) {
       c3s_issue_row<KS0, KS1, J, SEG>(a0, bd, id48, nullptr);
       if (J < SEG) tc::umma_commit(&b.acc_full[J % kSNB]);               // output J: its first row is in (arrival 1 of 2)
       if (J >= 2) tc::umma_commit(&b.acc_full[(J - 2) % kSNB]);          // output J-2: its last row is in (arrival 2 of 2)
       tc::umma_commit(&b.r_empty[s0]);                                   // the input row is not needed again
+    }
+    if (SPLIT) {
+      __syncwarp();
+      if (lane == 1) tc::mbar_wait(&b.rbar[s1], (st.rph >> s1) & 1u);
+      __syncwarp();
+      tc::tc_fence_after();
+    }
+    if (leader) {
       c3s_issue_row<KS0, KS1, J + 1, SEG>(a1, bd, id48, &b.baton[my ^ 1u]);
       if (J + 1 < SEG) tc::umma_commit(&b.acc_full[(J + 1) % kSNB]);
       if (J >= 1) tc::umma_commit(&b.acc_full[(J - 1) % kSNB]);
@@ -168,35 +194,87 @@ __device__ __forceinline__ void c3s_iteration(C3SState& st, const C3SBars& b, ui
   st.k += 1u;
 }
 
-// A work item of `seg` output rows (kSegBig or kSegSmall): rows 0, 1 (top edge), the interior rows decade by decade (the five
-// iterations of a decade have the same patterns in every decade), rows seg, seg+1 (bottom edge: they feed the outputs seg-2,
-// seg-1 = ring blocks 8, 9 only, whatever the length of the item -- the pattern of rows 10, 11 of a 10-row item).
-template <int KS0, int KS1, int R>
+// A work item of `seg` output rows (any multiple of the accumulator ring length kSNB): rows 0, 1 (top edge), the interior rows
+// decade by decade (the five iterations of a decade have the same patterns in every decade), rows seg, seg+1 (bottom edge: they
+// feed the outputs seg-2, seg-1 = ring blocks 8, 9 only, whatever the length of the item -- the pattern of rows 10, 11 of a
+// 10-row item).
+template <int KS0, int KS1, int R, bool SPLIT>
 __device__ __forceinline__ void c3s_run_item(C3SState& st, const C3SBars& b, int seg, uint64_t adesc0, uint64_t bdesc0, uint32_t id48,
                                              uint32_t row16, int lane, uint32_t my) {
   constexpr int INT = 1000;      // "long enough": rows 2 .. 11 of such an item are interior rows
-  c3s_iteration<KS0, KS1, R, 0, INT>(st, b, 0u, adesc0, bdesc0, id48, row16, lane, my);
+  c3s_iteration<KS0, KS1, R, 0, INT, SPLIT>(st, b, 0u, adesc0, bdesc0, id48, row16, lane, my);
   for (int m = 0; m * kSNB + 2 < seg; ++m) {
     const uint32_t um = (uint32_t)m;
-    c3s_iteration<KS0, KS1, R, 2, INT>(st, b, um, adesc0, bdesc0, id48, row16, lane, my);
-    c3s_iteration<KS0, KS1, R, 4, INT>(st, b, um, adesc0, bdesc0, id48, row16, lane, my);
-    c3s_iteration<KS0, KS1, R, 6, INT>(st, b, um, adesc0, bdesc0, id48, row16, lane, my);
-    c3s_iteration<KS0, KS1, R, 8, INT>(st, b, um, adesc0, bdesc0, id48, row16, lane, my);
-    if (m * kSNB + 10 < seg) c3s_iteration<KS0, KS1, R, 10, INT>(st, b, um + 1u, adesc0, bdesc0, id48, row16, lane, my);
+    c3s_iteration<KS0, KS1, R, 2, INT, SPLIT>(st, b, um, adesc0, bdesc0, id48, row16, lane, my);
+    c3s_iteration<KS0, KS1, R, 4, INT, SPLIT>(st, b, um, adesc0, bdesc0, id48, row16, lane, my);
+    c3s_iteration<KS0, KS1, R, 6, INT, SPLIT>(st, b, um, adesc0, bdesc0, id48, row16, lane, my);
+    c3s_iteration<KS0, KS1, R, 8, INT, SPLIT>(st, b, um, adesc0, bdesc0, id48, row16, lane, my);
+    if (m * kSNB + 10 < seg) c3s_iteration<KS0, KS1, R, 10, INT, SPLIT>(st, b, um + 1u, adesc0, bdesc0, id48, row16, lane, my);
   }
-  c3s_iteration<KS0, KS1, R, kSNB, kSNB>(st, b, 0u, adesc0, bdesc0, id48, row16, lane, my);
+  c3s_iteration<KS0, KS1, R, kSNB, kSNB, SPLIT>(st, b, 0u, adesc0, bdesc0, id48, row16, lane, my);
   st.accb += (uint32_t)(seg / kSNB);
 }
 
+// Work distribution.  The output is cut into DECADES (kSNB = 10 consecutive rows of one 128-column block of one image); the
+// decades of a slice are numbered image by image, column block by column block, top to bottom, and worker w of nw takes the
+// contiguous range [w*ndec/nw, (w+1)*ndec/nw): every CTA gets the same number of decades +-1 (the first version dealt 40- and
+// 10-row items round-robin: 12 % idle tail at 512x512, batch 16).  A work item is a maximal run of a worker's decades inside one
+// image column, so a worker has one or two items per column it touches and fetches two halo rows per item, not per decade.
+// Every role walks the same sequence with this iterator.
+struct C3SItems {
+  int d, d1;
+  __device__ __forceinline__ C3SItems(const Conv3SP& p, int wi, int nw) {
+    d = (int)(((int64_t)wi * p.ndec) / nw);
+    d1 = (int)(((int64_t)(wi + 1) * p.ndec) / nw);
+  }
+  // rows past the image end (last decade of a column) are zero-filled by TMA, multiplied like any other row and dropped by the
+  // epilogue, so that ring slots, accumulator blocks and barrier phases stay in step with the compile-time pattern of the MMA warp
+  __device__ __forceinline__ bool next(const Conv3SP& p, int& img, int& cb, int& r0, int& rows) {
+    if (d >= d1) return false;
+    const int col = d / p.dpc, dd = d - col * p.dpc;
+    const int n = min(p.dpc - dd, d1 - d);
+    cb = col % p.ncb; img = col / p.ncb;
+    r0 = dd * kSNB; rows = n * kSNB;
+    d += n;
+    return true;
+  }
+};
+
+template <uint32_t N> __device__ __forceinline__ void c3s_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <uint32_t N> __device__ __forceinline__ void c3s_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// Epilogue of 16 consecutive output channels (CH0 .. CH0+15 of the slice) of one pixel: + (bias + time embedding) + residual,
+// GroupNorm partial sums, one 32-byte store.  bb / rc: this thread's 48 additive constants / 48 residual values (16-bit pairs).
+template <typename T, int CH0, int CPG, int GPS>
+__device__ __forceinline__ void c3s_epi16(const uint32_t (&v)[16], const float2 (&bb)[24], const uint4 (&rc)[6], bool has_res, bool has_stats,
+                                          float2 (&gs)[GPS], float2 (&gq)[GPS], T* dst) {
+  uint32_t pk[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = CH0 + 2 * j;
+    float2 r = tc::fadd2(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bb[ch / 2]);
+    if (has_res) {
+      const uint4& q = rc[ch / 8];
+      const uint32_t w = (ch % 8) / 2 == 0 ? q.x : (ch % 8) / 2 == 1 ? q.y : (ch % 8) / 2 == 2 ? q.z : q.w;
+      r = tc::fadd2(r, tc::unpack2<T>(w));
+    }
+    if (has_stats) {
+      const int g = ch / CPG;                         // both channels of a pair lie in the same group (CPG is even)
+      gs[g] = tc::fadd2(gs[g], r);
+      gq[g] = tc::ffma2(r, r, gq[g]);
+    }
+    pk[j] = tc::pack2<T>(r.x, r.y);
+  }
+  tc::st_global_v8(dst + CH0, make_uint4(pk[0], pk[1], pk[2], pk[3]), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+}
+
 // KS0 / KS1: 16-channel k-steps of chunk 0 / chunk 1 (KS1 = 0: one chunk); R: ring rows; NSL: output slices of 48 (1 or 2);
-// GN: GroupNorm + SiLU applied to the landed rows.  Work items are segments of kSegBig or kSegSmall output rows (both multiples
-// of the accumulator ring, with an even number of input rows): the MMA warp walks them two input rows per iteration.
+// GN: GroupNorm + SiLU applied to the landed rows.
 template <typename T, int KS0, int KS1, int R, int NSL, bool GN>
 __global__ void __launch_bounds__(GN ? kSThreadsGN : kSThreads, 1)
 k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB,
          const Conv3SP p) {
   constexpr int NCH = KS1 ? 2 : 1;
-  constexpr int COUT = 48;
   constexpr int CPG = (48 * NSL) / 8;                       // channels per GroupNorm group of the WHOLE output (8 groups)
   constexpr int GPS = 8 / NSL;                              // groups per slice
   constexpr uint32_t ROW_BYTES = NCH * kSSlot;
@@ -207,8 +285,7 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                        // [R][NCH][17 KB]
   uint8_t* sB = sA + (size_t)R * ROW_BYTES;                  // [NCH][3 dx][3 blocks][6 KB]
-  float* s_badd = (float*)(sB + (size_t)NCH * 9 * kSBlk);    // [8 warps][48]
-  uint64_t* bars = (uint64_t*)(s_badd + 8 * COUT);
+  uint64_t* bars = (uint64_t*)(sB + (size_t)NCH * 9 * kSBlk);
   uint64_t* r_full = bars;                 // [R]  TMA landed
   uint64_t* r_ready = bars + R;            // [R]  GN variant: transformed
   uint64_t* r_empty = bars + 2 * R;        // [R]  the MMAs that read the row have completed
@@ -245,117 +322,115 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
     __trap();
   }
 
-  // item q -> (image, column block, first row, rows of the segment).  Every item spans a FULL segment (kSegBig or kSegSmall
-  // rows) even when the image ends inside it: the rows past the end are zero-filled by TMA, multiplied like any other row and
-  // dropped by the epilogue, so that ring slots, accumulator blocks and barrier phases stay in step with the compile-time
-  // pattern of the MMA warp (at most 9 of them per image column).
-  auto item = [&](int q, int& img, int& cb, int& r0, int& rows) {
-    const int sg = q % p.nseg; q /= p.nseg;
-    cb = q % p.ncb; img = q / p.ncb;
-    if (sg < p.nbig) { r0 = sg * kSegBig; rows = kSegBig; }
-    else { r0 = p.nbig * kSegBig + (sg - p.nbig) * kSegSmall; rows = kSegSmall; }
-  };
-
-  if (warp == 0) {
-    // ===================== TMA producer: one box per (input row, chunk) =====================
-    if (tc::elect_one()) {
-      // resident weights of this slice, restacked: slot (chunk, dx, block b) <- tap (dy = 2 - b, dx) of the chunk
-      tc::mbar_expect_tx(w_full, (uint32_t)(NCH * 9) * kSBlk);
-      for (int c = 0; c < NCH; ++c)
-        for (int dx = 0; dx < 3; ++dx)
-          for (int b = 0; b < 3; ++b)
-            tc::tma_load_3d(sB + (size_t)((c * 3 + dx) * 3 + b) * kSBlk, &tmB, w_full, 0, slice * 48, c * 9 + (2 - b) * 3 + dx);
-      uint32_t slot = 0, phase = 0;
-      for (int q = wi; q < p.nitems; q += nw) {
+  if (warp < 4) {
+    c3s_reg_dec<GN ? kSRegLowGN : kSRegLow>();
+    if (warp == 0) {
+      // ===================== TMA producer: one box per (input row, chunk) =====================
+      if (tc::elect_one()) {
+        // resident weights of this slice, restacked: slot (chunk, dx, block b) <- tap (dy = 2 - b, dx) of the chunk
+        tc::mbar_expect_tx(w_full, (uint32_t)(NCH * 9) * kSBlk);
+        for (int c = 0; c < NCH; ++c)
+          for (int dx = 0; dx < 3; ++dx)
+            for (int b = 0; b < 3; ++b)
+              tc::tma_load_3d(sB + (size_t)((c * 3 + dx) * 3 + b) * kSBlk, &tmB, w_full, 0, slice * 48, c * 9 + (2 - b) * 3 + dx);
+        uint32_t slot = 0, phase = 0;
+        C3SItems it(p, wi, nw);
         int img, cb, r0, rows;
-        item(q, img, cb, r0, rows);
-        for (int j = 0; j < rows + 2; ++j) {
-          tc::mbar_wait(&r_empty[slot], phase ^ 1);
-          tc::mbar_expect_tx(&r_full[slot], (uint32_t)NCH * kSBox * 128u);
-          uint8_t* dst = sA + (size_t)slot * ROW_BYTES;
-          tc::tma_load_4d(dst, &tmA0, &r_full[slot], 0, cb * 128 - 1, r0 - 1 + j, img);      // rows / columns outside the image: zero fill
-          if (NCH == 2) {
-            if (p.two_src) tc::tma_load_4d(dst + kSSlot, &tmA1, &r_full[slot], 0, cb * 128 - 1, r0 - 1 + j, img);
-            else tc::tma_load_4d(dst + kSSlot, &tmA0, &r_full[slot], 64, cb * 128 - 1, r0 - 1 + j, img);
+        while (it.next(p, img, cb, r0, rows)) {
+          for (int j = 0; j < rows + 2; ++j) {
+            tc::mbar_wait(&r_empty[slot], phase ^ 1);
+            tc::mbar_expect_tx(&r_full[slot], (uint32_t)NCH * kSBox * 128u);
+            uint8_t* dst = sA + (size_t)slot * ROW_BYTES;
+            tc::tma_load_4d(dst, &tmA0, &r_full[slot], 0, cb * 128 - 1, r0 - 1 + j, img);      // rows / columns outside the image: zero fill
+            if (NCH == 2) {
+              if (p.two_src) tc::tma_load_4d(dst + kSSlot, &tmA1, &r_full[slot], 0, cb * 128 - 1, r0 - 1 + j, img);
+              else tc::tma_load_4d(dst + kSSlot, &tmA0, &r_full[slot], 64, cb * 128 - 1, r0 - 1 + j, img);
+            }
+            if (++slot == R) { slot = 0; phase ^= 1; }
           }
-          if (++slot == R) { slot = 0; phase ^= 1; }
         }
       }
-    }
-    __syncwarp();
-  } else if (warp == 1 || warp == kSWarpB) {
-    // ===================== MMA issuers (two warps, alternating iterations) =====================
-    const uint32_t my = warp == 1 ? 0u : 1u;
-    tc::mbar_wait(w_full, 0);
-    const uint32_t id48 = tc::umma_idesc(128, 48, tc::umma_fmt<T>());
-    const uint64_t adesc0 = tc::umma_desc_sw128(tc::smem_u32(sA));
-    const uint64_t bdesc0 = tc::umma_desc_sw128(tc::smem_u32(sB));
-    C3SState st{0u, 0u, 0u, 0u};
-    const C3SBars bs{GN ? r_ready : r_full, r_empty, acc_full, acc_empty, baton};
-    for (int q = wi; q < p.nitems; q += nw) {
+      __syncwarp();
+    } else if (warp == 1 || warp == kSWarpB) {
+      // ===================== MMA issuers (two warps, alternating iterations) =====================
+      const uint32_t my = warp == 1 ? 0u : 1u;
+      tc::mbar_wait(w_full, 0);
+      const uint32_t id48 = tc::umma_idesc(128, 48, tc::umma_fmt<T>());
+      const uint64_t adesc0 = tc::umma_desc_sw128(tc::smem_u32(sA));
+      const uint64_t bdesc0 = tc::umma_desc_sw128(tc::smem_u32(sB));
+      C3SState st{0u, 0u, 0u, 0u};
+      const C3SBars bs{GN ? r_ready : r_full, r_empty, acc_full, acc_empty, baton};
+      C3SItems it(p, wi, nw);
       int img, cb, r0, rows;
-      item(q, img, cb, r0, rows);
-      c3s_run_item<KS0, KS1, R>(st, bs, rows, adesc0, bdesc0, id48, ROW_BYTES >> 4, lane, my);
+      while (it.next(p, img, cb, r0, rows)) c3s_run_item<KS0, KS1, R, (GN && R < 4)>(st, bs, rows, adesc0, bdesc0, id48, ROW_BYTES >> 4, lane, my);
     }
-  } else if (GN && warp >= 11) {
-    // ===================== input transform (warps 10..13): a = SiLU(GroupNorm(x)) in place, once per landed row =====================
+  } else if (GN && warp >= 12) {
+    // ===================== input transform (warps 12..19): a = SiLU(GroupNorm(x)) in place, once per landed row =====================
+    // two warpgroups, each taking every other landed row
     // thread = (16-byte chunk j of the valid channels, pixel lane); logical chunk j of ring pixel sp sits at physical
     // chunk j ^ (sp & 7) (128B swizzle on absolute addresses; slots are 1024-aligned).  Out-of-image pixels stay zero.
-    const int tt = threadIdx.x - 352;
-    float sc[NCH][8], sh[NCH][8];
+    // Arithmetic on packed fp32 pairs (FFMA2): x*sigmoid(x) = h*tanh(h) + h with h = x/2 folded into the coefficients.
+    c3s_reg_dec<kSRegXf>();
+    const uint32_t xw = (uint32_t)(warp - 12) >> 2;
+    const int tt = threadIdx.x - 384 - (int)xw * 128;
+    // a thread works on ONE chunk (its 8 coefficient pairs stay in registers): with two chunks the warpgroup's threads are split
+    // between them in proportion to their channel counts -- NP pixel lanes of NV0 + NV1 16-byte channel chunks each
+    constexpr int NV0 = KS0 * 2, NV1 = KS1 * 2, NP = 128 / (NV0 + NV1);
+    const int cm = (NCH == 2 && tt >= NP * NV0) ? 1 : 0;
+    const int t2 = cm ? tt - NP * NV0 : tt;
+    const int nvc = cm ? NV1 : NV0;
+    const int j8 = t2 % nvc, plane = t2 / nvc;
+    const bool active = plane < NP;
+    float2 sc[4], sh[4];
     int cur_img = -1;
-    uint32_t slot = 0, phase = 0;
-    for (int q = wi; q < p.nitems; q += nw) {
-      int img, cb, r0, rows;
-      item(q, img, cb, r0, rows);
+    uint32_t slot = 0, phase = 0, nrow = 0;
+    C3SItems it(p, wi, nw);
+    int img, cb, r0, rows;
+    while (it.next(p, img, cb, r0, rows)) {
       if (img != cur_img) {
+        const float2* cf = p.in_coef + (size_t)img * (p.c0 + p.c1) + (cm ? p.c0 : 0) + j8 * 8;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int nvc = (c ? KS1 : KS0) * 2;
-          const int j8 = tt % nvc;
-          const float2* cf = p.in_coef + (size_t)img * (p.c0 + p.c1) + (c ? p.c0 : 0) + j8 * 8;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { const float2 v = __ldg(cf + i); sc[c][i] = v.x; sh[c][i] = v.y; }
+        for (int i = 0; i < 4; ++i) {
+          const float2 a = __ldg(cf + 2 * i), b = __ldg(cf + 2 * i + 1);
+          sc[i] = make_float2(a.x, b.x); sh[i] = make_float2(a.y, b.y);
         }
       }
       cur_img = img;
       const int w0 = cb * 128 - 1;
-      for (int j = 0; j < rows + 2; ++j) {
+      for (int j = 0; j < rows + 2; ++j, ++nrow) {
+        if ((nrow & 1u) != xw) {
+          if (++slot == R) { slot = 0; phase ^= 1; }
+          continue;
+        }
         tc::mbar_wait(&r_full[slot], phase);
         const int ih = r0 - 1 + j;
-        if (ih >= 0 && ih < p.H) {
+        if (ih >= 0 && ih < p.H && active) {
+          const uint32_t sbase = tc::smem_u32(sA + (size_t)slot * ROW_BYTES + (size_t)cm * kSSlot);
+          constexpr int U = 4;
+          for (int c0 = plane; c0 < kSBox; c0 += U * NP) {
+            uint32_t addr[U]; bool ok[U]; uint4 qv[U];
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            const int nvc = (c ? KS1 : KS0) * 2, npl = 128 / nvc;
-            const int j8 = tt % nvc, plane = tt / nvc;
-            if (plane >= npl) continue;
-            const uint32_t sbase = tc::smem_u32(sA + (size_t)slot * ROW_BYTES + (size_t)c * kSSlot);
-            constexpr int U = 4;
-            for (int c0 = plane; c0 < kSBox; c0 += U * npl) {
-              uint32_t addr[U]; bool ok[U]; uint4 qv[U];
+            for (int u = 0; u < U; ++u) {
+              const int cc = c0 + u * NP;
+              const int iw = w0 + cc;
+              ok[u] = cc < kSBox && iw >= 0 && iw < p.W;
+              addr[u] = sbase + (uint32_t)cc * 128u + (uint32_t)((j8 ^ (cc & 7)) << 4);
+              if (ok[u]) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qv[u].x), "=r"(qv[u].y), "=r"(qv[u].z), "=r"(qv[u].w) : "r"(addr[u]));
+            }
 #pragma unroll
-              for (int u = 0; u < U; ++u) {
-                const int cc = c0 + u * npl;
-                const int iw = w0 + cc;
-                ok[u] = cc < kSBox && iw >= 0 && iw < p.W;
-                addr[u] = sbase + (uint32_t)cc * 128u + (uint32_t)((j8 ^ (cc & 7)) << 4);
-                if (ok[u]) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qv[u].x), "=r"(qv[u].y), "=r"(qv[u].z), "=r"(qv[u].w) : "r"(addr[u]));
+            for (int u = 0; u < U; ++u) {
+              if (!ok[u]) continue;
+              uint32_t w[4] = {qv[u].x, qv[u].y, qv[u].z, qv[u].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 h = tc::ffma2(tc::unpack2<T>(w[i]), sc[i], sh[i]);    // 0.5 * GroupNorm(x)
+                float2 th;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(h.x));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(h.y));
+                const float2 o = tc::ffma2(h, th, h);
+                w[i] = tc::pack2<T>(o.x, o.y);
               }
-#pragma unroll
-              for (int u = 0; u < U; ++u) {
-                if (!ok[u]) continue;
-                float v[8];
-                tc::unpack8<T>(qv[u], v);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float h = fmaf(v[i], sc[c][i], sh[c][i]);    // 0.5 * GroupNorm(x)
-                  float th;
-                  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
-                  v[i] = fmaf(h, th, h);                              // x*sigmoid(x) = h*tanh(h) + h, h = x/2
-                }
-                qv[u].x = tc::pack2<T>(v[0], v[1]); qv[u].y = tc::pack2<T>(v[2], v[3]); qv[u].z = tc::pack2<T>(v[4], v[5]); qv[u].w = tc::pack2<T>(v[6], v[7]);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr[u]), "r"(qv[u].x), "r"(qv[u].y), "r"(qv[u].z), "r"(qv[u].w) : "memory");
-              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr[u]), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
             }
           }
         }
@@ -364,20 +439,23 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
         if (++slot == R) { slot = 0; phase ^= 1; }
       }
     }
-  } else {
-    // ===================== epilogue (warps 2..9): group g drains the output rows whose running index is == g mod 2 =====================
+  } else if (warp < 12) {
+    // ===================== epilogue (warps 4..11): group g drains the output rows whose running index is == g mod 2 =====================
+    c3s_reg_inc<GN ? kSRegEpiGN : kSRegEpi>();
     const int quad = warp & 3;
-    const int grp = (warp - 2) >> 2;
+    const int grp = (warp - 4) >> 2;
     const int CT = p.cout_total;
     T* yp = (T*)p.y + slice * 48;
     const T* rp = p.resid ? (const T*)p.resid + slice * 48 : nullptr;
-    float* badd = s_badd + (warp - 2) * COUT;
+    const bool has_res = rp != nullptr, has_stats = p.stats != nullptr;
+    // this thread's pixel gets the same 48 additive constants (bias + time-embedding row of the image) in every row: registers
+    float2 bb[24];
     // GroupNorm partial sums of this thread's pixels, two lanes per group (even / odd channel of each pair: CPG is even)
     float2 gs[GPS], gq[GPS];
 #pragma unroll
     for (int g = 0; g < GPS; ++g) { gs[g] = make_float2(0.f, 0.f); gq[g] = make_float2(0.f, 0.f); }
     auto flush_stats = [&](int img) {
-      if (!p.stats || img < 0) return;
+      if (!has_stats || img < 0) return;
       float s1[GPS], s2[GPS];
 #pragma unroll
       for (int g = 0; g < GPS; ++g) {
@@ -399,68 +477,55 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
     };
     uint32_t o = 0;
     int cur_img = -1;
-    for (int q = wi; q < p.nitems; q += nw) {
-      int img, cb, r0, rows;
-      item(q, img, cb, r0, rows);
+    C3SItems it(p, wi, nw);
+    int img, cb, r0, rows;
+    while (it.next(p, img, cb, r0, rows)) {
       if (img != cur_img) {
         flush_stats(cur_img);
-        __syncwarp();
-        for (int cc = lane; cc < COUT; cc += 32)
-          badd[cc] = (p.bias ? __ldg(p.bias + slice * 48 + cc) : 0.f) +
-                     (p.chan_add ? __ldg(p.chan_add + (int64_t)img * p.chan_add_bstride + slice * 48 + cc) : 0.f);
+#pragma unroll
+        for (int j = 0; j < 24; ++j) {
+          float2 b = make_float2(0.f, 0.f);
+          if (p.bias) { b.x = __ldg(p.bias + slice * 48 + 2 * j); b.y = __ldg(p.bias + slice * 48 + 2 * j + 1); }
+          if (p.chan_add) {
+            const float* ca = p.chan_add + (int64_t)img * p.chan_add_bstride + slice * 48 + 2 * j;
+            b.x += __ldg(ca); b.y += __ldg(ca + 1);
+          }
+          bb[j] = b;
+        }
         cur_img = img;
-        __syncwarp();
       }
       for (int r = 0; r < rows; ++r, ++o) {
         if ((int)(o & 1) != grp) continue;
         const uint32_t a = o % kSNB, use = o / kSNB;
-        const bool row_ok = r0 + r < p.H;                    // rows past the image end (last segment) are computed and dropped
+        const bool row_ok = r0 + r < p.H;                    // rows past the image end (last decade) are computed and dropped
         const int64_t pix = ((int64_t)img * p.H + r0 + r) * p.W + cb * 128 + quad * 32 + lane;
-        uint4 rcur[6];
-        if (rp && row_ok) {
+        uint4 rc[6];
+        if (has_res && row_ok) {
 #pragma unroll
-          for (int j = 0; j < 6; ++j) rcur[j] = __ldg(reinterpret_cast<const uint4*>(rp + pix * CT) + j);
+          for (int j = 0; j < 6; ++j) rc[j] = __ldg(reinterpret_cast<const uint4*>(rp + pix * CT) + j);
         }
         tc::mbar_wait(&acc_full[a], use & 1);
         tc::tc_fence_after();
+        if (!row_ok) {                                       // nothing to read: hand the block straight back
+          tc::tc_fence_before();
+          tc::mbar_arrive(&acc_empty[a]);
+          continue;
+        }
         const uint32_t tacc = a * 48u + ((uint32_t)(quad * 32) << 16);
-        uint32_t v[48];
-        uint4 pk_even;
-        s3_tmem_ld16(tacc, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-        s3_tmem_ld16(tacc + 16u, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-        s3_tmem_ld16(tacc + 32u, *reinterpret_cast<uint32_t(*)[16]>(&v[32]));
+        T* dst = yp + pix * CT;
+        // 16 columns at a time, the next load in flight under the arithmetic of the previous one
+        uint32_t va[16], vb[16];
+        s3_tmem_ld16(tacc, va);
+        s3_tmem_ld16(tacc + 16u, vb);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        // the block is in registers: hand it back to the MMA warp before the arithmetic and the stores
+        c3s_epi16<T, 0, CPG, GPS>(va, bb, rc, has_res, has_stats, gs, gq, dst);
+        s3_tmem_ld16(tacc + 32u, va);
+        c3s_epi16<T, 16, CPG, GPS>(vb, bb, rc, has_res, has_stats, gs, gq, dst);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // the block is in registers: hand it back to the MMA warps before the last third of the arithmetic and its store
         tc::tc_fence_before();
         tc::mbar_arrive(&acc_empty[a]);
-        if (!row_ok) continue;
-#pragma unroll
-        for (int h8 = 0; h8 < 6; ++h8) {
-          const int co = h8 * 8;
-          const float4 b0 = *reinterpret_cast<const float4*>(badd + co), b1 = *reinterpret_cast<const float4*>(badd + co + 4);
-          float2 r2[4];
-          r2[0] = tc::fadd2(make_float2(__uint_as_float(v[co + 0]), __uint_as_float(v[co + 1])), make_float2(b0.x, b0.y));
-          r2[1] = tc::fadd2(make_float2(__uint_as_float(v[co + 2]), __uint_as_float(v[co + 3])), make_float2(b0.z, b0.w));
-          r2[2] = tc::fadd2(make_float2(__uint_as_float(v[co + 4]), __uint_as_float(v[co + 5])), make_float2(b1.x, b1.y));
-          r2[3] = tc::fadd2(make_float2(__uint_as_float(v[co + 6]), __uint_as_float(v[co + 7])), make_float2(b1.z, b1.w));
-          if (rp) {
-            r2[0] = tc::fadd2(r2[0], tc::unpack2<T>(rcur[h8].x)); r2[1] = tc::fadd2(r2[1], tc::unpack2<T>(rcur[h8].y));
-            r2[2] = tc::fadd2(r2[2], tc::unpack2<T>(rcur[h8].z)); r2[3] = tc::fadd2(r2[3], tc::unpack2<T>(rcur[h8].w));
-          }
-          if (p.stats) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int g = (co + 2 * j) / CPG;               // both channels of a pair lie in the same group (CPG is even)
-              gs[g] = tc::fadd2(gs[g], r2[j]);
-              gq[g] = tc::ffma2(r2[j], r2[j], gq[g]);
-            }
-          }
-          uint4 pk;
-          pk.x = tc::pack2<T>(r2[0].x, r2[0].y); pk.y = tc::pack2<T>(r2[1].x, r2[1].y);
-          pk.z = tc::pack2<T>(r2[2].x, r2[2].y); pk.w = tc::pack2<T>(r2[3].x, r2[3].y);
-          // two 16-byte halves -> one 32-byte store of a whole sector
-          if (h8 & 1) tc::st_global_v8(yp + pix * CT + co - 8, pk_even, pk); else pk_even = pk;
-        }
+        c3s_epi16<T, 32, CPG, GPS>(va, bb, rc, has_res, has_stats, gs, gq, dst);
       }
     }
     flush_stats(cur_img);
@@ -523,15 +588,8 @@ void conv3s(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, 
   static int nsm = 0;
   if (!nsm) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
   p.ncb = x1.w / 128;
-  // segments: as many 40-row items as fit, 10-row items for the rest of the image -- or 10-row items only when the long ones
-  // would leave SMs without work (small maps, batch 1)
-  const int workers = std::max(1, nsm / nsl);
-  auto nsmall = [&](int nbig) { return cdiv(x1.h - nbig * kSegBig, kSegSmall); };
-  int nbig = x1.h / kSegBig;
-  if (c3s_env("XRD_C3S_SMALL", 0) || (int64_t)p.ncb * (nbig + nsmall(nbig)) * x1.n < 2 * (int64_t)workers) nbig = 0;
-  p.nbig = nbig;
-  p.nseg = nbig + nsmall(nbig);
-  p.nitems = p.ncb * p.nseg * x1.n;
+  p.dpc = cdiv(x1.h, kSNB);
+  p.ndec = x1.n * p.ncb * p.dpc;
   p.bias = w.bias;
   p.chan_add = e.chan_add; p.chan_add_bstride = e.chan_add_bstride;
   p.resid = e.resid.p; p.y = y.p;
@@ -560,8 +618,8 @@ void conv3s(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, 
     if (r != CUDA_SUCCESS) fail(XRD_ERR_CUDA, "cuTensorMapEncodeTiled(conv3s weights) failed: %d", (int)r);
   }
   const int R = nch == 1 ? 8 : 3;
-  const size_t smem = 1024 + (size_t)R * nch * kSSlot + (size_t)nch * 9 * kSBlk + 8 * 48 * 4 + (3 * R + 2 * kSNB + 3) * 8 + 64;
-  int grid = std::min(p.nitems * nsl, (nsm / nsl) * nsl);
+  const size_t smem = 1024 + (size_t)R * nch * kSSlot + (size_t)nch * 9 * kSBlk + (3 * R + 2 * kSNB + 3) * 8 + 64;
+  int grid = std::min(p.ndec * nsl, (nsm / nsl) * nsl);
   grid = std::max(nsl, (grid / nsl) * nsl);
   const bool gn = e.in_coef != nullptr;
   const int k0 = p.c0 / 16, k1 = p.c1 / 16;

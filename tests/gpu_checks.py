@@ -477,11 +477,15 @@ def check_unet_teacher_256(mode, evals=3):
 
 
 def check_modes_agree_512_b16(steps=50):
+    return check_modes_agree_512(16, steps, 21)
+
+
+def check_modes_agree_512(batch=16, steps=50, seed=21):
     """configs[2] as benched (512x512, batch 16, DDIM-50, the CUDA-graph path with micro-batching): the default f16 mode against
     the fp32 check mode of the same library, which check_hybrid_512 / the goldens pin to the oracle."""
     m, _ = _hybrid("fp16")
     m.inference_diffusion_steps = steps
-    _, noisy = O.synthetic_xray(16, 512, 512, seed=21)
+    _, noisy = O.synthetic_xray(batch, 512, 512, seed=seed)
     x = noisy.to(DEV)
     y16, p16 = m(x, return_parts=True)
     m.set_native_mode("fp32")
