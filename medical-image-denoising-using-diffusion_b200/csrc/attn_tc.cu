@@ -2,8 +2,12 @@
 //
 //   per CTA: 256 queries (two 128-row Q tiles) of one (image, head); loop over 64-key tiles j; for each Q tile t:
 //     S_t,j = Q_t K_j^T     tcgen05.mma, A = Q smem (K-major), B = K smem (K-major), D = TMEM S[t][j&1]
-//     P_t,j = exp2((S - m) * scale * log2e)   softmax warps: one tcgen05.ld pass -> registers -> f16/bf16 -> smem P[t][j&1]
-//     O_t  += P_t,j V_j     tcgen05.mma, A = P smem, B = V smem (MN-major: keys are the K dimension), D = TMEM O[t]
+//     P_t,j = exp2((S - m) * scale * log2e)   softmax warps: one tcgen05.ld pass -> registers -> f16/bf16 -> tcgen05.st back into
+//                                             the first 32 columns of S[t][j&1] (two keys per 32-bit column)
+//     O_t  += P_t,j V_j     tcgen05.mma, A = P in TENSOR MEMORY, B = V smem (MN-major: keys are the K dimension), D = TMEM O[t]
+//   * P never touches shared memory: the first version stored it there (32 KB of stores + 32 KB of operand reads per key tile on
+//     top of the 130 KB the Q/K/V operands cost: ~1470 cycles of the 128 B/clk shared-memory port per step against 1024 cycles of
+//     MMA work, plus a fence.proxy.async per step); with the A operand in TMEM the port carries ~960 cycles per step.
 //   * K/V tiles are what every CTA re-streams from L2 (measured: that traffic, not the tensor pipe, bounded the
 //     one-Q-tile version); two Q tiles per CTA halve it, and two softmax warpgroups keep the MUFU pipe busy.
 //   * The running output never leaves TMEM: the reference maximum m is only raised when a row's new maximum exceeds
@@ -30,10 +34,11 @@ struct AttnTcP {
   void* out;
 };
 
-constexpr int kAttThreads = 320;       // warp 0 TMA, warp 1 MMA issuer, warps 2..9 softmax
+constexpr int kAttThreads = 352;       // warp 0 TMA, warps 1 / 10 MMA issuers of Q tile 0 / 1, warps 2..9 softmax
+constexpr int kAttWarpB = 10;
 constexpr int kTile = 128 * 128;       // Q / P tile: [128 rows x 64 x 16-bit], 128B-swizzled = 16 KB
 constexpr int kKvTile = 64 * 128;      // K / V chunk tile: [64 keys x 64 ch] = 8 KB
-constexpr int kRing = 3;               // K ring slots and V ring slots (2 chunk tiles each)
+constexpr int kRing = 4;               // K ring slots and V ring slots (2 chunk tiles each)
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -90,10 +95,130 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// tcgen05.mma with the A operand in tensor memory (lanes = rows, one 32-bit column = two consecutive 16-bit K elements)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// which of every 8 key pairs take the polynomial exp2 (bit i = pair i): 3 of 8, spread so both paths stay interleaved
+constexpr uint32_t kEmuMask = 0x00;     // measured: 0x92 (3 of 8) 0.307 ms vs 0.297 ms with none -- the MUFU pipe is not what paces the kernel
+
+// (measured and dropped: ex2.approx.f16x2 -- one MUFU per two keys -- 0.389 ms against 0.381 ms, errors 1.5-2x: the MUFU pipe does not
+// pace this kernel)
 constexpr float kRescaleLog2 = 8.0f;   // raise the reference maximum only when P would exceed 2^8
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+
+// ---- MMA-issuing warp: barrier block layout (byte offsets from `bars`) and the per-tile issue routines --------------------------
+constexpr uint32_t kOffKFull = 8, kOffKEmpty = kOffKFull + 8 * kRing, kOffVFull = kOffKEmpty + 8 * kRing, kOffVEmpty = kOffVFull + 8 * kRing;
+constexpr uint32_t kOffSFull = kOffVEmpty + 8 * kRing, kOffPFull = kOffSFull + 32, kOffPFree = kOffPFull + 32, kOffOFinal = kOffPFree + 32;
+
+__device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) break;
+    if (++spins > (1u << 22)) { printf("libxrd: attn_tc MMA warp: barrier %u timed out (block %d,%d,%d)\n", addr, blockIdx.x, blockIdx.y, blockIdx.z); __trap(); }
+  }
+}
+__device__ __forceinline__ void umma_commit_addr(uint32_t addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
+}
+
+// S_t = Q_t K^T for Q tile MT, K from ring slot SLOT, into S buffer B.  One thread.
+template <typename T, int D16, int MT, int SLOT, int B>
+__device__ __forceinline__ void att_issue_qk(uint32_t bar0, uint64_t dQ, uint64_t dK) {
+  constexpr int D = 16 * D16;
+  constexpr int KS0 = (D < 64 ? D : 64) / 16, KS1 = D > 64 ? (D - 64) / 16 : 0;
+  constexpr uint32_t IDESC_QK = tc::umma_idesc(128, 64, tc::umma_fmt<T>());
+  asm volatile("" : "+l"(dQ), "+l"(dK));        // keep `base + constant` in the uniform datapath (no hoisting into vector registers)
+  const uint64_t bD = dK + (uint64_t)(SLOT * (2 * kKvTile >> 4));
+  const uint64_t aD = dQ + (uint64_t)(MT * (2 * kTile >> 4));
+  constexpr uint32_t tS = (uint32_t)MT * 128u + (uint32_t)B * 64u;
+#pragma unroll
+  for (int k = 0; k < KS0; ++k) tc::umma_f16(tS, aD + (uint64_t)(k * 2), bD + (uint64_t)(k * 2), IDESC_QK, k ? 1u : 0u);
+#pragma unroll
+  for (int k = 0; k < KS1; ++k) tc::umma_f16(tS, aD + (uint64_t)((kTile >> 4) + k * 2), bD + (uint64_t)((kKvTile >> 4) + k * 2), IDESC_QK, 1u);
+  umma_commit_addr(bar0 + kOffSFull + 8u * (uint32_t)(MT * 2 + B));
+  umma_commit_addr(bar0 + kOffKEmpty + 8u * SLOT);       // one of two arrivals (one per issuing warp)
+}
+
+// Key tile j = 4*m + S (ring slot S, S / P buffer S & 1) of Q tile MT: wait for V_j, P_MT,j and K_j+2 at once, then P V of tile j and
+// Q K^T of tile j+2.  `ph`: parity of the ring barriers for the tiles of this round of four.
+template <typename T, int D16, int MT, int S>
+__device__ __forceinline__ void att_mma_step(int j, int nkv, uint32_t ph, uint32_t bar0, uint64_t dQ, uint64_t dK, uint64_t dV, int lane) {
+  constexpr int D = 16 * D16;
+  constexpr uint32_t IDESC_PV = tc::umma_idesc(128, D, tc::umma_fmt<T>()) | (1u << 16);     // B (V) is MN-major
+  constexpr int B = S & 1, U1 = (S >> 1) & 1, S2 = (S + 2) & 3;
+  const bool more = j + 2 < nkv;
+  if (lane < 3) {
+    const uint32_t addr = bar0 + (lane == 0 ? kOffVFull + 8u * S : lane == 1 ? kOffPFull + 8u * (MT * 2 + B) : kOffKFull + 8u * S2);
+    const uint32_t par = lane == 0 ? ph : lane == 2 ? (ph ^ (S >= 2 ? 1u : 0u)) : (uint32_t)U1;
+    if (lane < 2 || more) mbar_wait_addr(addr, par);
+  }
+  __syncwarp();
+  tc::tc_fence_after();
+  if (tc::elect_one()) {
+    uint64_t v_ = dV;
+    asm volatile("" : "+l"(v_));
+    const uint64_t bD = v_ + (uint64_t)(S * (2 * kKvTile >> 4));
+    const uint32_t acc0 = j ? 1u : 0u;
+    constexpr uint32_t tP = (uint32_t)MT * 128u + (uint32_t)B * 64u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)     // 4 x 16 keys: +8 columns (two keys each) of P in TMEM, +2048 B (16 key rows) in the MN-major V tile
+      umma_f16_ts(256u + (uint32_t)MT * 128u, tP + (uint32_t)(k * 8), bD + (uint64_t)(k * (2048 >> 4)), IDESC_PV, k ? 1u : acc0);
+    umma_commit_addr(bar0 + kOffPFree + 8u * (MT * 2 + B));
+    if (j == nkv - 1) umma_commit_addr(bar0 + kOffOFinal + 8u * MT);
+    umma_commit_addr(bar0 + kOffVEmpty + 8u * S);         // one of two arrivals
+    if (more) att_issue_qk<T, D16, MT, S2, B>(bar0, dQ, dK);
+  }
+  __syncwarp();
+}
+
+// The whole job of one MMA-issuing warp: every tensor-core instruction of Q tile MT.  Issue order: QK(0), QK(1), then per key
+// tile j:  P V of tile j,  Q K^T of tile j+2  (S is double buffered; S[t][j&1] is rewritten by Q K^T of tile j+2 right behind the
+// P V that read P_t,j out of it -- same thread, so the tensor pipe orders them).
+// Measured on the one-warp version (ncu source view + a run with the softmax arithmetic removed: 0.371 ms against 0.384 ms with
+// it): the kernel is paced by THIS instruction stream, not by the softmax -- 20 MMAs + 8 commits per key tile of 48 cycles each
+// leave the single issuing thread ~4 cycles per instruction for its ~230 instructions.  Two issuing warps (one per Q tile) halve the
+// stream each has to retire and decouple the two tiles' softmax -> P V -> Q K^T chains.
+template <typename T, int D16, int MT>
+__device__ __forceinline__ void att_mma_warp(int nkv, uint32_t bar0, uint64_t dQ, uint64_t dK, uint64_t dV, int lane) {
+  if (lane == 0) mbar_wait_addr(bar0, 0);                              // q_full
+  if (lane == 1) mbar_wait_addr(bar0 + kOffKFull, 0);
+  if (lane == 2 && nkv > 1) mbar_wait_addr(bar0 + kOffKFull + 8u, 0);
+  __syncwarp();
+  tc::tc_fence_after();
+  if (tc::elect_one()) {
+    att_issue_qk<T, D16, MT, 0, 0>(bar0, dQ, dK);
+    if (nkv > 1) att_issue_qk<T, D16, MT, 1, 1>(bar0, dQ, dK);
+  }
+  __syncwarp();
+  uint32_t ph = 0;                  // parity of the K / V ring barriers for the four tiles of this round
+  for (int j0 = 0; j0 < nkv; j0 += 4, ph ^= 1u) {
+    att_mma_step<T, D16, MT, 0>(j0, nkv, ph, bar0, dQ, dK, dV, lane);
+    if (j0 + 1 < nkv) att_mma_step<T, D16, MT, 1>(j0 + 1, nkv, ph, bar0, dQ, dK, dV, lane);
+    if (j0 + 2 < nkv) att_mma_step<T, D16, MT, 2>(j0 + 2, nkv, ph, bar0, dQ, dK, dV, lane);
+    if (j0 + 3 < nkv) att_mma_step<T, D16, MT, 3>(j0 + 3, nkv, ph, bar0, dQ, dK, dV, lane);
+  }
 }
 
 template <typename T, int D16>   // head dim d = 16 * D16 (compile time: the MMA issue loop must not carry runtime predicates)
@@ -105,10 +230,9 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
   constexpr int KS0 = (D < 64 ? D : 64) / 16, KS1 = D > 64 ? (D - 64) / 16 : 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  // layout: Q [2 q-tiles][2 chunks] | P [2 q-tiles][2 buffers] | K ring [kRing][2 chunks] | V ring [kRing][2 chunks] | barriers
+  // layout: Q [2 q-tiles][2 chunks] | K ring [kRing][2 chunks] | V ring [kRing][2 chunks] | barriers
   uint8_t* sQ = smem;
-  uint8_t* sP = sQ + 4 * kTile;
-  uint8_t* sK = sP + 4 * kTile;
+  uint8_t* sK = sQ + 4 * kTile;
   uint8_t* sV = sK + kRing * 2 * kKvTile;
   uint64_t* bars = (uint64_t*)(sV + kRing * 2 * kKvTile);
   uint64_t* q_full = bars + 0;
@@ -117,9 +241,8 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
   uint64_t* v_full = k_empty + kRing;       // [kRing]
   uint64_t* v_empty = v_full + kRing;       // [kRing]
   uint64_t* s_full = v_empty + kRing;       // [2 q-tiles][2]
-  uint64_t* s_free = s_full + 4;
-  uint64_t* p_full = s_free + 4;
-  uint64_t* p_free = p_full + 4;
+  uint64_t* p_full = s_full + 4;            // P_t,j stored to TMEM (and, implied, S_t,j read)
+  uint64_t* p_free = p_full + 4;            // P V of that tile completed (waited for only by the lazy rescale)
   uint64_t* o_final = p_free + 4;           // [2] completes once, after the last P V
   uint32_t* tmem_slot = (uint32_t*)(o_final + 2);
 
@@ -132,10 +255,10 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     tc::tma_prefetch_desc(&tmKV);
     tc::mbar_init(q_full, 1);
     for (int s = 0; s < kRing; ++s) {
-      tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1); tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], 1);
+      tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 2); tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], 2);   // released by both issuing warps
     }
     for (int s = 0; s < 4; ++s) {
-      tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_free[s], 128);
+      tc::mbar_init(&s_full[s], 1);
       tc::mbar_init(&p_full[s], 128); tc::mbar_init(&p_free[s], 1);
     }
     tc::mbar_init(&o_final[0], 1); tc::mbar_init(&o_final[1], 1);
@@ -155,7 +278,10 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     __trap();
   }
   constexpr uint32_t tmem_base = 0u;
-  // TMEM columns: S[t][b] at t*128 + b*64 (64 wide), O[t] at 256 + t*128 (d <= 128 wide)
+  // TMEM columns: S[t][b] at t*128 + b*64 (64 wide; P[t][b] = its first 32 columns, 16-bit pairs), O[t] at 256 + t*128 (d <= 128 wide)
+  // Hazards on S / P are ordered by the tensor pipe itself (MMAs execute in issue order): Q K^T of tile j+2 overwrites S[t][b] only
+  // after P V of tile j, issued before it, has read P[t][b]; P V of tile j is issued only after the softmax published P_t,j, i.e.
+  // after it read S_t,j.  No "S free" / "P free" waits remain on the critical path.
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -175,99 +301,14 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer (one elected lane; the warp stays converged) =====================
-    // per step j: P V of tile j for both Q tiles as soon as its P tiles are published, then Q K^T of tile j+2.
-    // The ncu source view of the previous version showed this warp, not the softmax warps, on the critical path: ~135 cycles per
-    // MMA, i.e. ~14 instructions (R2UR moves, runtime k-step predicates, per-MMA constant loads) retired at the single-thread rate
-    // of one per ~4-8 cycles, while the softmax warps sat in the S-ready wait for 47 % of their time.  Now: everything that
-    // varies is a 64-bit descriptor base computed once per block of 8-12 MMAs, every per-MMA offset is a compile-time constant,
-    // the head dim and both instruction descriptors are template constants, and one elect block covers both Q tiles.
-    constexpr uint32_t IDESC_QK = tc::umma_idesc(128, 64, tc::umma_fmt<T>());
-    constexpr uint32_t IDESC_PV = tc::umma_idesc(128, D, tc::umma_fmt<T>()) | (1u << 16);     // B (V) is MN-major
+  } else if (warp == 1 || warp == kAttWarpB) {
+    // ===================== MMA issuers: warp 1 = Q tile 0, warp 10 = Q tile 1 (see att_mma_warp) =====================
+    const uint32_t bar0 = tc::smem_u32(bars);
     const uint64_t dQ = tc::umma_desc_sw128(tc::smem_u32(sQ));           // + t * (2 * kTile >> 4)
     const uint64_t dK = tc::umma_desc_sw128(tc::smem_u32(sK));           // + slot * (2 * kKvTile >> 4)
-    const uint64_t dP = tc::umma_desc_sw128(tc::smem_u32(sP));           // + (t * 2 + b) * (kTile >> 4)
     const uint64_t dV = umma_desc_mn_sw128(tc::smem_u32(sV), kKvTile);   // + slot * (2 * kKvTile >> 4)
-    uint32_t kslot = 0, kphase = 0, vslot = 0, vphase = 0;
-    bool qk_probed = false;           // this lane's barrier of the next Q K^T block was already seen complete
-    auto issue_pv = [&](int j, int qk_next) {      // O_t (+)= P_t,j V_j for both Q tiles; qk_next: key tile of the Q K^T block that follows (-1: none)
-      const int b = j & 1, u = j >> 1;
-      {   // the three waits as ONE instruction on three lanes (each wait in front of the MMAs idles the tensor pipe for its latency)
-        uint64_t* const bar = lane == 0 ? &v_full[vslot] : &p_full[(lane == 1 ? 0 : 2) + b];
-        if (lane < 3) tc::mbar_wait(bar, lane == 0 ? vphase : (uint32_t)(u & 1));
-        __syncwarp();
-      }
-      tc::tc_fence_after();
-      if (p.probe && qk_next >= 0 && lane < 3) {   // probe the barriers of the next Q K^T block now: the round trip runs under the MMAs below
-        const int bn = qk_next & 1, un = qk_next >> 1;
-        uint64_t* const bar = lane == 0 ? &k_full[kslot] : &s_free[(lane == 1 ? 0 : 2) + bn];
-        qk_probed = tc::mbar_test(bar, lane == 0 ? kphase : (uint32_t)((un & 1) ^ 1));
-      }
-      if (tc::elect_one()) {
-        const uint64_t bD = dV + (uint64_t)(vslot * (2 * kKvTile >> 4));
-        const uint64_t aD0 = dP + (uint64_t)(b * (kTile >> 4));
-        const uint32_t acc0 = j ? 1u : 0u;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const uint64_t aD = aD0 + (uint64_t)(t * 2 * (kTile >> 4));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)     // 4 x 16 keys: +32 B in the K-major P tile, +2048 B (16 key rows) in the MN-major V tile
-            tc::umma_f16(256u + (uint32_t)t * 128u, aD + (uint64_t)(k * 2), bD + (uint64_t)(k * (2048 >> 4)), IDESC_PV, k ? 1u : acc0);
-        }
-        tc::umma_commit(&p_free[b]);
-        tc::umma_commit(&p_free[2 + b]);
-        if (j == p.nkv - 1) { tc::umma_commit(&o_final[0]); tc::umma_commit(&o_final[1]); }
-        tc::umma_commit(&v_empty[vslot]);
-      }
-      __syncwarp();
-      if (++vslot == kRing) { vslot = 0; vphase ^= 1; }
-    };
-    auto issue_qk = [&](int j) {      // S_t,j = Q_t K_j^T for both Q tiles
-      const int b = j & 1, u = j >> 1;
-      {   // K_j landed; softmax has drained S_t,j-2 from these TMEM buffers -- one wait instruction on three lanes
-        uint64_t* const bar = lane == 0 ? &k_full[kslot] : &s_free[(lane == 1 ? 0 : 2) + b];
-        if (lane < 3) tc::mbar_wait_probed(qk_probed, bar, lane == 0 ? kphase : (uint32_t)((u & 1) ^ 1));
-        qk_probed = false;
-        __syncwarp();
-      }
-      tc::tc_fence_after();
-      if (tc::elect_one()) {
-        const uint64_t bD = dK + (uint64_t)(kslot * (2 * kKvTile >> 4));
-        const uint32_t tS0 = (uint32_t)b * 64u;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const uint64_t aD = dQ + (uint64_t)(t * (2 * kTile >> 4));
-          const uint32_t tS = tS0 + (uint32_t)t * 128u;
-#pragma unroll
-          for (int k = 0; k < KS0; ++k) tc::umma_f16(tS, aD + (uint64_t)(k * 2), bD + (uint64_t)(k * 2), IDESC_QK, k ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < KS1; ++k)
-            tc::umma_f16(tS, aD + (uint64_t)((kTile >> 4) + k * 2), bD + (uint64_t)((kKvTile >> 4) + k * 2), IDESC_QK, 1u);
-          tc::umma_commit(&s_full[t * 2 + b]);
-        }
-        tc::umma_commit(&k_empty[kslot]);
-      }
-      __syncwarp();
-      if (++kslot == kRing) { kslot = 0; kphase ^= 1; }
-    };
-    // Q K^T runs one key tile ahead of P V (S is double buffered).  Two ahead (p.ahead == 2: S_j+2 reuses the TMEM buffer the
-    // softmax of tile j drained at its start) measured 4 % slower: the kernel is bound by the MIO queue the MUFU.EX2 stream,
-    // the P stores and the UTCHMMA issue share, not by S arriving late.
-    tc::mbar_wait(q_full, 0);
-    issue_qk(0);
-    if (p.ahead == 2) {
-      if (p.nkv > 1) issue_qk(1);
-      for (int j = 0; j < p.nkv; ++j) {
-        issue_pv(j, j + 2 < p.nkv ? j + 2 : -1);
-        if (j + 2 < p.nkv) issue_qk(j + 2);
-      }
-    } else {
-      for (int j = 0; j < p.nkv; ++j) {
-        if (j + 1 < p.nkv) issue_qk(j + 1);
-        issue_pv(j, j + 2 < p.nkv ? j + 2 : -1);
-      }
-    }
+    if (warp == 1) att_mma_warp<T, D16, 0>(p.nkv, bar0, dQ, dK, dV, lane);
+    else att_mma_warp<T, D16, 1>(p.nkv, bar0, dQ, dK, dV, lane);
   } else {
     // ===================== softmax / correction / epilogue (warps 2..9, one query row per thread) =====================
     const int t = (warp - 2) >> 2;                 // Q tile
@@ -277,8 +318,6 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     const int q = q0 + t * 128 + row;
     const uint32_t tO = tmem_base + 256u + (uint32_t)t * 128u + lane_addr;
     float m_run = -INFINITY, l_run = 0.f;
-    const int sw = row & 7;
-    const uint32_t prow0 = tc::smem_u32(sP) + (uint32_t)(t * 2) * kTile + (uint32_t)row * 128u;
     auto step = [&](const int j, auto ragged) {
       const int b = j & 1, u = j >> 1;
       tc::mbar_wait(&s_full[t * 2 + b], u & 1);
@@ -288,22 +327,32 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       tmem_ld32_nowait(tS, v);
       tmem_ld32_nowait(tS + 32, v + 32);
       tmem_ld_wait();
-      tc::tc_fence_before();
-      tc::mbar_arrive(&s_free[t * 2 + b]);           // S is in registers: Q K^T of tile j+2 may overwrite this buffer
       if (decltype(ragged)::value) {               // only the last, partial key tile pays for the masking (64 compare + select)
         const int kvalid = p.HW - j * 64;
 #pragma unroll
         for (int i = 0; i < 64; ++i)
           if (i >= kvalid) v[i] = -INFINITY;
       }
-      float mx0 = v[0], mx1 = v[1], mx2 = v[2], mx3 = v[3];
+      if (p.probe == 2) {        // timing experiment only (wrong results): no max / exp, P = packed raw S
+        uint32_t pk[32];
 #pragma unroll
-      for (int i = 4; i < 64; i += 4) {
-        mx0 = fmaxf(mx0, v[i]); mx1 = fmaxf(mx1, v[i + 1]); mx2 = fmaxf(mx2, v[i + 2]); mx3 = fmaxf(mx3, v[i + 3]);
+        for (int i = 0; i < 32; ++i) pk[i] = pack2<T>(v[2 * i], v[2 * i + 1]);
+        tmem_st32(tS, reinterpret_cast<const float*>(pk));
+        tmem_st_wait();
+        tc::tc_fence_before();
+        tc::mbar_arrive(&p_full[t * 2 + b]);
+        l_run = 1.f;
+        return;
       }
+      // row maximum: three-input max (FMNMX3), four independent chains
+      float mx0 = max3(v[0], v[1], v[2]), mx1 = max3(v[3], v[4], v[5]), mx2 = max3(v[6], v[7], v[8]), mx3 = max3(v[9], v[10], v[11]);
+#pragma unroll
+      for (int i = 12; i < 60; i += 8) {
+        mx0 = max3(mx0, v[i], v[i + 1]); mx1 = max3(mx1, v[i + 2], v[i + 3]);
+        mx2 = max3(mx2, v[i + 4], v[i + 5]); mx3 = max3(mx3, v[i + 6], v[i + 7]);
+      }
+      mx0 = max3(mx0, v[60], v[61]); mx1 = max3(mx1, v[62], v[63]);
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      // P V of tile j-2 has consumed P[t][b]
-      tc::mbar_wait(&p_free[t * 2 + b], (u & 1) ^ 1);
       // lazy reference maximum: keep m_run unless this tile would push P above 2^kRescaleLog2
       const bool need = (mx - m_run) * p.scale_log2e > kRescaleLog2;      // true on the first tile (m_run = -inf)
       if (__any_sync(0xffffffffu, need)) {
@@ -331,19 +380,39 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       }
       const float sc = p.scale_log2e;
       const float mb = m_run * sc;
-      // P = exp2(S*c - m*c), rounded to the MMA operand format, written K-major / 128B-swizzled into P[t][b]
-      const uint32_t prow = prow0 + (uint32_t)b * kTile;
-      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+      // P = exp2(S*c - m*c), rounded to the MMA operand format, stored over the first 32 columns of S[t][b] (two keys per column).
+      // The MUFU pipe (4 lanes per scheduler: 8 cycles per warp instruction) is the busiest unit of this kernel -- 64 exponentials
+      // per thread and key tile, two softmax warps per scheduler = 1024 cycles per step against ~960 of MMA work.  kEmu of every 8
+      // key pairs therefore take exp2 on the FMA / ALU pipes instead (packed fp32 pairs): x = n + f with n = round(x) from the
+      // magic-number add, 2^f by a degree-3 polynomial on [-1/2, 1/2] (max relative error 7.5e-5, a third of the 16-bit rounding
+      // of P that follows), 2^n by an integer add into the exponent field.  Scale, subtraction and row sums are packed too.
+      const float2 sc2 = make_float2(sc, sc), nmb2 = make_float2(-mb, -mb);
+      float2 rsa = make_float2(0.f, 0.f), rsb = make_float2(0.f, 0.f);
+      uint32_t pk[32];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {                 // 8 keys = one 16-byte chunk of this row
-        const float e0 = ex2(fmaf(v[c * 8 + 0], sc, -mb)), e1 = ex2(fmaf(v[c * 8 + 1], sc, -mb));
-        const float e2 = ex2(fmaf(v[c * 8 + 2], sc, -mb)), e3 = ex2(fmaf(v[c * 8 + 3], sc, -mb));
-        const float e4 = ex2(fmaf(v[c * 8 + 4], sc, -mb)), e5 = ex2(fmaf(v[c * 8 + 5], sc, -mb));
-        const float e6 = ex2(fmaf(v[c * 8 + 6], sc, -mb)), e7 = ex2(fmaf(v[c * 8 + 7], sc, -mb));
-        rs0 += e0; rs1 += e1; rs2 += e2; rs3 += e3; rs0 += e4; rs1 += e5; rs2 += e6; rs3 += e7;
-        st_shared_v4(prow + (uint32_t)((c ^ sw) << 4), pack2<T>(e0, e1), pack2<T>(e2, e3), pack2<T>(e4, e5), pack2<T>(e6, e7));
+      for (int i = 0; i < 32; ++i) {                 // pair i = keys 2i, 2i+1
+        float2 x = tc::ffma2(make_float2(v[2 * i], v[2 * i + 1]), sc2, nmb2);
+        float2 e;
+        if (kEmuMask >> (i & 7) & 1) {
+          x.x = fmaxf(x.x, -126.f); x.y = fmaxf(x.y, -126.f);
+          const float2 tt = tc::fadd2(x, make_float2(12582912.f, 12582912.f));            // 1.5 * 2^23: the low mantissa bits are round(x)
+          const float2 rr = tc::fadd2(tt, make_float2(-12582912.f, -12582912.f));
+          const float2 f = tc::ffma2(rr, make_float2(-1.f, -1.f), x);                        // x - round(x)
+          float2 q = tc::ffma2(f, make_float2(0.05517165f, 0.05517165f), make_float2(0.24261113f, 0.24261113f));
+          q = tc::ffma2(q, f, make_float2(0.69326097f, 0.69326097f));
+          q = tc::ffma2(q, f, make_float2(0.99992806f, 0.99992806f));
+          e.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(tt.x) << 23));
+          e.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(tt.y) << 23));
+        } else {
+          e.x = ex2(x.x); e.y = ex2(x.y);
+        }
+        if (i & 1) rsb = tc::fadd2(rsb, e); else rsa = tc::fadd2(rsa, e);
+        pk[i] = pack2<T>(e.x, e.y);
       }
-      tc::fence_async_smem();                       // generic-proxy stores -> visible to the tensor core (async proxy)
+      const float rs0 = rsa.x + rsa.y, rs1 = rsb.x + rsb.y, rs2 = 0.f, rs3 = 0.f;
+      tmem_st32(tS, reinterpret_cast<const float*>(pk));
+      tmem_st_wait();
+      tc::tc_fence_before();
       tc::mbar_arrive(&p_full[t * 2 + b]);
       l_run += (rs0 + rs1) + (rs2 + rs3);
     };
@@ -417,7 +486,7 @@ void attention_tc(Ctx& c, const Tens& qkv, int heads, Tens& out) {
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) fail(XRD_ERR_CUDA, "cuTensorMapEncodeTiled(qkv) failed: %d", (int)r);
   }
-  const size_t smem = 1024 + (size_t)8 * kTile + (size_t)2 * kRing * 2 * kKvTile + 64 * 8;
+  const size_t smem = 1024 + (size_t)4 * kTile + (size_t)2 * kRing * 2 * kKvTile + 64 * 8;
   dim3 grid(cdiv(HW, 256), heads, qkv.n);
   const int dc = d / 16;
 #define XRD_ATT_CASE(TT, DCV)                                                                                             \
