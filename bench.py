@@ -219,21 +219,22 @@ def run_reference(args, rank, world):
 # roofline of the dominant kernel class: every conv layer of one UNet evaluation, through the kernel the engine dispatches
 # ------------------------------------------------------------------------------------------------
 def unet_conv_layers(s):
-    """(count per eval, Cin, Cout, H, k, stride, fused_gn): the convolutions of UNetDiffusion.forward at the reference topology.
-    fused_gn marks the layers whose GroupNorm+SiLU the engine applies inside the conv kernel (engine.cu resblock)."""
-    L = [(5, 48, 48, s, 3, 1, True), (1, 96, 48, s, 3, 1, False), (2, 48, 48, s // 2, 3, 1, False), (1, 48, 96, s // 2, 3, 1, False),
-         (4, 96, 96, s // 2, 3, 1, False), (1, 192, 96, s // 2, 3, 1, False), (1, 96, 96, s // 2, 3, 1, False), (1, 96, 48, s // 2, 3, 1, False),
-         (1, 192, 48, s // 2, 3, 1, False), (2, 96, 96, s // 4, 3, 1, False), (1, 96, 144, s // 4, 3, 1, False), (4, 144, 144, s // 4, 3, 1, False),
-         (1, 288, 144, s // 4, 3, 1, False), (1, 144, 144, s // 4, 3, 1, False), (1, 192, 96, s // 4, 3, 1, False), (1, 288, 96, s // 4, 3, 1, False),
-         (2, 144, 144, s // 8, 3, 1, False), (1, 144, 192, s // 8, 3, 1, False), (10, 192, 192, s // 8, 3, 1, False), (3, 384, 192, s // 8, 3, 1, False),
-         (1, 192, 192, s // 8, 3, 1, False), (1, 384, 144, s // 8, 3, 1, False), (1, 288, 144, s // 8, 3, 1, False),
-         (6, 192, 576, s // 8, 1, 1, False), (6, 192, 192, s // 8, 1, 1, False),
-         (1, 48, 48, s, 3, 2, False), (1, 96, 96, s // 2, 3, 2, False), (1, 144, 144, s // 4, 3, 2, False),
+    """(count per eval, Cin, Cout, H, k, stride, flags): the convolutions of UNetDiffusion.forward at the reference topology.
+    flags: "gn" = the engine applies GroupNorm+SiLU of the input inside the conv kernel (engine.cu resblock); "cat" = the input is
+    the virtual concat of two tensors (torch.cat([x, skip]) of the up path, never materialised)."""
+    L = [(5, 48, 48, s, 3, 1, "gn"), (1, 96, 48, s, 3, 1, "gn cat"), (2, 48, 48, s // 2, 3, 1, "gn"), (1, 48, 96, s // 2, 3, 1, "gn"),
+         (4, 96, 96, s // 2, 3, 1, "gn"), (1, 192, 96, s // 2, 3, 1, ""), (1, 96, 96, s // 2, 3, 1, ""), (1, 96, 48, s // 2, 3, 1, "gn cat"),
+         (1, 192, 48, s // 2, 3, 1, ""), (2, 96, 96, s // 4, 3, 1, "gn"), (1, 96, 144, s // 4, 3, 1, ""), (4, 144, 144, s // 4, 3, 1, ""),
+         (1, 288, 144, s // 4, 3, 1, ""), (1, 144, 144, s // 4, 3, 1, ""), (1, 192, 96, s // 4, 3, 1, ""), (1, 288, 96, s // 4, 3, 1, ""),
+         (2, 144, 144, s // 8, 3, 1, ""), (1, 144, 192, s // 8, 3, 1, ""), (10, 192, 192, s // 8, 3, 1, ""), (3, 384, 192, s // 8, 3, 1, ""),
+         (1, 192, 192, s // 8, 3, 1, ""), (1, 384, 144, s // 8, 3, 1, ""), (1, 288, 144, s // 8, 3, 1, ""),
+         (6, 192, 576, s // 8, 1, 1, ""), (6, 192, 192, s // 8, 1, 1, ""),
+         (1, 48, 48, s, 3, 2, ""), (1, 96, 96, s // 2, 3, 2, ""), (1, 144, 144, s // 4, 3, 2, ""),
          # the 15 res_conv 1x1s (every ResidualBlock whose channel count changes)
-         (1, 48, 96, s // 2, 1, 1, False), (1, 96, 144, s // 4, 1, 1, False), (1, 144, 192, s // 8, 1, 1, False), (3, 384, 192, s // 8, 1, 1, False),
-         (1, 384, 144, s // 8, 1, 1, False), (1, 288, 144, s // 8, 1, 1, False), (1, 288, 144, s // 4, 1, 1, False), (1, 288, 96, s // 4, 1, 1, False),
-         (1, 192, 96, s // 4, 1, 1, False), (1, 192, 96, s // 2, 1, 1, False), (1, 192, 48, s // 2, 1, 1, False), (1, 96, 48, s // 2, 1, 1, False),
-         (1, 96, 48, s, 1, 1, False)]
+         (1, 48, 96, s // 2, 1, 1, ""), (1, 96, 144, s // 4, 1, 1, ""), (1, 144, 192, s // 8, 1, 1, ""), (3, 384, 192, s // 8, 1, 1, ""),
+         (1, 384, 144, s // 8, 1, 1, ""), (1, 288, 144, s // 8, 1, 1, ""), (1, 288, 144, s // 4, 1, 1, ""), (1, 288, 96, s // 4, 1, 1, ""),
+         (1, 192, 96, s // 4, 1, 1, ""), (1, 192, 96, s // 2, 1, 1, ""), (1, 192, 48, s // 2, 1, 1, ""), (1, 96, 48, s // 2, 1, 1, ""),
+         (1, 96, 48, s, 1, 1, "")]
     return L
 
 
@@ -251,16 +252,20 @@ def conv_roofline(mode, dev, batch, size):
     tot_ms, tot_fl, launches = 0.0, 0.0, 0
     per_kernel = {}
     ms = C.c_float()
-    for cnt, ci, co, hh, k, st, fused in unet_conv_layers(size):
+    for cnt, ci, co, hh, k, st, flags in unet_conv_layers(size):
         x = torch.randn(batch, ci, hh, hh, device=dev)
         w = torch.randn(co, ci, k, k, device=dev) * 0.05
         b = torch.zeros(co, device=dev)
         ho = (hh + 2 * (k // 2) - k) // st + 1
         y = torch.empty(batch, co, ho, ho, device=dev)
-        # same dispatch as the engine (engine.cu conv()): conv3r (<= 64 input channels, W >= 256; with GroupNorm+SiLU applied in place
-        # at W >= 512), conv3 (W % 128 == 0), conv3w (W == 64), conv1 (1x1), else per-tap
-        if k == 3 and st == 1 and hh % 128 == 0 and hh >= 256 and ci <= 64 and co in (48, 96):
-            impl, kern = (12, "k_conv3r+gn") if (fused and hh >= 512) else (11, "k_conv3r")
+        # same dispatch as the engine (engine.cu conv() / resblock()): the N-stacked row-ring kernel conv3s for 3x3 / stride 1 layers
+        # with 48 or 96 outputs and up to 96 inputs on maps >= 128 wide (GroupNorm+SiLU of the input applied inside it in the residual
+        # blocks, the up path's concat read from its two sources), conv3 (other W % 128 == 0 layers), conv3w (W == 64), conv1 (1x1),
+        # else the per-tap kernel (the three stride-2 convolutions)
+        if k == 3 and st == 1 and hh % 128 == 0 and hh >= 128 and co in (48, 96) and ci in (48, 96):
+            gn, cat = "gn" in flags, "cat" in flags
+            impl = (18 if gn else 17) if cat else (16 if gn else 15)
+            kern = "k_conv3s" + ("+gn" if gn else "") + ("(cat)" if cat else "")
         elif k == 3 and st == 1 and hh % 128 == 0 and co in (48, 96, 144):
             impl, kern = 2, "k_conv3"
         elif k == 3 and st == 1 and hh == 64 and co in (144, 192):
@@ -443,7 +448,7 @@ def main():
                    "parallelism": f"image-sharded x{world}, output all_gather only"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": B * S * S * 4, "d2h_bytes_per_step": B * S * S * 4},
-        "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convolutions (k_conv3, k_conv3r, k_conv3w, k_conv1, k_conv_tc): every conv layer shape of one UNet "
+        "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convolutions (k_conv3s, k_conv3, k_conv3w, k_conv1, k_conv_tc): every conv layer shape of one UNet "
                                "evaluation at batch 16 / 512x512, each timed live with CUDA events through the C-ABI op hook on the kernel variant the engine "
                                "dispatches (fused GroupNorm+SiLU where the network fuses it), launch weighted",
                      "achieved": conv_tf if do_roof else None, "peak": pk["burst"], "unit": "TFLOP/s",

@@ -125,6 +125,21 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 // ---- MMA-issuing warp: barrier block layout (byte offsets from `bars`) and the per-tile issue routines --------------------------
 constexpr uint32_t kOffKFull = 8, kOffKEmpty = kOffKFull + 8 * kRing, kOffVFull = kOffKEmpty + 8 * kRing, kOffVEmpty = kOffVFull + 8 * kRing;
 constexpr uint32_t kOffSFull = kOffVEmpty + 8 * kRing, kOffPFull = kOffSFull + 32, kOffPFree = kOffPFull + 32, kOffOFinal = kOffPFree + 32;
+constexpr uint32_t kOffSFree = kOffOFinal + 16;
+
+// TMEM map.  Two layouts exist.  Default (SEP = false): S[t][b] at t*128 + b*64, P[t][b] aliased onto the first 32 columns of S[t][b],
+// O[t] at 256 + t*128; Q K^T of tile j+2 then queues behind the P V of tile j on the tensor pipe (same issuing thread).
+// SEP (head dims <= 96 only): O[t] at 256 + t*96 and P[t] in its own 32 columns at 448 + t*32, so that Q K^T of tile j+2 may
+// overwrite S[t][b] as soon as the softmax has READ S_t,j.  Measured at B=16, 4096 tokens, d=96: 0.401 ms against 0.279 ms for the
+// aliased layout -- the extra "S read" barrier (128 arrivals per tile and step) and the second wait point in each issuing warp
+// cost more than the earlier Q K^T buys.  Kept for experiments, off.
+template <int D> struct AttMap {
+  static constexpr bool SEP = false && D <= 96;
+  static constexpr uint32_t OW = SEP ? 96u : 128u;
+  __host__ __device__ static constexpr uint32_t S(int t, int b) { return (uint32_t)t * 128u + (uint32_t)b * 64u; }
+  __host__ __device__ static constexpr uint32_t O(int t) { return 256u + (uint32_t)t * OW; }
+  __host__ __device__ static constexpr uint32_t P(int t, int b) { return SEP ? 448u + (uint32_t)t * 32u : S(t, b); }
+};
 
 __device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
   uint32_t spins = 0;
@@ -152,7 +167,7 @@ __device__ __forceinline__ void att_issue_qk(uint32_t bar0, uint64_t dQ, uint64_
   asm volatile("" : "+l"(dQ), "+l"(dK));        // keep `base + constant` in the uniform datapath (no hoisting into vector registers)
   const uint64_t bD = dK + (uint64_t)(SLOT * (2 * kKvTile >> 4));
   const uint64_t aD = dQ + (uint64_t)(MT * (2 * kTile >> 4));
-  constexpr uint32_t tS = (uint32_t)MT * 128u + (uint32_t)B * 64u;
+  constexpr uint32_t tS = AttMap<D>::S(MT, B);
 #pragma unroll
   for (int k = 0; k < KS0; ++k) tc::umma_f16(tS, aD + (uint64_t)(k * 2), bD + (uint64_t)(k * 2), IDESC_QK, k ? 1u : 0u);
 #pragma unroll
@@ -161,18 +176,32 @@ __device__ __forceinline__ void att_issue_qk(uint32_t bar0, uint64_t dQ, uint64_
   umma_commit_addr(bar0 + kOffKEmpty + 8u * SLOT);       // one of two arrivals (one per issuing warp)
 }
 
-// Key tile j = 4*m + S (ring slot S, S / P buffer S & 1) of Q tile MT: wait for V_j, P_MT,j and K_j+2 at once, then P V of tile j and
-// Q K^T of tile j+2.  `ph`: parity of the ring barriers for the tiles of this round of four.
+// Key tile j = 4*m + S (ring slot S, S buffer S & 1) of Q tile MT.  `ph`: parity of the ring barriers for this round of four tiles.
+//   separate P columns:  wait K_j+2 landed + S_MT,j read  ->  Q K^T of tile j+2;   wait V_j landed + P_MT,j stored  ->  P V of tile j
+//   P aliased onto S:    wait V_j, P_MT,j, K_j+2 at once  ->  P V of tile j, then Q K^T of tile j+2 (ordered by the tensor pipe)
 template <typename T, int D16, int MT, int S>
 __device__ __forceinline__ void att_mma_step(int j, int nkv, uint32_t ph, uint32_t bar0, uint64_t dQ, uint64_t dK, uint64_t dV, int lane) {
   constexpr int D = 16 * D16;
+  using Map = AttMap<D>;
   constexpr uint32_t IDESC_PV = tc::umma_idesc(128, D, tc::umma_fmt<T>()) | (1u << 16);     // B (V) is MN-major
   constexpr int B = S & 1, U1 = (S >> 1) & 1, S2 = (S + 2) & 3;
   const bool more = j + 2 < nkv;
-  if (lane < 3) {
-    const uint32_t addr = bar0 + (lane == 0 ? kOffVFull + 8u * S : lane == 1 ? kOffPFull + 8u * (MT * 2 + B) : kOffKFull + 8u * S2);
-    const uint32_t par = lane == 0 ? ph : lane == 2 ? (ph ^ (S >= 2 ? 1u : 0u)) : (uint32_t)U1;
-    if (lane < 2 || more) mbar_wait_addr(addr, par);
+  const uint32_t kpar = ph ^ (S >= 2 ? 1u : 0u);
+  if (Map::SEP) {
+    if (more) {
+      if (lane < 2) mbar_wait_addr(bar0 + (lane == 0 ? kOffKFull + 8u * S2 : kOffSFree + 8u * (MT * 2 + B)), lane == 0 ? kpar : (uint32_t)U1);
+      __syncwarp();
+      tc::tc_fence_after();
+      if (tc::elect_one()) att_issue_qk<T, D16, MT, S2, B>(bar0, dQ, dK);
+      __syncwarp();
+    }
+    if (lane < 2) mbar_wait_addr(bar0 + (lane == 0 ? kOffVFull + 8u * S : kOffPFull + 8u * (MT * 2 + B)), lane == 0 ? ph : (uint32_t)U1);
+  } else {
+    if (lane < 3) {
+      const uint32_t addr = bar0 + (lane == 0 ? kOffVFull + 8u * S : lane == 1 ? kOffPFull + 8u * (MT * 2 + B) : kOffKFull + 8u * S2);
+      const uint32_t par = lane == 0 ? ph : lane == 2 ? kpar : (uint32_t)U1;
+      if (lane < 2 || more) mbar_wait_addr(addr, par);
+    }
   }
   __syncwarp();
   tc::tc_fence_after();
@@ -181,14 +210,13 @@ __device__ __forceinline__ void att_mma_step(int j, int nkv, uint32_t ph, uint32
     asm volatile("" : "+l"(v_));
     const uint64_t bD = v_ + (uint64_t)(S * (2 * kKvTile >> 4));
     const uint32_t acc0 = j ? 1u : 0u;
-    constexpr uint32_t tP = (uint32_t)MT * 128u + (uint32_t)B * 64u;
 #pragma unroll
     for (int k = 0; k < 4; ++k)     // 4 x 16 keys: +8 columns (two keys each) of P in TMEM, +2048 B (16 key rows) in the MN-major V tile
-      umma_f16_ts(256u + (uint32_t)MT * 128u, tP + (uint32_t)(k * 8), bD + (uint64_t)(k * (2048 >> 4)), IDESC_PV, k ? 1u : acc0);
-    umma_commit_addr(bar0 + kOffPFree + 8u * (MT * 2 + B));
+      umma_f16_ts(Map::O(MT), Map::P(MT, B) + (uint32_t)(k * 8), bD + (uint64_t)(k * (2048 >> 4)), IDESC_PV, k ? 1u : acc0);
+    umma_commit_addr(bar0 + kOffPFree + 8u * (MT * 2 + (Map::SEP ? 0 : B)));
     if (j == nkv - 1) umma_commit_addr(bar0 + kOffOFinal + 8u * MT);
     umma_commit_addr(bar0 + kOffVEmpty + 8u * S);         // one of two arrivals
-    if (more) att_issue_qk<T, D16, MT, S2, B>(bar0, dQ, dK);
+    if (!Map::SEP && more) att_issue_qk<T, D16, MT, S2, B>(bar0, dQ, dK);
   }
   __syncwarp();
 }
@@ -244,7 +272,9 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
   uint64_t* p_full = s_full + 4;            // P_t,j stored to TMEM (and, implied, S_t,j read)
   uint64_t* p_free = p_full + 4;            // P V of that tile completed (waited for only by the lazy rescale)
   uint64_t* o_final = p_free + 4;           // [2] completes once, after the last P V
-  uint32_t* tmem_slot = (uint32_t*)(o_final + 2);
+  uint64_t* s_free = o_final + 2;           // [2 q-tiles][2] S_t,j is in the softmax warps' registers (separate-P map only)
+  uint32_t* tmem_slot = (uint32_t*)(s_free + 4);
+  using Map = AttMap<D>;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256, head = blockIdx.y, img = blockIdx.z;
@@ -258,7 +288,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 2); tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], 2);   // released by both issuing warps
     }
     for (int s = 0; s < 4; ++s) {
-      tc::mbar_init(&s_full[s], 1);
+      tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_free[s], 128);
       tc::mbar_init(&p_full[s], 128); tc::mbar_init(&p_free[s], 1);
     }
     tc::mbar_init(&o_final[0], 1); tc::mbar_init(&o_final[1], 1);
@@ -278,10 +308,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     __trap();
   }
   constexpr uint32_t tmem_base = 0u;
-  // TMEM columns: S[t][b] at t*128 + b*64 (64 wide; P[t][b] = its first 32 columns, 16-bit pairs), O[t] at 256 + t*128 (d <= 128 wide)
-  // Hazards on S / P are ordered by the tensor pipe itself (MMAs execute in issue order): Q K^T of tile j+2 overwrites S[t][b] only
-  // after P V of tile j, issued before it, has read P[t][b]; P V of tile j is issued only after the softmax published P_t,j, i.e.
-  // after it read S_t,j.  No "S free" / "P free" waits remain on the critical path.
+  // TMEM columns: see AttMap.
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -316,17 +343,21 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int q = q0 + t * 128 + row;
-    const uint32_t tO = tmem_base + 256u + (uint32_t)t * 128u + lane_addr;
+    const uint32_t tO = tmem_base + Map::O(t) + lane_addr;
     float m_run = -INFINITY, l_run = 0.f;
     auto step = [&](const int j, auto ragged) {
       const int b = j & 1, u = j >> 1;
       tc::mbar_wait(&s_full[t * 2 + b], u & 1);
       tc::tc_fence_after();
       float v[64];
-      const uint32_t tS = tmem_base + (uint32_t)t * 128u + (uint32_t)b * 64u + lane_addr;
+      const uint32_t tS = tmem_base + Map::S(t, b) + lane_addr;
       tmem_ld32_nowait(tS, v);
       tmem_ld32_nowait(tS + 32, v + 32);
       tmem_ld_wait();
+      if (Map::SEP) {                                // S is in registers: Q K^T of tile j+2 may overwrite this buffer
+        tc::tc_fence_before();
+        tc::mbar_arrive(&s_free[t * 2 + b]);
+      }
       if (decltype(ragged)::value) {               // only the last, partial key tile pays for the masking (64 compare + select)
         const int kvalid = p.HW - j * 64;
 #pragma unroll
@@ -337,7 +368,8 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         uint32_t pk[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) pk[i] = pack2<T>(v[2 * i], v[2 * i + 1]);
-        tmem_st32(tS, reinterpret_cast<const float*>(pk));
+        if (Map::SEP && j > 0) { tc::mbar_wait(&p_free[t * 2], (j - 1) & 1); tc::tc_fence_after(); }
+        tmem_st32(tmem_base + Map::P(t, b) + lane_addr, reinterpret_cast<const float*>(pk));
         tmem_st_wait();
         tc::tc_fence_before();
         tc::mbar_arrive(&p_full[t * 2 + b]);
@@ -361,7 +393,8 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
           const float alpha = need ? ex2((m_run - m_new) * p.scale_log2e) : 1.0f;
           // P V of tile j-1 has landed in O: it is the event that frees P[t][(j-1)&1], phase (j-1)>>1 of that barrier.  At this
           // point the barrier has completed either that phase or only the one before, so the parity wait is unambiguous.
-          tc::mbar_wait(&p_free[t * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
+          if (Map::SEP) tc::mbar_wait(&p_free[t * 2], (j - 1) & 1);       // one barrier per Q tile, one phase per key tile
+          else tc::mbar_wait(&p_free[t * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
           tc::tc_fence_after();
 #pragma unroll
           for (int c = 0; c < DC; ++c) {
@@ -410,7 +443,11 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         pk[i] = pack2<T>(e.x, e.y);
       }
       const float rs0 = rsa.x + rsa.y, rs1 = rsb.x + rsb.y, rs2 = 0.f, rs3 = 0.f;
-      tmem_st32(tS, reinterpret_cast<const float*>(pk));
+      if (Map::SEP && j > 0) {                       // P[t] is single buffered: P V of tile j-1 must have read it
+        tc::mbar_wait(&p_free[t * 2], (j - 1) & 1);
+        tc::tc_fence_after();
+      }
+      tmem_st32(tmem_base + Map::P(t, b) + lane_addr, reinterpret_cast<const float*>(pk));
       tmem_st_wait();
       tc::tc_fence_before();
       tc::mbar_arrive(&p_full[t * 2 + b]);

@@ -55,9 +55,9 @@ struct Conv3SP {
 // epilogue spilled; ptxas -v of that version: 88 bytes of spill stores, 320 of spill loads.)
 constexpr int kSThreads = 384, kSThreadsGN = 640;
 constexpr int kSWarpB = 2;                          // the second MMA-issuing warp
-constexpr int kSRegLow = 56, kSRegLowGN = 40, kSRegXf = 64, kSRegEpiGN = 152, kSRegEpi = 216;
+constexpr int kSRegLow = 56, kSRegLowGN = 40, kSRegXf = 80, kSRegEpiGN = 136, kSRegEpi = 216;
 // The pool setmaxnreg draws from is what the CTA was LAUNCHED with (threads x registers per thread), not the whole register file:
-// GN variant 640 x 96 = 480 x 128 >= (40 + 2 * 152 + 2 * 64) x 128; plain 384 x 168 = 504 x 128 >= (56 + 2 * 216) x 128.  An inc beyond the
+// GN variant 640 x 96 = 480 x 128 >= (40 + 2 * 136 + 2 * 80) x 128 (measured: 80 / 136 beats 64 / 152 -- GN / plain time 1.13 against 1.37); plain 384 x 168 = 504 x 128 >= (56 + 2 * 216) x 128.  An inc beyond the
 // pool never returns (first 640-thread version: 48 + 2*160 + 2*72 = 512 units against 480 -- the second epilogue group hung).
 static_assert(kSRegLowGN + 2 * kSRegEpiGN + 2 * kSRegXf <= (kSThreadsGN * 96) / 128, "GN variant: setmaxnreg budget exceeds the launch allocation");
 static_assert(kSRegLow + 2 * kSRegEpi <= (kSThreads * 168) / 128, "plain variant: setmaxnreg budget exceeds the launch allocation");
@@ -408,30 +408,34 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
           const uint32_t sbase = tc::smem_u32(sA + (size_t)slot * ROW_BYTES + (size_t)cm * kSSlot);
           constexpr int U = 4;
           for (int c0 = plane; c0 < kSBox; c0 += U * NP) {
-            uint32_t addr[U]; bool ok[U]; uint4 qv[U];
+            // straight-line code for the U pixels (loads and arithmetic unconditional, only the store is predicated): with a branch
+            // per pixel the compiler ran the four dependent chains LDS -> cvt -> FFMA2 -> MUFU -> FFMA2 -> cvt -> STS one after the
+            // other (ncu: the transform warps issued on 14 % of their cycles and still paced the kernel)
+            uint32_t addr[U]; bool ok[U]; uint32_t w[U][4];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
               const int cc = c0 + u * NP;
               const int iw = w0 + cc;
               ok[u] = cc < kSBox && iw >= 0 && iw < p.W;
-              addr[u] = sbase + (uint32_t)cc * 128u + (uint32_t)((j8 ^ (cc & 7)) << 4);
-              if (ok[u]) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qv[u].x), "=r"(qv[u].y), "=r"(qv[u].z), "=r"(qv[u].w) : "r"(addr[u]));
+              const int cs = cc < kSBox ? cc : kSBox - 1;             // a pixel past the box reads (and drops) the last one
+              addr[u] = sbase + (uint32_t)cs * 128u + (uint32_t)((j8 ^ (cs & 7)) << 4);
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[u][0]), "=r"(w[u][1]), "=r"(w[u][2]), "=r"(w[u][3]) : "r"(addr[u]));
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-              if (!ok[u]) continue;
-              uint32_t w[4] = {qv[u].x, qv[u].y, qv[u].z, qv[u].w};
+            for (int i = 0; i < 4; ++i) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 h = tc::ffma2(tc::unpack2<T>(w[i]), sc[i], sh[i]);    // 0.5 * GroupNorm(x)
+              for (int u = 0; u < U; ++u) {
+                const float2 h = tc::ffma2(tc::unpack2<T>(w[u][i]), sc[i], sh[i]);    // 0.5 * GroupNorm(x)
                 float2 th;
                 asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(h.x));
                 asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(h.y));
                 const float2 o = tc::ffma2(h, th, h);
-                w[i] = tc::pack2<T>(o.x, o.y);
+                w[u][i] = tc::pack2<T>(o.x, o.y);
               }
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr[u]), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
             }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              if (ok[u]) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr[u]), "r"(w[u][0]), "r"(w[u][1]), "r"(w[u][2]), "r"(w[u][3]) : "memory");
           }
         }
         tc::fence_async_smem();
