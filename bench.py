@@ -290,6 +290,43 @@ def conv_roofline(mode, dev, batch, size):
     return tot_fl / tot_ms / 1e9, tot_ms, launches, tot_fl, by_kernel
 
 
+def insitu_profile(model, x_dev, evals, conv_flops_per_eval):
+    """Per-kernel times of the sampler measured WHERE THE KERNELS RUN: one whole reverse loop (all `evals` UNet evaluations of
+    the step, the launch sequence the CUDA graph replays) launched eagerly with every kernel bracketed by two CUDA events on its
+    stream (include/xrd.h: xrd_profile_begin / _end).  A kernel timed in a loop of its own runs at the clock the power cap
+    allows THAT kernel (conv3s 48->48 @512x512 alone: 1.24 GHz at 990 W); here it runs between its real neighbours at the clock of
+    the real mix, which is what the step is made of.  Returns the conv class's launch-weighted TFLOP/s and the table."""
+    from xrd_b200 import _lib
+    w = model.diffusion_wrapper
+    model.use_cuda_graph = False
+    model.diffusion_unet.use_cuda_graph = False
+    steps = model.inference_diffusion_steps
+    try:
+        w.denoise(x_dev, steps)                  # eager warm-up (plans, packs)
+        torch.cuda.synchronize()
+        _lib.profile_begin()
+        try:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            w.denoise(x_dev, steps)
+            e1.record()
+            torch.cuda.synchronize()
+        finally:
+            prof = _lib.profile_end()
+        loop_ms = e0.elapsed_time(e1)
+    finally:
+        model.use_cuda_graph = True
+        model.diffusion_unet.use_cuda_graph = True
+    conv = ("k_conv3s", "k_conv3", "k_conv3r", "k_conv3w", "k_conv1", "k_conv_tc")
+    tot = sum(v[1] for v in prof.values())
+    conv_ms = sum(v[1] for k, v in prof.items() if k in conv)
+    table = {k: {"launches_per_eval": v[0] / evals, "ms_per_eval": v[1] / evals, "share": v[1] / tot} for k, v in prof.items() if v[1] / tot >= 0.002}
+    return {"how": "eager replay of the step's reverse loop, two CUDA events around every launch (xrd_profile_begin/_end), same batch and "
+                   "inputs as the timed region, taken right after it",
+            "conv_tflops": conv_flops_per_eval * evals / conv_ms / 1e9, "conv_ms_per_eval": conv_ms / evals,
+            "kernels_ms_per_eval": tot / evals, "eager_loop_ms": loop_ms, "evals": evals, "by_kernel": table}
+
+
 _REAL_STDOUT = None
 
 
@@ -437,6 +474,12 @@ def main():
     conv_tf, conv_ms, conv_launches, conv_fl, conv_by = conv_roofline(args.mode, dev, 16, spec["tile"] or S) if do_roof else (0.0, 0.0, 0, 0.0, {})
     step_tf = ips / world * spec["gf_per_image"] / 1000.0
     traffic = top_kernel_traffic(16, spec["tile"] or S)
+    insitu = None
+    if do_roof and not spec["tile"] and B == 16:
+        try:
+            insitu = insitu_profile(model, x_dev, spec["evals"], conv_fl)
+        except Exception as e:  # noqa: BLE001  -- the measurement aid must not cost the bench line
+            insitu = {"error": str(e)[:300]}
     line = {
         "metric": spec["metric"], "value": ips, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -455,7 +498,8 @@ def main():
                      "frac": (conv_tf / pk["burst"]) if (do_roof and pk["burst"]) else None,
                      "peak_kind": f"bf16 dense burst, {pk['src']}",
                      "traffic": traffic["dram_bytes"] if traffic else None, "traffic_source": traffic if traffic else "no ncu capture of this tree for this shape",
-                     "by_kernel": conv_by, "flops_per_eval": conv_fl, "ms_per_eval_isolated": conv_ms, "launches_per_eval": conv_launches},
+                     "by_kernel": conv_by, "flops_per_eval": conv_fl, "ms_per_eval_isolated": conv_ms, "launches_per_eval": conv_launches,
+                     "in_situ": insitu},
         "roofline_step": {"bound": "tensor", "achieved": step_tf, "peak": pk["sustained"], "unit": "TFLOP/s",
                           "frac": step_tf / pk["sustained"], "note": f"images/s x {spec['gf_per_image']:.0f} GF algorithmic per image, of sustained measured peak"},
     }

@@ -112,6 +112,13 @@ const char* xrd_last_error(void);
  * process since load (monotonic; used by bench.py for "gpu_launches"). */
 uint64_t xrd_kernel_launch_count(void);
 
+/* In-situ launch profile (measurement aid; no reference counterpart): between xrd_profile_begin and xrd_profile_end every kernel
+ * this library launches FROM THE CALLING THREAD is bracketed by two CUDA events on its stream.  xrd_profile_end waits for them and
+ * writes "kernel<TAB>launches<TAB>total_ms\n" lines (call with buf = NULL for *need).  Works on eager launches only: run the
+ * sampler with xrd_set_use_graph(h, 0) while profiling. */
+int xrd_profile_begin(void);
+int xrd_profile_end(char* buf, uint64_t cap, uint64_t* need);
+
 /* Replaces: constructing the reference nn.Modules and `.to(device)` (RUN:34-36,46-47,64-68). */
 int xrd_create(int device, const xrd_config* cfg, xrd_handle** out);
 void xrd_destroy(xrd_handle* h);

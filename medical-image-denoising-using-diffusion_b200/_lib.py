@@ -67,6 +67,8 @@ SYMBOLS = {
     "xrd_destroy": (None, [_P]),
     "xrd_set_param": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int, C.c_int]),
     "xrd_finalize_weights": (C.c_int, [_P, C.c_int]),
+    "xrd_profile_begin": (C.c_int, []),
+    "xrd_profile_end": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "xrd_export_weights": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "xrd_import_weights": (C.c_int, [_P, _P, C.c_uint64]),
     "xrd_set_mode": (C.c_int, [_P, C.c_int]),
@@ -142,3 +144,22 @@ def default_config() -> XrdConfig:
     cfg = XrdConfig()
     load().xrd_default_config(C.byref(cfg))
     return cfg
+
+
+def profile_begin() -> None:
+    """Start the in-situ launch profile of the calling thread (include/xrd.h: xrd_profile_begin).  Eager launches only: set
+    ``model.use_cuda_graph = False`` for the profiled calls."""
+    check(load().xrd_profile_begin())
+
+
+def profile_end() -> dict:
+    """Stop it; returns {kernel: (launches, total_ms)} in order of first launch."""
+    lib = load()
+    need = C.c_uint64(0)
+    buf = C.create_string_buffer(1 << 16)
+    check(lib.xrd_profile_end(buf, len(buf), C.byref(need)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.split("\t")
+        out[name] = (int(n), float(ms))
+    return out

@@ -160,6 +160,51 @@ XRD_EXPORT int xrd_api_version(void) { return XRD_API_VERSION; }
 XRD_EXPORT const char* xrd_last_error(void) { return g_last_error.c_str(); }
 XRD_EXPORT uint64_t xrd_kernel_launch_count(void) { return g_launches.load(); }
 
+// ---- in-situ launch profile (common.cuh: LaunchProf) ------------------------------------------------------------------------
+XRD_EXPORT int xrd_profile_begin(void) {
+  return guarded([&] {
+    XRD_REQUIRE(!g_prof, "a launch profile is already running on this thread");
+    g_prof = new LaunchProf();
+    g_prof->recs.reserve(1 << 14);
+  });
+}
+// Ends the profile of the calling thread and writes one line per kernel, "name<TAB>launches<TAB>total_ms\n" (kernel = the launch
+// expression, template arguments as written in the source), in order of first launch.  buf = NULL / too small: *need only.
+XRD_EXPORT int xrd_profile_end(char* buf, uint64_t cap, uint64_t* need) {
+  return guarded([&] {
+    XRD_REQUIRE(g_prof && need, "no launch profile is running on this thread");
+    LaunchProf* pr = g_prof;
+    g_prof = nullptr;
+    std::vector<std::string> order;
+    std::unordered_map<std::string, std::pair<uint64_t, double>> agg;
+    cudaError_t first_err = cudaSuccess;
+    for (auto& r : pr->recs) {
+      float ms = 0.f;
+      cudaError_t e = cudaEventSynchronize(r.e1);
+      if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.e0, r.e1);
+      if (e != cudaSuccess && first_err == cudaSuccess) first_err = e;
+      cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+      std::string name = r.name;
+      const size_t lt = name.find('<');
+      if (lt != std::string::npos) name.resize(lt);
+      while (!name.empty() && (name[0] == '(' || name[0] == ' ')) name.erase(0, 1);
+      auto it = agg.find(name);
+      if (it == agg.end()) { order.push_back(name); it = agg.emplace(name, std::make_pair(0ull, 0.0)).first; }
+      it->second.first += 1; it->second.second += ms;
+    }
+    delete pr;
+    if (first_err != cudaSuccess) fail(XRD_ERR_CUDA, "launch profile: %s (profiles need eager launches, not a graph capture)", cudaGetErrorString(first_err));
+    std::string out;
+    char line[256];
+    for (auto& n : order) {
+      snprintf(line, sizeof(line), "%s\t%llu\t%.6f\n", n.c_str(), (unsigned long long)agg[n].first, agg[n].second);
+      out += line;
+    }
+    *need = out.size() + 1;
+    if (buf && cap >= *need) memcpy(buf, out.c_str(), *need);
+  });
+}
+
 XRD_EXPORT int xrd_ddim_num_evals(int noise_steps, int inference_steps) {
   if (noise_steps < 1) return 0;
   return (int)ddim_timesteps(noise_steps, inference_steps).size();

@@ -7,6 +7,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <atomic>
+#include <vector>
 #include <stdexcept>
 #include <string>
 
@@ -43,6 +44,14 @@ struct Error : public std::runtime_error {
   } while (0)
 
 extern std::atomic<uint64_t> g_launches;
+
+// In-situ launch profile (xrd_profile_begin / xrd_profile_end): while it is on for the calling thread every XRD_LAUNCH is bracketed
+// by two CUDA events on the launching stream, so that a kernel's duration is measured where it runs -- between its real
+// neighbours, at the clocks of the real kernel mix -- and not in a loop of its own.  Eager launches only (events recorded into a
+// stream capture carry no time).
+struct LaunchRec { const char* name; cudaEvent_t e0, e1; };
+struct LaunchProf { std::vector<LaunchRec> recs; };
+extern thread_local LaunchProf* g_prof;
 
 // Makes `dev` the calling thread's current device for the lifetime of the object and restores the previous one afterwards
 // (the C entry points must not leave the caller's thread on another device).
@@ -139,7 +148,15 @@ struct Ctx {
 #define XRD_LAUNCH(ctx, kernel, grid, block, smem, ...)                                   \
   do {                                                                                    \
     if (!(ctx).dry) {                                                                     \
+      ::xrd::LaunchRec* pr__ = nullptr;                                                   \
+      if (::xrd::g_prof) {                                                                \
+        ::xrd::g_prof->recs.push_back({#kernel, nullptr, nullptr});                       \
+        pr__ = &::xrd::g_prof->recs.back();                                               \
+        cudaEventCreate(&pr__->e0); cudaEventCreate(&pr__->e1);                           \
+        cudaEventRecord(pr__->e0, (ctx).s);                                               \
+      }                                                                                   \
       kernel<<<(grid), (block), (smem), (ctx).s>>>(__VA_ARGS__);                          \
+      if (pr__) cudaEventRecord(pr__->e1, (ctx).s);                                       \
       ::xrd::g_launches.fetch_add(1, std::memory_order_relaxed);                          \
       cudaError_t e__ = cudaPeekAtLastError();                                            \
       if (e__ != cudaSuccess)                                                             \

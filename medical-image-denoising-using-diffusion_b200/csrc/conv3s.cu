@@ -145,7 +145,7 @@ __device__ __forceinline__ void c3s_iteration(C3SState& st, const C3SBars& b, ui
     // shares a slot with the previous one (the other warp's), and probing that slot's barrier before the other warp's wait has
     // been satisfied would succeed on the WRONG phase.  There the baton (passed after the other warp's waits) is taken first.
     if (R < 4) {
-      if (lane == 2 && st.k > 0u) tc::mbar_wait(&b.baton[my], ((st.k >> 1) & 1u) ^ (my ? 0u : 1u));
+      if (lane == 2 && st.k > 0u) tc::mbar_wait(&b.baton[my], ((st.k >> 1) & 1u) ^ (my ? 0u : 1u), 34);
       __syncwarp();
     }
     // SPLIT (shallow ring + input transform: the two-chunk GN variants): the ring cannot hold the two rows of the NEXT iteration
@@ -154,12 +154,12 @@ __device__ __forceinline__ void c3s_iteration(C3SState& st, const C3SBars& b, ui
     // transform the split costs more than it hides (plain 96->48 @512: 370 us up front, 426 us split).
     if (lane < (SPLIT ? 1 : 2)) {
       const uint32_t sx = lane ? s1 : s0;
-      tc::mbar_wait(&b.rbar[sx], (st.rph >> sx) & 1u);
+      tc::mbar_wait(&b.rbar[sx], (st.rph >> sx) & 1u, 32);
     } else if (lane >= 8 && lane < 10 && J + (lane - 8) < SEG) {
       const int o = J + (lane - 8);
-      tc::mbar_wait(&b.acc_empty[o % kSNB], ((st.accb + dec) & 1u) ^ 1u);
+      tc::mbar_wait(&b.acc_empty[o % kSNB], ((st.accb + dec) & 1u) ^ 1u, 33);
     } else if (R >= 4 && lane == 2 && st.k > 0u) {
-      tc::mbar_wait(&b.baton[my], ((st.k >> 1) & 1u) ^ (my ? 0u : 1u));
+      tc::mbar_wait(&b.baton[my], ((st.k >> 1) & 1u) ^ (my ? 0u : 1u), 34);
     }
     __syncwarp();
     tc::tc_fence_after();
@@ -177,7 +177,7 @@ __device__ __forceinline__ void c3s_iteration(C3SState& st, const C3SBars& b, ui
     }
     if (SPLIT) {
       __syncwarp();
-      if (lane == 1) tc::mbar_wait(&b.rbar[s1], (st.rph >> s1) & 1u);
+      if (lane == 1) tc::mbar_wait(&b.rbar[s1], (st.rph >> s1) & 1u, 32);
       __syncwarp();
       tc::tc_fence_after();
     }
@@ -337,15 +337,32 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
         C3SItems it(p, wi, nw);
         int img, cb, r0, rows;
         while (it.next(p, img, cb, r0, rows)) {
-          for (int j = 0; j < rows + 2; ++j) {
-            tc::mbar_wait(&r_empty[slot], phase ^ 1);
-            tc::mbar_expect_tx(&r_full[slot], (uint32_t)NCH * kSBox * 128u);
-            uint8_t* dst = sA + (size_t)slot * ROW_BYTES;
-            tc::tma_load_4d(dst, &tmA0, &r_full[slot], 0, cb * 128 - 1, r0 - 1 + j, img);      // rows / columns outside the image: zero fill
+          auto fetch = [&](int j, uint32_t sl, uint32_t ph) {
+            tc::mbar_wait_relaxed(&r_empty[sl], ph ^ 1, 31);
+            tc::mbar_expect_tx(&r_full[sl], (uint32_t)NCH * kSBox * 128u);
+            uint8_t* dst = sA + (size_t)sl * ROW_BYTES;
+            tc::tma_load_4d(dst, &tmA0, &r_full[sl], 0, cb * 128 - 1, r0 - 1 + j, img);      // rows / columns outside the image: zero fill
             if (NCH == 2) {
-              if (p.two_src) tc::tma_load_4d(dst + kSSlot, &tmA1, &r_full[slot], 0, cb * 128 - 1, r0 - 1 + j, img);
-              else tc::tma_load_4d(dst + kSSlot, &tmA0, &r_full[slot], 64, cb * 128 - 1, r0 - 1 + j, img);
+              if (p.two_src) tc::tma_load_4d(dst + kSSlot, &tmA1, &r_full[sl], 0, cb * 128 - 1, r0 - 1 + j, img);
+              else tc::tma_load_4d(dst + kSSlot, &tmA0, &r_full[sl], 64, cb * 128 - 1, r0 - 1 + j, img);
             }
+          };
+          for (int j = 0; j < rows + 2; ++j) {
+#ifdef XRD_C3S_RACE_TEST
+            // Fault injection (tools/race_c3s.sh): every few rows the NEXT row is fetched first and this one several microseconds
+            // later -- an exaggerated out-of-order completion of two TMA loads.  The row protocol must not care in which order rows land.
+            if ((j % 5) == 1 && j + 1 < rows + 2) {
+              uint32_t s2 = slot + 1, p2 = phase;
+              if (s2 == R) { s2 = 0; p2 ^= 1; }
+              fetch(j + 1, s2, p2);
+              __nanosleep(6000);
+              fetch(j, slot, phase);
+              slot = s2; phase = p2; ++j;
+              if (++slot == R) { slot = 0; phase ^= 1; }
+              continue;
+            }
+#endif
+            fetch(j, slot, phase);
             if (++slot == R) { slot = 0; phase ^= 1; }
           }
         }
@@ -354,7 +371,7 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
     } else if (warp == 1 || warp == kSWarpB) {
       // ===================== MMA issuers (two warps, alternating iterations) =====================
       const uint32_t my = warp == 1 ? 0u : 1u;
-      tc::mbar_wait(w_full, 0);
+      tc::mbar_wait(w_full, 0, 37);
       const uint32_t id48 = tc::umma_idesc(128, 48, tc::umma_fmt<T>());
       const uint64_t adesc0 = tc::umma_desc_sw128(tc::smem_u32(sA));
       const uint64_t bdesc0 = tc::umma_desc_sw128(tc::smem_u32(sB));
@@ -399,10 +416,20 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
       const int w0 = cb * 128 - 1;
       for (int j = 0; j < rows + 2; ++j, ++nrow) {
         if ((nrow & 1u) != xw) {
+          // A parity wait can only tell "the current phase" from "the one before".  With an ODD ring the two warpgroups alternate on
+          // every slot (row n and row n + R have different parities), so a group that simply skipped the other group's rows would
+          // see only every other phase of r_full[slot]: its next wait on the slot (row n + 2R... same parity as row n) passes on
+          // the STALE phase if the other group's row has not landed yet (TMA loads complete out of order under load), the group
+          // then runs ahead of the producer through every later wait and its arrivals scramble r_ready (seen once in ~1e5 launches
+          // as an MMA-warp time-out on r_ready).  It therefore observes the skipped row's landing too; with an even ring a slot
+          // always belongs to the same group and nothing is skipped.
+#ifndef XRD_C3S_RACE_NOFIX
+          if (R & 1) tc::mbar_wait_relaxed(&r_full[slot], phase, 38);
+#endif
           if (++slot == R) { slot = 0; phase ^= 1; }
           continue;
         }
-        tc::mbar_wait(&r_full[slot], phase);
+        tc::mbar_wait_relaxed(&r_full[slot], phase, 35);
         const int ih = r0 - 1 + j;
         if (ih >= 0 && ih < p.H && active) {
           const uint32_t sbase = tc::smem_u32(sA + (size_t)slot * ROW_BYTES + (size_t)cm * kSSlot);
@@ -508,7 +535,7 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
 #pragma unroll
           for (int j = 0; j < 6; ++j) rc[j] = __ldg(reinterpret_cast<const uint4*>(rp + pix * CT) + j);
         }
-        tc::mbar_wait(&acc_full[a], use & 1);
+        tc::mbar_wait_relaxed(&acc_full[a], use & 1, 36);
         tc::tc_fence_after();
         if (!row_ok) {                                       // nothing to read: hand the block straight back
           tc::tc_fence_before();

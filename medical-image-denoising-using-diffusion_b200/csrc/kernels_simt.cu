@@ -7,6 +7,7 @@
 namespace xrd {
 
 std::atomic<uint64_t> g_launches{0};
+thread_local LaunchProf* g_prof = nullptr;
 
 // =====================================================================================
 // generic implicit-GEMM convolution on CUDA cores (fp32 accumulate)

@@ -65,11 +65,28 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 // during which the (shallow) MMA queue drains; probing the NEXT barrier before issuing the current MMAs hides that round trip.
 __device__ __forceinline__ void mbar_wait_probed(bool first, uint64_t* bar, uint32_t parity);
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// `tag`: which wait of which kernel (printed on a time-out; each kernel numbers its own).
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
-      printf("libxrd: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, parity);
+    if (++spins > (1u << 24)) {
+      printf("libxrd: mbarrier wait timed out (tag %d, block %d,%d of %d, thread %d of %d, parity %u, barrier +%u)\n", tag, blockIdx.x, blockIdx.y,
+             gridDim.x, threadIdx.x, blockDim.x, parity, smem_u32(bar));
+      __trap();
+    }
+  }
+}
+
+// Wait of a role that has slack (epilogue, input transform, TMA producer): back off between probes instead of re-issuing the probe
+// at full rate.  (ncu of conv3s: the epilogue warps executed 29 probes per output row; on a power-capped part every issued
+// instruction of a waiting warp is paid for in SM clock.)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int tag = 0) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(32);
+    if (++spins > (1u << 24)) {
+      printf("libxrd: mbarrier wait timed out (tag %d, block %d,%d of %d, thread %d of %d, parity %u, barrier +%u)\n", tag, blockIdx.x, blockIdx.y,
+             gridDim.x, threadIdx.x, blockDim.x, parity, smem_u32(bar));
       __trap();
     }
   }
