@@ -2,6 +2,8 @@
 // exception at the boundary, plans/grows the arena, captures and replays the sampler graph,
 // splits large batches into micro-batches.
 #include <functional>
+#include <cxxabi.h>
+#include <stdlib.h>
 #include "engine.cuh"
 
 #include <string.h>
@@ -185,9 +187,18 @@ XRD_EXPORT int xrd_profile_end(char* buf, uint64_t cap, uint64_t* need) {
       if (e != cudaSuccess && first_err == cudaSuccess) first_err = e;
       cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
       std::string name = r.name;
-      const size_t lt = name.find('<');
-      if (lt != std::string::npos) name.resize(lt);
+      if (name.rfind("_Z", 0) == 0) {
+        int st = 0;
+        char* dm = abi::__cxa_demangle(name.c_str(), nullptr, nullptr, &st);
+        if (dm) { if (st == 0) name = dm; free(dm); }
+      }
+      // "void xrd::k_conv3s<__half, 3, 0, 8, 1, true>(CUtensorMap_st, ...)" (or the launch expression "(k_foo<T, 1>)") -> "k_conv3s"
       while (!name.empty() && (name[0] == '(' || name[0] == ' ')) name.erase(0, 1);
+      if (name.compare(0, 5, "void ") == 0) name.erase(0, 5);
+      const size_t lt = name.find_first_of("<(");
+      if (lt != std::string::npos) name.resize(lt);
+      const size_t ns = name.rfind("::");
+      if (ns != std::string::npos) name.erase(0, ns + 2);
       auto it = agg.find(name);
       if (it == agg.end()) { order.push_back(name); it = agg.emplace(name, std::make_pair(0ull, 0.0)).first; }
       it->second.first += 1; it->second.second += ms;

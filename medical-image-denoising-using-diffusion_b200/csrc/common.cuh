@@ -150,7 +150,9 @@ struct Ctx {
     if (!(ctx).dry) {                                                                     \
       ::xrd::LaunchRec* pr__ = nullptr;                                                   \
       if (::xrd::g_prof) {                                                                \
-        ::xrd::g_prof->recs.push_back({#kernel, nullptr, nullptr});                       \
+        const char* nm__ = nullptr;   /* the launched function's own (mangled) name: #kernel is "kern" inside a dispatch lambda */ \
+        if (cudaFuncGetName(&nm__, (const void*)(kernel)) != cudaSuccess || !nm__) { (void)cudaGetLastError(); nm__ = #kernel; } \
+        ::xrd::g_prof->recs.push_back({nm__, nullptr, nullptr});                          \
         pr__ = &::xrd::g_prof->recs.back();                                               \
         cudaEventCreate(&pr__->e0); cudaEventCreate(&pr__->e1);                           \
         cudaEventRecord(pr__->e0, (ctx).s);                                               \

@@ -29,6 +29,10 @@
 #include <vector>
 #include <stdlib.h>
 
+#ifndef XRD_C3S_XF_BOTH
+#define XRD_C3S_XF_BOTH 1
+#endif
+
 namespace xrd {
 
 struct Conv3SP {
@@ -48,12 +52,13 @@ struct Conv3SP {
 // Warp roles, aligned to warpgroups so that each role gets its own register budget (setmaxnreg):
 //   warpgroup 0: warp 0 TMA producer, warps 1 + 2 MMA issuers (ping-pong), warp 3 idle        -> 56 registers
 //   warpgroups 1, 2: the two epilogue groups (warps 4..7, 8..11; warp % 4 = its TMEM lane quarter) -> 184 (GN) / 216
-//   warpgroups 3, 4 (GN variant only): input transform, warps 12..15 take the even landed rows, 16..19 the odd ones -> 72
+//   warpgroups 3, 4 (GN variant only): input transform, warps 12..15 take the even landed rows, 16..19 the odd ones -> 80
 //     (ncu of the version with ONE transform warpgroup: its warps were busy 90 % of the time, 2150 cycles per row against 1160
 //     of the plain kernel -- the transform, not the tensor pipe, paced the kernel)
 // (the first version had 11 / 15 warps under one budget: the GN variant's 480 threads left 128 registers per thread and its
 // epilogue spilled; ptxas -v of that version: 88 bytes of spill stores, 320 of spill loads.)
 constexpr int kSThreads = 384, kSThreadsGN = 640;
+constexpr bool kSXfBoth = XRD_C3S_XF_BOTH;         // both transform warpgroups work on every landed row (half the pixels each)
 constexpr int kSWarpB = 2;                          // the second MMA-issuing warp
 constexpr int kSRegLow = 56, kSRegLowGN = 40, kSRegXf = 80, kSRegEpiGN = 136, kSRegEpi = 216;
 // The pool setmaxnreg draws from is what the CTA was LAUNCHED with (threads x registers per thread), not the whole register file:
@@ -303,7 +308,7 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
     tc::tma_prefetch_desc(&tmA0);
     tc::tma_prefetch_desc(&tmA1);
     tc::tma_prefetch_desc(&tmB);
-    for (int s = 0; s < R; ++s) { tc::mbar_init(&r_full[s], 1); tc::mbar_init(&r_ready[s], 128); tc::mbar_init(&r_empty[s], 1); }
+    for (int s = 0; s < R; ++s) { tc::mbar_init(&r_full[s], 1); tc::mbar_init(&r_ready[s], kSXfBoth ? 256 : 128); tc::mbar_init(&r_empty[s], 1); }
     // acc_full: two arrivals per use -- a commit of the warp that issued the output's first row and one of the warp that issued its last
     for (int s = 0; s < kSNB; ++s) { tc::mbar_init(&acc_full[s], 2); tc::mbar_init(&acc_empty[s], 128); }
     tc::mbar_init(&baton[0], 1); tc::mbar_init(&baton[1], 1);
@@ -388,16 +393,23 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
     // chunk j ^ (sp & 7) (128B swizzle on absolute addresses; slots are 1024-aligned).  Out-of-image pixels stay zero.
     // Arithmetic on packed fp32 pairs (FFMA2): x*sigmoid(x) = h*tanh(h) + h with h = x/2 folded into the coefficients.
     c3s_reg_dec<kSRegXf>();
-    const uint32_t xw = (uint32_t)(warp - 12) >> 2;
+    const uint32_t xw = kSXfBoth ? 0u : (uint32_t)(warp - 12) >> 2;
     const int tt = threadIdx.x - 384 - (int)xw * 128;
-    // a thread works on ONE chunk (its 8 coefficient pairs stay in registers): with two chunks the warpgroup's threads are split
-    // between them in proportion to their channel counts -- NP pixel lanes of NV0 + NV1 16-byte channel chunks each
-    constexpr int NV0 = KS0 * 2, NV1 = KS1 * 2, NP = 128 / (NV0 + NV1);
-    const int cm = (NCH == 2 && tt >= NP * NV0) ? 1 : 0;
-    const int t2 = cm ? tt - NP * NV0 : tt;
-    const int nvc = cm ? NV1 : NV0;
-    const int j8 = t2 % nvc, plane = t2 / nvc;
-    const bool active = plane < NP;
+    // a thread works on ONE 16-byte channel chunk (its 8 coefficient pairs stay in registers) of every pixel it visits.
+    // Quarter-warp q (8 consecutive threads: one shared-memory wavefront of a 16-byte access) = chunk v of EIGHT CONSECUTIVE
+    // pixels: their physical chunks v ^ (pixel & 7) are the eight different 16-byte bank groups, so every LDS.128 / STS.128 is one
+    // wavefront.  (The first mapping put the chunks of one pixel on consecutive threads; with 6 of 8 chunks valid a quarter-warp
+    // straddled two pixels whose swizzled chunks collided: ncu counted 510 shared-memory wavefronts per row for 196 ideal, on a
+    // pipe the N=144 MMAs alone keep ~95 % busy.)  With NVT chunks per pixel the 16 quarter-warps of the warpgroup form
+    // OL = 16 / NVT octet lanes (48 channels: 2 lanes, the fourth warp idles; two chunks of 48: one lane).
+    constexpr int NV0 = KS0 * 2, NV1 = KS1 * 2, NVT = NV0 + NV1, OL = (kSXfBoth ? 32 : 16) / NVT;
+    constexpr int NOCT = (kSBox + 7) / 8, SLOTS = (NOCT + OL - 1) / OL;       // pixel octets per row; octets a thread visits
+    constexpr int U = SLOTS <= 5 ? SLOTS : 3;                                  // pixels in flight per thread
+    const int q = tt >> 3, l8 = tt & 7;
+    const int v = q % NVT, ol = q / NVT;
+    const bool active = q < OL * NVT;
+    const int cm = (NCH == 2 && v >= NV0) ? 1 : 0;
+    const int j8 = cm ? v - NV0 : v;
     float2 sc[4], sh[4];
     int cur_img = -1;
     uint32_t slot = 0, phase = 0, nrow = 0;
@@ -415,7 +427,7 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
       cur_img = img;
       const int w0 = cb * 128 - 1;
       for (int j = 0; j < rows + 2; ++j, ++nrow) {
-        if ((nrow & 1u) != xw) {
+        if (!kSXfBoth && (nrow & 1u) != xw) {
           // A parity wait can only tell "the current phase" from "the one before".  With an ODD ring the two warpgroups alternate on
           // every slot (row n and row n + R have different parities), so a group that simply skipped the other group's rows would
           // see only every other phase of r_full[slot]: its next wait on the slot (row n + 2R... same parity as row n) passes on
@@ -433,15 +445,15 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
         const int ih = r0 - 1 + j;
         if (ih >= 0 && ih < p.H && active) {
           const uint32_t sbase = tc::smem_u32(sA + (size_t)slot * ROW_BYTES + (size_t)cm * kSSlot);
-          constexpr int U = 4;
-          for (int c0 = plane; c0 < kSBox; c0 += U * NP) {
+#pragma unroll 1
+          for (int c0 = ol * 8 + l8; c0 < kSBox; c0 += U * OL * 8) {
             // straight-line code for the U pixels (loads and arithmetic unconditional, only the store is predicated): with a branch
             // per pixel the compiler ran the four dependent chains LDS -> cvt -> FFMA2 -> MUFU -> FFMA2 -> cvt -> STS one after the
             // other (ncu: the transform warps issued on 14 % of their cycles and still paced the kernel)
             uint32_t addr[U]; bool ok[U]; uint32_t w[U][4];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-              const int cc = c0 + u * NP;
+              const int cc = c0 + u * OL * 8;
               const int iw = w0 + cc;
               ok[u] = cc < kSBox && iw >= 0 && iw < p.W;
               const int cs = cc < kSBox ? cc : kSBox - 1;             // a pixel past the box reads (and drops) the last one
