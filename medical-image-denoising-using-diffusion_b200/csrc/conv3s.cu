@@ -410,7 +410,16 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
     const bool active = q < OL * NVT;
     const int cm = (NCH == 2 && v >= NV0) ? 1 : 0;
     const int j8 = cm ? v - NV0 : v;
-    float2 sc[4], sh[4];
+    // Everything that does not depend on the row is computed once: the thread's byte offset inside a row slot (pixel ol*8 + l8 of
+    // the first octet it visits, its physical 16-byte chunk j8 ^ l8 -- every octet starts at a multiple of 8 pixels, so the swizzle
+    // term is the same for all of them; later octets are +OL KB, an immediate of the load), the coefficient pairs as 64-bit
+    // operands of the packed FMAs, and -- per work item -- one bit per visited octet saying whether the pixel is inside the image
+    // and the box.  (SASS of the version that recomputed addresses and predicates per pixel and passed the coefficients as scalar
+    // floats: 230 instructions per body of which 120 were loads, conversions, FMAs, MUFU and stores -- 68 MOVs re-pairing the
+    // coefficient registers for every pixel, 40 address / predicate instructions; ncu: IPC 0.63 per scheduler, the transform's
+    // 64 M warp instructions against 45 M of the whole plain kernel.)
+    uint64_t sc[4], sh[4];
+    const uint32_t toff = (uint32_t)((ol * 8 + l8) * 128) + (uint32_t)((j8 ^ l8) << 4) + (uint32_t)cm * kSSlot;
     int cur_img = -1;
     uint32_t slot = 0, phase = 0, nrow = 0;
     C3SItems it(p, wi, nw);
@@ -421,20 +430,28 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float2 a = __ldg(cf + 2 * i), b = __ldg(cf + 2 * i + 1);
-          sc[i] = make_float2(a.x, b.x); sh[i] = make_float2(a.y, b.y);
+          // "+ 0" makes each pair the RESULT of a packed instruction, i.e. a value living in its own aligned register pair; a bare
+          // mov.b64 {a.x, b.x} is rematerialised by ptxas in front of every use (two MOVs per packed operand per pixel)
+          sc[i] = tc::fadd2_64(tc::pack_f32x2(a.x, b.x), 0ull); sh[i] = tc::fadd2_64(tc::pack_f32x2(a.y, b.y), 0ull);
         }
       }
       cur_img = img;
-      const int w0 = cb * 128 - 1;
+      uint32_t okmask = 0;                  // bit s: the pixel of octet ol + OL*s this thread visits is inside the box and the image
+      if (active) {
+#pragma unroll
+        for (int sx = 0; sx < SLOTS; ++sx) {
+          const int cc = (ol + OL * sx) * 8 + l8, iw = cb * 128 - 1 + cc;
+          if (cc < kSBox && iw >= 0 && iw < p.W) okmask |= 1u << sx;
+        }
+      }
       for (int j = 0; j < rows + 2; ++j, ++nrow) {
         if (!kSXfBoth && (nrow & 1u) != xw) {
-          // A parity wait can only tell "the current phase" from "the one before".  With an ODD ring the two warpgroups alternate on
-          // every slot (row n and row n + R have different parities), so a group that simply skipped the other group's rows would
-          // see only every other phase of r_full[slot]: its next wait on the slot (row n + 2R... same parity as row n) passes on
-          // the STALE phase if the other group's row has not landed yet (TMA loads complete out of order under load), the group
-          // then runs ahead of the producer through every later wait and its arrivals scramble r_ready (seen once in ~1e5 launches
-          // as an MMA-warp time-out on r_ready).  It therefore observes the skipped row's landing too; with an even ring a slot
-          // always belongs to the same group and nothing is skipped.
+          // A parity wait can only tell "the current phase" from "the one before".  With an ODD ring two warpgroups taking alternate
+          // rows alternate on every slot too, so a group that simply skipped the other group's rows would see only every other
+          // phase of r_full[slot]: its next wait on the slot passes on the STALE phase if the other group's row has not landed
+          // yet (TMA loads complete out of order under load), the group then runs ahead of the producer through every later
+          // wait and its arrivals scramble r_ready (seen once in ~1e5 launches as an MMA-warp time-out on r_ready).  It therefore
+          // observes the skipped row's landing too.  (Default build: both groups work on every row and nothing is skipped.)
 #ifndef XRD_C3S_RACE_NOFIX
           if (R & 1) tc::mbar_wait_relaxed(&r_full[slot], phase, 38);
 #endif
@@ -443,38 +460,38 @@ k_conv3s(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
         }
         tc::mbar_wait_relaxed(&r_full[slot], phase, 35);
         const int ih = r0 - 1 + j;
-        if (ih >= 0 && ih < p.H && active) {
-          const uint32_t sbase = tc::smem_u32(sA + (size_t)slot * ROW_BYTES + (size_t)cm * kSSlot);
-#pragma unroll 1
-          for (int c0 = ol * 8 + l8; c0 < kSBox; c0 += U * OL * 8) {
-            // straight-line code for the U pixels (loads and arithmetic unconditional, only the store is predicated): with a branch
-            // per pixel the compiler ran the four dependent chains LDS -> cvt -> FFMA2 -> MUFU -> FFMA2 -> cvt -> STS one after the
-            // other (ncu: the transform warps issued on 14 % of their cycles and still paced the kernel)
-            uint32_t addr[U]; bool ok[U]; uint32_t w[U][4];
+        if (ih >= 0 && ih < p.H && okmask) {
+          const uint32_t sbase = tc::smem_u32(sA + (size_t)slot * ROW_BYTES) + toff;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const int cc = c0 + u * OL * 8;
-              const int iw = w0 + cc;
-              ok[u] = cc < kSBox && iw >= 0 && iw < p.W;
-              const int cs = cc < kSBox ? cc : kSBox - 1;             // a pixel past the box reads (and drops) the last one
-              addr[u] = sbase + (uint32_t)cs * 128u + (uint32_t)((j8 ^ (cs & 7)) << 4);
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[u][0]), "=r"(w[u][1]), "=r"(w[u][2]), "=r"(w[u][3]) : "r"(addr[u]));
-            }
+          for (int s0 = 0; s0 < SLOTS; s0 += U) {
+            // straight-line code for the U pixels in flight (loads and arithmetic unconditional, only the store is predicated; an
+            // octet past the box reads whatever follows in shared memory and drops it): with a branch per pixel the compiler ran
+            // the dependent chains LDS -> cvt -> FFMA2 -> MUFU -> FFMA2 -> cvt -> STS one after the other
+            uint32_t w[U][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              if (s0 + u < SLOTS)
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[u][0]), "=r"(w[u][1]), "=r"(w[u][2]), "=r"(w[u][3])
+                             : "r"(sbase + (uint32_t)((s0 + u) * OL * 1024)));      // base + constant: folded into the instruction's immediate
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
 #pragma unroll
               for (int u = 0; u < U; ++u) {
-                const float2 h = tc::ffma2(tc::unpack2<T>(w[u][i]), sc[i], sh[i]);    // 0.5 * GroupNorm(x)
+                if (s0 + u >= SLOTS) continue;
+                const uint64_t h = tc::ffma2_64(tc::pack_f32x2(tc::unpack2<T>(w[u][i])), sc[i], sh[i]);    // 0.5 * GroupNorm(x)
+                const float2 hf = tc::unpack_f32x2(h);
                 float2 th;
-                asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(h.x));
-                asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(h.y));
-                const float2 o = tc::ffma2(h, th, h);
+                asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(hf.x));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(hf.y));
+                const float2 o = tc::unpack_f32x2(tc::ffma2_64(h, tc::pack_f32x2(th), h));
                 w[u][i] = tc::pack2<T>(o.x, o.y);
               }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
-              if (ok[u]) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr[u]), "r"(w[u][0]), "r"(w[u][1]), "r"(w[u][2]), "r"(w[u][3]) : "memory");
+              if (s0 + u < SLOTS && (okmask >> (s0 + u) & 1u))
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + (uint32_t)((s0 + u) * OL * 1024)), "r"(w[u][0]), "r"(w[u][1]),
+                             "r"(w[u][2]), "r"(w[u][3]) : "memory");
           }
         }
         tc::fence_async_smem();

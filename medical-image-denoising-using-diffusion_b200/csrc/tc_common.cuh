@@ -247,6 +247,29 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
       : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
   return r;
 }
+// packed fp32 pairs held as ONE 64-bit register value (loop-invariant operands keep their aligned register pair; with scalar "f"
+// operands the compiler re-pairs them with MOVs in front of every packed instruction)
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack_f32x2(float2 v) { return pack_f32x2(v.x, v.y); }
+__device__ __forceinline__ float2 unpack_f32x2(uint64_t v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ uint64_t fadd2_64(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t ffma2_64(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t u);
 template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
 template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u)); }
