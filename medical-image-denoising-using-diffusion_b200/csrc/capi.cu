@@ -195,6 +195,7 @@ XRD_EXPORT int xrd_profile_end(char* buf, uint64_t cap, uint64_t* need) {
       // "void xrd::k_conv3s<__half, 3, 0, 8, 1, true>(CUtensorMap_st, ...)" (or the launch expression "(k_foo<T, 1>)") -> "k_conv3s"
       while (!name.empty() && (name[0] == '(' || name[0] == ' ')) name.erase(0, 1);
       if (name.compare(0, 5, "void ") == 0) name.erase(0, 5);
+      for (size_t an; (an = name.find("(anonymous namespace)::")) != std::string::npos;) name.erase(an, 23);
       const size_t lt = name.find_first_of("<(");
       if (lt != std::string::npos) name.resize(lt);
       const size_t ns = name.rfind("::");
