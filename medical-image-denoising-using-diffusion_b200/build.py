@@ -12,6 +12,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 OUT = os.path.join(_HERE, "libxrd.so")
+# Test-only twin of the library: conv3s.cu compiled with XRD_C3S_RACE_TEST (its TMA producer fetches rows out of order, microseconds
+# apart) so that the GPU suite can run the row protocol under an exaggerated out-of-order completion of TMA loads
+# (tests/test_gpu_parity.py::test_conv3s_row_protocol_under_fault_injection).  Never loaded by the package.
+OUT_FAULTINJ = os.path.join(_HERE, "libxrd_faultinj.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -31,9 +35,9 @@ def _sources():
 
 
 def _stale() -> bool:
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or not os.path.exists(OUT_FAULTINJ):
         return True
-    t = os.path.getmtime(OUT)
+    t = min(os.path.getmtime(OUT), os.path.getmtime(OUT_FAULTINJ))
     deps = _sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
         glob.glob(os.path.join(_ROOT, "include", "*.h"))
     return any(os.path.getmtime(d) > t for d in deps)
@@ -59,6 +63,10 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
         procs.append((src, subprocess.Popen([nvcc, "-c", src, "-o", obj] + common,
                                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    fi_obj = os.path.join(objdir, "conv3s_faultinj.o")
+    procs.append((os.path.join(CSRC, "conv3s.cu") + " [fault injection]",
+                  subprocess.Popen([nvcc, "-c", os.path.join(CSRC, "conv3s.cu"), "-o", fi_obj, "-DXRD_C3S_RACE_TEST"] + common,
+                                   stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
         out, _ = p.communicate()
@@ -69,10 +77,13 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed")
     link = [nvcc, "-shared", "-o", OUT] + objs + flags + ["-cudart", "static", "-Xlinker", "--no-undefined",
                                                            "-lpthread", "-ldl", "-lrt"]
-    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout)
-        raise RuntimeError("link failed")
+    link_fi = [nvcc, "-shared", "-o", OUT_FAULTINJ] + [o for o in objs if os.path.basename(o) != "conv3s.o"] + [fi_obj] + flags + \
+        ["-cudart", "static", "-Xlinker", "--no-undefined", "-lpthread", "-ldl", "-lrt"]
+    for cmd in (link, link_fi):
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout)
+            raise RuntimeError("link failed")
     return OUT
 
 

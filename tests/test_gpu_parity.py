@@ -306,6 +306,51 @@ def test_expert_denoiser_fp32_and_f16():
     assert max(r["golden64_b2"], r["golden40x56"], r["golden40x56_base32"], r["oracle512"]) < 2e-3, r
 
 
+# ------------------------------------------------------------------ barrier protocol under fault injection; launch profile
+def test_conv3s_row_protocol_under_fault_injection():
+    """conv3s's row ring with an exaggerated out-of-order completion of its TMA loads (libxrd_faultinj.so: conv3s.cu built with
+    XRD_C3S_RACE_TEST -- every few rows the NEXT row is fetched first and the current one 6 us later).  The protocol must not
+    care in which order rows land: numerics against fp64 F.conv2d for every stacked-kernel case (plain, fused GroupNorm+SiLU, virtual
+    concat = the three-row ring), then 200 launches of each benched shape.  (The pre-fix protocol traps here within 200 launches:
+    profiles/r02_conv3s_race_injection.log.)  Runs in its own process: a second copy of the library must not share this one's."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "medical-image-denoising-using-diffusion_b200", "libxrd_faultinj.so")
+    assert os.path.exists(lib), "libxrd_faultinj.so is not built (python -c 'import __graft_entry__ as g; g.build()')"
+    env = dict(os.environ, XRD_RACE_LIB=lib)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "race_c3s.py")], capture_output=True, text=True, timeout=420, env=env, cwd=root)
+    assert r.returncode == 0 and "race test ok" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
+
+
+def test_in_situ_launch_profile():
+    """xrd_profile_begin / xrd_profile_end: every kernel of an eager sampler run, by name, with times; launch counts agree with
+    xrd_kernel_launch_count."""
+    import xrd_b200
+    from xrd_b200 import _lib
+    m, _ = G.seeded_state_dict("unet")
+    m = m.to(G.DEV)
+    w = xrd_b200.DiffusionDenoiser(m)
+    m.use_cuda_graph = False
+    x = torch.rand(1, 1, 64, 64, device=G.DEV)
+    w.denoise(x, 2)
+    torch.cuda.synchronize()
+    n0 = xrd_b200.native_kernel_launches()
+    _lib.profile_begin()
+    try:
+        w.denoise(x, 2)
+    finally:
+        prof = _lib.profile_end()
+    n = xrd_b200.native_kernel_launches() - n0
+    assert n > 100 and sum(v[0] for v in prof.values()) == n, (n, prof)
+    assert all(k.startswith("k_") for k in prof), list(prof)            # real kernel names, not launch-site expressions
+    assert any(k.startswith("k_attn") for k in prof) and any(k.startswith("k_conv") for k in prof), list(prof)
+    assert all(v[1] > 0 for v in prof.values()), prof
+    with pytest.raises(xrd_b200.XrdError):
+        _lib.profile_end()                                               # nothing running
+
+
 # ------------------------------------------------------------------ edge cases / boundary behaviour
 def test_errors_are_loud():
     import xrd_b200
