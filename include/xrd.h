@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define XRD_API_VERSION 2
+#define XRD_API_VERSION 3
 #define XRD_MAX_LEVELS 8
 
 typedef struct xrd_handle xrd_handle;
@@ -154,6 +154,12 @@ int xrd_get_mode(xrd_handle* h);
 /* 0 = plain stream launches, 1 (default) = the sampler loop is captured into one CUDA graph
  * per (B,H,W,evals,mode) and replayed. */
 int xrd_set_use_graph(xrd_handle* h, int enable);
+/* xrd_hybrid only.  1 (default; XRD_OVERLAP=0 in the environment makes 0 the default) = the three branches of
+ * HybridDenoisingRouter.forward that share nothing but their input (HYB:612-624: NAFNet, the sampler, the routing mask) are
+ * enqueued on three streams -- NAFNet and the router on two private streams of the handle with private workspaces, the sampler
+ * graph on the caller's stream -- and joined by events in front of the fusion stack; 0 = one stream, in the reference's order.
+ * The arithmetic is the same either way.  Everything stays ordered on the caller's stream as seen from outside. */
+int xrd_set_side_branches(xrd_handle* h, int enable);
 
 /* Replaces: UNetDiffusion.forward(x, condition, t) (HYB:359-388, DDIM:219-248).
  * `t` = B int64 timestep values on the device.  eps: (B,1,H,W) float32, unclamped. */

@@ -17,7 +17,7 @@ XRD_MAX_LEVELS = 8
 MODE_BF16, MODE_FP32_CHECK, MODE_FP16 = 0, 1, 2
 PART_UNET, PART_NAFNET, PART_ROUTER, PART_FUSION, PART_ALL = 1, 2, 4, 8, 15
 PART_EXPERT = 16
-API_VERSION = 2
+API_VERSION = 3
 
 _I8 = C.c_int32 * XRD_MAX_LEVELS
 
@@ -74,6 +74,7 @@ SYMBOLS = {
     "xrd_set_mode": (C.c_int, [_P, C.c_int]),
     "xrd_get_mode": (C.c_int, [_P]),
     "xrd_set_use_graph": (C.c_int, [_P, C.c_int]),
+    "xrd_set_side_branches": (C.c_int, [_P, C.c_int]),
     "xrd_unet_eps": (C.c_int, [_P, _F, _F, _P, _F, C.c_int, C.c_int, C.c_int, _P]),
     "xrd_ddim_denoise": (C.c_int, [_P, _F, C.c_int, _F, _F, _F, _F, C.c_int, C.c_int, C.c_int, _P]),
     "xrd_ddim_num_evals": (C.c_int, [C.c_int, C.c_int]),

@@ -45,6 +45,13 @@ struct xrd_handle {
   DType packed_dt = DT_F32;
   float* scratch = nullptr;            // hybrid: sanitised NAFNet / sampler / mask planes of one micro-batch
   size_t scratch_n = 0;
+  // hybrid side branches (HYB:612-624: the fast path, the quality path and the routing mask only share their input): NAFNet and
+  // the router run on two private streams with private workspaces beside the sampler graph and join before the fusion stack
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  Arena side_arena[2];
+  bool overlap = true;
+  int64_t overlap_max_px = INT64_MAX;  // side branches only for micro-batches of at most this many pixels (XRD_OVERLAP_MAXPIX)
   // op-hook state
   ConvW op_w;
   std::vector<void*> op_owned;
@@ -89,9 +96,11 @@ static void bind_stream(xrd_handle* H, cudaStream_t s) {
   }
 }
 
-// Plan (dry run) + grow the arena, then run `fn` for real with the arena reset.
-static void with_arena(xrd_handle* H, cudaStream_t s, const std::string& key, const std::function<void(Ctx&)>& fn) {
+// Plan (dry run) + grow the arena, then run `fn` for real with the arena reset.  `A` is the handle's main arena (the one
+// the captured graphs point into: growing it drops them) or one of the side-branch arenas.
+static void with_arena_in(xrd_handle* H, cudaStream_t s, const std::string& key, Arena& A, const std::function<void(Ctx&)>& fn) {
   Handle& h = H->h;
+  const bool main_arena = &A == &h.arena;
   size_t need;
   auto it = h.plan_cache.find(key);
   if (it != h.plan_cache.end()) {
@@ -104,19 +113,22 @@ static void with_arena(xrd_handle* H, cudaStream_t s, const std::string& key, co
     need = dry.peak + 4096;
     h.plan_cache[key] = need;
   }
-  if (need > h.arena.cap) {
+  if (need > A.cap) {
     XRD_CUDA(cudaDeviceSynchronize());
-    h.drop_graphs();
-    if (h.arena.base) XRD_CUDA(cudaFree(h.arena.base));
-    h.arena.base = nullptr; h.arena.cap = 0;
+    if (main_arena) h.drop_graphs();
+    if (A.base) XRD_CUDA(cudaFree(A.base));
+    A.base = nullptr; A.cap = 0;
     size_t cap = need + (need >> 4);
-    cudaError_t e = cudaMalloc((void**)&h.arena.base, cap);
+    cudaError_t e = cudaMalloc((void**)&A.base, cap);
     if (e != cudaSuccess) fail(XRD_ERR_CUDA, "cannot allocate a %zu MiB workspace: %s", cap >> 20, cudaGetErrorString(e));
-    h.arena.cap = cap;
+    A.cap = cap;
   }
-  h.arena.off = 0; h.arena.peak = 0; h.arena.dry = false;
-  Ctx c = make_ctx(H, s, false, &h.arena);
+  A.off = 0; A.peak = 0; A.dry = false;
+  Ctx c = make_ctx(H, s, false, &A);
   fn(c);
+}
+static void with_arena(xrd_handle* H, cudaStream_t s, const std::string& key, const std::function<void(Ctx&)>& fn) {
+  with_arena_in(H, s, key, H->h.arena, fn);
 }
 
 // images per micro-batch: bounds the workspace (and keeps one graph shape for any batch size)
@@ -243,7 +255,18 @@ XRD_EXPORT int xrd_create(int device, const xrd_config* cfg, xrd_handle** out) {
     H->h.cfg = *cfg;
     H->h.cfg.unet_prefix[63] = H->h.cfg.naf_prefix[63] = H->h.cfg.router_prefix[63] = H->h.cfg.fusion_prefix[63] = 0;
     H->h.cfg.expert_prefix[63] = 0;
-    XRD_CUDA(cudaStreamCreateWithFlags(&H->cap_stream, cudaStreamNonBlocking));
+    // kernel nodes inherit the priority of the stream they were captured on: the sampler graph (the critical path of the hybrid)
+    // is captured at the highest priority, so the side branches below fill the SMs it leaves idle instead of competing with it
+    int prio_least = 0, prio_greatest = 0;
+    XRD_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    XRD_CUDA(cudaStreamCreateWithPriority(&H->cap_stream, cudaStreamNonBlocking, prio_greatest));
+    for (int i = 0; i < 2; ++i) {
+      XRD_CUDA(cudaStreamCreateWithFlags(&H->side[i], cudaStreamNonBlocking));
+      XRD_CUDA(cudaEventCreateWithFlags(&H->ev_join[i], cudaEventDisableTiming));
+    }
+    XRD_CUDA(cudaEventCreateWithFlags(&H->ev_fork, cudaEventDisableTiming));
+    H->overlap = !(getenv("XRD_OVERLAP") && atoi(getenv("XRD_OVERLAP")) == 0);
+    if (getenv("XRD_OVERLAP_MAXPIX")) H->overlap_max_px = atoll(getenv("XRD_OVERLAP_MAXPIX"));
     *out = H;
   });
 }
@@ -270,6 +293,12 @@ XRD_EXPORT void xrd_destroy(xrd_handle* H) {
   if (H->scratch) cudaFree(H->scratch);
   if (H->h.audit_dev) cudaFree(H->h.audit_dev);
   if (H->cap_stream) cudaStreamDestroy(H->cap_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (H->side_arena[i].base) cudaFree(H->side_arena[i].base);
+    if (H->side[i]) cudaStreamDestroy(H->side[i]);
+    if (H->ev_join[i]) cudaEventDestroy(H->ev_join[i]);
+  }
+  if (H->ev_fork) cudaEventDestroy(H->ev_fork);
   if (prev >= 0) cudaSetDevice(prev);
   delete H;
 }
@@ -424,6 +453,13 @@ XRD_EXPORT int xrd_get_mode(xrd_handle* H) { return H ? H->h.mode : XRD_ERR_INVA
 XRD_EXPORT int xrd_set_use_graph(xrd_handle* H, int enable) {
   if (!H) return XRD_ERR_INVALID;
   H->h.use_graph = enable != 0;
+  return XRD_OK;
+}
+
+XRD_EXPORT int xrd_set_side_branches(xrd_handle* H, int enable) {
+  if (!H) return XRD_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(H->h.mu);
+  H->overlap = enable != 0;
   return XRD_OK;
 }
 
@@ -709,6 +745,7 @@ XRD_EXPORT int xrd_hybrid(xrd_handle* H, const float* noisy, int inference_steps
       H->scratch_n = need;
     }
     float* scratch = H->scratch;
+    try {
     for (int b0 = 0; b0 < B; b0 += mb) {
       const int nb = std::min(mb, B - b0);
       const size_t plane = (size_t)nb * img;
@@ -716,8 +753,26 @@ XRD_EXPORT int xrd_hybrid(xrd_handle* H, const float* noisy, int inference_steps
       float* difp = diff_out ? diff_out + b0 * img : scratch + (size_t)mb * img;
       float* mskp = mask_out ? mask_out + b0 * img : scratch + 2 * (size_t)mb * img;
       const float* in = noisy + b0 * img;
+      // The three branches read only `in` (HYB:612-624).  With side branches on, NAFNet and the router are enqueued on the two
+      // private streams behind a fork event and work out of their own arenas; the sampler graph stays on the caller's stream; the
+      // fusion stack waits for both joins.  The next micro-batch forks after this one's fusion, so the scratch planes are never
+      // overwritten while they are read.  The range audit and the in-situ launch profile want one ordered stream: serial then.
+      const bool par = H->overlap && !h.audit && !g_prof && (int64_t)nb * Hh * W <= H->overlap_max_px;
+      cudaStream_t s_naf = par ? H->side[0] : s, s_rt = par ? H->side[1] : s;
+      if (par) {
+        XRD_CUDA(cudaEventRecord(H->ev_fork, s));
+        XRD_CUDA(cudaStreamWaitEvent(s_naf, H->ev_fork, 0));
+        XRD_CUDA(cudaStreamWaitEvent(s_rt, H->ev_fork, 0));
+      }
       // fast path: NAFNet -> nan_to_num + clamp (HYB:614-616)
-      with_arena(H, s, keyf("naf", H, nb, Hh, W, 1), [&](Ctx& c) { run_nafnet(c, h, in, nafp, nb, Hh, W, 1); });
+      with_arena_in(H, s_naf, keyf("naf", H, nb, Hh, W, 1), par ? H->side_arena[0] : h.arena,
+                    [&](Ctx& c) { run_nafnet(c, h, in, nafp, nb, Hh, W, 1); });
+      if (par) {
+        XRD_CUDA(cudaEventRecord(H->ev_join[0], s_naf));
+        // routing mask (HYB:622-624)
+        with_arena_in(H, s_rt, keyf("router", H, nb, Hh, W, 1), H->side_arena[1], [&](Ctx& c) { run_router(c, h, in, mskp, nb, Hh, W, 1); });
+        XRD_CUDA(cudaEventRecord(H->ev_join[1], s_rt));
+      }
       // quality path: sampler -> nan_to_num + clamp (HYB:618-620); x is already clamped to [0,1] by the last update
       ddim_chunk(H, s, in, inference_steps, difp, nullptr, nullptr, nullptr, 0, nb, Hh, W);
       {
@@ -725,9 +780,19 @@ XRD_EXPORT int xrd_hybrid(xrd_handle* H, const float* noisy, int inference_steps
         Ctx c = make_ctx(H, s, false, &none);
         sanitize_plane(c, difp, difp, plane);
       }
-      // routing mask (HYB:622-624), then fusion (HYB:626)
-      with_arena(H, s, keyf("router", H, nb, Hh, W, 1), [&](Ctx& c) { run_router(c, h, in, mskp, nb, Hh, W, 1); });
+      if (par) {
+        XRD_CUDA(cudaStreamWaitEvent(s, H->ev_join[0], 0));
+        XRD_CUDA(cudaStreamWaitEvent(s, H->ev_join[1], 0));
+      } else {
+        with_arena(H, s, keyf("router", H, nb, Hh, W, 1), [&](Ctx& c) { run_router(c, h, in, mskp, nb, Hh, W, 1); });
+      }
+      // fusion (HYB:626)
       with_arena(H, s, keyf("fusion", H, nb, Hh, W), [&](Ctx& c) { run_fusion(c, h, nafp, difp, mskp, out + b0 * img, nb, Hh, W); });
+    }
+    } catch (...) {
+      // a failed stage must not leave a side branch running behind the caller's back (it reads the caller's input)
+      for (int i = 0; i < 2; ++i) cudaStreamSynchronize(H->side[i]);
+      throw;
     }
   });
 }

@@ -80,7 +80,12 @@ k_conv1(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   constexpr int EB = (OC % 48 == 0) ? 48 : 32;             // epilogue block: columns drained per TMEM round trip
   constexpr int CPG = OC / 8;
   constexpr int NBLK = OC / EB;
-  constexpr uint32_t TMEM_COLS = 2 * COUT <= 64 ? 64 : (2 * COUT <= 128 ? 128 : (2 * COUT <= 256 ? 256 : 512));
+  // The whole TMEM, whatever the two accumulators need: the MMA and epilogue addresses below are compile-time constants relative
+  // to base 0, and only a 512-column allocation is guaranteed to start there once CTAs of OTHER kernels may share the SM (the
+  // hybrid's side branches run NAFNet / the router on their own streams).  A partial allocation by a co-resident CTA makes this
+  // one wait in tcgen05.alloc until that CTA has released its columns -- no CTA of this library allocates twice, so nobody holds
+  // columns while waiting for more.
+  constexpr uint32_t TMEM_COLS = 512;
   static_assert(OC % EB == 0 && COUT % 16 == 0 && COUT <= 256 && 2 * COUT <= 512, "two accumulators must fit TMEM");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];

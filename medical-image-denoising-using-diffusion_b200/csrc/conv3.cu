@@ -137,8 +137,9 @@ k_conv3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   constexpr uint32_t B_BYTES = COUT * 128;
   constexpr int CPG = COUT / 8;                            // channels per GroupNorm group (8 groups)
   constexpr int NBLK = COUT / 48;                          // 48-column epilogue blocks
-  constexpr uint32_t TMEM_COLS = (NACC * TH * COUT <= 32) ? 32 : (NACC * TH * COUT <= 64) ? 64 : (NACC * TH * COUT <= 128) ? 128
-                                 : (NACC * TH * COUT <= 256) ? 256 : 512;
+  // the whole TMEM: a 512-column allocation always starts at column 0, which the compile-time accumulator addresses below rely on,
+  // also when a CTA of another kernel shares the SM (side branches of xrd_hybrid); see conv1.cu
+  constexpr uint32_t TMEM_COLS = 512;
   static_assert(COUT % 48 == 0 && NACC * TH * COUT <= 512, "accumulators must fit TMEM");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];

@@ -133,6 +133,7 @@ class _NativeModel(nn.Module):
         object.__setattr__(self, "_xrd_audit", False)
         self.native_mode = _default_mode()
         self.use_cuda_graph = True
+        self.side_branches = None     # hybrid: None = the library default (on unless XRD_OVERLAP=0), True / False = forced
 
     # -- configuration ------------------------------------------------------
     def _xrd_fill_config(self, cfg: _lib.XrdConfig) -> None:
@@ -254,7 +255,7 @@ class _NativeModel(nn.Module):
                 _lib.check(lib.xrd_finalize_weights(ent["h"], self._xrd_parts))
                 del keep
                 ent["fp"] = fp
-                ent["mode"] = ent["graph"] = ent["audit"] = None
+                ent["mode"] = ent["graph"] = ent["audit"] = ent["side"] = None
             mode, graph, audit = _MODE_NAMES[self.native_mode], 1 if self.use_cuda_graph else 0, 1 if self._xrd_audit else 0
             if ent.get("mode") != mode:
                 _lib.check(lib.xrd_set_mode(ent["h"], mode)); ent["mode"] = mode
@@ -262,6 +263,8 @@ class _NativeModel(nn.Module):
                 _lib.check(lib.xrd_set_use_graph(ent["h"], graph)); ent["graph"] = graph
             if ent.get("audit") != audit:
                 _lib.check(lib.xrd_set_range_audit(ent["h"], audit)); ent["audit"] = audit
+            if self.side_branches is not None and ent.get("side") != bool(self.side_branches):
+                _lib.check(lib.xrd_set_side_branches(ent["h"], 1 if self.side_branches else 0)); ent["side"] = bool(self.side_branches)
             return ent["h"]
 
     # -- weight blob (include/xrd.h: xrd_export_weights / xrd_import_weights) ------------------------

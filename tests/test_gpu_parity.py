@@ -414,6 +414,34 @@ def test_weight_blob_roundtrip(tmp_path):
         xrd_b200.ExpertDenoiser().to(G.DEV).load_weight_blob(pe)
 
 
+def test_hybrid_side_branches_equal_the_serial_order():
+    """xrd_hybrid with NAFNet and the router on the handle's side streams (the default) against the same handle with
+    xrd_set_side_branches(0) (one stream, the reference's order, HYB:612-626): 18 images at 512x512 = two micro-batches, so the
+    fork of the second micro-batch behind the first one's fusion is exercised; a different batch in between must not leak
+    through the scratch planes or the side workspaces.  Equal up to the GroupNorm atomics' summation order."""
+    from oracle import xrd_oracle as O
+    m, _ = G._hybrid("fp16")
+    m.inference_diffusion_steps = 2
+    _, noisy = O.synthetic_xray(18, 512, 512, seed=41)
+    x = noisy.to(G.DEV)
+    m.side_branches = False
+    y0, p0 = m(x, return_parts=True)
+    m.side_branches = True
+    y1, p1 = m(x, return_parts=True)
+    m(torch.flip(x, dims=(0, 3)).contiguous())
+    y2 = m(x)
+    assert torch.isfinite(y1).all()
+    assert (p1["mask"] - p0["mask"]).abs().max() < 1e-5 and (p1["naf"] - p0["naf"]).abs().max() < 5e-3
+    assert (p1["diff"] - p0["diff"]).abs().max() < 5e-3
+    assert (y1 - y0).abs().max() < 5e-3 and (y2 - y0).abs().max() < 5e-3
+    m.set_native_mode("fp32")
+    m.side_branches = False
+    z0 = m(x[:2])
+    m.side_branches = True
+    z1 = m(x[:2])
+    assert (z1 - z0).abs().max() < 2e-5
+
+
 def test_full_size_properties_config3():
     """BASELINE configs[2] size (512x512, batch 16, DDIM-50): too large for the CPU oracle in test time, so
     check size-independent properties: per-image independence of the batch, determinism of the graph replay,

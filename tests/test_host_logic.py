@@ -82,7 +82,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"libxrd.so does not export {name}"
     assert declared == set(xrd_b200._lib.SYMBOLS), "ctypes table and header disagree"
-    assert xrd_b200.load_library().xrd_api_version() == xrd_b200._lib.API_VERSION == 2
+    assert xrd_b200.load_library().xrd_api_version() == xrd_b200._lib.API_VERSION == 3
 
 
 def test_pure_host_entry_points_without_gpu():
