@@ -322,7 +322,9 @@ def insitu_profile(model, x_dev, evals, conv_flops_per_eval):
     conv_ms = sum(v[1] for k, v in prof.items() if k in conv)
     table = {k: {"launches_per_eval": v[0] / evals, "ms_per_eval": v[1] / evals, "share": v[1] / tot} for k, v in prof.items() if v[1] / tot >= 0.002}
     return {"how": "eager replay of the step's reverse loop, two CUDA events around every launch (xrd_profile_begin/_end), same batch and "
-                   "inputs as the timed region, taken right after it",
+                   "inputs as the timed region, taken right after it; the conv class is the tcgen05 kernels of unet_conv_layers() "
+                   "(the two-plane first conv, k_first_conv_mma, and out_conv are HBM-bound edge kernels: neither their FLOPs nor their "
+                   "time are in it)",
             "conv_tflops": conv_flops_per_eval * evals / conv_ms / 1e9, "conv_ms_per_eval": conv_ms / evals,
             "kernels_ms_per_eval": tot / evals, "eager_loop_ms": loop_ms, "evals": evals, "by_kernel": table}
 

@@ -246,7 +246,8 @@ int xrd_unit_to_u8(const float* src, uint8_t* dst, int64_t n, void* stream);
 /* conv2d: weight (Cout,Cin,kh,kw), bias nullable.  impl: 0 = CUDA-core kernel, 1 = tcgen05 per-tap
  * implicit-GEMM kernel (3x3/s1/p1, 3x3/s2/p1, 2x2/s2/p0 and 1x1 only), 2 = persistent halo-reusing
  * tcgen05 kernel (3x3/s1/p1, W % 128 == 0, Cout in {48,96,144}), 3 / 4 = kernels 2 / 1 reading x as a
- * virtual concat of its two channel halves (B must be 1). */
+ * virtual concat of its two channel halves (B must be 1); 5..18 = the other tcgen05 kernels (listed in csrc/capi.cu);
+ * 19 = the UNet's first conv on cat([x, condition]) in one pass (first_conv.cu: B == 1, Cin == 2, Cout == 48; HYB:335,362-363). */
 int xrd_op_conv2d(xrd_handle* h, int impl, const float* x, const float* weight, const float* bias,
                   float* y, int B, int Cin, int H, int W, int Cout, int k, int stride, int pad,
                   void* stream);

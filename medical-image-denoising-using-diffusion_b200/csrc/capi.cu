@@ -834,6 +834,27 @@ XRD_EXPORT int xrd_op_conv2d_stats(xrd_handle* H, int impl, const float* x, cons
     // 14 = conv1 with the scaled-residual epilogue (HYB:161): y = (conv(x) + bias) * bias + x  (Cin == Cout); bias doubles as the scale
     // 15 = N-stacked row-ring kernel (conv3s), 16 = conv3s with GroupNorm(8) + SiLU of the input applied inside the kernel,
     // 17 / 18 = the same two over the virtual concat of the channel halves
+    // 19 = the UNet's first conv (first_conv.cu): Cin == 2, Cout == 48, the two input channels read as fp32 planes (B must be 1)
+    if (impl == 19) {
+      XRD_REQUIRE(dt != DT_F32 && B == 1 && Cin == 2 && k == 3 && stride == 1 && pad == 1, "hook 19: B == 1, Cin == 2, 3x3/s1/p1, 16-bit mode");
+      H->h.last_op = nullptr;
+      with_arena(H, s, keyf("opfirst", H, B, Hh, W, Cin, Cout), [&](Ctx& c) {
+        Tens yo = c.alloc(B, Hh, W, Cout);
+        double* st = c.allocd((size_t)B * 16);
+        XRD_REQUIRE(first_conv_mma_supported(yo, H->op_w), "hook 19: unsupported shape");
+        auto run = [H, x, yo, st, Hh, W](Ctx& cc) mutable {
+          Tens yy = yo;
+          zero_async(cc, st, (size_t)yo.n * 16 * sizeof(double));
+          first_conv_mma(cc, x, x + (size_t)Hh * W, H->op_w, yy, st);
+        };
+        run(c);
+        nhwc_to_nchw(c, yo, y);
+        if (stats && !c.dry) XRD_CUDA(cudaMemcpyAsync(stats, st, (size_t)B * 16 * sizeof(double), cudaMemcpyDeviceToDevice, c.s));
+        H->h.last_op = run;
+        H->h.last_op_bytes = yo.bytes() + (size_t)2 * Hh * W * 4;
+      });
+      return;
+    }
     const bool split = impl == 3 || impl == 4 || impl == 6 || impl == 8 || impl == 10 || impl == 17 || impl == 18;
     const bool fuse_gn = impl == 9 || impl == 10 || impl == 12 || impl == 16 || impl == 18;
     if (split) XRD_REQUIRE(Cin % 32 == 0, "split-input conv hook needs Cin %% 32 == 0");

@@ -619,7 +619,12 @@ static void unet_eval(Ctx& c, UNetW& u, const float* x, const float* cond, const
     e0.stats_out = st;
     Tens col;
     col.n = B; col.h = H; col.w = W; col.c = 32; col.dt = c.adt;
-    if (c.tc && u.in_conv_g.w && conv1_supported(col, nullptr, u.in_conv_g, e0)) {
+    if (c.tc && first_conv_mma_supported(h.t, u.in_conv)) {
+      // one pass: fp32 planes in, 16-bit NHWC activation and its GroupNorm sums out (first_conv.cu)
+      first_conv_mma(c, x, cond, u.in_conv, h.t, st);
+      h.st = st;
+      range_audit(c, h.t);
+    } else if (c.tc && u.in_conv_g.w && conv1_supported(col, nullptr, u.in_conv_g, e0)) {
       // tensor-core first conv: 16-bit im2col rows [pixel][9 taps x (x, cond) | zero pad] (64 B each), then the persistent
       // 1x1 GEMM with GroupNorm sums in its epilogue.  cat([x, condition]) is still never materialised.
       col = c.alloc(B, H, W, 32);

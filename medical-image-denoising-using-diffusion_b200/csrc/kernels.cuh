@@ -88,6 +88,9 @@ void gn_coef(Ctx& c, const double* sums, const float* gamma, const float* beta, 
 void gn_merge_stats(Ctx& c, const double* a, const double* b, double* out, int N);
 // col[n,h,w, 0..31] = 3x3 neighbourhood (zero padded) of the two fp32 planes a, b: column tap*2 + {0: a, 1: b}, columns 18..31 zero
 void im2col_3x3_2ch(Ctx& c, const float* a, const float* b, Tens& col);
+// first_conv.cu: in_conv on cat([x, condition]) in one pass (warp-level MMA on an in-smem 16-bit copy of the two planes)
+bool first_conv_mma_supported(const Tens& y, const ConvW& w);
+void first_conv_mma(Ctx& c, const float* a, const float* b, const ConvW& w, Tens& y, double* stats);
 void upsample2x(Ctx& c, const Tens& x, Tens& y);       // bilinear, align_corners=False, exact 2x
 // same, 16 bytes per access, fused with the GroupNorm sums of y (stats nullable, [N][8][2], zeroed by the caller)
 void upsample2x_stats(Ctx& c, const Tens& x, Tens& y, double* stats);

@@ -194,6 +194,136 @@ __global__ void __launch_bounds__(256, 2) k_dwconv_gate_pool16(const T* __restri
   for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&pool[(int64_t)n * C + i], s_pool[i]);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same layer with the input rows staged through shared memory by 1-D bulk copies (round 2).  The register version above
+// holds 72 weights + 24 accumulators per thread, so it cannot also hold more than one prefetched row: ~8 KB of distinct
+// bytes in flight per SM, and the measured 1.36 TB/s (21 % of the copy rate) is exactly what Little's law gives for that at
+// ~800 ns of HBM latency.  Here one thread of the block keeps a ring of S row segments ((PX + 2) pixels x 2C channels,
+// 4.3-5.1 KB each, one cp.async.bulk request per row) in flight on mbarriers, independent of anyone's registers: 2 blocks x 4
+// slots = 35-40 KB in flight per SM.  The compute is unchanged (same thread mapping, sliding three-row accumulators, same
+// summation order, gate by one shuffle), it just reads its three 16-byte neighbours from the ring (a warp reads 512
+// contiguous bytes: conflict-free).  Halo pixels outside the image are zeroed once per slot and never overwritten; rows
+// outside the image are never fetched (their barrier phase is completed by a plain arrive).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kDwSlots = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2) k_dwconv_gate_pool16s(const T* __restrict__ u, const float* __restrict__ w9,
+                                                                const float* __restrict__ bias, T* __restrict__ g, float* __restrict__ pool,
+                                                                int H, int W, int C, int rows_per_block) {
+  extern __shared__ __align__(128) uint8_t s_raw[];
+  const int nq = C >> 3;                       // 8-channel chunks per half: 4, 8 or 16
+  const int ppw = 32 / (2 * nq);               // pixels per warp
+  const int PX = 8 * ppw;                      // pixel columns per block
+  const int C2 = 2 * C;
+  const uint32_t pix_bytes = (uint32_t)C2 * sizeof(T);
+  const uint32_t slot_bytes = (uint32_t)(PX + 2) * pix_bytes;
+  uint8_t* ring = s_raw;                                                      // [kDwSlots][(PX + 2) * 2C] T
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + kDwSlots * slot_bytes);
+  float* s_pool = reinterpret_cast<float*>(full + kDwSlots);                  // [C]
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = lane & (nq - 1);
+  const int half = (lane / nq) & 1;
+  const int px = warp * ppw + lane / (2 * nq); // pixel column within the block
+  const int x0 = blockIdx.x * PX;
+  const int x = x0 + px;
+  const int n = blockIdx.z;
+  const int y0 = blockIdx.y * rows_per_block;
+  const int y1 = min(y0 + rows_per_block, H);
+  const int n_in = y1 - y0 + 2;                // input rows y0-1 .. y1
+  const int cb = half * C + q * 8;             // first of this thread's 8 channels in the 2C-channel tensor
+
+  // the part of a row segment that exists in the image: pixels [xs, xe) land at slot pixel xs - (x0 - 1)
+  const int xs = max(x0 - 1, 0), xe = min(x0 + PX + 1, W);
+  const uint32_t dst_off = (uint32_t)(xs - (x0 - 1)) * pix_bytes;
+  const uint32_t row_bytes = (uint32_t)(xe - xs) * pix_bytes;
+  const T* row0 = u + ((int64_t)n * H * W + xs) * C2;                          // + r * W * C2 per image row
+
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_pool[i] = 0.f;
+  // zero the slot pixels no copy will ever write (image borders, ragged right edge)
+  for (uint32_t i = threadIdx.x * 16u; i < kDwSlots * slot_bytes; i += blockDim.x * 16u) {
+    const uint32_t o = i % slot_bytes;
+    if (o < dst_off || o >= dst_off + row_bytes) *reinterpret_cast<uint4*>(ring + i) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kDwSlots; ++s) tc::mbar_init(&full[s], 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int i) {                    // thread 0: input row i of this block into slot i % kDwSlots
+    const int r = y0 - 1 + i;
+    uint64_t* bar = &full[i % kDwSlots];
+    if (r >= 0 && r < H) {
+      tc::mbar_expect_tx(bar, row_bytes);
+      tc::bulk_load_1d(ring + (size_t)(i % kDwSlots) * slot_bytes + dst_off, row0 + (int64_t)r * W * C2, row_bytes, bar);
+    } else {
+      tc::mbar_arrive(bar);                    // nothing to fetch: the row is zero padding
+    }
+  };
+  if (threadIdx.x == 0)
+    for (int i = 0; i < kDwSlots && i < n_in; ++i) issue(i);
+
+  float w[9][8], bs[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w9 + t * C2 + cb)), b = __ldg(reinterpret_cast<const float4*>(w9 + t * C2 + cb + 4));
+    w[t][0] = a.x; w[t][1] = a.y; w[t][2] = a.z; w[t][3] = a.w; w[t][4] = b.x; w[t][5] = b.y; w[t][6] = b.z; w[t][7] = b.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bs[i] = __ldg(bias + cb + i);
+
+  const bool xin = x < W;
+  float a0[8], a1[8], a2[8], ps[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a0[i] = bs[i]; a1[i] = bs[i]; a2[i] = bs[i]; ps[i] = 0.f; }
+  const uint32_t my_off = (uint32_t)px * pix_bytes + (uint32_t)cb * sizeof(T);   // pixel x-1 of this thread's chunk inside a slot
+  for (int i = 0; i < n_in; ++i) {
+    const int r = y0 - 1 + i;
+    const int slot = i % kDwSlots;
+    tc::mbar_wait_relaxed(&full[slot], (uint32_t)(i / kDwSlots) & 1u, 70);
+    if (r >= 0 && r < H) {                      // block-uniform
+      const uint8_t* sp = ring + (size_t)slot * slot_bytes + my_off;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(sp + (uint32_t)k * pix_bytes);
+        float v[8];
+        tc::unpack8<T>(raw, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a0[j] = fmaf(v[j], w[6 + k][j], a0[j]);   // output row r-1 sees this row through ky = 2
+          a1[j] = fmaf(v[j], w[3 + k][j], a1[j]);   // output row r   through ky = 1
+          a2[j] = fmaf(v[j], w[k][j], a2[j]);       // output row r+1 through ky = 0
+        }
+      }
+    }
+    // output row r-1 is complete
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = a0[j] * __shfl_xor_sync(0xffffffffu, a0[j], nq);
+    if (r - 1 >= y0 && xin && half == 0) {
+      uint4 pk;
+      pk.x = tc::pack2<T>(o[0], o[1]); pk.y = tc::pack2<T>(o[2], o[3]); pk.z = tc::pack2<T>(o[4], o[5]); pk.w = tc::pack2<T>(o[6], o[7]);
+      *reinterpret_cast<uint4*>(g + (((int64_t)n * H + (r - 1)) * W + x) * C + q * 8) = pk;
+      float st[8];
+      tc::unpack8<T>(pk, st);                    // the pool must see what the next layer sees: the value as stored
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ps[j] += st[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a0[j] = a1[j]; a1[j] = a2[j]; a2[j] = bs[j]; }
+    __syncthreads();                             // every thread has read slot `slot`: it may be refilled
+    if (threadIdx.x == 0 && i + kDwSlots < n_in) issue(i + kDwSlots);
+  }
+  if (half == 0 && xin) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_pool[q * 8 + j], ps[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&pool[(int64_t)n * C + i], s_pool[i]);
+}
+
 bool dwconv_gate_pool16_supported(const Tens& u, const Tens& g) {
   static const int enabled = getenv("XRD_DW16") ? atoi(getenv("XRD_DW16")) : 1;
   if (!enabled || u.dt == DT_F32 || g.dt != u.dt) return false;
@@ -206,6 +336,13 @@ void dwconv_gate_pool16(Ctx& c, const Tens& u, const float* w9, const float* bia
   const int ppb = 8 * (32 / (2 * (C / 8)));          // pixel columns per block
   const int rows = u.h >= 256 ? 32 : 16;
   dim3 grid(cdiv(u.w, ppb), cdiv(u.h, rows), u.n);
+  static const int staged = getenv("XRD_DW16_STAGED") ? atoi(getenv("XRD_DW16_STAGED")) : 1;
+  if (staged) {
+    const size_t smem = (size_t)kDwSlots * (ppb + 2) * 2 * C * dsize(u.dt) + kDwSlots * sizeof(uint64_t) + C * sizeof(float);
+    if (u.dt == DT_F16) XRD_LAUNCH(c, (k_dwconv_gate_pool16s<__half>), grid, 256, smem, (const __half*)u.p, w9, bias, (__half*)g.p, pool, u.h, u.w, C, rows);
+    else XRD_LAUNCH(c, (k_dwconv_gate_pool16s<__nv_bfloat16>), grid, 256, smem, (const __nv_bfloat16*)u.p, w9, bias, (__nv_bfloat16*)g.p, pool, u.h, u.w, C, rows);
+    return;
+  }
   if (u.dt == DT_F16) XRD_LAUNCH(c, (k_dwconv_gate_pool16<__half>), grid, 256, C * sizeof(float), (const __half*)u.p, w9, bias, (__half*)g.p, pool, u.h, u.w, C, rows);
   else XRD_LAUNCH(c, (k_dwconv_gate_pool16<__nv_bfloat16>), grid, 256, C * sizeof(float), (const __nv_bfloat16*)u.p, w9, bias, (__nv_bfloat16*)g.p, pool, u.h, u.w, C, rows);
 }

@@ -128,6 +128,10 @@ CONV_CASES_1X1_SCALE = [(1, 32, 24, 40, 32, 1, 1, 0), (2, 64, 16, 24, 64, 1, 1, 
                         (1, 96, 16, 16, 96, 1, 1, 0)]
 CONV_CASES_1X1_CAT = [(1, 384, 16, 16, 192, 1, 1, 0), (1, 192, 32, 32, 96, 1, 1, 0), (1, 96, 24, 40, 48, 1, 1, 0), (1, 288, 16, 24, 144, 1, 1, 0),
                       (1, 192, 16, 16, 48, 1, 1, 0)]
+# the UNet's first conv (hook 19, first_conv.cu): B = 1, two input planes, 48 outputs; full tiles, ragged tiles (W % 16 != 0,
+# H % 8 != 0), one image-wide tile row, the benched 512x512 plane
+CONV_CASES_FIRST = [(1, 2, 64, 64, 48, 3, 1, 1), (1, 2, 40, 56, 48, 3, 1, 1), (1, 2, 13, 200, 48, 3, 1, 1), (1, 2, 8, 136, 48, 3, 1, 1),
+                    (1, 2, 512, 512, 48, 3, 1, 1)]
 CONV_CASES_1X1_STATS = [(2, 192, 16, 16, 192, 1, 1, 0), (1, 96, 32, 32, 48, 1, 1, 0), (3, 144, 16, 24, 144, 1, 1, 0), (2, 48, 64, 64, 96, 1, 1, 0)]
 
 
@@ -650,6 +654,9 @@ CHECKS = {
     "conv1_naf_epilogues_fp16": lambda: check_conv1_naf_epilogues("fp16"),
     "conv1_cat_fp16": lambda: check_conv("fp16", 6, CONV_CASES_1X1_CAT),
     "conv1_stats_fp16": lambda: check_conv_stats("fp16", 5, CONV_CASES_1X1_STATS),
+    "first_conv_fp16": lambda: check_conv("fp16", 19, CONV_CASES_FIRST),
+    "first_conv_bf16": lambda: check_conv("bf16", 19, CONV_CASES_FIRST),
+    "first_conv_stats_fp16": lambda: check_conv_stats("fp16", 19, CONV_CASES_FIRST),
     "attention_tc_bf16": lambda: check_attention("bf16", 1),
     "attention_tc_fp16": lambda: check_attention("fp16", 1),
     "nafnet_fp32": lambda: check_nafnet("fp32"),

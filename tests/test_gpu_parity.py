@@ -118,6 +118,17 @@ def test_conv_tcgen05_1x1_persistent():
         assert e < 2e-3, (k, e)
 
 
+def test_first_conv_one_pass():
+    """in_conv on cat([x, condition]) (HYB:335, 362-363) as one pass over HBM (first_conv.cu, op hook 19) against fp64 F.conv2d on the
+    same 16-bit-rounded operands, with the GroupNorm sums of its epilogue; ragged tiles included."""
+    for k, e in G.check_conv("fp16", 19, G.CONV_CASES_FIRST).items():
+        assert e < 6e-4, (k, e)
+    for k, e in G.check_conv("bf16", 19, G.CONV_CASES_FIRST).items():
+        assert e < 5e-3, (k, e)
+    for k, e in G.check_conv_stats("fp16", 19, G.CONV_CASES_FIRST).items():
+        assert e < 1e-3, (k, e)
+
+
 def test_conv_tcgen05_1x1_nafblock_shapes_and_epilogues():
     # the same kernel on the NAFBlock 1x1 shapes (powers of two, 32..1024 channels) and its two NAFBlock epilogues:
     # SimpleGate * gamma + y (HYB:165-169) and (conv + bias) * beta + inp (HYB:161)
