@@ -324,15 +324,168 @@ __global__ void __launch_bounds__(256, 2) k_dwconv_gate_pool16s(const T* __restr
   for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&pool[(int64_t)n * C + i], s_pool[i]);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Third version (round 2): the staged kernel above still synchronised the whole block once per row (the thread that refills
+// the ring is one of the computing threads), which left it at 1.9 TB/s.  Here the ring has a warp of its own -- a ninth warp
+// whose lane 0 waits on per-slot `empty` barriers and issues the bulk copies -- so the eight computing warps only ever wait
+// for data.  The thread mapping changes so that the gate needs no shuffle and any C in {32 .. 512} fits: a thread owns four
+// channels c..c+3 of the first half AND the four partner channels C+c..C+c+3 of one pixel (two 8-byte shared loads per
+// neighbour), multiplies them in registers and stores 8 bytes; a pixel is C/4 consecutive threads, so warp-wide accesses
+// stay contiguous.  C = 256 and 512 (the NAFNet levels the 16-byte kernels did not cover: 0.7 TB/s in the generic kernel)
+// run here too.  Arithmetic and summation order per output are those of the kernels above.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kDw3Slots = 4;
+constexpr int kDw3Threads = 288;               // 8 computing warps + the ring warp
+
+template <typename T>
+__global__ void __maxnreg__(112) k_dwconv_gate_pool16v3(const T* __restrict__ u, const float* __restrict__ w9,
+                                                                         const float* __restrict__ bias, T* __restrict__ g,
+                                                                         float* __restrict__ pool, int H, int W, int C, int rows_per_block) {
+  extern __shared__ __align__(128) uint8_t s_raw[];
+  const int tpp = C >> 2;                      // threads per pixel: 8 .. 128
+  const int PX = 256 / tpp;                    // pixel columns per block: 32 .. 2
+  const int C2 = 2 * C;
+  const uint32_t pix_bytes = (uint32_t)C2 * sizeof(T);
+  const uint32_t slot_bytes = (uint32_t)(PX + 2) * pix_bytes;
+  uint8_t* ring = s_raw;                                                      // [kDw3Slots][(PX + 2) * 2C] T
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + kDw3Slots * slot_bytes);
+  uint64_t* empty = full + kDw3Slots;
+  float* s_pool = reinterpret_cast<float*>(empty + kDw3Slots);                // [C]
+  float* s_bias = s_pool + C;                                                 // [2C]: the accumulators restart from it every row
+
+  const int warp = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * PX;
+  const int n = blockIdx.z;
+  const int y0 = blockIdx.y * rows_per_block;
+  const int y1 = min(y0 + rows_per_block, H);
+  const int n_in = y1 - y0 + 2;                // input rows y0-1 .. y1
+
+  // the part of a row segment that exists in the image: pixels [xs, xe) land at slot pixel xs - (x0 - 1)
+  const int xs = max(x0 - 1, 0), xe = min(x0 + PX + 1, W);
+  const uint32_t dst_off = (uint32_t)(xs - (x0 - 1)) * pix_bytes;
+  const uint32_t row_bytes = (uint32_t)(xe - xs) * pix_bytes;
+
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_pool[i] = 0.f;
+  for (int i = threadIdx.x; i < C2; i += blockDim.x) s_bias[i] = __ldg(bias + i);
+  // zero the slot pixels no copy will ever write (image borders, ragged right edge)
+  for (uint32_t i = threadIdx.x * 16u; i < kDw3Slots * slot_bytes; i += blockDim.x * 16u) {
+    const uint32_t o = i % slot_bytes;
+    if (o < dst_off || o >= dst_off + row_bytes) *reinterpret_cast<uint4*>(ring + i) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kDw3Slots; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 256); }
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == 8) {
+    // ===================== ring warp =====================
+    if ((threadIdx.x & 31) == 0) {
+      const T* row0 = u + ((int64_t)n * H * W + xs) * C2;                       // + r * W * C2 per image row
+      for (int i = 0; i < n_in; ++i) {
+        const int slot = i % kDw3Slots;
+        if (i >= kDw3Slots) tc::mbar_wait_relaxed(&empty[slot], (uint32_t)(i / kDw3Slots - 1) & 1u, 71);
+        const int r = y0 - 1 + i;
+        if (r >= 0 && r < H) {
+          tc::mbar_expect_tx(&full[slot], row_bytes);
+          tc::bulk_load_1d(ring + (size_t)slot * slot_bytes + dst_off, row0 + (int64_t)r * W * C2, row_bytes, &full[slot]);
+        } else {
+          tc::mbar_arrive(&full[slot]);        // nothing to fetch: the row is zero padding
+        }
+      }
+    }
+  } else {
+    // ===================== computing warps =====================
+    const int px = threadIdx.x / tpp;            // pixel column within the block
+    const int q4 = (threadIdx.x - px * tpp) * 4; // first of this thread's four channels in each half
+    const int x = x0 + px;
+    const bool xin = x < W;
+    float w[9][8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(w9 + t * C2 + q4)), b = __ldg(reinterpret_cast<const float4*>(w9 + t * C2 + C + q4));
+      w[t][0] = a.x; w[t][1] = a.y; w[t][2] = a.z; w[t][3] = a.w; w[t][4] = b.x; w[t][5] = b.y; w[t][6] = b.z; w[t][7] = b.w;
+    }
+    float a0[8], a1[8], a2[8], ps[4];
+    {
+      const float4 a = *reinterpret_cast<const float4*>(s_bias + q4), b = *reinterpret_cast<const float4*>(s_bias + C + q4);
+      a0[0] = a1[0] = a2[0] = a.x; a0[1] = a1[1] = a2[1] = a.y; a0[2] = a1[2] = a2[2] = a.z; a0[3] = a1[3] = a2[3] = a.w;
+      a0[4] = a1[4] = a2[4] = b.x; a0[5] = a1[5] = a2[5] = b.y; a0[6] = a1[6] = a2[6] = b.z; a0[7] = a1[7] = a2[7] = b.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ps[i] = 0.f;
+    const uint32_t off_lo = (uint32_t)px * pix_bytes + (uint32_t)q4 * sizeof(T);   // pixel x-1, first half
+    const uint32_t off_hi = off_lo + (uint32_t)C * sizeof(T);                      // same pixel, partner channels
+    for (int i = 0; i < n_in; ++i) {
+      const int r = y0 - 1 + i;
+      const int slot = i % kDw3Slots;
+      tc::mbar_wait(&full[slot], (uint32_t)(i / kDw3Slots) & 1u, 72);
+      if (r >= 0 && r < H) {                      // block-uniform
+        const uint8_t* sp = ring + (size_t)slot * slot_bytes;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const uint2 lo = *reinterpret_cast<const uint2*>(sp + off_lo + (uint32_t)k * pix_bytes);
+          const uint2 hi = *reinterpret_cast<const uint2*>(sp + off_hi + (uint32_t)k * pix_bytes);
+          float v[8];
+          { const float2 f0 = tc::unpack2<T>(lo.x), f1 = tc::unpack2<T>(lo.y), f2 = tc::unpack2<T>(hi.x), f3 = tc::unpack2<T>(hi.y);
+            v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y; v[4] = f2.x; v[5] = f2.y; v[6] = f3.x; v[7] = f3.y; }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            a0[j] = fmaf(v[j], w[6 + k][j], a0[j]);   // output row r-1 sees this row through ky = 2
+            a1[j] = fmaf(v[j], w[3 + k][j], a1[j]);   // output row r   through ky = 1
+            a2[j] = fmaf(v[j], w[k][j], a2[j]);       // output row r+1 through ky = 0
+          }
+        }
+      }
+      tc::mbar_arrive(&empty[slot]);              // release semantics: this thread's reads of the slot are ordered before it
+      // output row r-1 is complete: SimpleGate in registers
+      if (r - 1 >= y0 && xin) {
+        uint2 pk;
+        pk.x = tc::pack2<T>(a0[0] * a0[4], a0[1] * a0[5]); pk.y = tc::pack2<T>(a0[2] * a0[6], a0[3] * a0[7]);
+        *reinterpret_cast<uint2*>(g + (((int64_t)n * H + (r - 1)) * W + x) * C + q4) = pk;
+        const float2 s0 = tc::unpack2<T>(pk.x), s1 = tc::unpack2<T>(pk.y);   // the pool must see the value as stored
+        ps[0] += s0.x; ps[1] += s0.y; ps[2] += s1.x; ps[3] += s1.y;
+      }
+      {
+        const float4 a = *reinterpret_cast<const float4*>(s_bias + q4), b = *reinterpret_cast<const float4*>(s_bias + C + q4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a0[j] = a1[j]; a1[j] = a2[j]; }
+        a2[0] = a.x; a2[1] = a.y; a2[2] = a.z; a2[3] = a.w; a2[4] = b.x; a2[5] = b.y; a2[6] = b.z; a2[7] = b.w;
+      }
+    }
+    if (xin) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&s_pool[q4 + j], ps[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&pool[(int64_t)n * C + i], s_pool[i]);
+}
+
 bool dwconv_gate_pool16_supported(const Tens& u, const Tens& g) {
   static const int enabled = getenv("XRD_DW16") ? atoi(getenv("XRD_DW16")) : 1;
   if (!enabled || u.dt == DT_F32 || g.dt != u.dt) return false;
+  static const int v3 = getenv("XRD_DW16_V3") ? atoi(getenv("XRD_DW16_V3")) : 1;
+  if (v3 && (g.c == 256 || g.c == 512)) return true;
   return g.c == 32 || g.c == 64 || g.c == 128;
 }
 
 void dwconv_gate_pool16(Ctx& c, const Tens& u, const float* w9, const float* bias, Tens& g, float* pool) {
   const int C = g.c;
   XRD_REQUIRE(dwconv_gate_pool16_supported(u, g) && u.c == 2 * C && g.n == u.n && g.h == u.h && g.w == u.w, "dwconv_gate_pool16: shape");
+  // measured per launch at batch 16 (gpurun_out r4d): C = 256 @64x64 91 us here against 150 us in the generic kernel, C = 512 @32x32
+  // 54 against 69; at C <= 128 the 16-byte staged kernel below wins (432 against 674 us at C = 32 @512x512): 8-byte accesses and
+  // the ninth warp's register squeeze (112 per thread, 28 spilled) cost more than the per-row block barrier
+  static const int v3 = getenv("XRD_DW16_V3") ? atoi(getenv("XRD_DW16_V3")) : 1;
+  if ((v3 == 1 && C >= 256) || v3 == 2) {
+    const int px = 256 / (C / 4);
+    const int rows3 = u.h >= 256 ? 32 : 16;
+    dim3 grid3(cdiv(u.w, px), cdiv(u.h, rows3), u.n);
+    const size_t smem = (size_t)kDw3Slots * (px + 2) * 2 * C * dsize(u.dt) + 2 * kDw3Slots * sizeof(uint64_t) + 3 * C * sizeof(float);
+    if (u.dt == DT_F16) XRD_LAUNCH(c, (k_dwconv_gate_pool16v3<__half>), grid3, kDw3Threads, smem, (const __half*)u.p, w9, bias, (__half*)g.p, pool, u.h, u.w, C, rows3);
+    else XRD_LAUNCH(c, (k_dwconv_gate_pool16v3<__nv_bfloat16>), grid3, kDw3Threads, smem, (const __nv_bfloat16*)u.p, w9, bias, (__nv_bfloat16*)g.p, pool, u.h, u.w, C, rows3);
+    return;
+  }
   const int ppb = 8 * (32 / (2 * (C / 8)));          // pixel columns per block
   const int rows = u.h >= 256 ? 32 : 16;
   dim3 grid(cdiv(u.w, ppb), cdiv(u.h, rows), u.n);

@@ -547,12 +547,14 @@ void dwconv_gate_pool(Ctx& c, const Tens& u, const float* w9, const float* bias,
 
 __global__ void __launch_bounds__(256) k_sca(const float* __restrict__ pool, int C, float inv_hw, const float* __restrict__ W,
                                              const float* __restrict__ b, float* __restrict__ scale) {
+  // grid (N, ceil(C / warps per block)): one output channel per warp.  (Round 1 ran ONE block per image looping over all C
+  // outputs: 36 us per launch x 30 launches for a C x C mat-vec.)  Same per-output summation order.
   extern __shared__ float s_mean[];
   const int n = blockIdx.x;
   for (int i = threadIdx.x; i < C; i += blockDim.x) s_mean[i] = pool[(int64_t)n * C + i] * inv_hw;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int co = warp; co < C; co += nw) {
+  for (int co = blockIdx.y * nw + warp; co < C; co += gridDim.y * nw) {
     float s = 0.f;
     for (int j = lane; j < C; j += 32) s = fmaf(W[(int64_t)co * C + j], s_mean[j], s);
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -561,7 +563,7 @@ __global__ void __launch_bounds__(256) k_sca(const float* __restrict__ pool, int
 }
 
 void sca_scale(Ctx& c, const float* pool, int N, int C, int HW, const float* W, const float* b, float* scale) {
-  XRD_LAUNCH(c, k_sca, N, 256, C * sizeof(float), pool, C, 1.0f / (float)HW, W, b, scale);
+  XRD_LAUNCH(c, k_sca, dim3(N, cdiv(C, 8)), 256, C * sizeof(float), pool, C, 1.0f / (float)HW, W, b, scale);
 }
 
 // =====================================================================================
