@@ -3,7 +3,7 @@ import csv, collections, re, sys
 path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/launches_ddim.csv"
 lines = [l for l in open(path) if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
-idx = [i for i, r in enumerate(rows) if "k_conv_smallcin" in r["Kernel Name"] or "k_im2col_3x3_2ch" in r["Kernel Name"]]   # first kernel of an evaluation
+idx = [i for i, r in enumerate(rows) if "k_conv_smallcin" in r["Kernel Name"] or "k_im2col_3x3_2ch" in r["Kernel Name"] or "k_first_conv_mma" in r["Kernel Name"]]   # first kernel of an evaluation
 sel = rows[idx[-1]:]
 agg = collections.OrderedDict(); tot = 0
 for r in sel:
