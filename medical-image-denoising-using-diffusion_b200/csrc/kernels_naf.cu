@@ -107,103 +107,18 @@ void layernorm16(Ctx& c, const Tens& x, const float* g, const float* b, float ep
 // ---------------------------------------------------------------------------------------------------------------
 // depthwise 3x3 (2C channels) + SimpleGate + global-average-pool partial sums, C in {32, 64, 128}.
 //   thread = (pixel column x, 8 consecutive channels of the 2C-channel tensor); it walks down a strip of rows.
-//   Each loaded row (pixels x-1, x, x+1: three 16-byte loads) is unpacked once and feeds the three output rows it
-//   touches (ky = 2, 1, 0) held as running accumulators, so every input element is loaded 3x (L1 hits) instead of 9x and
-//   converted once.  The 72 weights of the thread's 8 channels live in registers.  Lanes l and l ^ nq hold channel c
-//   and channel C + c of the same pixel: one shuffle exchange forms the gate product; the lower lane stores 16 bytes.
-// ---------------------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256, 2) k_dwconv_gate_pool16(const T* __restrict__ u, const float* __restrict__ w9,
-                                                               const float* __restrict__ bias, T* __restrict__ g, float* __restrict__ pool,
-                                                               int H, int W, int C, int rows_per_block) {
-  extern __shared__ float s_pool[];  // [C]
-  const int nq = C >> 3;                       // 8-channel chunks per half: 4, 8 or 16
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ppw = 32 / (2 * nq);               // pixels per warp
-  const int q = lane & (nq - 1);
-  const int half = (lane / nq) & 1;
-  const int x = (blockIdx.x * 8 + warp) * ppw + lane / (2 * nq);
-  const int n = blockIdx.z;
-  const int y0 = blockIdx.y * rows_per_block;
-  const int y1 = min(y0 + rows_per_block, H);
-  const int C2 = 2 * C;
-  const int cb = half * C + q * 8;             // first of this thread's 8 channels in the 2C-channel tensor
-  for (int i = threadIdx.x; i < C; i += blockDim.x) s_pool[i] = 0.f;
-  __syncthreads();
-
-  float w[9][8], bs[8];
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(w9 + t * C2 + cb)), b = __ldg(reinterpret_cast<const float4*>(w9 + t * C2 + cb + 4));
-    w[t][0] = a.x; w[t][1] = a.y; w[t][2] = a.z; w[t][3] = a.w; w[t][4] = b.x; w[t][5] = b.y; w[t][6] = b.z; w[t][7] = b.w;
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) bs[i] = __ldg(bias + cb + i);
-
-  const bool xin = x < W;
-  const T* base = u + (int64_t)n * H * W * C2 + cb;
-  auto load_row = [&](int r, uint4 (&d)[3]) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int xx = x + k - 1;
-      if (xin && r >= 0 && r < H && xx >= 0 && xx < W) d[k] = __ldg(reinterpret_cast<const uint4*>(base + ((int64_t)r * W + xx) * C2));
-      else d[k] = make_uint4(0u, 0u, 0u, 0u);
-    }
-  };
-  float a0[8], a1[8], a2[8], ps[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { a0[i] = bs[i]; a1[i] = bs[i]; a2[i] = bs[i]; ps[i] = 0.f; }
-  uint4 cur[3], nxt[3];
-  load_row(y0 - 1, cur);
-  for (int r = y0 - 1; r <= y1; ++r) {
-    if (r < y1) load_row(r + 1, nxt);           // next row in flight while this one is consumed
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      float v[8];
-      tc::unpack8<T>(cur[k], v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        a0[i] = fmaf(v[i], w[6 + k][i], a0[i]);   // output row r-1 sees this row through ky = 2
-        a1[i] = fmaf(v[i], w[3 + k][i], a1[i]);   // output row r   through ky = 1
-        a2[i] = fmaf(v[i], w[k][i], a2[i]);       // output row r+1 through ky = 0
-      }
-    }
-    // output row r-1 is complete
-    float o[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = a0[i] * __shfl_xor_sync(0xffffffffu, a0[i], nq);
-    if (r - 1 >= y0 && xin && half == 0) {
-      uint4 pk;
-      pk.x = tc::pack2<T>(o[0], o[1]); pk.y = tc::pack2<T>(o[2], o[3]); pk.z = tc::pack2<T>(o[4], o[5]); pk.w = tc::pack2<T>(o[6], o[7]);
-      *reinterpret_cast<uint4*>(g + (((int64_t)n * H + (r - 1)) * W + x) * C + q * 8) = pk;
-      float st[8];
-      tc::unpack8<T>(pk, st);                    // the pool must see what the next layer sees: the value as stored
-#pragma unroll
-      for (int i = 0; i < 8; ++i) ps[i] += st[i];
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { a0[i] = a1[i]; a1[i] = a2[i]; a2[i] = bs[i]; }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) cur[k] = nxt[k];
-  }
-  if (half == 0 && xin) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(&s_pool[q * 8 + i], ps[i]);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&pool[(int64_t)n * C + i], s_pool[i]);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// The same layer with the input rows staged through shared memory by 1-D bulk copies (round 2).  The register version above
-// holds 72 weights + 24 accumulators per thread, so it cannot also hold more than one prefetched row: ~8 KB of distinct
-// bytes in flight per SM, and the measured 1.36 TB/s (21 % of the copy rate) is exactly what Little's law gives for that at
-// ~800 ns of HBM latency.  Here one thread of the block keeps a ring of S row segments ((PX + 2) pixels x 2C channels,
-// 4.3-5.1 KB each, one cp.async.bulk request per row) in flight on mbarriers, independent of anyone's registers: 2 blocks x 4
-// slots = 35-40 KB in flight per SM.  The compute is unchanged (same thread mapping, sliding three-row accumulators, same
-// summation order, gate by one shuffle), it just reads its three 16-byte neighbours from the ring (a warp reads 512
-// contiguous bytes: conflict-free).  Halo pixels outside the image are zeroed once per slot and never overwritten; rows
-// outside the image are never fetched (their barrier phase is completed by a plain arrive).
+//   Each input row (pixels x-1, x, x+1: three 16-byte chunks) is unpacked once and feeds the three output rows it
+//   touches (ky = 2, 1, 0) held as running accumulators, so every input element is converted once.  The 72 weights of the
+//   thread's 8 channels live in registers.  Lanes l and l ^ nq hold channel c and channel C + c of the same pixel: one
+//   shuffle exchange forms the gate product; the lower lane stores 16 bytes.
+//   Round 1 read the rows straight from global memory with one row prefetched per thread in registers (72 weights + 24
+//   accumulators leave room for no more): ~8 KB of distinct bytes in flight per SM, and the 1.36 TB/s (21 % of the copy
+//   rate) it measured is what Little's law gives for that at ~800 ns of HBM latency.  Here (round 2) one thread of the block
+//   keeps a ring of S row segments ((PX + 2) pixels x 2C channels, 4.3-5.1 KB each, one cp.async.bulk request per row) in
+//   flight on mbarriers, independent of anyone's registers: 2 blocks x 4 slots = 35-40 KB in flight per SM.  The compute reads
+//   its three 16-byte neighbours from the ring (a warp reads 512 contiguous bytes: conflict-free).  Halo pixels outside the
+//   image are zeroed once per slot and never overwritten; rows outside the image are never fetched (their barrier phase is
+//   completed by a plain arrive).  432 us at C = 32 @512x512, batch 16 (1.9 TB/s; 592 us before).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kDwSlots = 4;
 
@@ -325,7 +240,7 @@ __global__ void __launch_bounds__(256, 2) k_dwconv_gate_pool16s(const T* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Third version (round 2): the staged kernel above still synchronised the whole block once per row (the thread that refills
+// Variant for C = 256 / 512 (round 2): the staged kernel above synchronises the whole block once per row (the thread that refills
 // the ring is one of the computing threads), which left it at 1.9 TB/s.  Here the ring has a warp of its own -- a ninth warp
 // whose lane 0 waits on per-slot `empty` barriers and issues the bulk copies -- so the eight computing warps only ever wait
 // for data.  The thread mapping changes so that the gate needs no shuffle and any C in {32 .. 512} fits: a thread owns four
@@ -474,7 +389,7 @@ void dwconv_gate_pool16(Ctx& c, const Tens& u, const float* w9, const float* bia
   const int C = g.c;
   XRD_REQUIRE(dwconv_gate_pool16_supported(u, g) && u.c == 2 * C && g.n == u.n && g.h == u.h && g.w == u.w, "dwconv_gate_pool16: shape");
   // measured per launch at batch 16 (gpurun_out r4d): C = 256 @64x64 91 us here against 150 us in the generic kernel, C = 512 @32x32
-  // 54 against 69; at C <= 128 the 16-byte staged kernel below wins (432 against 674 us at C = 32 @512x512): 8-byte accesses and
+  // 54 against 69; at C <= 128 the 16-byte staged kernel wins (432 against 674 us at C = 32 @512x512): 8-byte accesses and
   // the ninth warp's register squeeze (112 per thread, 28 spilled) cost more than the per-row block barrier
   static const int v3 = getenv("XRD_DW16_V3") ? atoi(getenv("XRD_DW16_V3")) : 1;
   if ((v3 == 1 && C >= 256) || v3 == 2) {
@@ -489,15 +404,9 @@ void dwconv_gate_pool16(Ctx& c, const Tens& u, const float* w9, const float* bia
   const int ppb = 8 * (32 / (2 * (C / 8)));          // pixel columns per block
   const int rows = u.h >= 256 ? 32 : 16;
   dim3 grid(cdiv(u.w, ppb), cdiv(u.h, rows), u.n);
-  static const int staged = getenv("XRD_DW16_STAGED") ? atoi(getenv("XRD_DW16_STAGED")) : 1;
-  if (staged) {
-    const size_t smem = (size_t)kDwSlots * (ppb + 2) * 2 * C * dsize(u.dt) + kDwSlots * sizeof(uint64_t) + C * sizeof(float);
-    if (u.dt == DT_F16) XRD_LAUNCH(c, (k_dwconv_gate_pool16s<__half>), grid, 256, smem, (const __half*)u.p, w9, bias, (__half*)g.p, pool, u.h, u.w, C, rows);
-    else XRD_LAUNCH(c, (k_dwconv_gate_pool16s<__nv_bfloat16>), grid, 256, smem, (const __nv_bfloat16*)u.p, w9, bias, (__nv_bfloat16*)g.p, pool, u.h, u.w, C, rows);
-    return;
-  }
-  if (u.dt == DT_F16) XRD_LAUNCH(c, (k_dwconv_gate_pool16<__half>), grid, 256, C * sizeof(float), (const __half*)u.p, w9, bias, (__half*)g.p, pool, u.h, u.w, C, rows);
-  else XRD_LAUNCH(c, (k_dwconv_gate_pool16<__nv_bfloat16>), grid, 256, C * sizeof(float), (const __nv_bfloat16*)u.p, w9, bias, (__nv_bfloat16*)g.p, pool, u.h, u.w, C, rows);
+  const size_t smem = (size_t)kDwSlots * (ppb + 2) * 2 * C * dsize(u.dt) + kDwSlots * sizeof(uint64_t) + C * sizeof(float);
+  if (u.dt == DT_F16) XRD_LAUNCH(c, (k_dwconv_gate_pool16s<__half>), grid, 256, smem, (const __half*)u.p, w9, bias, (__half*)g.p, pool, u.h, u.w, C, rows);
+  else XRD_LAUNCH(c, (k_dwconv_gate_pool16s<__nv_bfloat16>), grid, 256, smem, (const __nv_bfloat16*)u.p, w9, bias, (__nv_bfloat16*)g.p, pool, u.h, u.w, C, rows);
 }
 
 }  // namespace xrd
