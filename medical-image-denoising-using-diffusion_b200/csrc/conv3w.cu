@@ -13,7 +13,10 @@
 //   * A stage = one (64-channel chunk, dx) copy, 48 KB, three stages; weight blocks stream through a small ring in the
 //     order (chunk, dx, dy);
 //   * issue loop with compile-time descriptor offsets, 8-warp register epilogue with bias + time-embedding row +
-//     residual + GroupNorm sums, as in conv3.cu.
+//     residual + GroupNorm sums, as in conv3.cu;
+//   * small batches (the served shape is ONE image: 16 tiles for 148 SMs, each CTA streaming the whole 192 x 192 x 9 weight
+//     block): the 192 output channels are split over blockIdx.y into two halves of 96 -- twice the CTAs, half the weight
+//     stream and half the MMA columns per CTA; a half covers GroupNorm groups 4*y .. 4*y+3 exactly, so the sums need no care.
 #include "kernels.cuh"
 #include "tc_common.cuh"
 
@@ -34,6 +37,8 @@ struct Conv3WP {
   void* y;
   double* stats;
   const void* wsw;          // pre-swizzled weight blocks for 1-D bulk loads (null: tensor-map loads)
+  int ldc;                  // channels of the output / residual tensors (= COUT of the kernel unless the outputs are split)
+  uint32_t wblk;            // bytes of one whole packed weight block (ldc rows of 128 bytes)
 };
 
 constexpr int kW3Threads = 320;
@@ -87,14 +92,18 @@ __device__ __forceinline__ void w3_issue_dx(uint64_t adesc0, uint32_t sB_addr, u
   }
 }
 
-template <typename T, int COUT>
+// COUT: output channels this CTA computes = columns [blockIdx.y * COUT, +COUT) of the layer's p.ldc; CPG: channels per GroupNorm
+// group of the whole layer (p.ldc / 8).
+template <typename T, int COUT, int CPG = COUT / 8>
 __global__ void __launch_bounds__(kW3Threads, 1)
 k_conv3w(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB,
          const Conv3WP p) {
   constexpr uint32_t B_BYTES = COUT * 128;
-  constexpr int CPG = COUT / 8;
   constexpr int NBLK = COUT / 48;
+  constexpr int GL = COUT / CPG;            // GroupNorm groups this CTA's columns cover (8, or 4 for a half)
   static_assert(COUT % 48 == 0 && 2 * COUT <= 512, "two accumulators must fit TMEM");
+  static_assert(COUT % CPG == 0 && GL <= 8, "an output split must cover whole GroupNorm groups");
+  const int coff = blockIdx.y * COUT;       // first output channel of this CTA
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -152,8 +161,10 @@ k_conv3w(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
             for (int dy = 0; dy < 3; ++dy) {
               tc::mbar_wait(&b_empty[ws], wph ^ 1);
               tc::mbar_expect_tx(&b_full[ws], B_BYTES);
-              if (p.wsw) tc::bulk_load_1d(sB + (size_t)ws * B_BYTES, (const char*)p.wsw + (size_t)(c * 9 + dy * 3 + dx) * B_BYTES, B_BYTES, &b_full[ws]);
-              else tc::tma_load_3d(sB + (size_t)ws * B_BYTES, &tmB, &b_full[ws], 0, 0, c * 9 + dy * 3 + dx);
+              // rows [coff, coff + COUT) of the block: whole 8-row swizzle atoms (COUT % 8 == 0), so a slab of the pre-swizzled copy is
+              // itself a correctly swizzled [COUT x 64] operand
+              if (p.wsw) tc::bulk_load_1d(sB + (size_t)ws * B_BYTES, (const char*)p.wsw + (size_t)(c * 9 + dy * 3 + dx) * p.wblk + (size_t)coff * 128, B_BYTES, &b_full[ws]);
+              else tc::tma_load_3d(sB + (size_t)ws * B_BYTES, &tmB, &b_full[ws], 0, coff, c * 9 + dy * 3 + dx);
               if (++ws == (uint32_t)p.nb) { ws = 0; wph ^= 1; }
             }
           }
@@ -222,11 +233,11 @@ k_conv3w(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
           gq[g] += __shfl_xor_sync(0xffffffffu, gq[g], o);
         }
       }
-      if (lane < 16) {
+      if (lane < 2 * GL) {                   // this CTA's columns are groups coff / CPG .. + GL - 1 of the layer
         float v = 0.f;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) { if (lane == 2 * g) v = gs[g]; if (lane == 2 * g + 1) v = gq[g]; }
-        atomicAdd(p.stats + (size_t)img * 16 + lane, (double)v);
+        for (int g = 0; g < GL; ++g) { if (lane == 2 * g) v = gs[g]; if (lane == 2 * g + 1) v = gq[g]; }
+        atomicAdd(p.stats + (size_t)img * 16 + 2 * (coff / CPG) + lane, (double)v);
       }
 #pragma unroll
       for (int g = 0; g < 8; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
@@ -239,7 +250,7 @@ k_conv3w(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
         flush_stats(cur_img);
         __syncwarp();
         for (int cc = lane; cc < COUT; cc += 32)
-          badd[cc] = (p.bias ? __ldg(p.bias + cc) : 0.f) + (p.chan_add ? __ldg(p.chan_add + (int64_t)img * p.chan_add_bstride + cc) : 0.f);
+          badd[cc] = (p.bias ? __ldg(p.bias + coff + cc) : 0.f) + (p.chan_add ? __ldg(p.chan_add + (int64_t)img * p.chan_add_bstride + coff + cc) : 0.f);
         cur_img = img;
         __syncwarp();
       }
@@ -248,7 +259,7 @@ k_conv3w(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
       uint4 rcur[6], rnext[6];
       if (rp) {
 #pragma unroll
-        for (int j = 0; j < 6; ++j) rcur[j] = __ldg(reinterpret_cast<const uint4*>(rp + pix * COUT) + j);
+        for (int j = 0; j < 6; ++j) rcur[j] = __ldg(reinterpret_cast<const uint4*>(rp + pix * p.ldc + coff) + j);
       }
       tc::mbar_wait(acc_full, ti & 1);
       tc::tc_fence_after();
@@ -263,7 +274,7 @@ k_conv3w(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
         const bool has_next = rp && cb + 1 < NBLK;
         if (has_next) {
 #pragma unroll
-          for (int j = 0; j < 6; ++j) rnext[j] = __ldg(reinterpret_cast<const uint4*>(rp + pix * COUT + (cb + 1) * 48) + j);
+          for (int j = 0; j < 6; ++j) rnext[j] = __ldg(reinterpret_cast<const uint4*>(rp + pix * p.ldc + coff + (cb + 1) * 48) + j);
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
@@ -292,7 +303,7 @@ k_conv3w(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUten
           uint4 pk;
           pk.x = tc::pack2<T>(r8[0], r8[1]); pk.y = tc::pack2<T>(r8[2], r8[3]);
           pk.z = tc::pack2<T>(r8[4], r8[5]); pk.w = tc::pack2<T>(r8[6], r8[7]);
-          if (h8 & 1) tc::st_global_v8(yp + pix * COUT + co - 8, pk_even, pk); else pk_even = pk;   // 32-byte sector stores
+          if (h8 & 1) tc::st_global_v8(yp + pix * p.ldc + coff + co - 8, pk_even, pk); else pk_even = pk;   // 32-byte sector stores
         }
         if (has_next) {
 #pragma unroll
@@ -339,8 +350,17 @@ void conv3w(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, 
   p.nchunk0 = (c0 + 63) / 64;
   p.nchunk = p.nchunk0 + (c1 + 63) / 64;
   XRD_REQUIRE(p.nchunk * 9 == w.tc_nkb && w.tc_npad == w.cout, "conv3w: packed weights out of date");
-  const size_t bb = (size_t)w.cout * 128;
-  const size_t fixed = (size_t)kW3Stages * kW3ABytes + 8 * w.cout * 4 + 32 * 8 + 64;
+  static int nsm = 0;
+  if (!nsm) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+  // output split for small batches (see the header): only where a half is whole GroupNorm groups and whole 48-column epilogue
+  // blocks, i.e. 192 outputs, and only while twice the tiles still fit the machine
+  static const int split_on = getenv("XRD_C3W_SPLIT") ? atoi(getenv("XRD_C3W_SPLIT")) : 1;
+  const int nsplit = (split_on && w.cout == 192 && 2 * p.ntiles <= nsm) ? 2 : 1;
+  const int co = w.cout / nsplit;
+  p.ldc = w.cout;
+  p.wblk = (uint32_t)w.cout * 128u;
+  const size_t bb = (size_t)co * 128;
+  const size_t fixed = (size_t)kW3Stages * kW3ABytes + 8 * co * 4 + 32 * 8 + 64;
   p.nb = (int)std::min<size_t>(8, (227 * 1024 - 1024 - fixed) / bb);
   XRD_REQUIRE(p.nb >= 2, "conv3w: shared memory budget exceeded");
   p.bias = w.bias;
@@ -364,16 +384,14 @@ void conv3w(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, 
   {
     const cuuint64_t dims[3] = {64, (cuuint64_t)w.cout, (cuuint64_t)w.tc_nkb};
     const cuuint64_t strides[2] = {128, (cuuint64_t)w.cout * 128};
-    const cuuint32_t box[3] = {64, (cuuint32_t)w.cout, 1};
+    const cuuint32_t box[3] = {64, (cuuint32_t)co, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = get_encode_tiled()(&tmB, tmap_dtype(x1.dt), 3, w.wtc[x1.dt], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) fail(XRD_ERR_CUDA, "cuTensorMapEncodeTiled(conv3w weights) failed: %d", (int)r);
   }
   const size_t smem = 1024 + fixed + (size_t)p.nb * bb;
-  static int nsm = 0;
-  if (!nsm) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
-  const int grid = std::min(p.ntiles, nsm);
+  const dim3 grid(std::min(p.ntiles, nsm), nsplit);
   auto launch = [&](auto kern) {
     static std::mutex mu;
     static std::vector<const void*> done;
@@ -386,8 +404,15 @@ void conv3w(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, 
     }
     XRD_LAUNCH(c, kern, grid, kW3Threads, smem, tmA0, tmA1, tmB, p);
   };
-  if (x1.dt == DT_BF16) { if (w.cout == 144) launch(k_conv3w<__nv_bfloat16, 144>); else launch(k_conv3w<__nv_bfloat16, 192>); }
-  else { if (w.cout == 144) launch(k_conv3w<__half, 144>); else launch(k_conv3w<__half, 192>); }
+  if (x1.dt == DT_BF16) {
+    if (w.cout == 144) launch(k_conv3w<__nv_bfloat16, 144>);
+    else if (nsplit == 2) launch(k_conv3w<__nv_bfloat16, 96, 24>);
+    else launch(k_conv3w<__nv_bfloat16, 192>);
+  } else {
+    if (w.cout == 144) launch(k_conv3w<__half, 144>);
+    else if (nsplit == 2) launch(k_conv3w<__half, 96, 24>);
+    else launch(k_conv3w<__half, 192>);
+  }
 }
 
 }  // namespace xrd
