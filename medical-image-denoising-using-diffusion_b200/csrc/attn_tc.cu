@@ -31,6 +31,8 @@ struct AttnTcP {
   float scale_log2e;       // d^-0.5 * log2(e)
   int ahead;               // key tiles Q K^T runs ahead of P V: 1 or 2
   int probe;               // probe the next Q K^T block's barriers under the P V MMAs
+  int ntq;                 // Q tiles per CTA: 2 (throughput shape: the two tiles share every K/V tile), or 1 when the whole launch
+                           // is so small (one or two images) that twice the CTAs of half the work fill more of the machine
   void* out;
 };
 
@@ -277,7 +279,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
   using Map = AttMap<D>;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 256, head = blockIdx.y, img = blockIdx.z;
+  const int q0 = blockIdx.x * 128 * p.ntq, head = blockIdx.y, img = blockIdx.z;
   const int qoff = head * p.d, koff = p.heads * p.d + head * p.d, voff = 2 * p.heads * p.d + head * p.d;
 
   if (warp == 0 && lane == 0) {
@@ -285,7 +287,8 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     tc::tma_prefetch_desc(&tmKV);
     tc::mbar_init(q_full, 1);
     for (int s = 0; s < kRing; ++s) {
-      tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 2); tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], 2);   // released by both issuing warps
+      // K / V slots are released by every issuing warp at work: one per Q tile
+      tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], (uint32_t)p.ntq); tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], (uint32_t)p.ntq);
     }
     for (int s = 0; s < 4; ++s) {
       tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_free[s], 128);
@@ -313,8 +316,8 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (tc::elect_one()) {
-      tc::mbar_expect_tx(q_full, (uint32_t)(2 * NCH) * kTile);
-      for (int t = 0; t < 2; ++t)
+      tc::mbar_expect_tx(q_full, (uint32_t)(p.ntq * NCH) * kTile);
+      for (int t = 0; t < p.ntq; ++t)
         for (int c = 0; c < NCH; ++c) tc::tma_load_3d(sQ + (t * 2 + c) * kTile, &tmQ, q_full, qoff + 64 * c, q0 + t * 128, img);
       uint32_t slot = 0, phase = 0;
       for (int j = 0; j < p.nkv; ++j) {
@@ -335,8 +338,8 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     const uint64_t dK = tc::umma_desc_sw128(tc::smem_u32(sK));           // + slot * (2 * kKvTile >> 4)
     const uint64_t dV = umma_desc_mn_sw128(tc::smem_u32(sV), kKvTile);   // + slot * (2 * kKvTile >> 4)
     if (warp == 1) att_mma_warp<T, D16, 0>(p.nkv, bar0, dQ, dK, dV, lane);
-    else att_mma_warp<T, D16, 1>(p.nkv, bar0, dQ, dK, dV, lane);
-  } else {
+    else if (p.ntq == 2) att_mma_warp<T, D16, 1>(p.nkv, bar0, dQ, dK, dV, lane);
+  } else if (((warp - 2) >> 2) < p.ntq) {
     // ===================== softmax / correction / epilogue (warps 2..9, one query row per thread) =====================
     const int t = (warp - 2) >> 2;                 // Q tile
     const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
@@ -524,7 +527,13 @@ void attention_tc(Ctx& c, const Tens& qkv, int heads, Tens& out) {
     if (r != CUDA_SUCCESS) fail(XRD_ERR_CUDA, "cuTensorMapEncodeTiled(qkv) failed: %d", (int)r);
   }
   const size_t smem = 1024 + (size_t)4 * kTile + (size_t)2 * kRing * 2 * kKvTile + 64 * 8;
-  dim3 grid(cdiv(HW, 256), heads, qkv.n);
+  // one Q tile per CTA while twice the CTAs still fit the 148 SMs (one or two images at 64x64): the served shape ran 32 CTAs
+  // of 72 us each (profiles/r02_launches_ddim_b1.csv)
+  static const int ntq_env = getenv("XRD_ATT_NTQ") ? atoi(getenv("XRD_ATT_NTQ")) : 0;
+  static int nsm = 0;
+  if (!nsm) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+  p.ntq = (ntq_env == 1 || ntq_env == 2) ? ntq_env : (2 * cdiv(HW, 256) * heads * qkv.n <= nsm ? 1 : 2);
+  dim3 grid(cdiv(HW, 128 * p.ntq), heads, qkv.n);
   const int dc = d / 16;
 #define XRD_ATT_CASE(TT, DCV)                                                                                             \
   case DCV: {                                                                                                             \

@@ -280,7 +280,10 @@ def check_attention(mode, impl):
         for (B, heads, d, H, W, peaked) in [(2, 2, 96, 8, 8, 0), (1, 2, 96, 16, 16, 0), (1, 2, 96, 4, 4, 0), (1, 2, 96, 32, 32, 0),
                                             (1, 1, 64, 12, 10, 0), (1, 2, 96, 32, 32, 1), (2, 2, 96, 24, 24, 1),
                                             # production size of the 512x512 configurations: 64x64 = 4096 tokens (64 key tiles)
-                                            (1, 2, 96, 64, 64, 0), (2, 2, 96, 64, 64, 1)]:
+                                            (1, 2, 96, 64, 64, 0), (2, 2, 96, 64, 64, 1),
+                                            # launches of more than 74 (image, head, query-pair) items keep two Q tiles per CTA, smaller
+                                            # ones run one (attn_tc.cu: ntq): 10 x 2 x 4 = 80 items and 20 x 2 x 3 ragged = 120
+                                            (10, 2, 96, 32, 32, 1), (20, 2, 96, 24, 24, 0)]:
             qkv = torch.randn(B, 3 * heads * d, H, W, generator=g)
             if peaked:
                 ramp = torch.linspace(0.2, 4.0, H * W).reshape(1, 1, H, W)
