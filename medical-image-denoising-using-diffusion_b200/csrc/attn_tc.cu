@@ -530,15 +530,13 @@ void attention_tc(Ctx& c, const Tens& qkv, int heads, Tens& out) {
   // one Q tile per CTA while twice the CTAs still fit the 148 SMs (one or two images at 64x64): the served shape ran 32 CTAs
   // of 72 us each (profiles/r02_launches_ddim_b1.csv)
   static const int ntq_env = getenv("XRD_ATT_NTQ") ? atoi(getenv("XRD_ATT_NTQ")) : 0;
-  static int nsm = 0;
-  if (!nsm) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+  const int nsm = sm_count();
   p.ntq = (ntq_env == 1 || ntq_env == 2) ? ntq_env : (2 * cdiv(HW, 256) * heads * qkv.n <= nsm ? 1 : 2);
   dim3 grid(cdiv(HW, 128 * p.ntq), heads, qkv.n);
   const int dc = d / 16;
 #define XRD_ATT_CASE(TT, DCV)                                                                                             \
   case DCV: {                                                                                                             \
-    static bool attr = false;                                                                                             \
-    if (!attr) { XRD_CUDA(cudaFuncSetAttribute(k_attn_tc<TT, DCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; } \
+    ensure_dyn_smem(k_attn_tc<TT, DCV>, (int)smem);                                                                       \
     XRD_LAUNCH(c, (k_attn_tc<TT, DCV>), grid, kAttThreads, smem, tmQ, tmKV, p);                                                  \
   } break;
   if (qkv.dt == DT_BF16) {

@@ -6,7 +6,10 @@
 #include <stdint.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <algorithm>
 #include <atomic>
+#include <mutex>
+#include <utility>
 #include <vector>
 #include <stdexcept>
 #include <string>
@@ -73,6 +76,37 @@ inline int device_of(const void* p) {
   if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged)
     fail(XRD_ERR_INVALID, "pointer %p is not device memory (this library has no CPU path)", p);
   return a.device;
+}
+
+// Per-device launch state.  cudaFuncSetAttribute and the SM count belong to the CURRENT device, and a process may hold handles on
+// several GPUs (xrd_create(device, ...); one serving thread per GPU): a process-wide "done once" flag would leave every device but
+// the first at the 48 KB default and fail its first launch of a large-shared-memory kernel.
+inline void ensure_dyn_smem(const void* kern, int bytes) {
+  static std::mutex mu;
+  static std::vector<std::pair<int, const void*>> done;       // (device, kernel) pairs whose limit was raised
+  int dev = 0;
+  XRD_CUDA(cudaGetDevice(&dev));
+  const std::pair<int, const void*> key(dev, kern);
+  std::lock_guard<std::mutex> lk(mu);
+  if (std::find(done.begin(), done.end(), key) != done.end()) return;
+  XRD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.push_back(key);
+}
+template <typename F> inline void ensure_dyn_smem(F* kern, int bytes) { ensure_dyn_smem((const void*)kern, bytes); }
+// SMs of the current device (grids of the persistent kernels are sized by it)
+inline int sm_count() {
+  constexpr int kMaxDev = 64;
+  static std::atomic<int> cache[kMaxDev];
+  int dev = 0;
+  XRD_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < kMaxDev) {
+    const int v = cache[dev].load(std::memory_order_relaxed);
+    if (v > 0) return v;
+  }
+  int n = 0;
+  XRD_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  if (dev >= 0 && dev < kMaxDev) cache[dev].store(n, std::memory_order_relaxed);
+  return n;
 }
 
 // ---------------------------------------------------------------- dtypes / tensors

@@ -382,20 +382,11 @@ void conv1(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, T
     if (r != CUDA_SUCCESS) fail(XRD_ERR_CUDA, "cuTensorMapEncodeTiled(conv1 weights) failed: %d", (int)r);
   }
   const size_t smem = 1024 + (size_t)kC1Stages * kC1ATile + (size_t)p.nchunk * slice * 128 + (size_t)slice * 8 + 256;
-  static int nsm = 0;
-  if (!nsm) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+  const int nsm = sm_count();
   const int nslices = w.cout / slice;
   dim3 grid(std::max(1, std::min(p.ntiles, nsm / nslices)), nslices);
   auto launch = [&](auto kern) {
-    static std::mutex mu;
-    static std::vector<const void*> done;
-    {
-      std::lock_guard<std::mutex> lk(mu);
-      if (std::find(done.begin(), done.end(), (const void*)kern) == done.end()) {
-        XRD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        done.push_back((const void*)kern);
-      }
-    }
+    ensure_dyn_smem(kern, 227 * 1024);
     XRD_LAUNCH(c, kern, grid, kC1Threads, smem, tmA0, tmA1, tmB, p);
   };
   auto pick = [&](auto tag) {

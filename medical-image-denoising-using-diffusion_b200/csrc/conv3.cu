@@ -575,12 +575,8 @@ C3Cfg c3_plan(int cout, int nkb) {
 
 template <typename T, int COUT, int TH, int NACC, bool WRES>
 void c3_launch(Ctx& c, int grid, size_t smem, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const Conv3P& p) {
-  static bool attr = false;
-  if (!attr) {
-    XRD_CUDA(cudaFuncSetAttribute(k_conv3<T, COUT, TH, NACC, WRES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    XRD_CUDA(cudaFuncSetAttribute(k_conv3<T, COUT, TH, NACC, WRES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
-  }
+  if (p.in_coef) ensure_dyn_smem(k_conv3<T, COUT, TH, NACC, WRES, true>, 227 * 1024);
+  else ensure_dyn_smem(k_conv3<T, COUT, TH, NACC, WRES, false>, 227 * 1024);
   if (p.in_coef) XRD_LAUNCH(c, (k_conv3<T, COUT, TH, NACC, WRES, true>), grid, kC3ThreadsGN, smem, a0, a1, b, p);
   else XRD_LAUNCH(c, (k_conv3<T, COUT, TH, NACC, WRES, false>), grid, kC3Threads, smem, a0, a1, b, p);
 }
@@ -663,8 +659,7 @@ void conv3(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, T
                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) fail(XRD_ERR_CUDA, "cuTensorMapEncodeTiled(conv3 weights) failed: %d", (int)r);
   }
-  static int nsm = 0;
-  if (!nsm) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+  const int nsm = sm_count();
   const int grid = std::min(p.ntiles, nsm);
   if (x1.dt == DT_BF16) c3_dispatch<__nv_bfloat16>(c, w.cout, g, grid, tmA0, tmA1, tmB, p);
   else c3_dispatch<__half>(c, w.cout, g, grid, tmA0, tmA1, tmB, p);

@@ -476,20 +476,11 @@ void conv3r(Ctx& c, const Tens& x, ConvW& w, const ConvEpi& e, Tens& y) {
   }
   const int R = w.cout == 48 ? 8 : 6, NA = w.cout == 48 ? 8 : 4;
   const size_t smem = 1024 + (size_t)R * kRSlot + 9 * (size_t)w.cout * 128 + 8 * w.cout * 4 + (3 * R + 2 * NA + 1) * 8 + 64;
-  static int nsm = 0;
-  if (!nsm) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+  const int nsm = sm_count();
   const int grid = std::min(p.nitems, nsm);
   const bool gn = e.in_coef != nullptr;
   auto launch = [&](auto kern) {
-    static std::mutex mu;
-    static std::vector<const void*> done;
-    {
-      std::lock_guard<std::mutex> lk(mu);
-      if (std::find(done.begin(), done.end(), (const void*)kern) == done.end()) {
-        XRD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        done.push_back((const void*)kern);
-      }
-    }
+    ensure_dyn_smem(kern, 227 * 1024);
     XRD_LAUNCH(c, kern, grid, gn ? kRThreadsGN : kRThreads, smem, tmA, tmB, p);
   };
   auto pick = [&](auto tag, auto ks_tag) {

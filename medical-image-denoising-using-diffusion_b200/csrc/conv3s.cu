@@ -645,8 +645,7 @@ void conv3s(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, 
   else { p.c0 = std::min(x1.c, 64); p.c1 = x1.c - p.c0; p.two_src = 0; }
   const int nch = p.c1 ? 2 : 1;
   XRD_REQUIRE(w.tc_nkb == nch * 9 && w.tc_npad == w.cout, "conv3s: packed weights out of date (nkb %d, npad %d)", w.tc_nkb, w.tc_npad);
-  static int nsm = 0;
-  if (!nsm) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+  const int nsm = sm_count();
   p.ncb = x1.w / 128;
   p.dpc = cdiv(x1.h, kSNB);
   p.ndec = x1.n * p.ncb * p.dpc;
@@ -684,15 +683,7 @@ void conv3s(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, 
   const bool gn = e.in_coef != nullptr;
   const int k0 = p.c0 / 16, k1 = p.c1 / 16;
   auto launch = [&](auto kern) {
-    static std::mutex mu;
-    static std::vector<const void*> done;
-    {
-      std::lock_guard<std::mutex> lk(mu);
-      if (std::find(done.begin(), done.end(), (const void*)kern) == done.end()) {
-        XRD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        done.push_back((const void*)kern);
-      }
-    }
+    ensure_dyn_smem(kern, 227 * 1024);
     XRD_LAUNCH(c, kern, grid, gn ? kSThreadsGN : kSThreads, smem, tmA0, tmA1, tmB, p);
   };
   auto pick = [&](auto tag) {

@@ -350,8 +350,7 @@ void conv3w(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, 
   p.nchunk0 = (c0 + 63) / 64;
   p.nchunk = p.nchunk0 + (c1 + 63) / 64;
   XRD_REQUIRE(p.nchunk * 9 == w.tc_nkb && w.tc_npad == w.cout, "conv3w: packed weights out of date");
-  static int nsm = 0;
-  if (!nsm) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+  const int nsm = sm_count();
   // output split for small batches (see the header): only where a half is whole GroupNorm groups and whole 48-column epilogue
   // blocks, i.e. 192 outputs, and only while twice the tiles still fit the machine
   static const int split_on = getenv("XRD_C3W_SPLIT") ? atoi(getenv("XRD_C3W_SPLIT")) : 1;
@@ -393,15 +392,7 @@ void conv3w(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e, 
   const size_t smem = 1024 + fixed + (size_t)p.nb * bb;
   const dim3 grid(std::min(p.ntiles, nsm), nsplit);
   auto launch = [&](auto kern) {
-    static std::mutex mu;
-    static std::vector<const void*> done;
-    {
-      std::lock_guard<std::mutex> lk(mu);
-      if (std::find(done.begin(), done.end(), (const void*)kern) == done.end()) {
-        XRD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        done.push_back((const void*)kern);
-      }
-    }
+    ensure_dyn_smem(kern, 227 * 1024);
     XRD_LAUNCH(c, kern, grid, kW3Threads, smem, tmA0, tmA1, tmB, p);
   };
   if (x1.dt == DT_BF16) {

@@ -448,15 +448,7 @@ void conv_tc(Ctx& c, const Tens& x1, const Tens* x2, ConvW& w, const ConvEpi& e,
   if (want_stats) XRD_REQUIRE(!w.d2s && bn == w.cout && (bn == 48 || bn == 96 || bn == 144 || bn == 192), "conv_tc: no statistics epilogue for cout=%d", w.cout);
   p.stats = e.stats_out;
   auto launch = [&](auto kern) {
-    static std::mutex mu;
-    static std::vector<const void*> done;          // kernels whose dynamic shared-memory limit was already raised
-    {
-      std::lock_guard<std::mutex> lk(mu);
-      if (std::find(done.begin(), done.end(), (const void*)kern) == done.end()) {
-        XRD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        done.push_back((const void*)kern);
-      }
-    }
+    ensure_dyn_smem(kern, 227 * 1024);
     XRD_LAUNCH(c, kern, grid, kTcThreads, smem, tmA0, tmA1, tmB, p);
   };
   if (x1.dt == DT_BF16) {

@@ -464,18 +464,15 @@ void conv_cout1(Ctx& c, const Cout1Args& a) {
   if (c.dry) return;
   switch (a.x.dt) {
     case DT_F32: {
-      static bool attr = false;
-      if (!attr) { XRD_CUDA(cudaFuncSetAttribute(k_conv_cout1_tiled<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+      ensure_dyn_smem(k_conv_cout1_tiled<float, false>, 200 * 1024);
       XRD_LAUNCH(c, (k_conv_cout1_tiled<float, false>), grid, 256, smem, p);
     } break;
     case DT_BF16: {
-      static bool attr = false;
-      if (!attr) { XRD_CUDA(cudaFuncSetAttribute(k_conv_cout1_tiled<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+      ensure_dyn_smem(k_conv_cout1_tiled<__nv_bfloat16, true>, 200 * 1024);
       XRD_LAUNCH(c, (k_conv_cout1_tiled<__nv_bfloat16, true>), grid, 256, smem, p);
     } break;
     case DT_F16: {
-      static bool attr = false;
-      if (!attr) { XRD_CUDA(cudaFuncSetAttribute(k_conv_cout1_tiled<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+      ensure_dyn_smem(k_conv_cout1_tiled<__half, true>, 200 * 1024);
       XRD_LAUNCH(c, (k_conv_cout1_tiled<__half, true>), grid, 256, smem, p);
     } break;
   }

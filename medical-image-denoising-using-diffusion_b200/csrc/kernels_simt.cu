@@ -771,11 +771,7 @@ template <typename T, int D>
 static void launch_attn_simt(Ctx& c, const Tens& qkv, int heads, Tens& out) {
   const int HW = qkv.h * qkv.w;
   size_t smem = (size_t)(3 * 64 * (D + 4) + 64 * 68) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    XRD_CUDA(cudaFuncSetAttribute(k_attn_simt<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  ensure_dyn_smem(k_attn_simt<T, D>, (int)smem);
   dim3 grid(cdiv(HW, 64), heads, qkv.n);
   float scale = 1.0f / sqrtf((float)D);
   XRD_LAUNCH(c, (k_attn_simt<T, D>), grid, 256, smem, (const T*)qkv.p, (T*)out.p, HW, heads, scale);

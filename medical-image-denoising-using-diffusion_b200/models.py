@@ -331,7 +331,7 @@ class _NativeModel(nn.Module):
         _lib.check(lib.xrd_import_weights(ent["h"], C.c_void_p(raw.ctypes.data), len(raw)))
         _lib.check(lib.xrd_finalize_weights(ent["h"], self._xrd_parts))
         ent["fp"] = self._xrd_fingerprint(dev)
-        ent["mode"] = ent["graph"] = ent["audit"] = None
+        ent["mode"] = ent["graph"] = ent["audit"] = ent["side"] = None
         return self
 
     def _xrd_handle_raw(self, device: torch.device) -> dict:

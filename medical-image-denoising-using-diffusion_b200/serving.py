@@ -2,7 +2,7 @@
 
 `/denoise` as deployed calls every model with ONE 512x512 image from its own worker thread
 (`asyncio.to_thread`, RUN:85-91; `_process_diffusion/_process_nafnet/_process_hybrid`, RUN:104-141).  One image
-under-fills a B200: the sampler takes 24.5 ms for a single image and 13.4 ms per evaluation *for sixteen*.  A
+under-fills a B200: the 9-evaluation sampler takes 18 ms for a single image and 10.8 ms per evaluation *for sixteen*.  A
 `MicroBatcher` sits between those worker threads and a model: requests that arrive within `max_delay_ms` of each
 other (and share shape, dtype and device) are concatenated, run as one batch through the same library call, and
 split again.  Images never interact inside the networks, so a request's result does not
@@ -16,6 +16,7 @@ consumed after the submitting stream produced them, outputs are visible to the s
 """
 from __future__ import annotations
 
+import collections
 import queue
 import threading
 import time
@@ -32,7 +33,9 @@ class MicroBatcher:
         self.fn = fn
         self.max_batch = int(max_batch)
         self.max_delay = float(max_delay_ms) / 1e3
-        self.batches: List[int] = []          # sizes of the batches actually run (observability / tests)
+        # sizes of the most recent batches actually run (observability / tests); bounded: a server lives for months
+        self.batches: "collections.deque[int]" = collections.deque(maxlen=4096)
+        self._submit_lock = threading.Lock()   # orders submit() against close(): nothing is enqueued behind the stop sentinel
         self._q: "queue.Queue[Optional[Tuple[torch.Tensor, Optional[torch.cuda.Event], Future]]]" = queue.Queue()
         self._closed = False
         self._worker = threading.Thread(target=self._run, name="xrd-microbatcher", daemon=True)
@@ -44,8 +47,6 @@ class MicroBatcher:
 
     def submit(self, x: torch.Tensor) -> Future:
         """Enqueue a (k,1,H,W) request (k >= 1); the Future resolves to the (k,1,H,W) result."""
-        if self._closed:
-            raise RuntimeError("MicroBatcher is closed")
         if not isinstance(x, torch.Tensor) or x.dim() != 4:
             raise ValueError(f"expected a (k,C,H,W) tensor, got {type(x).__name__} {tuple(getattr(x, 'shape', ()))}")
         ev = None
@@ -53,14 +54,28 @@ class MicroBatcher:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(x.device))
         fut: Future = Future()
-        self._q.put((x, ev, fut))
+        with self._submit_lock:
+            if self._closed:
+                raise RuntimeError("MicroBatcher is closed")
+            self._q.put((x, ev, fut))
         return fut
 
     def close(self) -> None:
-        if not self._closed:
+        """Stop accepting requests, run what was already submitted, stop the worker.  Idempotent."""
+        with self._submit_lock:
+            if self._closed:
+                return
             self._closed = True
             self._q.put(None)
-            self._worker.join(timeout=30)
+        self._worker.join(timeout=30)
+        # a worker that died or is stuck in a long call must not leave waiters blocked for ever
+        while True:
+            try:
+                it = self._q.get_nowait()
+            except queue.Empty:
+                break
+            if it is not None and not it[2].done():
+                it[2].set_exception(RuntimeError("MicroBatcher closed before the request ran"))
 
     def __enter__(self):
         return self

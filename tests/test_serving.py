@@ -47,6 +47,18 @@ def test_shapes_are_not_mixed_and_multi_image_requests_stay_whole():
     assert sum(calls) == 7 and max(calls) <= 4
 
 
+def test_close_runs_what_was_submitted_and_refuses_later_requests():
+    calls = []
+    mb = xrd_b200.MicroBatcher(_fake_model(calls), max_batch=4, max_delay_ms=500.0)
+    futs = [mb.submit(torch.ones(1, 1, 8, 8) * i) for i in range(3)]
+    mb.close()                                          # the stop sentinel sits behind the three requests
+    assert all(f.done() for f in futs) and sum(calls) == 3
+    with pytest.raises(RuntimeError):
+        mb.submit(torch.ones(1, 1, 8, 8))
+    mb.close()                                          # idempotent
+    assert mb.batches.maxlen is not None                # the batch-size log is bounded
+
+
 def test_errors_reach_every_waiter_and_the_batcher_survives():
     def bad(x):
         if x.shape[-1] == 4:
