@@ -176,3 +176,21 @@ def test_ddim_shim_defaults_follow_their_reference_files():
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "compat"), ROOT, os.environ.get("PYTHONPATH", "")]))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and r.stdout.strip() == "25", r.stderr[-2000:]
+
+
+def test_launch_state_is_per_device_in_every_kernel_file():
+    """A process may hold handles on several GPUs (xrd_create(device, ...)): the dynamic shared-memory limit and the SM count are
+    properties of the CURRENT device, so no kernel file may remember them per process (csrc/common.cuh: ensure_dyn_smem, sm_count)."""
+    import glob
+    csrc = os.path.join(ROOT, "medical-image-denoising-using-diffusion_b200", "csrc")
+    files = sorted(glob.glob(os.path.join(csrc, "*.cu")) + glob.glob(os.path.join(csrc, "*.cuh")))
+    assert len(files) >= 15
+    users = 0
+    for f in files:
+        src = re.sub(r"//[^\n]*", "", open(f).read())
+        users += len(re.findall(r"\bensure_dyn_smem\s*\(", src))
+        if os.path.basename(f) == "common.cuh":
+            continue
+        assert "cudaFuncSetAttribute" not in src, f"{os.path.basename(f)} sets a function attribute itself"
+        assert "cudaDevAttrMultiProcessorCount" not in src, f"{os.path.basename(f)} queries the SM count itself"
+    assert users >= 12
