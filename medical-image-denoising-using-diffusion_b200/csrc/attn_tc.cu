@@ -14,6 +14,9 @@
 //     it by more than 2^8 (P stays below 256, exact after the final division by the row sum accumulated with the
 //     same m); only then is O rescaled in place (tcgen05.ld / tcgen05.st) -- after the first tiles almost never.
 //   * 64-key tiles keep S in 64 registers per thread and leave room for a 6-deep K/V ring in shared memory.
+//   * Launch shapes for small batches (attention_tc_shape): one Q tile per CTA while twice the CTAs still fit the SMs; for a single
+//     image two CTAs share a Q tile's key range and k_attn_combine merges their partial results (the per-CTA chain over the key
+//     tiles is latency-bound: 64 one-tile CTAs took 66 us, hardly less than 32 two-tile ones).
 //   warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 / 6..9 = softmax of Q tile 0 / 1.
 //   The (n, N, N) score matrix never exists in HBM.
 #include "kernels.cuh"
@@ -33,6 +36,12 @@ struct AttnTcP {
   int probe;               // probe the next Q K^T block's barriers under the P V MMAs
   int ntq;                 // Q tiles per CTA: 2 (throughput shape: the two tiles share every K/V tile), or 1 when the whole launch
                            // is so small (one or two images) that twice the CTAs of half the work fill more of the machine
+  int nsplit;              // key-range splits per Q tile: 1, or 2 for single-image launches (one-Q-tile CTAs would fill under half of
+                           // the SMs: 64 of 148 at 64x64).  With 2, CTA (x = 2*qtile + s) walks keys [s * nkv * 64, (s+1) * nkv * 64)
+                           // (nkv is then the tile count of ONE range) and writes its un-normalised fp32 output, reference maximum
+                           // and row sum; k_attn_combine merges the two ranges.
+  float* part;             // nsplit == 2: [split][image][query][heads*d] fp32 partial outputs
+  float2* ml;              // nsplit == 2: [split][image][head][query] (reference maximum * scale * log2 e, row sum)
   void* out;
 };
 
@@ -279,7 +288,8 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
   using Map = AttMap<D>;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128 * p.ntq, head = blockIdx.y, img = blockIdx.z;
+  // split launches: blockIdx.x = nsplit * (Q tile) + key range (recomputed where it is used: nothing extra stays live in the loops)
+  const int q0 = (p.nsplit > 1 ? (int)blockIdx.x / p.nsplit : (int)blockIdx.x) * 128 * p.ntq, head = blockIdx.y, img = blockIdx.z;
   const int qoff = head * p.d, koff = p.heads * p.d + head * p.d, voff = 2 * p.heads * p.d + head * p.d;
 
   if (warp == 0 && lane == 0) {
@@ -319,14 +329,15 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       tc::mbar_expect_tx(q_full, (uint32_t)(p.ntq * NCH) * kTile);
       for (int t = 0; t < p.ntq; ++t)
         for (int c = 0; c < NCH; ++c) tc::tma_load_3d(sQ + (t * 2 + c) * kTile, &tmQ, q_full, qoff + 64 * c, q0 + t * 128, img);
+      const int kbase = p.nsplit > 1 ? ((int)blockIdx.x % p.nsplit) * p.nkv * 64 : 0;      // first key of this CTA's range
       uint32_t slot = 0, phase = 0;
       for (int j = 0; j < p.nkv; ++j) {
         tc::mbar_wait(&k_empty[slot], phase ^ 1);
         tc::mbar_expect_tx(&k_full[slot], (uint32_t)NCH * kKvTile);
-        for (int c = 0; c < NCH; ++c) tc::tma_load_3d(sK + (slot * 2 + c) * kKvTile, &tmKV, &k_full[slot], koff + 64 * c, j * 64, img);
+        for (int c = 0; c < NCH; ++c) tc::tma_load_3d(sK + (slot * 2 + c) * kKvTile, &tmKV, &k_full[slot], koff + 64 * c, kbase + j * 64, img);
         tc::mbar_wait(&v_empty[slot], phase ^ 1);
         tc::mbar_expect_tx(&v_full[slot], (uint32_t)NCH * kKvTile);
-        for (int c = 0; c < NCH; ++c) tc::tma_load_3d(sV + (slot * 2 + c) * kKvTile, &tmKV, &v_full[slot], voff + 64 * c, j * 64, img);
+        for (int c = 0; c < NCH; ++c) tc::tma_load_3d(sV + (slot * 2 + c) * kKvTile, &tmKV, &v_full[slot], voff + 64 * c, kbase + j * 64, img);
         if (++slot == kRing) { slot = 0; phase ^= 1; }
       }
     }
@@ -362,7 +373,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         tc::mbar_arrive(&s_free[t * 2 + b]);
       }
       if (decltype(ragged)::value) {               // only the last, partial key tile pays for the masking (64 compare + select)
-        const int kvalid = p.HW - j * 64;
+        const int kvalid = p.HW - j * 64;            // (never a split launch: those have no partial tile)
 #pragma unroll
         for (int i = 0; i < 64; ++i)
           if (i >= kvalid) v[i] = -INFINITY;
@@ -456,12 +467,30 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       tc::mbar_arrive(&p_full[t * 2 + b]);
       l_run += (rs0 + rs1) + (rs2 + rs3);
     };
-    const int nfull = p.HW / 64;                   // full 64-key tiles; at most one partial tile follows
+    // full 64-key tiles; at most one partial tile follows (split launches need HW % 128 == 0: every tile of a range is full)
+    const int nfull = p.nsplit > 1 ? p.nkv : p.HW / 64;
     for (int j = 0; j < nfull; ++j) step(j, std::false_type());
     if (nfull < p.nkv) step(nfull, std::true_type());
     // epilogue: O / l -> 16-bit -> out[img, q, head*d + :]
     tc::mbar_wait(&o_final[t], 0);
     tc::tc_fence_after();
+    if (p.nsplit > 1) {
+      const int split = (int)blockIdx.x % p.nsplit;
+      // partial result of this key range: O (un-normalised, relative to the reference maximum), the maximum in exp2 units, the sum
+      float* dp = p.part + (((int64_t)split * gridDim.z + img) * p.HW + q) * (p.heads * p.d) + head * p.d;
+#pragma unroll
+      for (int c = 0; c < DC; ++c) {
+        float o[32];
+        tmem_ld32_nowait(tO + c * 32, o);
+        tmem_ld_wait();
+        if (q < p.HW) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            if (c * 32 + i < p.d) *reinterpret_cast<float4*>(dp + c * 32 + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+        }
+      }
+      if (q < p.HW) p.ml[(((int64_t)split * gridDim.z + img) * p.heads + head) * p.HW + q] = make_float2(m_run * p.scale_log2e, l_run);
+    } else {
     const float inv = 1.0f / l_run;
     T* dst = (T*)p.out + ((int64_t)img * p.HW + q) * (p.heads * p.d) + head * p.d;
 #pragma unroll
@@ -481,6 +510,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         }
       }
     }
+    }
     tc::tc_fence_before();
   }
   __syncthreads();
@@ -488,6 +518,55 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem_base, 512);
   }
+}
+
+// Merge of the two key ranges of a split launch: out = (w0 O0 + w1 O1) / (w0 l0 + w1 l1), w_s = 2^(m_s - max(m0, m1)).
+// One thread per (query, 8 channels): 2 x 32 B of partials in, 16 B out.
+template <typename T>
+__global__ void __launch_bounds__(256) k_attn_combine(const float* __restrict__ part, const float2* __restrict__ ml, T* __restrict__ out,
+                                                      int n, int HW, int heads, int d) {
+  const int C = heads * d, g8 = C / 8;
+  const int64_t rows = (int64_t)n * HW;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * g8) return;
+  const int64_t row = idx / g8;
+  const int ch = (int)(idx - row * g8) * 8;
+  const int head = ch / d;
+  const int64_t img = row / HW, q = row - img * HW;
+  const float2 a = ml[(img * heads + head) * HW + q];
+  const float2 b = ml[(((int64_t)n + img) * heads + head) * HW + q];
+  const float M = fmaxf(a.x, b.x);
+  float w0 = ex2(a.x - M), w1 = ex2(b.x - M);
+  const float inv = 1.0f / (w0 * a.y + w1 * b.y);
+  w0 *= inv; w1 *= inv;
+  const float4* p0 = reinterpret_cast<const float4*>(part + row * C + ch);
+  const float4* p1 = reinterpret_cast<const float4*>(part + (rows + row) * C + ch);
+  const float4 x0 = p0[0], x1 = p0[1], y0 = p1[0], y1 = p1[1];
+  uint4 w;
+  w.x = pack2<T>(w0 * x0.x + w1 * y0.x, w0 * x0.y + w1 * y0.y); w.y = pack2<T>(w0 * x0.z + w1 * y0.z, w0 * x0.w + w1 * y0.w);
+  w.z = pack2<T>(w0 * x1.x + w1 * y1.x, w0 * x1.y + w1 * y1.y); w.w = pack2<T>(w0 * x1.z + w1 * y1.z, w0 * x1.w + w1 * y1.w);
+  *reinterpret_cast<uint4*>(out + row * C + ch) = w;
+}
+
+// Launch shape.  ntq: one Q tile per CTA while twice the CTAs still fit the SMs (one or two images at 64x64: the served shape ran 32
+// CTAs of 72 us each, profiles/r02_launches_ddim_b1.csv).  nsplit: when even the one-tile CTAs fill under half of the machine (one
+// image: 64 CTAs of 66 us, each a serial chain over 64 key tiles), two CTAs share a Q tile's key range.
+static void attention_tc_shape(const Tens& qkv, int heads, int& ntq, int& nsplit) {
+  static const int ntq_env = getenv("XRD_ATT_NTQ") ? atoi(getenv("XRD_ATT_NTQ")) : 0;
+  static const int split_env = getenv("XRD_ATT_SPLIT") ? atoi(getenv("XRD_ATT_SPLIT")) : 1;
+  const int HW = qkv.h * qkv.w, nsm = sm_count();
+  ntq = (ntq_env == 1 || ntq_env == 2) ? ntq_env : (2 * cdiv(HW, 256) * heads * qkv.n <= nsm ? 1 : 2);
+  nsplit = 1;
+  if (split_env && ntq == 1 && HW % 128 == 0 && HW / 64 >= 8 && 2 * (HW / 128) * heads * qkv.n <= nsm) nsplit = 2;
+}
+
+size_t attention_tc_scratch_floats(const Tens& qkv, int heads) {
+  if (!attention_tc_supported(qkv, heads)) return 0;
+  int ntq, nsplit;
+  attention_tc_shape(qkv, heads, ntq, nsplit);
+  if (nsplit == 1) return 0;
+  const size_t rows = (size_t)qkv.n * qkv.h * qkv.w;
+  return (size_t)nsplit * rows * (size_t)(qkv.c / 3) + (size_t)nsplit * rows * heads * 2;
 }
 
 bool attention_tc_supported(const Tens& qkv, int heads) {
@@ -499,7 +578,7 @@ bool attention_tc_supported(const Tens& qkv, int heads) {
   return true;
 }
 
-void attention_tc(Ctx& c, const Tens& qkv, int heads, Tens& out) {
+void attention_tc(Ctx& c, const Tens& qkv, int heads, Tens& out, float* scratch) {
   XRD_REQUIRE(attention_tc_supported(qkv, heads), "attention_tc: unsupported shape (C=%d heads=%d)", qkv.c, heads);
   const int d = qkv.c / (3 * heads);
   XRD_REQUIRE(out.c == heads * d && out.n == qkv.n && out.h == qkv.h && out.w == qkv.w && out.dt == qkv.dt, "attention_tc: output shape");
@@ -507,7 +586,11 @@ void attention_tc(Ctx& c, const Tens& qkv, int heads, Tens& out) {
   const int HW = qkv.h * qkv.w;
   AttnTcP p;
   p.HW = HW; p.heads = heads; p.d = d;
-  p.nkv = cdiv(HW, 64);
+  attention_tc_shape(qkv, heads, p.ntq, p.nsplit);
+  if (!scratch) p.nsplit = 1;                       // no workspace for partial results: one CTA walks the whole key range
+  p.nkv = cdiv(HW, 64) / p.nsplit;                  // split launches: HW % 128 == 0
+  p.part = scratch;
+  p.ml = scratch ? reinterpret_cast<float2*>(scratch + (size_t)p.nsplit * qkv.n * HW * (heads * d)) : nullptr;
   p.nchunk = cdiv(d, 64);
   p.scale_log2e = (float)((1.0 / sqrt((double)d)) * 1.4426950408889634);
   static const int ahead = getenv("XRD_ATT_AHEAD") ? atoi(getenv("XRD_ATT_AHEAD")) : 1;   // measured: 0.327 ms (1) vs 0.340 ms (2) at B=16
@@ -527,12 +610,7 @@ void attention_tc(Ctx& c, const Tens& qkv, int heads, Tens& out) {
     if (r != CUDA_SUCCESS) fail(XRD_ERR_CUDA, "cuTensorMapEncodeTiled(qkv) failed: %d", (int)r);
   }
   const size_t smem = 1024 + (size_t)4 * kTile + (size_t)2 * kRing * 2 * kKvTile + 64 * 8;
-  // one Q tile per CTA while twice the CTAs still fit the 148 SMs (one or two images at 64x64): the served shape ran 32 CTAs
-  // of 72 us each (profiles/r02_launches_ddim_b1.csv)
-  static const int ntq_env = getenv("XRD_ATT_NTQ") ? atoi(getenv("XRD_ATT_NTQ")) : 0;
-  const int nsm = sm_count();
-  p.ntq = (ntq_env == 1 || ntq_env == 2) ? ntq_env : (2 * cdiv(HW, 256) * heads * qkv.n <= nsm ? 1 : 2);
-  dim3 grid(cdiv(HW, 128 * p.ntq), heads, qkv.n);
+  dim3 grid(cdiv(HW, 128 * p.ntq) * p.nsplit, heads, qkv.n);
   const int dc = d / 16;
 #define XRD_ATT_CASE(TT, DCV)                                                                                             \
   case DCV: {                                                                                                             \
@@ -547,6 +625,12 @@ void attention_tc(Ctx& c, const Tens& qkv, int heads, Tens& out) {
                   XRD_ATT_CASE(__half, 5) XRD_ATT_CASE(__half, 6) XRD_ATT_CASE(__half, 7) XRD_ATT_CASE(__half, 8) }
   }
 #undef XRD_ATT_CASE
+  if (p.nsplit > 1) {
+    const int64_t items = (int64_t)qkv.n * HW * (heads * d / 8);
+    const int blocks = (int)cdiv64(items, 256);
+    if (qkv.dt == DT_BF16) XRD_LAUNCH(c, k_attn_combine<__nv_bfloat16>, blocks, 256, 0, p.part, p.ml, (__nv_bfloat16*)out.p, qkv.n, HW, heads, d);
+    else XRD_LAUNCH(c, k_attn_combine<__half>, blocks, 256, 0, p.part, p.ml, (__half*)out.p, qkv.n, HW, heads, d);
+  }
 }
 
 }  // namespace xrd

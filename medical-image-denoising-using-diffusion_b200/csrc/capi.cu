@@ -991,10 +991,15 @@ XRD_EXPORT int xrd_op_attention(xrd_handle* H, int impl, const float* qkv, float
     with_arena(H, s, keyf("opattn", H, B, Hh, W, heads, d, impl), [&](Ctx& c) {
       Tens q = c.alloc(B, Hh, W, 3 * heads * d);
       Tens o = c.alloc(B, Hh, W, heads * d);
+      float* ws = nullptr;                       // workspace of the split-key launch shape (single images)
+      if (impl == 1 && attention_tc_supported(q, heads)) {
+        const size_t nf = attention_tc_scratch_floats(q, heads);
+        if (nf) ws = c.allocf(nf);
+      }
       nchw_to_nhwc(c, qkv, q);
-      auto run = [q, o, heads, impl](Ctx& cc) mutable {
+      auto run = [q, o, heads, impl, ws](Ctx& cc) mutable {
         Tens oo = o;
-        if (impl == 1) attention_tc(cc, q, heads, oo);
+        if (impl == 1) attention_tc(cc, q, heads, oo, ws);
         else attention_simt(cc, q, heads, oo);
       };
       run(c);

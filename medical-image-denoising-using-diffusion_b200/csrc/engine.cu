@@ -567,8 +567,12 @@ static void resblock(Ctx& c, UNetW& u, ResW& r, const TS& x1, const TS* x2, cons
 }
 
 static void attention(Ctx& c, const Tens& qkv, int heads, Tens& o) {
-  if (c.tc && attention_tc_supported(qkv, heads)) attention_tc(c, qkv, heads, o);
-  else attention_simt(c, qkv, heads, o);
+  if (c.tc && attention_tc_supported(qkv, heads)) {
+    const size_t nf = attention_tc_scratch_floats(qkv, heads);       // released with the block's other temporaries
+    attention_tc(c, qkv, heads, o, nf ? c.allocf(nf) : nullptr);
+  } else {
+    attention_simt(c, qkv, heads, o);
+  }
 }
 
 static void attnblock(Ctx& c, UNetW& u, AttnW& a, const TS& x, TS& out) {

@@ -71,7 +71,10 @@ void conv_smallcin2(Ctx& c, const Tens& x1, const Tens* x2, const ConvW& w, Tens
 
 // softmax(q^T k / sqrt(d)) v; qkv [N,HW,3*heads*d] (channel = s*heads*d + head*d + j), out [N,HW,heads*d]
 void attention_simt(Ctx& c, const Tens& qkv, int heads, Tens& out);
-void attention_tc(Ctx& c, const Tens& qkv, int heads, Tens& out);
+// `scratch`: attention_tc_scratch_floats() floats of workspace for the split-key launch shape of single images (null or a zero count:
+// every CTA walks the whole key range)
+void attention_tc(Ctx& c, const Tens& qkv, int heads, Tens& out, float* scratch = nullptr);
+size_t attention_tc_scratch_floats(const Tens& qkv, int heads);
 bool attention_tc_supported(const Tens& qkv, int heads);
 
 // --- normalisation / elementwise ---------------------------------------------

@@ -281,6 +281,9 @@ def check_attention(mode, impl):
                                             (1, 1, 64, 12, 10, 0), (1, 2, 96, 32, 32, 1), (2, 2, 96, 24, 24, 1),
                                             # production size of the 512x512 configurations: 64x64 = 4096 tokens (64 key tiles)
                                             (1, 2, 96, 64, 64, 0), (2, 2, 96, 64, 64, 1),
+                                            # a single image splits every Q tile's key range over two CTAs (attn_tc.cu: nsplit;
+                                            # also the 32x32 cases above): peaked, so the two ranges' maxima differ by far
+                                            (1, 2, 96, 64, 64, 1),
                                             # launches of more than 74 (image, head, query-pair) items keep two Q tiles per CTA, smaller
                                             # ones run one (attn_tc.cu: ntq): 10 x 2 x 4 = 80 items and 20 x 2 x 3 ragged = 120
                                             (10, 2, 96, 32, 32, 1), (20, 2, 96, 24, 24, 0)]:
